@@ -1,0 +1,148 @@
+"""ctypes wrapper over oracle/_build/libsphoracle.so (oracle/sph_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: the plain-C restatement of the reference hot path.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_build", "libsphoracle.so")
+
+
+class Params(C.Structure):
+    _fields_ = [("mass", C.c_float), ("visc", C.c_float), ("surf_tens", C.c_float), ("p0", C.c_float),
+                ("k", C.c_float), ("h", C.c_float), ("len", C.c_float), ("dt", C.c_float),
+                ("g", C.c_float * 3)]
+
+
+class Grid(C.Structure):
+    _fields_ = [("gmin", C.c_float * 3), ("cell", C.c_float), ("dim", C.c_int * 3)]
+
+    @property
+    def ncells(self):
+        return int(self.dim[0]) * int(self.dim[1]) * int(self.dim[2])
+
+
+class _State(C.Structure):
+    _fields_ = [("n", C.c_int)] + [(k, C.c_void_p) for k in
+                                   ("pos", "vel", "acc", "density", "pressure", "fpress", "fvisc", "fgrav",
+                                    "fsurf", "normal", "neighb")]
+
+
+def build(force=False):
+    src = [os.path.join(_HERE, f) for f in ("sph_oracle.c", "sph_oracle.h", "Makefile")]
+    if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "oracle"])
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB)
+        L.so_lattice.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        L.so_step_allpairs.argtypes = [C.c_void_p, C.c_void_p]
+        L.so_step_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.so_grid_for_box.argtypes = [C.c_void_p] * 4
+        L.so_bin.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
+        L.so_neighbours.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
+        L.so_neighbours.restype = C.c_long
+        L.so_default_params.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def default_params(**kw):
+    P = Params()
+    lib().so_default_params(C.byref(P))
+    for k, v in kw.items():
+        if k == "g":
+            P.g[:] = list(v)
+        else:
+            setattr(P, k, v)
+    return P
+
+
+def lattice(n, origin=(0.0, 0.0, 0.0)):
+    o = np.asarray(origin, np.float32)
+    cnt = lib().so_lattice(n, _p(o), None)
+    pos = np.zeros((cnt, 3), np.float32)
+    lib().so_lattice(n, _p(o), _p(pos))
+    return pos
+
+
+class State:
+    """SoA particle state + diagnostics, in particle-id order."""
+    V3 = ("pos", "vel", "acc", "fpress", "fvisc", "fgrav", "fsurf", "normal")
+    S1 = ("density", "pressure")
+
+    def __init__(self, pos, vel=None):
+        pos = np.ascontiguousarray(pos, np.float32)
+        n = pos.shape[0]
+        self.n = n
+        self.pos = pos.copy()
+        self.vel = np.zeros((n, 3), np.float32) if vel is None else np.ascontiguousarray(vel, np.float32).copy()
+        for k in self.V3[2:]:
+            setattr(self, k, np.zeros((n, 3), np.float32))
+        for k in self.S1:
+            setattr(self, k, np.zeros(n, np.float32))
+        self.neighb = np.zeros(n, np.int32)
+
+    def _c(self):
+        s = _State()
+        s.n = self.n
+        for k in self.V3 + self.S1 + ("neighb",):
+            setattr(s, k, _p(getattr(self, k)))
+        return s
+
+
+def step_allpairs(P, S, steps=1):
+    cs = S._c()
+    for _ in range(steps):
+        lib().so_step_allpairs(C.byref(P), C.byref(cs))
+
+
+def grid_for_box(P, lo, hi):
+    G = Grid()
+    lo = np.asarray(lo, np.float32); hi = np.asarray(hi, np.float32)
+    lib().so_grid_for_box(C.byref(P), _p(lo), _p(hi), C.byref(G))
+    return G
+
+
+def step_grid(P, G, S, steps=1):
+    cs = S._c()
+    for _ in range(steps):
+        lib().so_step_grid(C.byref(P), C.byref(G), C.byref(cs))
+
+
+def bin_particles(G, pos):
+    pos = np.ascontiguousarray(pos, np.float32)
+    n = pos.shape[0]
+    cell_of = np.zeros(n, np.int32); order = np.zeros(n, np.int32)
+    cell_start = np.zeros(G.ncells + 1, np.int32)
+    lib().so_bin(C.byref(G), n, _p(pos), _p(cell_of), _p(order), _p(cell_start))
+    return cell_of, order, cell_start
+
+
+def neighbours(P, G, pos, order, cell_start):
+    pos = np.ascontiguousarray(pos, np.float32)
+    n = pos.shape[0]
+    ns = np.zeros(n + 1, np.int64)
+    total = lib().so_neighbours(C.byref(P), C.byref(G), n, _p(pos), _p(order), _p(cell_start), _p(ns), None)
+    nb = np.zeros(max(total, 1), np.int32)
+    lib().so_neighbours(C.byref(P), C.byref(G), n, _p(pos), _p(order), _p(cell_start), _p(ns), _p(nb))
+    return ns, nb[:total]
+
+
+def omp_threads():
+    return lib().so_omp_threads()

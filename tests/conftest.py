@@ -1,0 +1,25 @@
+import importlib
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def product():
+    """The product package (directory name has a hyphen, so importlib)."""
+    return importlib.import_module("sph-erosion_b200")
+
+
+@pytest.fixture(scope="session")
+def pkg():
+    return product()

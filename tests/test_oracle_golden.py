@@ -1,0 +1,128 @@
+"""The C oracle (oracle/sph_oracle.c) against golden vectors produced by the unmodified reference
+(tests/golden/make_golden.py) and against the known-answer bit patterns of SURVEY.md section 4."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import port
+from oracle.ref import fnv1a64
+
+FLOAT_FIELDS = ["pos", "vel", "acc", "density", "pressure", "fpress", "fvisc", "fgrav", "fsurf", "normal"]
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def assert_bits(a, b, what):
+    assert np.array_equal(bits(a), bits(b)), "%s: %d of %d words differ" % (what, (bits(a) != bits(b)).sum(), a.size)
+
+
+@pytest.fixture(scope="module")
+def default_scene():
+    return np.load(os.path.join(GOLDEN, "default_scene.npz"))
+
+
+def test_lattice_matches_reference_initialize(default_scene):
+    assert_bits(port.lattice(1000), default_scene["pos0"], "Initialize(1000)")
+    # non-cube counts round up per axis (fluid_system.h:80-82)
+    assert port.lattice(999).shape[0] == 1000
+    assert port.lattice(1001).shape[0] == 11 ** 3
+
+
+def test_survey_known_answers(default_scene):
+    """Hex patterns from SURVEY.md section 4 (step 1, default scene)."""
+    S = port.State(port.lattice(1000))
+    port.step_allpairs(port.default_params(dt=0.01), S)
+    kat = {0: ([0xbe489570, 0xbd3ff50a, 0xbe15623d], 0x4436d10f, 0xc4484480, 0x46b887e2, 0x41a31a36),
+           555: ([0xbd99999a, 0x3d9796c0, 0xbccccccd], 0x449dfa17, 0x444724dd, 0x3c90a1d7, 0x35840000),
+           999: ([0x3cab11e6, 0x3e2dfa69, 0x3d912ae0], 0x4436d116, 0xc448446b, 0xc6b887d3, 0xc1a31a3c)}
+    for i, (pos, rho, pr, fpx, nx) in kat.items():
+        assert bits(S.pos[i]).tolist() == pos
+        assert int(bits(S.density[i:i + 1])[0]) == rho
+        assert int(bits(S.pressure[i:i + 1])[0]) == pr
+        assert int(bits(S.fpress[i])[0]) == fpx
+        assert int(bits(S.normal[i])[0]) == nx
+    assert int(bits(S.fgrav[0])[1]) == 0xc5e0684c
+    assert not S.fvisc.any()  # zero initial velocity
+
+
+@pytest.mark.parametrize("mode", ["allpairs", "grid"])
+def test_default_scene_100_steps_bit_exact(default_scene, mode):
+    g = default_scene
+    P = port.default_params(dt=0.01)
+    S = port.State(port.lattice(1000))
+    G = port.grid_for_box(P, [-0.25] * 3, [0.25] * 3)
+    want = dict(zip(g["hash_steps"].tolist(), g["hashes"].tolist()))
+    for step in range(1, 101):
+        if mode == "allpairs":
+            port.step_allpairs(P, S)
+        else:
+            port.step_grid(P, G, S)
+        if step == 1:
+            for f in FLOAT_FIELDS:
+                assert_bits(getattr(S, f), g["s1_" + f], "step1 " + f)
+            assert np.array_equal(S.neighb, g["s1_neighb"])
+        if step in want:
+            assert fnv1a64(S.pos, S.vel, S.density, S.pressure) == want[step], "state hash at step %d" % step
+        if step in (20, 100):
+            assert_bits(S.pos, g["s%d_pos" % step], "pos")
+            assert_bits(S.vel, g["s%d_vel" % step], "vel")
+    ke = float((0.5 * 0.02 * (S.vel.astype(np.float64) ** 2).sum(axis=1)).mean())
+    assert ke == pytest.approx(float(g["mean_ke"][-1]), rel=1e-12)
+
+
+@pytest.mark.parametrize("case", [0, 1, 2])
+@pytest.mark.parametrize("mode", ["allpairs", "grid"])
+def test_random_state_cases(case, mode):
+    g = np.load(os.path.join(GOLDEN, "random_state.npz"))
+    dt, length, h, mass, visc, surf, p0, gx, gy, gz = g["c%d_cfg" % case].tolist()
+    P = port.default_params(dt=dt, len=length, h=h, mass=mass, visc=visc, surf_tens=surf, p0=p0, g=(gx, gy, gz))
+    S = port.State(g["c%d_in_pos" % case], g["c%d_in_vel" % case])
+    if mode == "allpairs":
+        port.step_allpairs(P, S)
+    else:
+        lo = S.pos.min(axis=0) - 0.01
+        hi = S.pos.max(axis=0) + 0.01
+        port.step_grid(P, port.grid_for_box(P, lo, hi), S)
+    for f in FLOAT_FIELDS:
+        assert_bits(getattr(S, f), g["c%d_%s" % (case, f)], "case %d %s" % (case, f))
+
+
+def test_add_particles_coincident_branch():
+    """Initialize + AddParticles puts particles on top of each other -> dist < 1e-4 branch."""
+    g = np.load(os.path.join(GOLDEN, "add_particles.npz"))
+    P = port.default_params(dt=0.01)
+    S = port.State(g["added_pos"], g["added_vel"])
+    port.step_allpairs(P, S)
+    for f in FLOAT_FIELDS:
+        assert_bits(getattr(S, f), g["a1_" + f], f)
+    S2 = port.State(g["added_pos"], g["added_vel"])
+    port.step_grid(P, port.grid_for_box(P, [-0.3] * 3, [0.3] * 3), S2)
+    for f in FLOAT_FIELDS:
+        assert_bits(getattr(S2, f), g["a1_" + f], "grid " + f)
+    assert_bits(port.lattice(1000, (0.01, 0.02, -0.01)), g["reset_pos"], "Reset lattice")
+
+
+def test_grid_definition_invariants():
+    rng = np.random.default_rng(7)
+    P = port.default_params()
+    pos = rng.uniform(-0.22, 0.22, (4000, 3)).astype(np.float32)  # some outside the grid -> clamped
+    G = port.grid_for_box(P, [-0.2] * 3, [0.2] * 3)
+    cell_of, order, cell_start = port.bin_particles(G, pos)
+    assert cell_start[0] == 0 and cell_start[-1] == 4000
+    assert (np.diff(cell_start) >= 0).all()
+    keys = cell_of[order].astype(np.int64) * 4000 + order
+    assert (np.diff(keys) > 0).all()  # sorted by (cell, id)
+    ns, nb = port.neighbours(P, G, pos, order, cell_start)
+    # neighbour SETS equal the reference's all-pairs predicate
+    d = pos[:, None, :] - pos[None, :, :]
+    t = d * d
+    dist = np.sqrt((t[..., 0] + t[..., 1]) + t[..., 2], dtype=np.float32)
+    for s in range(0, 4000, 37):
+        i = order[s]
+        want = np.nonzero(dist[i] <= np.float32(P.h))[0]
+        got = np.sort(nb[ns[s]:ns[s + 1]])
+        assert np.array_equal(got, want)
