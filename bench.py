@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- particle-updates/s of the SPH-Erosion per-step hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|small] [--impl reference]
+
+One "step" = one FluidSystemSPH::Run over the synthetic scene: hash -> count/scan -> scatter ->
+rank+reorder -> density -> force+integrate+collide (+terrain/erosion when the workload has terrain).
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what every key means.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "sph_particle_updates_per_sec"
+UNIT = "particle-updates/s"
+SPACING = 0.025
+# algorithmic HBM bytes per particle per launch (SURVEY.md section 8d / DESIGN.md "kernels")
+ALGO_BYTES = {"hash": 20, "scatter": 16, "reorder": 92, "density": 44, "force": 72}
+
+
+# ----------------------------------------------------------------------------- scenes
+def scaled_dam_break(n_axis, jitter=False, nx_mult=1):
+    """box half-extent L = 0.02*n, lattice spacing 0.025, block corner at
+    (-L, -L/4, -3L/4); n_axis = 10 reproduces the reference default scene exactly.  nx_mult stretches
+    the block (and the box) along x for weak scaling over x-slabs."""
+    L = np.float32(0.02 * n_axis * nx_mult)
+    Lb = 0.02 * n_axis
+    ix = np.arange(n_axis * nx_mult)
+    i = np.arange(n_axis)
+    x = (-float(L) + ix * SPACING).astype(np.float32)
+    y = (-Lb / 4 + i * SPACING).astype(np.float32)
+    z = (-0.75 * Lb + i * SPACING).astype(np.float32)
+    pos = np.empty((x.size, y.size, z.size, 3), np.float32)
+    pos[..., 0] = x[:, None, None]; pos[..., 1] = y[None, :, None]; pos[..., 2] = z[None, None, :]
+    pos = pos.reshape(-1, 3)
+    if jitter:
+        rng = np.random.default_rng(0x5EED)
+        pos += rng.uniform(-0.2 * SPACING, 0.2 * SPACING, pos.shape).astype(np.float32)
+    return pos, float(L)
+
+
+WORKLOADS = {
+    # name: (n_axis, jitter, terrain, description)
+    "small": (32, False, False, "32^3 = 32,768-particle dam break (smoke-sized)"),
+    "c2": (100, False, False, "BASELINE configs[1]: 1M-particle dam break in a box, no terrain (n=100 -> 1,000,000)"),
+    "c3": (160, True, False, "BASELINE configs[2] particle scene: 4.096M-particle dam break (n=160), terrain/erosion stage not yet attached"),
+}
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- helpers
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel):
+    """dram read+write bytes per launch from the committed ncu summary, if one exists."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel)
+        except Exception:
+            return None
+    return None
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ----------------------------------------------------------------------------- CPU arms
+def cpu_port_baseline(pos, L, budget_s=20.0):
+    """Times oracle/sph_oracle.c so_step_grid (OpenMP, all host cores) on a bounded sample of the
+    same scene.  kind = "port": the cell-grid restatement, bit-identical to the reference's sums."""
+    from oracle import port
+    n = pos.shape[0]
+    sample_n = n
+    # ~1e6 updates/s on 8 cores: keep the sample around the budget
+    est = n / (1.2e5 * max(port.omp_threads(), 1))
+    if est > budget_s:
+        sample_n = int(n * budget_s / est)
+    # a contiguous x-slab of the block keeps the neighbour statistics of the full scene
+    order = np.argsort(pos[:, 0], kind="stable")[:sample_n]
+    sp = np.ascontiguousarray(pos[order])
+    P = port.default_params(dt=0.01, len=L)
+    S = port.State(sp)
+    G = port.grid_for_box(P, [-L - 0.1] * 3, [L + 0.1] * 3)
+    port.step_grid(P, G, S)  # warm (page faults, thread pool)
+    t = time.perf_counter()
+    steps = 2
+    port.step_grid(P, G, S, steps)
+    dt = (time.perf_counter() - t) / steps
+    return {"value": sample_n / dt, "unit": UNIT, "cores": port.omp_threads(), "kind": "port",
+            "sample": "%d of %d particles (x-slab of the same scene), %d steps of oracle so_step_grid (OpenMP cell grid, sums bit-identical to the reference), %.2f s/step" % (sample_n, n, steps, dt)}
+
+
+def run_reference_arm(args):
+    """--impl reference: the UNMODIFIED reference step (oracle/_ref/libsphref_omp.so, built in place
+    from the reference sources) on the host cores.  It is O(N^2), so each step runs a bounded sample
+    of the workload's scene."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    from oracle import ref
+    n_axis, jitter, _, desc = WORKLOADS[args.workload]
+    line = {"metric": METRIC, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic"}
+    if not ref.available(omp=True):
+        # the oracle always exists: fall back to the C port of the same algorithm
+        pos, L = scaled_dam_break(n_axis, jitter)
+        cb = cpu_port_baseline(pos, L)
+        line.update({"value": cb["value"], "ms_per_step": None, "cpu_baseline": cb,
+                     "config": {"workload": args.workload, "description": desc, "note": "oracle/_ref absent: timed the C port"},
+                     "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        print(json.dumps(line))
+        return
+    os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
+    sample_axis = 22
+    pos, L = scaled_dam_break(sample_axis, jitter)
+    sim = ref.RefSim(omp=True)
+    sim.set_len(L); sim.set_dt(0.01)
+    sim.set_state(pos, np.zeros_like(pos))
+    t = time.perf_counter(); sim.run(1); t1 = time.perf_counter() - t
+    if t1 * (args.steps + args.warmup) > 150.0:
+        sample_axis = 16
+        pos, L = scaled_dam_break(sample_axis, jitter)
+        sim = ref.RefSim(omp=True); sim.set_len(L); sim.set_dt(0.01); sim.set_state(pos, np.zeros_like(pos))
+    sim.run(args.warmup)
+    t = time.perf_counter(); sim.run(args.steps); dt = (time.perf_counter() - t) / max(args.steps, 1)
+    n = pos.shape[0]
+    full_n = n_axis ** 3
+    cores = ref._load(True).ref_omp_max_threads()
+    cb = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+          "sample": "%d^3 = %d-particle block of the same scaled dam break; reference is all-pairs O(N^2), "
+                    "so at the full %d particles it extrapolates to %.3g updates/s" % (sample_axis, n, full_n, (n / dt) * n / full_n)}
+    line.update({"value": n / dt, "ms_per_step": dt * 1e3, "cpu_baseline": cb,
+                 "config": {"workload": args.workload, "description": desc, "reference_sample_particles": n},
+                 "e2e": {"value": n / dt, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_gpu_arm(args):
+    import torch
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = importlib.import_module("sph-erosion_b200")
+    n_axis, jitter, terrain, desc = WORKLOADS[args.workload]
+
+    if world > 1:
+        from importlib import import_module
+        slabs = import_module("sph-erosion_b200.slabs")
+        return slabs.bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT)
+
+    pos, L = scaled_dam_break(n_axis, jitter)
+    n = pos.shape[0]
+    sim = pkg.FluidSystemSPH(device=local)
+    sim.params.len = L
+    sim.SetDeltaTime(0.01)
+    sim.set_variant(args.density_variant, args.force_variant)
+    sim.upload_state(pos, np.zeros_like(pos))
+    flush_bytes = 256 << 20
+    sim.set_l2_flush(flush_bytes)
+
+    sim.timed_steps(args.warmup, per_kernel=False)
+    sampler = ClockSampler(local)
+    sampler.start()
+    torch.cuda.synchronize()
+    ms, per_kernel, launches = sim.timed_steps(args.steps, per_kernel=True)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms_step = ms / args.steps
+    value = n / (ms_step * 1e-3)
+
+    # end to end: host (pinned) buffers in, host buffers out, every step, through sphe_step_host
+    e2e_steps = max(3, min(args.steps, 20))
+    hp = torch.from_numpy(pos).pin_memory(); hv = torch.zeros_like(hp).pin_memory()
+    op = torch.empty_like(hp).pin_memory(); ov = torch.empty_like(hp).pin_memory()
+    orho = torch.empty(n, dtype=torch.float32).pin_memory()
+    sim2 = pkg.FluidSystemSPH(device=local)
+    sim2.params.len = L; sim2.SetDeltaTime(0.01)
+    sim2.set_variant(args.density_variant, args.force_variant)
+    for _ in range(3):
+        sim2.step_host_ptr(n, hp.data_ptr(), hv.data_ptr(), op.data_ptr(), ov.data_ptr(), orho.data_ptr())
+    t = time.perf_counter()
+    for _ in range(e2e_steps):
+        sim2.step_host_ptr(n, hp.data_ptr(), hv.data_ptr(), op.data_ptr(), ov.data_ptr(), orho.data_ptr())
+        hp, op = op, hp
+        hv, ov = ov, hv
+    e2e_dt = (time.perf_counter() - t) / e2e_steps
+    e2e = {"value": n / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 28 * n,
+           "ms_per_step": e2e_dt * 1e3, "steps": e2e_steps,
+           "api": "sphe_step_host (pinned host pos/vel in, pos/vel/density out, id order)"}
+
+    peak, peak_src = measured_peak()
+    dom = max(("density", "force"), key=lambda k: per_kernel[k])
+    t_dom = per_kernel[dom] / args.steps * 1e-3
+    achieved = ALGO_BYTES[dom] * n / t_dom / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_%s" % dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": ncu_traffic(dom), "peak_source": peak_src,
+                "algorithmic_bytes_per_particle": ALGO_BYTES[dom],
+                "note": "neighbour passes are fp32-issue/LSU bound, not HBM bound (DESIGN.md); "
+                        "frac is reported against HBM as the contract asks",
+                "per_kernel_ms_per_step": {k: v / args.steps for k, v in per_kernel.items()},
+                "per_kernel_hbm_frac": {k: (ALGO_BYTES[k] * n / (per_kernel[k] / args.steps * 1e-3) / 1e9 / peak)
+                                        for k in ALGO_BYTES if per_kernel.get(k, 0) > 0}}
+    cb = cpu_port_baseline(pos, L) if not args.no_cpu_baseline else None
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "description": desc, "particles": n, "h": 0.0457, "spacing": SPACING,
+                       "dt": 0.01, "box_half_extent": L, "l2": "flushed between timed steps (%d MiB memset, outside the event brackets)" % (flush_bytes >> 20),
+                       "density_variant": args.density_variant, "force_variant": args.force_variant},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cb}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--density-variant", type=int, default=0)
+    ap.add_argument("--force-variant", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

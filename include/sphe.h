@@ -1,0 +1,164 @@
+/* sphe.h -- C ABI of the B200-native SPH-Erosion hot path (libsphe_b200.so).
+ *
+ * The reference has no FFI layer: its boundary is the public C++ surface of `FluidSystemSPH`
+ * (Erosion/fluid_system.h:66-289) and `Grid` (Erosion/grid.h:26-841) as used by Erosion/main.cpp.
+ * Every entry point below names the reference member it replaces.  The header-only shim classes in
+ * sph-erosion_b200/host/{fluid_system.h,grid.h} re-create that C++ surface on top of this ABI, so
+ * main.cpp (or a headless driver) compiles against them unchanged -- see INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only; every call returns SPHE_OK (0) or a negative error
+ * code and records a message retrievable with sphe_last_error(); all host arrays are in PARTICLE-ID
+ * order (the order of the reference's std::vector<FluidParticle>); vec3 arrays are packed xyz float32.
+ * Threading: like the reference (single render thread, main.cpp:197-357) a handle is not re-entrant.
+ * There is no CPU fallback: without a CUDA device every compute call fails with SPHE_ERR_CUDA.
+ */
+#ifndef SPHE_H
+#define SPHE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPHE_OK 0
+#define SPHE_ERR_CUDA (-1)     /* CUDA runtime error / no device */
+#define SPHE_ERR_ARG (-2)      /* bad argument */
+#define SPHE_ERR_STATE (-3)    /* call out of order (e.g. debug hook before any step) */
+#define SPHE_ERR_NOMEM (-4)
+
+typedef struct sphe_sim sphe_sim;         /* replaces a FluidSystemSPH instance */
+typedef struct sphe_terrain sphe_terrain; /* replaces a Grid instance */
+
+/* Host-resident simulation parameters.  The reference hands ImGui raw pointers into the object
+ * (GetMass/GetVisc/GetSurfTen/Getp0/GetGrav, fluid_system.h:261-284, used at main.cpp:278-290), so
+ * these live in host memory owned by the handle, are stable for its lifetime and are re-read by
+ * every sphe_step().  Defaults: fluid_system.h:460-478. */
+typedef struct sphe_params {
+    float mass;      /* MASS      0.02    */
+    float visc;      /* visc      3.5     */
+    float surf_tens; /* surf_tens 0.0728  */
+    float p0;        /* p0        998.29  */
+    float g[3];      /* g         (0,-9.82,0) */
+    float dt;        /* deltaT    0 (paused; main.cpp:476-485 toggles 0.01) */
+    float k;         /* k         3.0  (private, no setter in the reference) */
+    float h;         /* h = smoothRadius 0.0457 (private) */
+    float len;       /* box half extent 0.2 (private) */
+    float cR;        /* terrain restitution 0.5 (fluid_system.h:470, used only by the commented call :335-340) */
+} sphe_params;
+
+/* Mirror of `struct FluidParticle` (fluid_system.h:49-64), 112 bytes, what GetParticle returns. */
+typedef struct sphe_particle {
+    int id;
+    float position[3], velocity[3], acceleration[3];
+    float density, pressure;
+    float pressure_force[3], viscosity_force[3], gravity_force[3], surface_force[3], surface_normal[3];
+    int neighb_id;
+} sphe_particle;
+
+/* Field selectors for sphe_download (element type / width in brackets). */
+enum {
+    SPHE_F_POS = 0,      /* float[3] */
+    SPHE_F_VEL = 1,      /* float[3] */
+    SPHE_F_ACC = 2,      /* float[3]  diagnostics */
+    SPHE_F_DENSITY = 3,  /* float     */
+    SPHE_F_PRESSURE = 4, /* float     */
+    SPHE_F_FPRESS = 5,   /* float[3]  diagnostics */
+    SPHE_F_FVISC = 6,    /* float[3]  diagnostics */
+    SPHE_F_FGRAV = 7,    /* float[3]  diagnostics */
+    SPHE_F_FSURF = 8,    /* float[3]  diagnostics */
+    SPHE_F_NORMAL = 9,   /* float[3]  diagnostics */
+    SPHE_F_ID = 10,      /* int       */
+    SPHE_F_NEIGHB = 11,  /* int       diagnostics */
+    SPHE_F_SEDIMENT = 12 /* float     carried sediment (erosion model, not in the reference) */
+};
+
+/* Neighbour-grid description (this project's definition; the reference is all-pairs). */
+typedef struct sphe_grid_info {
+    float gmin[3];
+    float cell;   /* edge = h * (1 + 2^-10) */
+    int dim[3];   /* cell id = (cx*dim[1] + cy)*dim[2] + cz, coordinates clamped into the grid */
+} sphe_grid_info;
+
+/* Per-kernel device times of the timed steps (CUDA events on the launch stream). */
+enum { SPHE_K_HASH = 0, SPHE_K_SCAN, SPHE_K_SCATTER, SPHE_K_REORDER, SPHE_K_DENSITY, SPHE_K_FORCE,
+       SPHE_K_TERRAIN, SPHE_K_COUNT };
+
+const char* sphe_last_error(void);
+int sphe_abi_version(void);
+
+/* ---- lifetime ---- */
+/* FluidSystemSPH() (fluid_system.h:69-72).  Does NO CUDA work: the reference object is a global
+ * constructed before main() (main.cpp:50).  Device state is created lazily by the first call that
+ * needs it. */
+int sphe_create(sphe_sim** out);
+void sphe_destroy(sphe_sim* s);
+int sphe_set_device(sphe_sim* s, int device); /* before first use; default = current device */
+
+/* ---- scene ---- */
+int sphe_initialize(sphe_sim* s, int n_parts);   /* Initialize(int)   fluid_system.h:74-102  */
+int sphe_add_particles(sphe_sim* s, int n);      /* AddParticles(int) fluid_system.h:232-251 */
+int sphe_reset(sphe_sim* s);                     /* Reset()           fluid_system.h:253-259 */
+int sphe_set_origin(sphe_sim* s, const float o[3]); /* SetOrigin      fluid_system.h:206-209 */
+int sphe_get_origin(sphe_sim* s, float o[3]);       /* GetOrigin      fluid_system.h:211-214 */
+int sphe_set_dt(sphe_sim* s, float dt);             /* SetDeltaTime   fluid_system.h:216-219 */
+float sphe_get_dt(sphe_sim* s);                     /* GetDeltaTime   fluid_system.h:221-224 */
+sphe_params* sphe_params_ptr(sphe_sim* s);          /* GetMass..GetGrav fluid_system.h:261-284 */
+int sphe_count(sphe_sim* s);                        /* m_Particles.size() */
+int sphe_num(sphe_sim* s);                          /* `num` (what PrintCoords iterates, :226-230) */
+
+/* Neighbour-grid bounds.  Default: the box [-len,len]^3 padded by 2 cells.  Particles outside are
+ * clamped into the border cells (correctness is unaffected, only balance). */
+int sphe_set_grid_bounds(sphe_sim* s, const float lo[3], const float hi[3]);
+int sphe_grid_info_get(sphe_sim* s, sphe_grid_info* out);
+
+/* Replace the whole state (parity tests, checkpoints, the e2e host-buffer path); ids become 0..n-1. */
+int sphe_upload_state(sphe_sim* s, int n, const float* pos, const float* vel);
+
+/* ---- the hot path ---- */
+/* Run(Grid&) (fluid_system.h:104-183 + advance :306-353 + collisionS :355-407).  `t` may be NULL
+ * (the reference ignores its Grid argument: the call into Grid::collision is commented out,
+ * fluid_system.h:335-340).  With a terrain attached the particle-terrain contact of Grid::collision
+ * (grid.h:462-805) and the erosion model run after the box collision. */
+int sphe_step(sphe_sim* s, sphe_terrain* t);
+int sphe_sync(sphe_sim* s);
+
+/* One step with HOST buffers: upload pos/vel (id order), step, download pos/vel (+density if non-NULL).
+ * This is the end-to-end call bench.py times ("e2e"). */
+int sphe_step_host(sphe_sim* s, sphe_terrain* t, int n, const float* pos_in, const float* vel_in,
+                   float* pos_out, float* vel_out, float* density_out);
+
+/* Run `steps` steps, timing every step (summed into ms_total) and every kernel with CUDA events on the launch stream.
+ * ms_kernels[SPHE_K_COUNT] receives the summed device time per kernel class; launches receives the
+ * number of kernel launches issued. */
+/* Timing hygiene for sphe_timed_steps: write `bytes` (> L2 size) of scratch between timed steps, outside
+ * the timed brackets.  0 disables. */
+int sphe_set_l2_flush(sphe_sim* s, long long bytes);
+int sphe_timed_steps(sphe_sim* s, sphe_terrain* t, int steps, float* ms_total, float* ms_kernels, int* launches);
+
+/* ---- accessors ---- */
+/* Store the per-particle debug fields the reference keeps in FluidParticle (forces, normal,
+ * acceleration, NeighbId).  Off by default; sphe_get_particle switches it on. */
+int sphe_set_diagnostics(sphe_sim* s, int on);
+int sphe_get_particle(sphe_sim* s, int id, sphe_particle* out); /* GetParticle fluid_system.h:286-289 */
+int sphe_download(sphe_sim* s, int field, void* host_out);      /* whole field, id order */
+/* Packed positions for Draw() (fluid_system.h:185-204): xyz float32, id order. */
+int sphe_download_positions(sphe_sim* s, float* host_xyz);
+
+/* ---- neighbour-grid test hooks (state of the LAST step's binning) ---- */
+int sphe_debug_cells(sphe_sim* s, int* cell_of_id);          /* [n]  cell id per particle id       */
+int sphe_debug_sorted_order(sphe_sim* s, int* ids_sorted);   /* [n]  ids in (cell,id) order        */
+int sphe_debug_cell_start(sphe_sim* s, int* cell_start);     /* [ncells+1]                         */
+/* CSR neighbour lists by sorted slot, ids in grid-walk order, self included.  Call with nbr=NULL to
+ * get the total in *total. */
+int sphe_debug_neighbours(sphe_sim* s, long long* nbr_start, int* nbr, long long cap, long long* total);
+
+/* ---- raw device access for multi-GPU plumbing (halo exchange lives above this ABI) ---- */
+enum { SPHE_D_POSQ = 0, SPHE_D_VELV = 1, SPHE_D_IDS = 2, SPHE_D_RHO = 3 };
+void* sphe_device_ptr(sphe_sim* s, int which);
+int sphe_set_stream(sphe_sim* s, void* cuda_stream); /* run on a caller-provided cudaStream_t */
+/* Kernel-variant selector for the two neighbour passes (tuning / ncu A-B runs; 0 = default). */
+int sphe_set_variant(sphe_sim* s, int density_variant, int force_variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPHE_H */

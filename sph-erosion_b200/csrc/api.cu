@@ -1,0 +1,723 @@
+// C ABI (include/sphe.h) over the CUDA hot path.  Host-side state of one FluidSystemSPH replacement.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/sphe.h"
+#include "common.cuh"
+#include "sim.h"
+
+using namespace sphe;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(x)                                                                                   \
+    do {                                                                                        \
+        cudaError_t e_ = (x);                                                                   \
+        if (e_ != cudaSuccess)                                                                  \
+            return fail(SPHE_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
+    } while (0)
+#define TRY(x)                 \
+    do {                       \
+        int r_ = (x);          \
+        if (r_ != SPHE_OK) return r_; \
+    } while (0)
+
+struct KTimer {
+    int kind;
+    cudaEvent_t a, b;
+};
+
+struct sphe_sim {
+    sphe_params P;
+    float origin[3] = {0, 0, 0};
+    int num = 10, init_num = 0, next_label = 0;  // fluid_system.h:473-474,479
+    std::vector<int> labels;                     // reference `Id` labels when they differ from the index
+    bool labels_identity = true;
+
+    int device = -1;
+    bool ready = false;
+    cudaStream_t st = nullptr;
+    bool own_stream = false;
+
+    int n = 0, cap = 0;
+    float4 *posA = nullptr, *posB = nullptr, *posC = nullptr, *velA = nullptr, *velB = nullptr;
+    int *idsA = nullptr, *idsB = nullptr;
+    float *sedA = nullptr, *sedB = nullptr, *rho = nullptr;
+    uint32_t *cell = nullptr, *cell_sorted = nullptr;
+    uint2* tmp = nullptr;
+    float* stage = nullptr;  // 2 * 3 * cap floats: id-order staging for uploads/downloads
+    int* slot_of_id = nullptr;
+    bool slot_valid = false;
+
+    long long ncells = 0, ncells_cap = 0;
+    int *count = nullptr, *cell_start = nullptr, *cursor = nullptr, *tile_sum = nullptr;
+    GridP G{};
+    bool grid_user = false;
+    float glo[3], ghi[3];
+    float grid_h = -1.f, grid_len = -1.f;
+
+    bool diag = false;
+    int diag_cap = 0;
+    DiagOut D{};
+
+    bool binned = false;  // debug hooks valid
+    StepC lastC{};
+    int variant_density = 0, variant_force = 0;
+
+    bool timing = false;
+    void* flush_buf = nullptr;
+    size_t flush_bytes = 0;
+    std::vector<KTimer> timers;
+    int launches = 0;
+
+    sphe_sim() {
+        P.mass = 0.02f; P.visc = 3.5f; P.surf_tens = 0.0728f; P.p0 = 998.29f;
+        P.g[0] = 0.0f; P.g[1] = -9.82f; P.g[2] = 0.0f;
+        P.dt = 0.0f; P.k = 3.0f; P.h = 0.0457f; P.len = 0.2f; P.cR = 0.5f;
+    }
+};
+
+// ------------------------------------------------------------------ device plumbing
+static int ensure_device(sphe_sim* s) {
+    if (s->ready) {
+        CU(cudaSetDevice(s->device));
+        return SPHE_OK;
+    }
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt == 0)
+        return fail(SPHE_ERR_CUDA, "no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    if (s->device < 0) CU(cudaGetDevice(&s->device));
+    CU(cudaSetDevice(s->device));
+    if (!s->st) {
+        CU(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+        s->own_stream = true;
+    }
+    s->ready = true;
+    return SPHE_OK;
+}
+
+template <class T>
+static int grow(T** p, size_t old_count, size_t new_count, cudaStream_t st, bool keep) {
+    T* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, new_count * sizeof(T));
+    if (e != cudaSuccess) return fail(SPHE_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", new_count * sizeof(T), cudaGetErrorString(e));
+    if (keep && *p && old_count) CU(cudaMemcpyAsync(q, *p, old_count * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    if (*p) { CU(cudaStreamSynchronize(st)); CU(cudaFree(*p)); }
+    *p = q;
+    return SPHE_OK;
+}
+
+static int reserve(sphe_sim* s, int need) {
+    if (need <= s->cap) return SPHE_OK;
+    size_t nc = std::max<size_t>((size_t)need, (size_t)s->cap * 3 / 2);
+    nc = (nc + 255) & ~(size_t)255;
+    size_t live = (size_t)s->n;
+    TRY(grow(&s->posA, live, nc, s->st, true));
+    TRY(grow(&s->velA, live, nc, s->st, true));
+    TRY(grow(&s->idsA, live, nc, s->st, true));
+    TRY(grow(&s->sedA, live, nc, s->st, true));
+    TRY(grow(&s->posB, 0, nc, s->st, false));
+    TRY(grow(&s->posC, 0, nc, s->st, false));
+    TRY(grow(&s->velB, 0, nc, s->st, false));
+    TRY(grow(&s->idsB, 0, nc, s->st, false));
+    TRY(grow(&s->sedB, 0, nc, s->st, false));
+    TRY(grow(&s->rho, live, nc, s->st, true));
+    TRY(grow(&s->cell, 0, nc, s->st, false));
+    TRY(grow(&s->cell_sorted, 0, nc, s->st, false));
+    TRY(grow(&s->tmp, 0, nc, s->st, false));
+    TRY(grow(&s->stage, 0, nc * 8, s->st, false));
+    TRY(grow(&s->slot_of_id, 0, nc, s->st, false));
+    s->cap = (int)nc;
+    s->binned = false;
+    s->slot_valid = false;
+    return SPHE_OK;
+}
+
+static int reserve_diag(sphe_sim* s) {
+    if (!s->diag || s->diag_cap >= s->cap) return SPHE_OK;
+    size_t nc = (size_t)s->cap, old = (size_t)std::min(s->diag_cap, s->n);
+    TRY(grow(&s->D.acc, old, nc, s->st, true));
+    TRY(grow(&s->D.fpress, old, nc, s->st, true));
+    TRY(grow(&s->D.fvisc, old, nc, s->st, true));
+    TRY(grow(&s->D.fgrav, old, nc, s->st, true));
+    TRY(grow(&s->D.fsurf, old, nc, s->st, true));
+    TRY(grow(&s->D.normal, old, nc, s->st, true));
+    TRY(grow(&s->D.neighb, old, nc, s->st, true));
+    if (s->diag_cap == 0) {
+        // the reference leaves these fields uninitialised until the first Run; we define them as 0
+        CU(cudaMemsetAsync(s->D.acc, 0, nc * sizeof(float4), s->st));
+        CU(cudaMemsetAsync(s->D.fpress, 0, nc * sizeof(float4), s->st));
+        CU(cudaMemsetAsync(s->D.fvisc, 0, nc * sizeof(float4), s->st));
+        CU(cudaMemsetAsync(s->D.fgrav, 0, nc * sizeof(float4), s->st));
+        CU(cudaMemsetAsync(s->D.fsurf, 0, nc * sizeof(float4), s->st));
+        CU(cudaMemsetAsync(s->D.normal, 0, nc * sizeof(float4), s->st));
+        CU(cudaMemsetAsync(s->D.neighb, 0, nc * sizeof(int), s->st));
+    }
+    s->diag_cap = (int)nc;
+    return SPHE_OK;
+}
+
+// ------------------------------------------------------------------ per-step constants and grid
+static float sqrt_threshold(float h) {
+    // largest float T with sqrtf(T) <= h  => (sqrtf(d2) <= h) == (d2 <= T) for every float d2
+    float T = h * h;
+    while (sqrtf(T) > h) T = nextafterf(T, 0.0f);
+    while (sqrtf(nextafterf(T, INFINITY)) <= h) T = nextafterf(T, INFINITY);
+    return T;
+}
+
+static StepC make_consts(const sphe_params& P) {
+    const float PI_REF = 3.141592f;  // Erosion/sphere.h:8
+    StepC C;
+    float h = P.h;
+    C.h = h; C.hh = h * h; C.T = sqrt_threshold(h);
+    C.mass = P.mass; C.k = P.k; C.p0 = P.p0; C.visc = P.visc; C.surf = P.surf_tens;
+    C.gx = P.g[0]; C.gy = P.g[1]; C.gz = P.g[2];
+    C.dt = P.dt; C.len = P.len; C.cR = P.cR;
+    float c315 = (float)(315.0f / (64.0f * PI_REF * powf(h, 9.0f)));  // fluid_system.h:415
+    C.densK = P.mass * c315;
+    C.c45 = (float)(45.f / (PI_REF * powf(h, 6.0f)));                 // :442, :452
+    C.c945 = (float)(945.0f / (32.0f * PI_REF * powf(h, 9.0f)));      // :421, :427
+    C.hh3 = 3 * h * h;
+    return C;
+}
+
+static int setup_grid(sphe_sim* s) {
+    const sphe_params& P = s->P;
+    if (!(P.h > 0.0f) || !isfinite(P.h)) return fail(SPHE_ERR_ARG, "smoothing radius h must be positive");
+    bool same = (s->grid_h == P.h) && (s->grid_user || s->grid_len == P.len) && s->ncells > 0;
+    if (same) return SPHE_OK;
+    float cell = P.h * 1.0009765625f;  // h * (1 + 2^-10), see oracle so_grid_for_box
+    float lo[3], hi[3];
+    for (int a = 0; a < 3; a++) {
+        if (s->grid_user) { lo[a] = s->glo[a]; hi[a] = s->ghi[a]; }
+        else { lo[a] = -P.len - 2.0f * cell; hi[a] = P.len + 2.0f * cell; }
+    }
+    int dim[3];
+    for (int a = 0; a < 3; a++) {
+        float ext = hi[a] - lo[a];
+        int d = (int)ceilf(ext / cell);
+        if (d < 1) d = 1;
+        dim[a] = d;
+    }
+    long long nc = (long long)dim[0] * dim[1] * dim[2];
+    if (nc >= (1LL << 31) - 8) return fail(SPHE_ERR_ARG, "neighbour grid too large: %d x %d x %d cells", dim[0], dim[1], dim[2]);
+    s->G.gx = lo[0]; s->G.gy = lo[1]; s->G.gz = lo[2]; s->G.cell = cell;
+    s->G.nx = dim[0]; s->G.ny = dim[1]; s->G.nz = dim[2];
+    if (nc > s->ncells_cap) {
+        size_t padded = ((size_t)nc + 1 + 63) & ~(size_t)63;
+        TRY(grow(&s->count, 0, padded, s->st, false));
+        TRY(grow(&s->cell_start, 0, padded, s->st, false));
+        TRY(grow(&s->cursor, 0, padded, s->st, false));
+        TRY(grow(&s->tile_sum, 0, (size_t)scan_tiles_for(nc) + 1, s->st, false));
+        s->ncells_cap = nc;
+    }
+    CU(cudaMemsetAsync(s->count, 0, ((size_t)nc + 1) * sizeof(int), s->st));
+    s->ncells = nc;
+    s->grid_h = P.h; s->grid_len = P.len;
+    s->binned = false;
+    return SPHE_OK;
+}
+
+// ------------------------------------------------------------------ timing helpers
+struct Scope {
+    sphe_sim* s; int kind; KTimer t{}; bool on;
+    Scope(sphe_sim* s_, int kind_, int nlaunch = 1) : s(s_), kind(kind_), on(s_->timing) {
+        s->launches += nlaunch;
+        if (on) { t.kind = kind; cudaEventCreate(&t.a); cudaEventCreate(&t.b); cudaEventRecord(t.a, s->st); }
+    }
+    ~Scope() { if (on) { cudaEventRecord(t.b, s->st); s->timers.push_back(t); } }
+};
+
+// ------------------------------------------------------------------ the step
+static int step_device(sphe_sim* s, sphe_terrain* t) {
+    (void)t;
+    TRY(ensure_device(s));
+    if (s->n == 0) return SPHE_OK;
+    TRY(setup_grid(s));
+    TRY(reserve_diag(s));
+    StepC C = make_consts(s->P);
+    s->lastC = C;
+    int n = s->n;
+    { Scope k(s, SPHE_K_HASH); launch_hash(s->st, n, s->posA, s->G, s->cell, s->count); }
+    { Scope k(s, SPHE_K_SCAN, 3); launch_scan(s->st, s->ncells, n, s->count, s->tile_sum, s->cell_start, s->cursor); }
+    { Scope k(s, SPHE_K_SCATTER); launch_scatter(s->st, n, s->cell, s->idsA, s->cursor, s->tmp); }
+    { Scope k(s, SPHE_K_REORDER);
+      launch_rank_reorder(s->st, n, s->tmp, s->cell, s->cell_start, s->posA, s->velA, s->sedA, s->posB, s->velB, s->sedB,
+                          s->idsB, s->cell_sorted); }
+    { Scope k(s, SPHE_K_DENSITY);
+      launch_density(s->st, s->variant_density, n, s->posB, s->posC, s->velB, s->cell_sorted, s->cell_start, s->G, C, s->rho); }
+    { Scope k(s, SPHE_K_FORCE);
+      launch_force(s->st, s->variant_force, n, s->posC, s->velB, s->rho, s->idsB, s->cell_sorted, s->cell_start, s->G, C,
+                   s->posA, s->velA, s->diag ? &s->D : nullptr); }
+    std::swap(s->idsA, s->idsB);
+    std::swap(s->sedA, s->sedB);
+    s->binned = true;
+    s->slot_valid = false;
+    CU(cudaGetLastError());
+    return SPHE_OK;
+}
+
+// append m lattice particles (fluid_system.h:80-95 / :234-249) to the storage arrays
+static int append_lattice(sphe_sim* s, int count_arg) {
+    std::vector<float> pos;
+    for (int i = 0; i < cbrt(count_arg); i++)
+        for (int j = 0; j < cbrt(count_arg); j++)
+            for (int k = 0; k < cbrt(count_arg); k++) {
+                float x = -0.2 + i * 0.025;
+                float y = -0.05 + j * 0.025;
+                float z = -0.15 + k * 0.025;
+                pos.push_back(x + s->origin[0]);
+                pos.push_back(y + s->origin[1]);
+                pos.push_back(z + s->origin[2]);
+            }
+    int m = (int)(pos.size() / 3);
+    if (m == 0) return SPHE_OK;
+    TRY(ensure_device(s));
+    TRY(reserve(s, s->n + m));
+    std::vector<float4> p4(m), v4(m, make_float4(0, 0, 0, 0));
+    std::vector<int> ids(m);
+    for (int i = 0; i < m; i++) {
+        p4[i] = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], 0.f);
+        ids[i] = s->n + i;  // internal id == index in the reference's vector
+    }
+    CU(cudaMemcpyAsync(s->posA + s->n, p4.data(), m * sizeof(float4), cudaMemcpyHostToDevice, s->st));
+    CU(cudaMemcpyAsync(s->velA + s->n, v4.data(), m * sizeof(float4), cudaMemcpyHostToDevice, s->st));
+    CU(cudaMemcpyAsync(s->idsA + s->n, ids.data(), m * sizeof(int), cudaMemcpyHostToDevice, s->st));
+    CU(cudaMemsetAsync(s->sedA + s->n, 0, m * sizeof(float), s->st));
+    CU(cudaMemsetAsync(s->rho + s->n, 0, m * sizeof(float), s->st));
+    CU(cudaStreamSynchronize(s->st));
+    // reference labels: Id = id++ (may restart at 0 if Initialize is called on a non-empty system)
+    if (s->next_label != s->n) s->labels_identity = false;
+    if (!s->labels_identity || !s->labels.empty()) {
+        if ((int)s->labels.size() < s->n) { int o = (int)s->labels.size(); s->labels.resize(s->n); for (int i = o; i < s->n; i++) s->labels[i] = i; }
+        for (int i = 0; i < m; i++) s->labels.push_back(s->next_label + i);
+    }
+    s->next_label += m;
+    s->n += m;
+    s->binned = false;
+    s->slot_valid = false;
+    if (s->diag) TRY(reserve_diag(s));
+    return SPHE_OK;
+}
+
+static int ensure_slots(sphe_sim* s) {
+    if (s->slot_valid) return SPHE_OK;
+    launch_slot_of_id(s->st, s->n, s->idsA, s->slot_of_id);
+    s->slot_valid = true;
+    return SPHE_OK;
+}
+
+// ================================================================== C ABI
+extern "C" {
+
+const char* sphe_last_error(void) { return g_err; }
+int sphe_abi_version(void) { return 1; }
+
+int sphe_create(sphe_sim** out) {
+    if (!out) return fail(SPHE_ERR_ARG, "out is NULL");
+    *out = new sphe_sim();
+    return SPHE_OK;
+}
+
+void sphe_destroy(sphe_sim* s) {
+    if (!s) return;
+    if (s->ready) {
+        cudaSetDevice(s->device);
+        cudaStreamSynchronize(s->st);
+        void* ptrs[] = {s->posA, s->posB, s->posC, s->velA, s->velB, s->idsA, s->idsB, s->sedA, s->sedB, s->rho, s->cell,
+                        s->cell_sorted, s->tmp, s->stage, s->slot_of_id, s->count, s->cell_start, s->cursor, s->tile_sum,
+                        s->flush_buf, s->D.acc, s->D.fpress, s->D.fvisc, s->D.fgrav, s->D.fsurf, s->D.normal, s->D.neighb};
+        for (void* p : ptrs) if (p) cudaFree(p);
+        if (s->own_stream && s->st) cudaStreamDestroy(s->st);
+    }
+    delete s;
+}
+
+int sphe_set_device(sphe_sim* s, int device) {
+    if (!s) return fail(SPHE_ERR_ARG, "NULL handle");
+    if (s->ready) return fail(SPHE_ERR_STATE, "device already initialised");
+    s->device = device;
+    return SPHE_OK;
+}
+
+int sphe_set_stream(sphe_sim* s, void* stream) {
+    if (!s) return fail(SPHE_ERR_ARG, "NULL handle");
+    if (s->ready && s->own_stream) { cudaStreamSynchronize(s->st); cudaStreamDestroy(s->st); }
+    s->st = (cudaStream_t)stream;
+    s->own_stream = false;
+    return SPHE_OK;
+}
+
+int sphe_initialize(sphe_sim* s, int n_parts) {
+    if (!s) return fail(SPHE_ERR_ARG, "NULL handle");
+    // fluid_system.h:76-78
+    s->num = n_parts; s->init_num = n_parts; s->next_label = 0;
+    return append_lattice(s, n_parts);
+}
+
+int sphe_add_particles(sphe_sim* s, int n) {
+    if (!s) return fail(SPHE_ERR_ARG, "NULL handle");
+    TRY(append_lattice(s, n));
+    s->num += n;  // fluid_system.h:250
+    return SPHE_OK;
+}
+
+int sphe_reset(sphe_sim* s) {
+    if (!s) return fail(SPHE_ERR_ARG, "NULL handle");
+    // fluid_system.h:255-258
+    s->n = 0; s->num = 0; s->next_label = 0;
+    s->labels.clear(); s->labels_identity = true;
+    s->binned = false; s->slot_valid = false;
+    TRY(append_lattice(s, s->init_num));
+    s->num += s->init_num;
+    return SPHE_OK;
+}
+
+int sphe_set_origin(sphe_sim* s, const float o[3]) {
+    if (!s || !o) return fail(SPHE_ERR_ARG, "NULL argument");
+    memcpy(s->origin, o, sizeof s->origin);
+    return SPHE_OK;
+}
+int sphe_get_origin(sphe_sim* s, float o[3]) {
+    if (!s || !o) return fail(SPHE_ERR_ARG, "NULL argument");
+    memcpy(o, s->origin, sizeof s->origin);
+    return SPHE_OK;
+}
+int sphe_set_dt(sphe_sim* s, float dt) { if (!s) return fail(SPHE_ERR_ARG, "NULL handle"); s->P.dt = dt; return SPHE_OK; }
+float sphe_get_dt(sphe_sim* s) { return s ? s->P.dt : 0.0f; }
+sphe_params* sphe_params_ptr(sphe_sim* s) { return s ? &s->P : nullptr; }
+int sphe_count(sphe_sim* s) { return s ? s->n : 0; }
+int sphe_num(sphe_sim* s) { return s ? s->num : 0; }
+
+int sphe_set_grid_bounds(sphe_sim* s, const float lo[3], const float hi[3]) {
+    if (!s) return fail(SPHE_ERR_ARG, "NULL handle");
+    if (!lo || !hi) { s->grid_user = false; s->grid_h = -1.f; return SPHE_OK; }
+    for (int a = 0; a < 3; a++) {
+        if (!(hi[a] > lo[a])) return fail(SPHE_ERR_ARG, "grid bounds: hi must exceed lo on axis %d", a);
+        s->glo[a] = lo[a]; s->ghi[a] = hi[a];
+    }
+    s->grid_user = true;
+    s->grid_h = -1.f;  // force re-setup
+    return SPHE_OK;
+}
+
+int sphe_grid_info_get(sphe_sim* s, sphe_grid_info* out) {
+    if (!s || !out) return fail(SPHE_ERR_ARG, "NULL argument");
+    TRY(ensure_device(s));
+    TRY(setup_grid(s));
+    out->gmin[0] = s->G.gx; out->gmin[1] = s->G.gy; out->gmin[2] = s->G.gz;
+    out->cell = s->G.cell;
+    out->dim[0] = s->G.nx; out->dim[1] = s->G.ny; out->dim[2] = s->G.nz;
+    return SPHE_OK;
+}
+
+static int upload_from_host(sphe_sim* s, int n, const float* pos, const float* vel) {
+    TRY(ensure_device(s));
+    s->n = 0;
+    TRY(reserve(s, n));
+    float* dpos = s->stage;
+    float* dvel = s->stage + 3 * (size_t)s->cap;
+    CU(cudaMemcpyAsync(dpos, pos, 3 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s->st));
+    CU(cudaMemcpyAsync(dvel, vel, 3 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s->st));
+    launch_pack_state(s->st, n, dpos, dvel, s->posA, s->velA, s->idsA, s->sedA);
+    s->n = n;
+    s->binned = false; s->slot_valid = false;
+    return SPHE_OK;
+}
+
+int sphe_upload_state(sphe_sim* s, int n, const float* pos, const float* vel) {
+    if (!s || n < 0 || (n > 0 && (!pos || !vel))) return fail(SPHE_ERR_ARG, "bad arguments");
+    TRY(upload_from_host(s, n, pos, vel));
+    CU(cudaMemsetAsync(s->rho, 0, (size_t)std::max(n, 1) * sizeof(float), s->st));
+    s->num = n; s->init_num = n; s->next_label = n;
+    s->labels.clear(); s->labels_identity = true;
+    if (s->diag) { s->diag_cap = 0; TRY(reserve_diag(s)); }
+    CU(cudaStreamSynchronize(s->st));
+    return SPHE_OK;
+}
+
+int sphe_step(sphe_sim* s, sphe_terrain* t) {
+    if (!s) return fail(SPHE_ERR_ARG, "NULL handle");
+    return step_device(s, t);
+}
+
+int sphe_sync(sphe_sim* s) {
+    if (!s) return fail(SPHE_ERR_ARG, "NULL handle");
+    if (!s->ready) return SPHE_OK;
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->st));
+    return SPHE_OK;
+}
+
+int sphe_step_host(sphe_sim* s, sphe_terrain* t, int n, const float* pos_in, const float* vel_in, float* pos_out,
+                   float* vel_out, float* density_out) {
+    if (!s || n <= 0 || !pos_in || !vel_in || !pos_out || !vel_out) return fail(SPHE_ERR_ARG, "bad arguments");
+    TRY(upload_from_host(s, n, pos_in, vel_in));
+    TRY(step_device(s, t));
+    float* dpos = s->stage;
+    float* dvel = s->stage + 3 * (size_t)s->cap;
+    float* drho = s->stage + 6 * (size_t)s->cap;
+    launch_unsort_f4(s->st, n, s->posA, s->idsA, dpos);
+    launch_unsort_f4(s->st, n, s->velA, s->idsA, dvel);
+    CU(cudaMemcpyAsync(pos_out, dpos, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(vel_out, dvel, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->st));
+    if (density_out) {
+        launch_unsort_f1(s->st, n, s->rho, s->idsA, drho);
+        CU(cudaMemcpyAsync(density_out, drho, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->st));
+    }
+    CU(cudaStreamSynchronize(s->st));
+    return SPHE_OK;
+}
+
+int sphe_set_l2_flush(sphe_sim* s, long long bytes) {
+    if (!s || bytes < 0) return fail(SPHE_ERR_ARG, "bad arguments");
+    TRY(ensure_device(s));
+    if (s->flush_buf) { CU(cudaStreamSynchronize(s->st)); CU(cudaFree(s->flush_buf)); s->flush_buf = nullptr; }
+    s->flush_bytes = (size_t)bytes;
+    if (bytes > 0) {
+        cudaError_t e = cudaMalloc(&s->flush_buf, (size_t)bytes);
+        if (e != cudaSuccess) { s->flush_bytes = 0; return fail(SPHE_ERR_NOMEM, "flush buffer: %s", cudaGetErrorString(e)); }
+    }
+    return SPHE_OK;
+}
+
+int sphe_timed_steps(sphe_sim* s, sphe_terrain* t, int steps, float* ms_total, float* ms_kernels, int* launches) {
+    if (!s || steps < 0) return fail(SPHE_ERR_ARG, "bad arguments");
+    TRY(ensure_device(s));
+    std::vector<cudaEvent_t> ev((size_t)steps * 2);
+    for (auto& e : ev) CU(cudaEventCreate(&e));
+    s->timing = (ms_kernels != nullptr);
+    s->timers.clear();
+    s->launches = 0;
+    CU(cudaStreamSynchronize(s->st));
+    int rc = SPHE_OK;
+    for (int i = 0; i < steps && rc == SPHE_OK; i++) {
+        // optional L2 flush between timed steps, outside the per-step event bracket
+        if (s->flush_buf) CU(cudaMemsetAsync(s->flush_buf, i & 0xff, s->flush_bytes, s->st));
+        CU(cudaEventRecord(ev[2 * i], s->st));
+        rc = step_device(s, t);
+        CU(cudaEventRecord(ev[2 * i + 1], s->st));
+    }
+    CU(cudaStreamSynchronize(s->st));
+    s->timing = false;
+    float ms = 0.f;
+    if (rc == SPHE_OK)
+        for (int i = 0; i < steps; i++) { float m = 0.f; CU(cudaEventElapsedTime(&m, ev[2 * i], ev[2 * i + 1])); ms += m; }
+    if (ms_total) *ms_total = ms;
+    if (ms_kernels) {
+        for (int k = 0; k < SPHE_K_COUNT; k++) ms_kernels[k] = 0.f;
+        for (auto& kt : s->timers) {
+            float m = 0.f;
+            cudaEventElapsedTime(&m, kt.a, kt.b);
+            ms_kernels[kt.kind] += m;
+            cudaEventDestroy(kt.a); cudaEventDestroy(kt.b);
+        }
+        s->timers.clear();
+    }
+    if (launches) *launches = s->launches;
+    for (auto& e : ev) cudaEventDestroy(e);
+    return rc;
+}
+
+int sphe_set_diagnostics(sphe_sim* s, int on) {
+    if (!s) return fail(SPHE_ERR_ARG, "NULL handle");
+    s->diag = on != 0;
+    if (s->diag && s->ready) TRY(reserve_diag(s));
+    return SPHE_OK;
+}
+
+int sphe_set_variant(sphe_sim* s, int density_variant, int force_variant) {
+    if (!s) return fail(SPHE_ERR_ARG, "NULL handle");
+    s->variant_density = density_variant; s->variant_force = force_variant;
+    return SPHE_OK;
+}
+
+static int copy_f4_by_id(sphe_sim* s, const float4* by_id, float* host_xyz) {
+    // diagnostics are already indexed by id: strip the 4th lane on the host
+    std::vector<float4> tmp((size_t)s->n);
+    CU(cudaMemcpyAsync(tmp.data(), by_id, (size_t)s->n * sizeof(float4), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    for (int i = 0; i < s->n; i++) { host_xyz[3 * i] = tmp[i].x; host_xyz[3 * i + 1] = tmp[i].y; host_xyz[3 * i + 2] = tmp[i].z; }
+    return SPHE_OK;
+}
+
+int sphe_download(sphe_sim* s, int field, void* out) {
+    if (!s || !out) return fail(SPHE_ERR_ARG, "NULL argument");
+    if (s->n == 0) return SPHE_OK;
+    TRY(ensure_device(s));
+    int n = s->n;
+    float* stage = s->stage;
+    switch (field) {
+    case SPHE_F_POS:
+    case SPHE_F_VEL:
+        launch_unsort_f4(s->st, n, field == SPHE_F_POS ? s->posA : s->velA, s->idsA, stage);
+        CU(cudaMemcpyAsync(out, stage, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->st));
+        break;
+    case SPHE_F_DENSITY:
+        launch_unsort_f1(s->st, n, s->rho, s->idsA, stage);
+        CU(cudaMemcpyAsync(out, stage, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->st));
+        break;
+    case SPHE_F_PRESSURE: {
+        launch_unsort_f1(s->st, n, s->rho, s->idsA, stage);
+        CU(cudaMemcpyAsync(out, stage, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->st));
+        CU(cudaStreamSynchronize(s->st));
+        float* f = (float*)out;
+        // Pressure = k * (Density - p0) (fluid_system.h:123) with the parameters of the last step
+        for (int i = 0; i < n; i++) f[i] = s->lastC.k * (f[i] - s->lastC.p0);
+        break;
+    }
+    case SPHE_F_SEDIMENT:
+        launch_unsort_f1(s->st, n, s->sedA, s->idsA, stage);
+        CU(cudaMemcpyAsync(out, stage, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->st));
+        break;
+    case SPHE_F_ID: {
+        int* o = (int*)out;
+        if (s->labels.empty()) for (int i = 0; i < n; i++) o[i] = i;
+        else memcpy(o, s->labels.data(), (size_t)n * sizeof(int));
+        return SPHE_OK;
+    }
+    case SPHE_F_ACC: case SPHE_F_FPRESS: case SPHE_F_FVISC: case SPHE_F_FGRAV: case SPHE_F_FSURF: case SPHE_F_NORMAL: {
+        if (!s->diag || s->diag_cap < n) return fail(SPHE_ERR_STATE, "diagnostics are off: call sphe_set_diagnostics(s, 1) before stepping");
+        const float4* src = field == SPHE_F_ACC ? s->D.acc : field == SPHE_F_FPRESS ? s->D.fpress : field == SPHE_F_FVISC ? s->D.fvisc
+                          : field == SPHE_F_FGRAV ? s->D.fgrav : field == SPHE_F_FSURF ? s->D.fsurf : s->D.normal;
+        return copy_f4_by_id(s, src, (float*)out);
+    }
+    case SPHE_F_NEIGHB:
+        if (!s->diag || s->diag_cap < n) return fail(SPHE_ERR_STATE, "diagnostics are off");
+        CU(cudaMemcpyAsync(out, s->D.neighb, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s->st));
+        break;
+    default:
+        return fail(SPHE_ERR_ARG, "unknown field %d", field);
+    }
+    CU(cudaStreamSynchronize(s->st));
+    return SPHE_OK;
+}
+
+int sphe_download_positions(sphe_sim* s, float* host_xyz) { return sphe_download(s, SPHE_F_POS, host_xyz); }
+
+int sphe_get_particle(sphe_sim* s, int id, sphe_particle* out) {
+    if (!s || !out) return fail(SPHE_ERR_ARG, "NULL argument");
+    // the reference indexes unchecked (fluid_system.h:286-289); we report instead of reading out of bounds
+    if (id < 0 || id >= s->n) return fail(SPHE_ERR_ARG, "particle id %d out of range [0,%d)", id, s->n);
+    TRY(ensure_device(s));
+    if (!s->diag) { s->diag = true; TRY(reserve_diag(s)); }
+    TRY(ensure_slots(s));
+    int slot = 0;
+    CU(cudaMemcpyAsync(&slot, s->slot_of_id + id, sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    float4 p, v, a, fp, fv, fg, fs, nn;
+    float rho;
+    int nb;
+    CU(cudaMemcpyAsync(&p, s->posA + slot, sizeof p, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(&v, s->velA + slot, sizeof v, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(&rho, s->rho + slot, sizeof rho, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(&a, s->D.acc + id, sizeof a, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(&fp, s->D.fpress + id, sizeof fp, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(&fv, s->D.fvisc + id, sizeof fv, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(&fg, s->D.fgrav + id, sizeof fg, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(&fs, s->D.fsurf + id, sizeof fs, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(&nn, s->D.normal + id, sizeof nn, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(&nb, s->D.neighb + id, sizeof nb, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    out->id = s->labels.empty() ? id : s->labels[id];
+    out->position[0] = p.x; out->position[1] = p.y; out->position[2] = p.z;
+    out->velocity[0] = v.x; out->velocity[1] = v.y; out->velocity[2] = v.z;
+    out->acceleration[0] = a.x; out->acceleration[1] = a.y; out->acceleration[2] = a.z;
+    out->density = rho;
+    out->pressure = s->binned ? s->lastC.k * (rho - s->lastC.p0) : 0.0f;
+    out->pressure_force[0] = fp.x; out->pressure_force[1] = fp.y; out->pressure_force[2] = fp.z;
+    out->viscosity_force[0] = fv.x; out->viscosity_force[1] = fv.y; out->viscosity_force[2] = fv.z;
+    out->gravity_force[0] = fg.x; out->gravity_force[1] = fg.y; out->gravity_force[2] = fg.z;
+    out->surface_force[0] = fs.x; out->surface_force[1] = fs.y; out->surface_force[2] = fs.z;
+    out->surface_normal[0] = nn.x; out->surface_normal[1] = nn.y; out->surface_normal[2] = nn.z;
+    out->neighb_id = nb;
+    return SPHE_OK;
+}
+
+// ---- neighbour-grid test hooks
+static int need_binned(sphe_sim* s) {
+    if (!s) return fail(SPHE_ERR_ARG, "NULL handle");
+    if (!s->binned) return fail(SPHE_ERR_STATE, "no binning available: call sphe_step first");
+    return ensure_device(s);
+}
+
+int sphe_debug_cells(sphe_sim* s, int* cell_of_id) {
+    TRY(need_binned(s));
+    int* d = (int*)s->stage;
+    launch_unsort_u32(s->st, s->n, s->cell_sorted, s->idsA, d);
+    CU(cudaMemcpyAsync(cell_of_id, d, (size_t)s->n * sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    return SPHE_OK;
+}
+
+int sphe_debug_sorted_order(sphe_sim* s, int* ids_sorted) {
+    TRY(need_binned(s));
+    CU(cudaMemcpyAsync(ids_sorted, s->idsA, (size_t)s->n * sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    return SPHE_OK;
+}
+
+int sphe_debug_cell_start(sphe_sim* s, int* cell_start) {
+    TRY(need_binned(s));
+    CU(cudaMemcpyAsync(cell_start, s->cell_start, ((size_t)s->ncells + 1) * sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    return SPHE_OK;
+}
+
+int sphe_debug_neighbours(sphe_sim* s, long long* nbr_start, int* nbr, long long cap, long long* total) {
+    TRY(need_binned(s));
+    int n = s->n;
+    int* dcount = nullptr;
+    CU(cudaMalloc(&dcount, (size_t)n * sizeof(int)));
+    // posB still holds the sorted pre-integration positions of the last step
+    launch_neighbour_count(s->st, n, s->posB, s->cell_sorted, s->cell_start, s->G, s->lastC, dcount);
+    std::vector<int> counts((size_t)n);
+    CU(cudaMemcpyAsync(counts.data(), dcount, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    CU(cudaFree(dcount));
+    std::vector<long long> starts((size_t)n + 1);
+    starts[0] = 0;
+    for (int i = 0; i < n; i++) starts[i + 1] = starts[i] + counts[i];
+    if (total) *total = starts[n];
+    if (nbr_start) memcpy(nbr_start, starts.data(), ((size_t)n + 1) * sizeof(long long));
+    if (!nbr) return SPHE_OK;
+    if (cap < starts[n]) return fail(SPHE_ERR_ARG, "neighbour buffer too small: need %lld", starts[n]);
+    long long* dstart = nullptr;
+    int* dn = nullptr;
+    CU(cudaMalloc(&dstart, ((size_t)n + 1) * sizeof(long long)));
+    CU(cudaMalloc(&dn, (size_t)std::max<long long>(starts[n], 1) * sizeof(int)));
+    CU(cudaMemcpyAsync(dstart, starts.data(), ((size_t)n + 1) * sizeof(long long), cudaMemcpyHostToDevice, s->st));
+    launch_neighbour_fill(s->st, n, s->posB, s->idsA, s->cell_sorted, s->cell_start, s->G, s->lastC, dstart, dn);
+    CU(cudaMemcpyAsync(nbr, dn, (size_t)starts[n] * sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    CU(cudaFree(dstart)); CU(cudaFree(dn));
+    return SPHE_OK;
+}
+
+void* sphe_device_ptr(sphe_sim* s, int which) {
+    if (!s) return nullptr;
+    switch (which) {
+    case SPHE_D_POSQ: return s->posA;
+    case SPHE_D_VELV: return s->velA;
+    case SPHE_D_IDS: return s->idsA;
+    case SPHE_D_RHO: return s->rho;
+    }
+    return nullptr;
+}
+
+}  // extern "C"

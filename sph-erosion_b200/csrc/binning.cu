@@ -1,0 +1,238 @@
+// Binning: cell hash -> per-cell counts -> exclusive prefix scan (cell-start table) -> counting-sort
+// scatter -> deterministic in-cell ranking by particle id -> physical reorder of the SoA arrays.
+//
+// The result is the canonical order "sorted by (cell id, particle id)", bit-identical to
+// oracle/sph_oracle.c so_bin() regardless of storage history or atomic scheduling.
+// All kernels here are HBM-bandwidth bound (DESIGN.md section "kernels").
+#include "common.cuh"
+#include "sim.h"
+
+namespace sphe {
+
+// ---------------------------------------------------------------- hash + count
+// One thread per particle (storage order).  Storage order is last step's sorted order, so
+// consecutive lanes mostly share a cell: counts are aggregated per run of equal cells inside the
+// warp (shfl + ballot) and only the run head issues the atomic.
+__global__ void __launch_bounds__(256) k_hash(int n, const float4* __restrict__ posq, GridP G,
+                                              uint32_t* __restrict__ cell, int* __restrict__ count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned lane = threadIdx.x & 31;
+    uint32_t c = 0xffffffffu;
+    if (i < n) {
+        float4 p = posq[i];
+        int cx, cy, cz;
+        cell_coords(G, p.x, p.y, p.z, cx, cy, cz);
+        c = (uint32_t)((cx * G.ny + cy) * G.nz + cz);
+        cell[i] = c;
+    }
+    uint32_t prev = __shfl_up_sync(SPHE_FULL, c, 1);
+    bool head = (lane == 0) || (c != prev);
+    unsigned heads = __ballot_sync(SPHE_FULL, head);
+    if (head && c != 0xffffffffu) {
+        unsigned above = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
+        int next = above ? (__ffs(above) - 1) : 32;
+        atomicAdd(&count[c], next - (int)lane);
+    }
+}
+
+// ---------------------------------------------------------------- exclusive scan over cells
+// Reduce-then-scan in three launches: per-tile sums, scan of tile sums (one CTA), per-tile scan.
+// The final pass also primes the scatter cursor and clears the counts for the next step.
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ int warp_incl_scan(int v) {
+    unsigned lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(SPHE_FULL, v, o);
+        if (lane >= (unsigned)o) v += t;
+    }
+    return v;
+}
+
+// inclusive block scan of one value per thread; returns inclusive prefix, total in *total
+__device__ __forceinline__ int block_incl_scan(int v, int* total) {
+    __shared__ int ws[32];
+    unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = warp_incl_scan(v);
+    if (lane == 31) ws[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int nw = (blockDim.x + 31) >> 5;
+        int x = (int)lane < nw ? ws[lane] : 0;
+        x = warp_incl_scan(x);
+        ws[lane] = x;
+    }
+    __syncthreads();
+    int off = w ? ws[w - 1] : 0;
+    *total = ws[((blockDim.x + 31) >> 5) - 1];
+    __syncthreads();
+    return inc + off;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(long long ncells, const int* __restrict__ count,
+                                                               int* __restrict__ tile_sum) {
+    long long base = (long long)blockIdx.x * SCAN_TILE;
+    int s = 0;
+    // vectorised int4 loads: count is 16-byte aligned and SCAN_TILE is a multiple of 4
+    const int4* c4 = reinterpret_cast<const int4*>(count + base);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS / 4; k++) {
+        long long e = base + ((long long)k * SCAN_THREADS + threadIdx.x) * 4;
+        if (e + 3 < ncells) {
+            int4 v = c4[k * SCAN_THREADS + threadIdx.x];
+            s += v.x + v.y + v.z + v.w;
+        } else {
+            for (int q = 0; q < 4; q++) if (e + q < ncells) s += count[e + q];
+        }
+    }
+    int total;
+    block_incl_scan(s, &total);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_tiles(int ntiles, int* __restrict__ tile_sum) {
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int b = 0; b < ntiles; b += 1024) {
+        int i = b + threadIdx.x;
+        int v = i < ntiles ? tile_sum[i] : 0;
+        int total;
+        int inc = block_incl_scan(v, &total);
+        int carry = carry_s;
+        if (i < ntiles) tile_sum[i] = carry + inc - v;  // exclusive
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + total;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(long long ncells, int n_total, int* __restrict__ count,
+                                                             const int* __restrict__ tile_off,
+                                                             int* __restrict__ cell_start, int* __restrict__ cursor) {
+    long long base = (long long)blockIdx.x * SCAN_TILE;
+    // each thread owns SCAN_ITEMS consecutive cells (blocked arrangement)
+    long long e0 = base + (long long)threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int s = 0;
+    if (e0 + SCAN_ITEMS <= ncells) {
+        const int4* c4 = reinterpret_cast<const int4*>(count + e0);
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS / 4; k++) {
+            int4 t = c4[k];
+            v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) v[k] = (e0 + k < ncells) ? count[e0 + k] : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) s += v[k];
+    int total;
+    int inc = block_incl_scan(s, &total);
+    int run = tile_off[blockIdx.x] + inc - s;
+    if (e0 + SCAN_ITEMS <= ncells) {
+        int o[SCAN_ITEMS];
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) { o[k] = run; run += v[k]; }
+        int4* s4 = reinterpret_cast<int4*>(cell_start + e0);
+        int4* u4 = reinterpret_cast<int4*>(cursor + e0);
+        int4* z4 = reinterpret_cast<int4*>(count + e0);
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS / 4; k++) {
+            int4 t = make_int4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+            s4[k] = t; u4[k] = t; z4[k] = make_int4(0, 0, 0, 0);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            if (e0 + k < ncells) { cell_start[e0 + k] = run; cursor[e0 + k] = run; count[e0 + k] = 0; run += v[k]; }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) cell_start[ncells] = n_total;
+}
+
+// ---------------------------------------------------------------- counting-sort scatter
+// slot = cursor[cell]++ (run-aggregated).  The order INSIDE a cell is whatever the atomics give;
+// k_rank_reorder makes it canonical.
+__global__ void __launch_bounds__(256) k_scatter(int n, const uint32_t* __restrict__ cell, const int* __restrict__ ids,
+                                                 int* __restrict__ cursor, uint2* __restrict__ tmp) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned lane = threadIdx.x & 31;
+    uint32_t c = (i < n) ? cell[i] : 0xffffffffu;
+    uint32_t prev = __shfl_up_sync(SPHE_FULL, c, 1);
+    bool head = (lane == 0) || (c != prev);
+    unsigned heads = __ballot_sync(SPHE_FULL, head);
+    // lane of my run's head = highest head bit at or below my lane
+    unsigned below = heads & ((2u << lane) - 1u);
+    if (lane == 31) below = heads;
+    int hl = 31 - __clz(below);
+    int base = 0;
+    if (head && c != 0xffffffffu) {
+        unsigned above = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
+        int next = above ? (__ffs(above) - 1) : 32;
+        base = atomicAdd(&cursor[c], next - (int)lane);
+    }
+    base = __shfl_sync(SPHE_FULL, base, hl);
+    if (i < n) tmp[base + ((int)lane - hl)] = make_uint2((uint32_t)ids[i], (uint32_t)i);
+}
+
+// ---------------------------------------------------------------- rank inside the cell + reorder
+// One thread per scattered slot.  rank = number of particles of the same cell with a smaller id;
+// destination = cell_start + rank.  Then gather the particle's state from its old storage slot.
+__global__ void __launch_bounds__(256) k_rank_reorder(int n, const uint2* __restrict__ tmp, const uint32_t* __restrict__ cell,
+                                                      const int* __restrict__ cell_start,
+                                                      const float4* __restrict__ posq_in, const float4* __restrict__ velv_in,
+                                                      const float* __restrict__ sed_in,
+                                                      float4* __restrict__ posq_out, float4* __restrict__ velv_out,
+                                                      float* __restrict__ sed_out, int* __restrict__ ids_out,
+                                                      uint32_t* __restrict__ cell_sorted) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    uint2 me = tmp[s];
+    uint32_t c = cell[me.y];
+    int a = cell_start[c], b = cell_start[c + 1];
+    int rank = 0;
+    for (int k = a; k < b; k++) rank += (tmp[k].x < me.x) ? 1 : 0;
+    int dst = a + rank;
+    float4 p = posq_in[me.y];
+    float4 v = velv_in[me.y];
+    posq_out[dst] = p;
+    velv_out[dst] = v;
+    if (sed_in) sed_out[dst] = sed_in[me.y];
+    ids_out[dst] = (int)me.x;
+    cell_sorted[dst] = c;
+}
+
+// ---------------------------------------------------------------- launch wrappers
+void launch_hash(cudaStream_t st, int n, const float4* posq, const GridP& G, uint32_t* cell, int* count) {
+    if (n <= 0) return;
+    k_hash<<<(n + 255) / 256, 256, 0, st>>>(n, posq, G, cell, count);
+}
+
+int scan_tiles_for(long long ncells) { return (int)((ncells + SCAN_TILE - 1) / SCAN_TILE); }
+
+void launch_scan(cudaStream_t st, long long ncells, int n_total, int* count, int* tile_sum, int* cell_start, int* cursor) {
+    int ntiles = scan_tiles_for(ncells);
+    k_scan_reduce<<<ntiles, SCAN_THREADS, 0, st>>>(ncells, count, tile_sum);
+    k_scan_tiles<<<1, 1024, 0, st>>>(ntiles, tile_sum);
+    k_scan_final<<<ntiles, SCAN_THREADS, 0, st>>>(ncells, n_total, count, tile_sum, cell_start, cursor);
+}
+
+void launch_scatter(cudaStream_t st, int n, const uint32_t* cell, const int* ids, int* cursor, uint2* tmp) {
+    if (n <= 0) return;
+    k_scatter<<<(n + 255) / 256, 256, 0, st>>>(n, cell, ids, cursor, tmp);
+}
+
+void launch_rank_reorder(cudaStream_t st, int n, const uint2* tmp, const uint32_t* cell, const int* cell_start,
+                         const float4* posq_in, const float4* velv_in, const float* sed_in,
+                         float4* posq_out, float4* velv_out, float* sed_out, int* ids_out, uint32_t* cell_sorted) {
+    if (n <= 0) return;
+    k_rank_reorder<<<(n + 255) / 256, 256, 0, st>>>(n, tmp, cell, cell_start, posq_in, velv_in, sed_in,
+                                                    posq_out, velv_out, sed_out, ids_out, cell_sorted);
+}
+
+}  // namespace sphe

@@ -1,0 +1,48 @@
+// Shared device/host definitions for the sm_100a SPH-Erosion hot path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SPHE_FULL 0xffffffffu
+
+// Uniform neighbour grid (this project's definition; the reference is all-pairs).
+// cell id = (cx*ny + cy)*nz + cz -- x most significant so an x-slab is one contiguous range of the
+// sorted arrays (multi-GPU slabs), z least significant so the three z-neighbours of a cell are one
+// contiguous run of the sorted arrays (the 27-cell walk is 9 runs).
+struct GridP {
+    float gx, gy, gz, cell;
+    int nx, ny, nz;
+};
+
+// Per-step constants, computed on the HOST with the same libm calls as the reference
+// (powf(h,9), powf(h,6): Erosion/fluid_system.h:415-452) so they are bit-identical.
+struct StepC {
+    float h, hh, T;           // T = largest float with sqrtf(T) <= h  (exact neighbour predicate)
+    float mass, k, p0, visc, surf;
+    float gx, gy, gz;
+    float dt, len, cR;
+    float densK;              // mass * 315/(64 PI h^9)
+    float c45;                // 45/(PI h^6)
+    float c945;               // 945/(32 PI h^9)
+    float hh3;                // 3*h*h
+};
+
+__device__ __forceinline__ int cell_axis(float p, float gmin, float cell, int dim) {
+    // bit-identical to oracle/sph_oracle.c cell_axis(): IEEE sub, div, floor; clamp; NaN -> 0
+    float v = floorf(__fdiv_rn(__fsub_rn(p, gmin), cell));
+    if (!(v >= 0.0f)) return 0;
+    if (v >= (float)dim) return dim - 1;
+    return (int)v;
+}
+
+__device__ __forceinline__ void cell_coords(const GridP& G, float x, float y, float z, int& cx, int& cy, int& cz) {
+    cx = cell_axis(x, G.gx, G.cell, G.nx);
+    cy = cell_axis(y, G.gy, G.cell, G.ny);
+    cz = cell_axis(z, G.gz, G.cell, G.nz);
+}
+
+// Exact restatement of glm::length(xi - xj)^2 before the sqrt: ((dx*dx + dy*dy) + dz*dz) with
+// every operation rounded separately (no FMA contraction), vendor/glm func_geometric.inl:47-55.
+__device__ __forceinline__ float dist2_exact(float dx, float dy, float dz) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}

@@ -1,0 +1,49 @@
+// Internal declarations shared by the .cu translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "common.cuh"
+
+namespace sphe {
+
+// ---- binning.cu
+void launch_hash(cudaStream_t st, int n, const float4* posq, const GridP& G, uint32_t* cell, int* count);
+int scan_tiles_for(long long ncells);
+void launch_scan(cudaStream_t st, long long ncells, int n_total, int* count, int* tile_sum, int* cell_start, int* cursor);
+void launch_scatter(cudaStream_t st, int n, const uint32_t* cell, const int* ids, int* cursor, uint2* tmp);
+void launch_rank_reorder(cudaStream_t st, int n, const uint2* tmp, const uint32_t* cell, const int* cell_start,
+                         const float4* posq_in, const float4* velv_in, const float* sed_in,
+                         float4* posq_out, float4* velv_out, float* sed_out, int* ids_out, uint32_t* cell_sorted);
+
+// ---- sph.cu
+// Optional per-particle debug fields of the reference's FluidParticle (fluid_system.h:49-64),
+// indexed by PARTICLE ID (not by sorted slot).
+struct DiagOut {
+    float4* acc;
+    float4* fpress;
+    float4* fvisc;
+    float4* fgrav;
+    float4* fsurf;
+    float4* normal;
+    int* neighb;
+};
+
+struct TerrainDev;  // terrain.cu
+
+void launch_density(cudaStream_t st, int variant, int n, const float4* posq, float4* posq_q, float4* velv,
+                    const uint32_t* cell_sorted, const int* cell_start, const GridP& G, const StepC& C, float* rho);
+void launch_force(cudaStream_t st, int variant, int n, const float4* posq, const float4* velv, const float* rho,
+                  const int* ids, const uint32_t* cell_sorted, const int* cell_start, const GridP& G, const StepC& C,
+                  float4* posq_out, float4* velv_out, const DiagOut* diag);
+void launch_neighbour_count(cudaStream_t st, int n, const float4* posq, const uint32_t* cell_sorted, const int* cell_start,
+                            const GridP& G, const StepC& C, int* counts);
+void launch_neighbour_fill(cudaStream_t st, int n, const float4* posq, const int* ids, const uint32_t* cell_sorted,
+                           const int* cell_start, const GridP& G, const StepC& C, const long long* nbr_start, int* nbr);
+void launch_unsort_f4(cudaStream_t st, int n, const float4* src, const int* ids, float* dst_xyz);
+void launch_unsort_f1(cudaStream_t st, int n, const float* src, const int* ids, float* dst);
+void launch_unsort_u32(cudaStream_t st, int n, const uint32_t* src, const int* ids, int* dst);
+void launch_pack_state(cudaStream_t st, int n, const float* pos_xyz, const float* vel_xyz, float4* posq, float4* velv,
+                       int* ids, float* sed);
+void launch_slot_of_id(cudaStream_t st, int n, const int* ids, int* slot_of_id);
+
+}  // namespace sphe

@@ -1,0 +1,136 @@
+"""Python mirror of the reference's `FluidSystemSPH` public surface (Erosion/fluid_system.h:66-289)
+over the C ABI -- same method names and argument meaning, used by tests/, bench.py and the multi-GPU
+driver.  The C++ drop-in shim with the identical surface is host/fluid_system.h."""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class FluidSystemSPH:
+    def __init__(self, device=None):
+        self._L = capi.lib()
+        h = C.c_void_p()
+        capi.check(self._L.sphe_create(C.byref(h)))  # no CUDA work here (fluid_system.h:69-72)
+        self._h = h
+        if device is not None:
+            capi.check(self._L.sphe_set_device(h, int(device)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.sphe_destroy(self._h)
+            self._h = None
+
+    # ---- reference surface
+    def Initialize(self, nParts): capi.check(self._L.sphe_initialize(self._h, int(nParts)))
+    def AddParticles(self, n): capi.check(self._L.sphe_add_particles(self._h, int(n)))
+    def Reset(self): capi.check(self._L.sphe_reset(self._h))
+
+    def Run(self, grid=None):
+        capi.check(self._L.sphe_step(self._h, getattr(grid, "_t", None)))
+
+    def SetOrigin(self, o):
+        a = np.asarray(o, np.float32)
+        capi.check(self._L.sphe_set_origin(self._h, _p(a)))
+
+    def GetOrigin(self):
+        a = np.zeros(3, np.float32)
+        capi.check(self._L.sphe_get_origin(self._h, _p(a)))
+        return a
+
+    def SetDeltaTime(self, dt): capi.check(self._L.sphe_set_dt(self._h, float(dt)))
+    def GetDeltaTime(self): return self._L.sphe_get_dt(self._h)
+
+    @property
+    def params(self):
+        """The host-resident parameter block behind GetMass/GetVisc/GetSurfTen/Getp0/GetGrav."""
+        return self._L.sphe_params_ptr(self._h).contents
+
+    def GetParticle(self, id):
+        p = capi.Particle()
+        capi.check(self._L.sphe_get_particle(self._h, int(id), C.byref(p)))
+        return p
+
+    def PrintCoords(self):
+        pos = self.download("pos")
+        for i in range(min(self._L.sphe_num(self._h), pos.shape[0])):
+            print("[%d] %g %g %g" % (i, pos[i, 0], pos[i, 1], pos[i, 2]))
+
+    # ---- extras of the C ABI
+    def count(self): return self._L.sphe_count(self._h)
+    def sync(self): capi.check(self._L.sphe_sync(self._h))
+    def set_diagnostics(self, on=True): capi.check(self._L.sphe_set_diagnostics(self._h, int(on)))
+    def set_variant(self, density=0, force=0): capi.check(self._L.sphe_set_variant(self._h, density, force))
+
+    def set_grid_bounds(self, lo, hi):
+        lo = np.asarray(lo, np.float32); hi = np.asarray(hi, np.float32)
+        capi.check(self._L.sphe_set_grid_bounds(self._h, _p(lo), _p(hi)))
+
+    def grid_info(self):
+        g = capi.GridInfo()
+        capi.check(self._L.sphe_grid_info_get(self._h, C.byref(g)))
+        return g
+
+    def upload_state(self, pos, vel):
+        pos = np.ascontiguousarray(pos, np.float32); vel = np.ascontiguousarray(vel, np.float32)
+        assert pos.shape == vel.shape and pos.ndim == 2 and pos.shape[1] == 3
+        capi.check(self._L.sphe_upload_state(self._h, pos.shape[0], _p(pos), _p(vel)))
+
+    def download(self, name):
+        fid, w, dt = capi.FIELDS[name]
+        n = self.count()
+        out = np.zeros((n, w) if w > 1 else (n,), np.dtype(dt))
+        capi.check(self._L.sphe_download(self._h, fid, _p(out)))
+        return out
+
+    def step_host_ptr(self, n, pos_in, vel_in, pos_out, vel_out, rho_out=None, grid=None):
+        """End-to-end host-buffer step; arguments are raw host addresses (ints), e.g. pinned tensors."""
+        capi.check(self._L.sphe_step_host(self._h, getattr(grid, "_t", None), int(n), pos_in, vel_in, pos_out, vel_out, rho_out))
+
+    def step_host(self, pos, vel, grid=None):
+        pos = np.ascontiguousarray(pos, np.float32); vel = np.ascontiguousarray(vel, np.float32)
+        n = pos.shape[0]
+        po = np.empty_like(pos); vo = np.empty_like(vel); rho = np.empty(n, np.float32)
+        capi.check(self._L.sphe_step_host(self._h, getattr(grid, "_t", None), n, _p(pos), _p(vel), _p(po), _p(vo), _p(rho)))
+        return po, vo, rho
+
+    def set_l2_flush(self, nbytes): capi.check(self._L.sphe_set_l2_flush(self._h, int(nbytes)))
+
+    def timed_steps(self, steps, grid=None, per_kernel=True):
+        ms = C.c_float(0)
+        mk = (C.c_float * len(capi.K_NAMES))()
+        nl = C.c_int(0)
+        capi.check(self._L.sphe_timed_steps(self._h, getattr(grid, "_t", None), int(steps), C.byref(ms),
+                                            mk if per_kernel else None, C.byref(nl)))
+        return ms.value, dict(zip(capi.K_NAMES, [float(x) for x in mk])), nl.value
+
+    # ---- neighbour-grid test hooks
+    def debug_cells(self):
+        out = np.zeros(self.count(), np.int32)
+        capi.check(self._L.sphe_debug_cells(self._h, _p(out)))
+        return out
+
+    def debug_sorted_order(self):
+        out = np.zeros(self.count(), np.int32)
+        capi.check(self._L.sphe_debug_sorted_order(self._h, _p(out)))
+        return out
+
+    def debug_cell_start(self):
+        g = self.grid_info()
+        out = np.zeros(int(g.dim[0]) * int(g.dim[1]) * int(g.dim[2]) + 1, np.int32)
+        capi.check(self._L.sphe_debug_cell_start(self._h, _p(out)))
+        return out
+
+    def debug_neighbours(self):
+        n = self.count()
+        ns = np.zeros(n + 1, np.int64)
+        tot = C.c_longlong(0)
+        capi.check(self._L.sphe_debug_neighbours(self._h, _p(ns), None, 0, C.byref(tot)))
+        nb = np.zeros(max(tot.value, 1), np.int32)
+        capi.check(self._L.sphe_debug_neighbours(self._h, _p(ns), _p(nb), tot.value, C.byref(tot)))
+        return ns, nb[:tot.value]

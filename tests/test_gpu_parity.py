@@ -1,0 +1,242 @@
+"""GPU parity: the CUDA path, called through the C ABI (ctypes -> libsphe_b200.so), against
+ (a) golden vectors produced by the unmodified reference, and (b) the C oracle on the same inputs.
+
+Bars (BASELINE.json north_star):
+  * cell indices, sorted order, cell-start table, neighbour lists: BIT-EXACT
+  * densities, forces, positions, velocities after one step: fp32 tolerance RTOL = 1e-5, measured
+    against the magnitude of the quantity's own sum (forces cancel to ~1e-6 of their terms in the
+    interior, SURVEY.md section 7 "tolerances under cancellation"), i.e.
+        |gpu - ref| <= RTOL * scale,  scale = max_i |field_i|   (per field)
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, product
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+VEC_FIELDS = ["acc", "fpress", "fvisc", "fgrav", "fsurf", "normal"]
+
+
+def close(got, want, what, rtol=RTOL):
+    got = np.asarray(got, np.float64); want = np.asarray(want, np.float64)
+    scale = max(np.abs(want).max(), 1e-30)
+    err = np.abs(got - want).max()
+    assert err <= rtol * scale, "%s: max err %.3e > %.1e * scale %.3e (rel %.2e)" % (what, err, rtol, scale, err / scale)
+
+
+def make_sim(P=None, diag=True):
+    m = product()
+    s = m.FluidSystemSPH()
+    if P is not None:
+        q = s.params
+        q.mass, q.visc, q.surf_tens, q.p0, q.k, q.h, q.len, q.dt = P.mass, P.visc, P.surf_tens, P.p0, P.k, P.h, P.len, P.dt
+        q.g[0], q.g[1], q.g[2] = P.g[0], P.g[1], P.g[2]
+    if diag:
+        s.set_diagnostics(True)
+    return s
+
+
+def oracle_grid_like(s, P):
+    gi = s.grid_info()
+    G = port.Grid()
+    G.gmin[:] = list(gi.gmin); G.cell = gi.cell; G.dim[:] = list(gi.dim)
+    return G
+
+
+def check_binning(s, P, pos_before):
+    """cells / order / cell-start / neighbour lists of the last step: bit-exact vs the oracle."""
+    G = oracle_grid_like(s, P)
+    cell_of, order, cell_start = port.bin_particles(G, pos_before)
+    assert np.array_equal(s.debug_cells(), cell_of), "cell index per particle"
+    assert np.array_equal(s.debug_sorted_order(), order), "sorted order"
+    assert np.array_equal(s.debug_cell_start(), cell_start), "cell-start table"
+    ns, nb = port.neighbours(P, G, pos_before, order, cell_start)
+    gns, gnb = s.debug_neighbours()
+    assert np.array_equal(gns, ns), "neighbour counts"
+    assert np.array_equal(gnb, nb), "neighbour lists"
+
+
+def check_fields(s, S, tag=""):
+    close(s.download("density"), S.density, tag + "density")
+    pr_scale_tol = RTOL * max(np.abs(S.density).max(), 1.0) * 3.0 / max(np.abs(S.pressure).max(), 1e-30)
+    close(s.download("pressure"), S.pressure, tag + "pressure", rtol=max(RTOL, pr_scale_tol))
+    for f in VEC_FIELDS:
+        close(s.download(f), getattr(S, f), tag + f)
+    close(s.download("pos"), S.pos, tag + "pos")
+    close(s.download("vel"), S.vel, tag + "vel")
+
+
+def test_default_scene_step1_vs_reference_golden():
+    g = np.load(os.path.join(GOLDEN, "default_scene.npz"))
+    s = make_sim()
+    s.Initialize(1000)
+    assert np.array_equal(s.download("pos").view(np.uint32), g["pos0"].view(np.uint32))  # lattice bit-exact
+    s.SetDeltaTime(0.01)
+    s.Run()
+    close(s.download("density"), g["s1_density"], "density")
+    for f in VEC_FIELDS + ["pos", "vel"]:
+        close(s.download(f), g["s1_" + f], f)
+    assert np.array_equal(s.download("neighb"), g["s1_neighb"])
+    check_binning(s, port.default_params(dt=0.01), g["pos0"])
+    p = s.GetParticle(555)
+    assert p.id == 555 and abs(p.density - g["s1_density"][555]) <= RTOL * g["s1_density"][555]
+    assert np.allclose(list(p.position), g["s1_pos"][555], rtol=1e-5, atol=1e-7)
+
+
+def test_default_scene_100_steps_statistics():
+    """Over many steps trajectories diverge chaotically; compare mean kinetic energy and bounds."""
+    g = np.load(os.path.join(GOLDEN, "default_scene.npz"))
+    s = make_sim(diag=False)
+    s.Initialize(1000)
+    s.SetDeltaTime(0.01)
+    want = dict(zip(g["hash_steps"].tolist(), g["mean_ke"].tolist()))
+    for step in range(1, 101):
+        s.Run()
+        if step in want:
+            v = s.download("vel").astype(np.float64)
+            ke = float((0.5 * 0.02 * (v * v).sum(axis=1)).mean())
+            tol = 1e-4 if step <= 3 else (0.02 if step <= 20 else 0.25)
+            assert ke == pytest.approx(want[step], rel=tol), "mean KE at step %d" % step
+        if step == 20:
+            close(s.download("pos"), g["s20_pos"], "pos@20", rtol=2e-2)
+    pos = s.download("pos")
+    assert np.isfinite(pos).all() and np.abs(pos).max() < 0.25
+
+
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_random_state_cases_vs_reference_golden(case):
+    g = np.load(os.path.join(GOLDEN, "random_state.npz"))
+    dt, length, h, mass, visc, surf, p0, gx, gy, gz = g["c%d_cfg" % case].tolist()
+    P = port.default_params(dt=dt, len=length, h=h, mass=mass, visc=visc, surf_tens=surf, p0=p0, g=(gx, gy, gz))
+    s = make_sim(P)
+    s.upload_state(g["c%d_in_pos" % case], g["c%d_in_vel" % case])
+    s.Run()
+    close(s.download("density"), g["c%d_density" % case], "density")
+    for f in VEC_FIELDS + ["pos", "vel"]:
+        close(s.download(f), g["c%d_%s" % (case, f)], f)
+    check_binning(s, P, g["c%d_in_pos" % case])
+
+
+def test_add_particles_and_reset_vs_reference_golden():
+    g = np.load(os.path.join(GOLDEN, "add_particles.npz"))
+    s = make_sim()
+    s.SetOrigin((0.01, 0.02, -0.01))
+    s.Initialize(1000)
+    s.SetDeltaTime(0.01)
+    s.Run(); s.Run()
+    s.AddParticles(125)
+    assert s.count() == 1125
+    assert np.array_equal(s.download("id"), g["added_id"])
+    # replace the (chaotically drifting) state by the reference's, keep the appended block
+    assert np.array_equal(s.download("pos")[1000:].view(np.uint32), g["added_pos"][1000:].view(np.uint32))
+    s.upload_state(g["added_pos"], g["added_vel"])
+    s.Run()  # coincident particles -> dist < 1e-4 branch (fluid_system.h:438-440)
+    close(s.download("density"), g["a1_density"], "density")
+    for f in VEC_FIELDS + ["pos", "vel"]:
+        close(s.download(f), g["a1_" + f], f)
+    s2 = make_sim()
+    s2.SetOrigin((0.01, 0.02, -0.01)); s2.Initialize(1000); s2.AddParticles(125); s2.Reset()
+    assert s2.count() == 1000
+    assert np.array_equal(s2.download("pos").view(np.uint32), g["reset_pos"].view(np.uint32))
+
+
+def test_lockstep_vs_oracle_10k():
+    """22^3 block with the box half-extent injected (BASELINE config 1, '10k-50k' range): every step
+    the GPU starts from the oracle's state, so each comparison is a one-step comparison."""
+    n, length = 22 ** 3, 0.45
+    P = port.default_params(dt=0.01, len=length)
+    S = port.State(port.lattice(n))
+    s = make_sim(P)
+    G = None
+    for step in range(5):
+        s.upload_state(S.pos, S.vel)
+        before = S.pos.copy()
+        s.Run()
+        if G is None:
+            G = oracle_grid_like(s, P)
+        port.step_grid(P, G, S)
+        check_fields(s, S, "step %d " % step)
+        if step in (0, 4):
+            check_binning(s, P, before)
+
+
+def test_free_running_binning_stays_canonical():
+    """Without re-uploading, the storage order is last step's sorted order; the (cell,id) order must
+    still be canonical (independent of history and atomic scheduling)."""
+    P = port.default_params(dt=0.01)
+    s = make_sim(P, diag=False)
+    s.Initialize(3375)
+    for step in range(12):
+        before = s.download("pos")
+        s.Run()
+        G = oracle_grid_like(s, P)
+        cell_of, order, cell_start = port.bin_particles(G, before)
+        assert np.array_equal(s.debug_sorted_order(), order)
+        assert np.array_equal(s.debug_cell_start(), cell_start)
+
+
+def test_step_host_matches_resident_path():
+    rng = np.random.default_rng(3)
+    n = 5000
+    pos = rng.uniform(-0.19, 0.19, (n, 3)).astype(np.float32)
+    vel = rng.normal(0, 0.3, (n, 3)).astype(np.float32)
+    P = port.default_params(dt=0.005)
+    a = make_sim(P, diag=False); b = make_sim(P, diag=False)
+    a.upload_state(pos, vel); a.Run()
+    po, vo, rho = b.step_host(pos, vel)
+    assert np.array_equal(po.view(np.uint32), a.download("pos").view(np.uint32))
+    assert np.array_equal(vo.view(np.uint32), a.download("vel").view(np.uint32))
+    assert np.array_equal(rho.view(np.uint32), a.download("density").view(np.uint32))
+    S = port.State(pos, vel)
+    port.step_grid(P, oracle_grid_like(a, P), S)
+    close(po, S.pos, "pos"); close(vo, S.vel, "vel"); close(rho, S.density, "density")
+
+
+def test_dt_zero_recomputes_forces_but_does_not_move():
+    s = make_sim()
+    s.Initialize(1000)
+    p0 = s.download("pos")
+    s.Run()  # deltaT = 0 (paused, main.cpp:476-485)
+    assert np.array_equal(s.download("pos").view(np.uint32), p0.view(np.uint32))
+    assert s.download("density").min() > 300.0
+    assert np.abs(s.download("fpress")).max() > 0
+
+
+def test_million_particle_properties():
+    """BASELINE config 2 size: size-independent properties + binning/density against the oracle."""
+    n_axis = 100
+    n = n_axis ** 3
+    L = 0.02 * n_axis
+    P = port.default_params(dt=0.01, len=L)
+    i = np.arange(n_axis)
+    x = (-L + i * 0.025).astype(np.float32); y = (-L / 4 + i * 0.025).astype(np.float32); z = (-0.75 * L + i * 0.025).astype(np.float32)
+    pos = np.stack(np.meshgrid(x, y, z, indexing="ij"), axis=-1).reshape(-1, 3).astype(np.float32)
+    rng = np.random.default_rng(0x5EED)
+    pos += rng.uniform(-0.005, 0.005, pos.shape).astype(np.float32)
+    vel = np.zeros_like(pos)
+    s = make_sim(P, diag=False)
+    s.upload_state(pos, vel)
+    s.Run()
+    G = oracle_grid_like(s, P)
+    cell_of, order, cell_start = port.bin_particles(G, pos)
+    assert np.array_equal(s.debug_sorted_order(), order)
+    assert np.array_equal(s.debug_cell_start(), cell_start)
+    assert np.array_equal(s.debug_cells(), cell_of)
+    # sortedness: (cell, id) strictly increasing
+    key = cell_of[order].astype(np.int64) * n + order
+    assert (np.diff(key) > 0).all()
+    S = port.State(pos, vel)
+    port.step_grid(P, G, S)
+    close(s.download("density"), S.density, "density@1M")
+    close(s.download("pos"), S.pos, "pos@1M")
+    close(s.download("vel"), S.vel, "vel@1M")
+    # idempotence of binning: a second paused step bins the new positions canonically again
+    s.SetDeltaTime(0.0)
+    before = s.download("pos")
+    s.Run()
+    c2, o2, cs2 = port.bin_particles(G, before)
+    assert np.array_equal(s.debug_sorted_order(), o2)
