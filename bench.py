@@ -49,6 +49,16 @@ def scaled_dam_break(n_axis, jitter=False, nx_mult=1):
     return pos, float(L)
 
 
+def scene_gravity(n_axis, unscaled=False):
+    """Dynamic similarity with the reference default scene (n_axis = 10): the soft equation of state
+    (k = 3, fluid_system.h:467) lets a column of height H compress by ~ g*H/k, so a scene scaled by
+    n/10 with unscaled g free-falls 1.5 box units and compresses to ~40x rest density (measured:
+    180 neighbours/particle at 1M particles) -- neither the reference's regime nor a stationary
+    workload.  Scaling g by 10/n keeps g*H/k, the velocities and the neighbour counts of the reference
+    scene (15-33 per particle).  g is a UI-mutable parameter (GetGrav, :281-284)."""
+    return -9.82 if unscaled else -9.82 * 10.0 / n_axis
+
+
 WORKLOADS = {
     # name: (n_axis, jitter, terrain, description)
     "small": (32, False, False, "32^3 = 32,768-particle dam break (smoke-sized)"),
@@ -135,7 +145,7 @@ def dist_env():
 
 
 # ----------------------------------------------------------------------------- CPU arms
-def cpu_port_baseline(pos, L, budget_s=20.0):
+def cpu_port_baseline(pos, L, gy=-9.82, budget_s=20.0):
     """Times oracle/sph_oracle.c so_step_grid (OpenMP, all host cores) on a bounded sample of the
     same scene.  kind = "port": the cell-grid restatement, bit-identical to the reference's sums."""
     from oracle import port
@@ -148,7 +158,7 @@ def cpu_port_baseline(pos, L, budget_s=20.0):
     # a contiguous x-slab of the block keeps the neighbour statistics of the full scene
     order = np.argsort(pos[:, 0], kind="stable")[:sample_n]
     sp = np.ascontiguousarray(pos[order])
-    P = port.default_params(dt=0.01, len=L)
+    P = port.default_params(dt=0.01, len=L, g=(0.0, gy, 0.0))
     S = port.State(sp)
     G = port.grid_for_box(P, [-L - 0.1] * 3, [L + 0.1] * 3)
     port.step_grid(P, G, S)  # warm (page faults, thread pool)
@@ -175,7 +185,7 @@ def run_reference_arm(args):
     if not ref.available(omp=True):
         # the oracle always exists: fall back to the C port of the same algorithm
         pos, L = scaled_dam_break(n_axis, jitter)
-        cb = cpu_port_baseline(pos, L)
+        cb = cpu_port_baseline(pos, L, scene_gravity(n_axis, args.gravity_unscaled))
         line.update({"value": cb["value"], "ms_per_step": None, "cpu_baseline": cb,
                      "config": {"workload": args.workload, "description": desc, "note": "oracle/_ref absent: timed the C port"},
                      "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
@@ -184,14 +194,17 @@ def run_reference_arm(args):
     os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
     sample_axis = 22
     pos, L = scaled_dam_break(sample_axis, jitter)
+    gy_ref = scene_gravity(sample_axis, args.gravity_unscaled)
     sim = ref.RefSim(omp=True)
-    sim.set_len(L); sim.set_dt(0.01)
+    sim.set_len(L); sim.set_dt(0.01); sim.set_params(0.02, 3.5, 0.0728, 998.29, [0.0, gy_ref, 0.0])
     sim.set_state(pos, np.zeros_like(pos))
     t = time.perf_counter(); sim.run(1); t1 = time.perf_counter() - t
     if t1 * (args.steps + args.warmup) > 150.0:
         sample_axis = 16
         pos, L = scaled_dam_break(sample_axis, jitter)
-        sim = ref.RefSim(omp=True); sim.set_len(L); sim.set_dt(0.01); sim.set_state(pos, np.zeros_like(pos))
+        sim = ref.RefSim(omp=True); sim.set_len(L); sim.set_dt(0.01)
+        sim.set_params(0.02, 3.5, 0.0728, 998.29, [0.0, scene_gravity(sample_axis, args.gravity_unscaled), 0.0])
+        sim.set_state(pos, np.zeros_like(pos))
     sim.run(args.warmup)
     t = time.perf_counter(); sim.run(args.steps); dt = (time.perf_counter() - t) / max(args.steps, 1)
     n = pos.shape[0]
@@ -226,8 +239,10 @@ def run_gpu_arm(args):
 
     pos, L = scaled_dam_break(n_axis, jitter)
     n = pos.shape[0]
+    gy = scene_gravity(n_axis, args.gravity_unscaled)
     sim = pkg.FluidSystemSPH(device=local)
     sim.params.len = L
+    sim.params.g[1] = gy
     sim.SetDeltaTime(0.01)
     sim.set_variant(args.density_variant, args.force_variant)
     sim.upload_state(pos, np.zeros_like(pos))
@@ -250,7 +265,7 @@ def run_gpu_arm(args):
     op = torch.empty_like(hp).pin_memory(); ov = torch.empty_like(hp).pin_memory()
     orho = torch.empty(n, dtype=torch.float32).pin_memory()
     sim2 = pkg.FluidSystemSPH(device=local)
-    sim2.params.len = L; sim2.SetDeltaTime(0.01)
+    sim2.params.len = L; sim2.params.g[1] = gy; sim2.SetDeltaTime(0.01)
     sim2.set_variant(args.density_variant, args.force_variant)
     for _ in range(3):
         sim2.step_host_ptr(n, hp.data_ptr(), hv.data_ptr(), op.data_ptr(), ov.data_ptr(), orho.data_ptr())
@@ -276,12 +291,17 @@ def run_gpu_arm(args):
                 "per_kernel_ms_per_step": {k: v / args.steps for k, v in per_kernel.items()},
                 "per_kernel_hbm_frac": {k: (ALGO_BYTES[k] * n / (per_kernel[k] / args.steps * 1e-3) / 1e9 / peak)
                                         for k in ALGO_BYTES if per_kernel.get(k, 0) > 0}}
-    cb = cpu_port_baseline(pos, L) if not args.no_cpu_baseline else None
+    cb = cpu_port_baseline(pos, L, gy) if not args.no_cpu_baseline else None
+    ns_total = None
+    if n <= 4200000:
+        ns_total = int(sim.debug_neighbours_total())
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": args.workload, "description": desc, "particles": n, "h": 0.0457, "spacing": SPACING,
-                       "dt": 0.01, "box_half_extent": L, "l2": "flushed between timed steps (%d MiB memset, outside the event brackets)" % (flush_bytes >> 20),
+                       "dt": 0.01, "box_half_extent": L, "gravity_y": gy,
+                       "gravity_note": "g scaled by 10/n_axis: dynamic similarity with the reference default scene (see bench.scene_gravity)" if not args.gravity_unscaled else "unscaled g",
+                       "mean_neighbours_after_run": (ns_total / n) if ns_total else None, "l2": "flushed between timed steps (%d MiB memset, outside the event brackets)" % (flush_bytes >> 20),
                        "density_variant": args.density_variant, "force_variant": args.force_variant},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cb}
     print(json.dumps(line))
@@ -297,6 +317,7 @@ def main():
     ap.add_argument("--density-variant", type=int, default=0)
     ap.add_argument("--force-variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gravity-unscaled", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -61,6 +61,9 @@ struct sphe_sim {
     float* stage = nullptr;  // 2 * 3 * cap floats: id-order staging for uploads/downloads
     int* slot_of_id = nullptr;
     bool slot_valid = false;
+    int* nlist = nullptr;   // variant 3: [nlist_cap][pairs_pad] neighbour indices
+    int2* ncount = nullptr;
+    size_t nlist_pairs = 0;
 
     long long ncells = 0, ncells_cap = 0;
     int *count = nullptr, *cell_start = nullptr, *cursor = nullptr, *tile_sum = nullptr;
@@ -259,11 +262,21 @@ static int step_device(sphe_sim* s, sphe_terrain* t) {
     { Scope k(s, SPHE_K_REORDER);
       launch_rank_reorder(s->st, n, s->tmp, s->cell, s->cell_start, s->posA, s->velA, s->sedA, s->posB, s->velB, s->sedB,
                           s->idsB, s->cell_sorted); }
+    if (s->variant_density == 3 || s->variant_force == 3) {
+        if (s->variant_density != s->variant_force) return fail(SPHE_ERR_ARG, "variant 3 (neighbour lists) must be selected for both passes");
+        size_t pp = (size_t)nlist_pairs_pad(s->cap);
+        if (pp > s->nlist_pairs) {
+            TRY(grow(&s->nlist, 0, pp * (size_t)nlist_cap(), s->st, false));
+            TRY(grow(&s->ncount, 0, pp, s->st, false));
+            s->nlist_pairs = pp;
+        }
+    }
     { Scope k(s, SPHE_K_DENSITY);
-      launch_density(s->st, s->variant_density, n, s->posB, s->posC, s->velB, s->cell_sorted, s->cell_start, s->G, C, s->rho); }
+      launch_density(s->st, s->variant_density, n, s->posB, s->posC, s->velB, s->cell_sorted, s->cell_start, s->G, C, s->rho,
+                     s->nlist, s->ncount); }
     { Scope k(s, SPHE_K_FORCE);
       launch_force(s->st, s->variant_force, n, s->posC, s->velB, s->rho, s->idsB, s->cell_sorted, s->cell_start, s->G, C,
-                   s->posA, s->velA, s->diag ? &s->D : nullptr); }
+                   s->posA, s->velA, s->diag ? &s->D : nullptr, s->nlist, s->ncount); }
     std::swap(s->idsA, s->idsB);
     std::swap(s->sedA, s->sedB);
     s->binned = true;
@@ -340,7 +353,7 @@ void sphe_destroy(sphe_sim* s) {
         cudaSetDevice(s->device);
         cudaStreamSynchronize(s->st);
         void* ptrs[] = {s->posA, s->posB, s->posC, s->velA, s->velB, s->idsA, s->idsB, s->sedA, s->sedB, s->rho, s->cell,
-                        s->cell_sorted, s->tmp, s->stage, s->slot_of_id, s->count, s->cell_start, s->cursor, s->tile_sum,
+                        s->cell_sorted, s->tmp, s->stage, s->slot_of_id, s->nlist, s->ncount, s->count, s->cell_start, s->cursor, s->tile_sum,
                         s->flush_buf, s->D.acc, s->D.fpress, s->D.fvisc, s->D.fgrav, s->D.fsurf, s->D.normal, s->D.neighb};
         for (void* p : ptrs) if (p) cudaFree(p);
         if (s->own_stream && s->st) cudaStreamDestroy(s->st);

@@ -31,10 +31,13 @@ struct DiagOut {
 struct TerrainDev;  // terrain.cu
 
 void launch_density(cudaStream_t st, int variant, int n, const float4* posq, float4* posq_q, float4* velv,
-                    const uint32_t* cell_sorted, const int* cell_start, const GridP& G, const StepC& C, float* rho);
+                    const uint32_t* cell_sorted, const int* cell_start, const GridP& G, const StepC& C, float* rho,
+                    int* nlist, int2* ncount);
+int nlist_cap();
+int nlist_pairs_pad(int n);
 void launch_force(cudaStream_t st, int variant, int n, const float4* posq, const float4* velv, const float* rho,
                   const int* ids, const uint32_t* cell_sorted, const int* cell_start, const GridP& G, const StepC& C,
-                  float4* posq_out, float4* velv_out, const DiagOut* diag);
+                  float4* posq_out, float4* velv_out, const DiagOut* diag, const int* nlist, const int2* ncount);
 void launch_neighbour_count(cudaStream_t st, int n, const float4* posq, const uint32_t* cell_sorted, const int* cell_start,
                             const GridP& G, const StepC& C, int* counts);
 void launch_neighbour_fill(cudaStream_t st, int n, const float4* posq, const int* ids, const uint32_t* cell_sorted,

@@ -70,6 +70,108 @@ __global__ void __launch_bounds__(128) k_density_tpp(int n, const float4* __rest
     velv[i].w = C.mass / r;
 }
 
+// ------------------------------------------------------------------ pass 1, variant 1: two targets per thread
+// B200-specific: sm_100 has packed fp32 math (FADD2 / FMUL2 / FFMA2, PTX add/mul/fma.f32x2) whose
+// second operand can be a scalar broadcast.  A thread owns two consecutive sorted particles (a, b),
+// keeps their coordinates packed as (xa,xb),(ya,yb),(za,zb) and streams each candidate ONCE for both:
+// one LDG.128 + 9 packed ops + 2 FMNMX per candidate instead of 2 x (LDG + 12 scalar ops).  That
+// halves both the issue slots and the L1 wavefronts per (target,candidate) pair -- the two limits ncu
+// showed for the thread-per-particle kernel (profiles/r01_ncu_density_force_tpp.txt).
+// a and b are usually in the same cell; if they are in the same column and at most 3 cells apart the
+// walk covers the union z-range (extra candidates fail the distance test); otherwise two walks.
+// The weight is clamped, max(h^2 - d2, 0)^3, instead of predicated: contributions vanish continuously
+// at r = h so the FMA-contracted d2 is within tolerance (the exact predicate is only needed for the
+// neighbour LISTS, see k_nbr_fill).
+template <int S>
+__device__ __forceinline__ float2 density_walk_pair(const GridP& G, const int* __restrict__ cell_start,
+                                                    const float4* __restrict__ posq, int cx, int cy, int z0, int z1,
+                                                    float2 X, float2 Y, float2 Z, float hh, int slice) {
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll 1
+    for (int dx = -1; dx <= 1; dx++) {
+        int x = cx + dx;
+        if (x < 0 || x >= G.nx) continue;
+#pragma unroll 1
+        for (int dy = -1; dy <= 1; dy++) {
+            int y = cy + dy;
+            if (y < 0 || y >= G.ny) continue;
+            int base = (x * G.ny + y) * G.nz;
+            int s = __ldg(&cell_start[base + z0]);
+            int e = __ldg(&cell_start[base + z1 + 1]);
+#pragma unroll 4
+            for (int k = s + slice; k < e; k += S) {
+                float4 p = __ldg(&posq[k]);
+                float2 ddx = __fadd2_rn(X, make_float2(-p.x, -p.x));
+                float2 ddy = __fadd2_rn(Y, make_float2(-p.y, -p.y));
+                float2 ddz = __fadd2_rn(Z, make_float2(-p.z, -p.z));
+                float2 d2 = __fmul2_rn(ddx, ddx);
+                d2 = __ffma2_rn(ddy, ddy, d2);
+                d2 = __ffma2_rn(ddz, ddz, d2);
+                float2 w = __fadd2_rn(make_float2(hh, hh), make_float2(-d2.x, -d2.y));
+                w.x = fmaxf(w.x, 0.f);
+                w.y = fmaxf(w.y, 0.f);
+                acc = __ffma2_rn(__fmul2_rn(w, w), w, acc);
+            }
+        }
+    }
+    return acc;
+}
+
+// S lanes share one target pair and stride the candidate ranges (lane%S, step S): the S lanes read S
+// consecutive float4 (one or two 128-byte lines) instead of S unrelated ranges, which cuts the L1
+// wavefronts per request -- the limiter ncu reports for S = 1 (l1tex lsu wavefronts 91 % of peak) -- and
+// leaves fewer distinct cells per warp (less trip-count divergence).  Partial sums are combined with
+// __shfl_xor.
+template <int S>
+__global__ void __launch_bounds__(128) k_density_pair(int n, const float4* __restrict__ posq, float4* __restrict__ posq_q,
+                                                      float4* __restrict__ velv, const uint32_t* __restrict__ cell_sorted,
+                                                      const int* __restrict__ cell_start, GridP G, StepC C,
+                                                      float* __restrict__ rho) {
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int slice = gt % S;
+    int a = 2 * (gt / S);
+    if (a >= n) a = (n - 1) & ~1;  // keep whole warps alive for the shuffles; duplicates write identical values
+    int b = (a + 1 < n) ? a + 1 : a;
+    float4 pa = posq[a], pb = posq[b];
+    uint32_t ca = cell_sorted[a], cb = cell_sorted[b];
+    uint32_t cola = ca / (uint32_t)G.nz, colb = cb / (uint32_t)G.nz;
+    int cza = (int)(ca - cola * (uint32_t)G.nz), czb = (int)(cb - colb * (uint32_t)G.nz);
+    bool merged = (cola == colb) && (czb - cza <= 3);
+    // one walk over the union z-range when merged, else one walk per particle (single code copy so
+    // merged and split lanes of a warp stay converged inside the walk)
+    float ra = 0.f, rb = 0.f;
+    int npass = merged ? 1 : 2;
+#pragma unroll 1
+    for (int p = 0; p < npass; p++) {
+        float4 q0 = p ? pb : pa;
+        float4 q1 = merged ? pb : q0;
+        uint32_t col = p ? colb : cola;
+        int czlo = p ? czb : cza;
+        int czhi = merged ? czb : czlo;
+        int cy = (int)(col % (uint32_t)G.ny), cx = (int)(col / (uint32_t)G.ny);
+        int z0 = czlo > 0 ? czlo - 1 : 0, z1 = czhi < G.nz - 1 ? czhi + 1 : czhi;
+        float2 r = density_walk_pair<S>(G, cell_start, posq, cx, cy, z0, z1, make_float2(q0.x, q1.x), make_float2(q0.y, q1.y),
+                                        make_float2(q0.z, q1.z), C.hh, slice);
+        if (p == 0) { ra = r.x; rb = r.y; } else { rb = r.y; }
+    }
+#pragma unroll
+    for (int o = 1; o < S; o <<= 1) {
+        ra += __shfl_xor_sync(SPHE_FULL, ra, o);
+        rb += __shfl_xor_sync(SPHE_FULL, rb, o);
+    }
+    if (slice != 0) return;
+    ra *= C.densK; rb *= C.densK;
+    float Pa = C.k * (ra - C.p0), Pb = C.k * (rb - C.p0);
+    rho[a] = ra;
+    posq_q[a] = make_float4(pa.x, pa.y, pa.z, Pa / (ra * ra));
+    velv[a].w = C.mass / ra;
+    if (b != a) {
+        rho[b] = rb;
+        posq_q[b] = make_float4(pb.x, pb.y, pb.z, Pb / (rb * rb));
+        velv[b].w = C.mass / rb;
+    }
+}
+
 // ------------------------------------------------------------------ box collision, fluid_system.h:355-407
 __device__ __forceinline__ bool collision_box(float len, float x, float y, float z, float& cx, float& cy, float& cz,
                                               float& nx, float& ny, float& nz) {
@@ -85,6 +187,53 @@ __device__ __forceinline__ bool collision_box(float len, float x, float y, float
     else if (axis == 1) { if (y < -len) { cy = -len; ny = 1.0f; } else { cy = len; ny = -1.0f; } }
     else { if (z < -len) { cz = -len; nz = 1.0f; } else { cz = len; nz = -1.0f; } }
     return true;
+}
+
+// ------------------------------------------------------------------ force -> integrate -> collide (per particle)
+// PressureForce = -(fPress*rho_i), fPress = -mass*c45*A (fluid_system.h:145,151); ViscosityForce = c45*visc*F
+// (:146,153); SurfaceNormal = -c945*N (:147,154); colorFieldLapl = -c945*cf, SurfaceForce = -surf_tens*cfl*n
+// (:171,177); GravityForce = rho_i*g (:163); then advance() (:318-350) with collisionS (:342-347).
+template <bool DIAG>
+__device__ __forceinline__ void force_epilogue(int i, float4 pi, float4 vi, float rho_i, float ax, float ay, float az,
+                                               float fx, float fy, float fz, float nx, float ny, float nz, float cf, int maxid,
+                                               const StepC& C, const int* __restrict__ ids, float4* __restrict__ posq_out,
+                                               float4* __restrict__ velv_out, const DiagOut& D) {
+    float kp = rho_i * C.mass * C.c45;
+    float Fpx = kp * ax, Fpy = kp * ay, Fpz = kp * az;
+    float kv = C.visc * C.c45;
+    float Fvx = kv * fx, Fvy = kv * fy, Fvz = kv * fz;
+    float Nx = -C.c945 * nx, Ny = -C.c945 * ny, Nz = -C.c945 * nz;
+    float cfl = -C.c945 * cf;
+    float ks = -C.surf * cfl;
+    float Fsx = ks * Nx, Fsy = ks * Ny, Fsz = ks * Nz;
+    float Fgx = rho_i * C.gx, Fgy = rho_i * C.gy, Fgz = rho_i * C.gz;
+    float Fx = (Fpx + Fvx) + (Fgx + Fsx), Fy = (Fpy + Fvy) + (Fgy + Fsy), Fz = (Fpz + Fvz) + (Fgz + Fsz);
+    float acx = Fx / rho_i, acy = Fy / rho_i, acz = Fz / rho_i;
+    float dt = C.dt;
+    float vx = fmaf(acx, dt, vi.x), vy = fmaf(acy, dt, vi.y), vz = fmaf(acz, dt, vi.z);
+    float px = fmaf(vx, dt, pi.x), py = fmaf(vy, dt, pi.y), pz = fmaf(vz, dt, pi.z);
+    float cx, cy, cz, bx, by, bz;
+    if (collision_box(C.len, px, py, pz, cx, cy, cz, bx, by, bz) && dt != 0.0f) {
+        float ex = px - cx, ey = py - cy, ez = pz - cz;
+        float d = sqrtf(ex * ex + ey * ey + ez * ez);
+        float vlen = sqrtf(vx * vx + vy * vy + vz * vz);
+        float sc = 1.0f + 0.5f * d / (dt * vlen);
+        float vn = vx * bx + vy * by + vz * bz;
+        vx -= bx * sc * vn; vy -= by * sc * vn; vz -= bz * sc * vn;
+        px = cx; py = cy; pz = cz;
+    }
+    posq_out[i] = make_float4(px, py, pz, 0.0f);
+    velv_out[i] = make_float4(vx, vy, vz, 0.0f);
+    if (DIAG) {
+        int id = ids[i];
+        D.acc[id] = make_float4(acx, acy, acz, 0.f);
+        D.fpress[id] = make_float4(Fpx, Fpy, Fpz, 0.f);
+        D.fvisc[id] = make_float4(Fvx, Fvy, Fvz, 0.f);
+        D.fgrav[id] = make_float4(Fgx, Fgy, Fgz, 0.f);
+        D.fsurf[id] = make_float4(Fsx, Fsy, Fsz, 0.f);
+        D.normal[id] = make_float4(Nx, Ny, Nz, 0.f);
+        if (maxid >= 0) D.neighb[id] = maxid;  // last neighbour in ascending-id order (:144)
+    }
 }
 
 // ------------------------------------------------------------------ passes 2+3 + integrate + collide
@@ -181,6 +330,422 @@ __global__ void __launch_bounds__(128) k_force_tpp(int n, const float4* __restri
     }
 }
 
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ------------------------------------------------------------------ passes 2+3, variant 1: pair + compaction
+// ncu on k_force_tpp (profiles/r01_ncu_density_force_tpp.txt): 15.7 of 32 lanes active per instruction --
+// the ~45-instruction neighbour body ran on every candidate iteration with ~15 % of the lanes.  Here:
+//   phase 1 (test):    two targets per thread, packed FADD2/FMUL2/FFMA2 distance test per candidate, and the
+//                      indices of candidates that are a neighbour of EITHER target are appended to a
+//                      per-thread list in shared memory ([entry][thread] layout, conflict free);
+//   phase 2 (process): the thread walks its own dense list with the packed neighbour body for both targets.
+// Weights are clamped (max(h^2-d2,0), max(h-r,0)) so a candidate that is a neighbour of only one of the
+// two targets contributes exactly 0 to the other.  A full list is flushed in place (rare).
+constexpr int FORCE_LIST_CAP = 48;
+constexpr int FORCE_THREADS = 128;
+
+template <bool DIAG>
+__global__ void __launch_bounds__(FORCE_THREADS) k_force_pair(int n, const float4* __restrict__ posq_q, const float4* __restrict__ velv,
+                                                    const float* __restrict__ rho, const int* __restrict__ ids,
+                                                    const uint32_t* __restrict__ cell_sorted,
+                                                    const int* __restrict__ cell_start, GridP G, StepC C,
+                                                    float4* __restrict__ posq_out, float4* __restrict__ velv_out, DiagOut D) {
+    __shared__ int list[(FORCE_LIST_CAP + 1) * FORCE_THREADS];  // +1: trash slot for saturated appends
+    const int tid = threadIdx.x;
+    int a = 2 * (blockIdx.x * blockDim.x + tid);
+    if (a >= n) return;
+    int b = (a + 1 < n) ? a + 1 : a;
+    const float4 pa = posq_q[a], pb = posq_q[b];
+    const float4 va = velv[a], vb = velv[b];
+    const uint32_t ca = cell_sorted[a], cb = cell_sorted[b];
+    const uint32_t cola = ca / (uint32_t)G.nz, colb = cb / (uint32_t)G.nz;
+    const int cza = (int)(ca - cola * (uint32_t)G.nz), czb = (int)(cb - colb * (uint32_t)G.nz);
+    const bool merged = (b != a) && (cola == colb) && (czb - cza <= 3);
+    const float inv_sqrt3 = 0.57735026f;
+    const float FAR = 1.0e18f;  // dummy target: every weight clamps to exactly 0
+
+    float2 A_x = {0.f, 0.f}, A_y = {0.f, 0.f}, A_z = {0.f, 0.f};  // sum (q_i+q_j)(h-r)^2 dir
+    float2 F_x = {0.f, 0.f}, F_y = {0.f, 0.f}, F_z = {0.f, 0.f};  // sum (v_j-v_i) vol_j (h-r)
+    float2 N_x = {0.f, 0.f}, N_y = {0.f, 0.f}, N_z = {0.f, 0.f};  // sum vol_j (h^2-r^2)^2 d
+    float2 CF = {0.f, 0.f};                                        // sum vol_j (h^2-r^2)(3h^2-7r^2)
+    int maxa = -1, maxb = -1;
+
+    const int npass = (merged || b == a) ? 1 : 2;
+#pragma unroll 1
+    for (int p = 0; p < npass; p++) {
+        // targets of this pass: (a,b) merged, else (a,FAR) then (FAR,b)
+        const bool useA = merged || p == 0, useB = merged || p == 1;
+        const float2 X = make_float2(useA ? pa.x : FAR, useB ? pb.x : FAR);
+        const float2 Y = make_float2(useA ? pa.y : FAR, useB ? pb.y : FAR);
+        const float2 Z = make_float2(useA ? pa.z : FAR, useB ? pb.z : FAR);
+        const float2 Q = make_float2(pa.w, pb.w);
+        const float2 VX = make_float2(va.x, vb.x), VY = make_float2(va.y, vb.y), VZ = make_float2(va.z, vb.z);
+        const int ia = useA ? a : -1, ib = (useB && b != a) ? b : -1;
+        const uint32_t col = p ? colb : cola;
+        const int czlo = p ? czb : cza, czhi = merged ? czb : czlo;
+        const int cy = (int)(col % (uint32_t)G.ny), cx = (int)(col / (uint32_t)G.ny);
+        const int z0 = czlo > 0 ? czlo - 1 : 0, z1 = czhi < G.nz - 1 ? czhi + 1 : czhi;
+
+        // neighbour body for candidate k against both targets (packed)
+        auto body = [&](const int k) {
+            const float4 pj = __ldg(&posq_q[k]);
+            const float4 vj = __ldg(&velv[k]);
+            float2 dx = __fadd2_rn(X, make_float2(-pj.x, -pj.x));
+            float2 dy = __fadd2_rn(Y, make_float2(-pj.y, -pj.y));
+            float2 dz = __fadd2_rn(Z, make_float2(-pj.z, -pj.z));
+            float2 d2 = __fmul2_rn(dx, dx);
+            d2 = __ffma2_rn(dy, dy, d2);
+            d2 = __ffma2_rn(dz, dz, d2);
+            float2 w = __fadd2_rn(make_float2(C.hh, C.hh), make_float2(-d2.x, -d2.y));
+            w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f);
+            float2 vw = __fmul2_rn(w, make_float2(vj.w, vj.w));
+            float2 t7 = __ffma2_rn(d2, make_float2(-7.0f, -7.0f), make_float2(C.hh3, C.hh3));
+            CF = __ffma2_rn(vw, t7, CF);
+            float2 vww = __fmul2_rn(vw, w);
+            N_x = __ffma2_rn(vww, dx, N_x); N_y = __ffma2_rn(vww, dy, N_y); N_z = __ffma2_rn(vww, dz, N_z);
+            // d2 is clamped away from 0, so the flush-to-zero approximation never sees a denormal
+            float2 rinv = make_float2(rsqrt_ftz(fmaxf(d2.x, 1e-30f)), rsqrt_ftz(fmaxf(d2.y, 1e-30f)));
+            float2 r = __fmul2_rn(d2, rinv);
+            float2 hm = __fadd2_rn(make_float2(C.h, C.h), make_float2(-r.x, -r.y));
+            hm.x = fmaxf(hm.x, 0.f); hm.y = fmaxf(hm.y, 0.f);
+            float2 tv = __fmul2_rn(hm, make_float2(vj.w, vj.w));
+            float2 dvx = __fadd2_rn(make_float2(vj.x, vj.x), make_float2(-VX.x, -VX.y));
+            float2 dvy = __fadd2_rn(make_float2(vj.y, vj.y), make_float2(-VY.x, -VY.y));
+            float2 dvz = __fadd2_rn(make_float2(vj.z, vj.z), make_float2(-VZ.x, -VZ.y));
+            F_x = __ffma2_rn(tv, dvx, F_x); F_y = __ffma2_rn(tv, dvy, F_y); F_z = __ffma2_rn(tv, dvz, F_z);
+            float2 sq = __fadd2_rn(Q, make_float2(pj.w, pj.w));
+            float2 sc = __fmul2_rn(__fmul2_rn(sq, hm), hm);
+            // pressure excludes j == i (fluid_system.h:142)
+            if (k == ia) sc.x = 0.f;
+            if (k == ib) sc.y = 0.f;
+            float2 ux = __fmul2_rn(dx, rinv), uy = __fmul2_rn(dy, rinv), uz = __fmul2_rn(dz, rinv);
+            if (fminf(r.x, r.y) <= 1e-4f) {
+                // coincident pair: direction (1,1,1)/sqrt(3) (fluid_system.h:438-440); also taken by the
+                // self entry, whose pressure weight is already 0
+                if (r.x <= 1e-4f) { ux.x = inv_sqrt3; uy.x = inv_sqrt3; uz.x = inv_sqrt3; }
+                if (r.y <= 1e-4f) { ux.y = inv_sqrt3; uy.y = inv_sqrt3; uz.y = inv_sqrt3; }
+            }
+            A_x = __ffma2_rn(sc, ux, A_x); A_y = __ffma2_rn(sc, uy, A_y); A_z = __ffma2_rn(sc, uz, A_z);
+            if (DIAG) {
+                // NeighbId needs the reference's exact predicate (bit-exact neighbour set)
+                int idk = __ldg(&ids[k]);
+                if (k != ia && ia >= 0 && dist2_exact(pa.x - pj.x, pa.y - pj.y, pa.z - pj.z) <= C.T) maxa = max(maxa, idk);
+                if (k != ib && ib >= 0 && dist2_exact(pb.x - pj.x, pb.y - pj.y, pb.z - pj.z) <= C.T) maxb = max(maxb, idk);
+            }
+        };
+
+        // Phase 1: fill.  Same nested loops for every lane (warp stays converged) and a BRANCH-FREE append:
+        // every candidate is stored at the lane's current slot and the slot only advances on a pass, so a
+        // failing candidate is overwritten by the next one.  Slots saturate at CAP; overflow is detected
+        // afterwards and those (rare, strongly compressed) lanes redo the walk without a list.
+        int* const lbase = list + tid;
+        int off = 0;  // slot * FORCE_THREADS
+#pragma unroll 1
+        for (int r = 0; r < 9; r++) {
+            int x = cx + r / 3 - 1, y = cy + r % 3 - 1;
+            if (x < 0 || x >= G.nx || y < 0 || y >= G.ny) continue;
+            int base = (x * G.ny + y) * G.nz;
+            int s = __ldg(&cell_start[base + z0]);
+            int e = __ldg(&cell_start[base + z1 + 1]);
+#pragma unroll 4
+            for (int k = s; k < e; k++) {
+                float4 pj = __ldg(&posq_q[k]);
+                float2 dx = __fadd2_rn(X, make_float2(-pj.x, -pj.x));
+                float2 dy = __fadd2_rn(Y, make_float2(-pj.y, -pj.y));
+                float2 dz = __fadd2_rn(Z, make_float2(-pj.z, -pj.z));
+                float2 d2 = __fmul2_rn(dx, dx);
+                d2 = __ffma2_rn(dy, dy, d2);
+                d2 = __ffma2_rn(dz, dz, d2);
+                lbase[min(off, FORCE_LIST_CAP * FORCE_THREADS)] = k;
+                off += (fminf(d2.x, d2.y) <= C.hh) ? FORCE_THREADS : 0;
+            }
+        }
+        const int cnt = off / FORCE_THREADS;
+        if (cnt <= FORCE_LIST_CAP) {
+            // Phase 2: dense walk over the lane's own list
+#pragma unroll 1
+            for (int o = 0; o < off; o += FORCE_THREADS) body(lbase[o]);
+        } else {
+            // overflow: direct walk, body executed under the (divergent) predicate
+#pragma unroll 1
+            for (int r = 0; r < 9; r++) {
+                int x = cx + r / 3 - 1, y = cy + r % 3 - 1;
+                if (x < 0 || x >= G.nx || y < 0 || y >= G.ny) continue;
+                int base = (x * G.ny + y) * G.nz;
+                int s = __ldg(&cell_start[base + z0]);
+                int e = __ldg(&cell_start[base + z1 + 1]);
+#pragma unroll 1
+                for (int k = s; k < e; k++) {
+                    float4 pj = __ldg(&posq_q[k]);
+                    float ex = X.x - pj.x, ey = Y.x - pj.y, ez = Z.x - pj.z;
+                    float gx = X.y - pj.x, gy = Y.y - pj.y, gz = Z.y - pj.z;
+                    float da = fmaf(ez, ez, fmaf(ey, ey, ex * ex)), db = fmaf(gz, gz, fmaf(gy, gy, gx * gx));
+                    if (fminf(da, db) <= C.hh) body(k);
+                }
+            }
+        }
+    }
+
+    // epilogue per target
+#pragma unroll 1
+    for (int p = 0; p < 2; p++) {
+        if (p == 1 && b == a) break;
+        const int i = p ? b : a;
+        const float4 pi = p ? pb : pa;
+        const float4 vi = p ? vb : va;
+        const float ax = p ? A_x.y : A_x.x, ay = p ? A_y.y : A_y.x, az = p ? A_z.y : A_z.x;
+        const float fx = p ? F_x.y : F_x.x, fy = p ? F_y.y : F_y.x, fz = p ? F_z.y : F_z.x;
+        const float nx = p ? N_x.y : N_x.x, ny = p ? N_y.y : N_y.x, nz = p ? N_z.y : N_z.x;
+        const float cf = p ? CF.y : CF.x;
+        force_epilogue<DIAG>(i, pi, vi, rho[i], ax, ay, az, fx, fy, fz, nx, ny, nz, cf, p ? maxb : maxa, C, ids, posq_out, velv_out, D);
+    }
+}
+
+// ------------------------------------------------------------------ variant 2: test ONCE, neighbour lists in HBM
+// ncu on k_force_pair (profiles/r01_ncu_force_pair.txt): 82 registers -> 5 CTAs/SM, long-scoreboard bound
+// (issue active 44 %), and the candidate test duplicates what the density pass already did.  Variant 2
+// splits the work differently:
+//   k_density_list : pass 1 + the candidate test for BOTH passes.  Two targets per thread, packed math,
+//                    branch-free append of passing candidates into a per-thread shared-memory list, which is
+//                    then written to HBM entry-major ([entry][pair], fully coalesced).  ~40 registers.
+//   k_force_list   : passes 2+3 + integrate, walking the stored list only (no candidate test at all).
+// Cost: one extra 4-byte write + read per stored neighbour (about 40 per pair).
+constexpr int NLIST_CAP = 64;       // entries per pair (both split passes together)
+constexpr int NLIST_THREADS = 128;
+
+__global__ void __launch_bounds__(NLIST_THREADS) k_density_list(int n, int npairs_pad, const float4* __restrict__ posq,
+                                                                float4* __restrict__ posq_q, float4* __restrict__ velv,
+                                                                const uint32_t* __restrict__ cell_sorted,
+                                                                const int* __restrict__ cell_start, GridP G, StepC C,
+                                                                float* __restrict__ rho, int* __restrict__ nlist,
+                                                                int2* __restrict__ ncount) {
+    __shared__ int list[(NLIST_CAP + 1) * NLIST_THREADS];  // +1: trash slot for saturated appends
+    const int tid = threadIdx.x;
+    const int t = blockIdx.x * blockDim.x + tid;
+    int a = 2 * t;
+    const bool live = a < n;
+    if (!live) a = 0;
+    const int b = (a + 1 < n) ? a + 1 : a;
+    const float4 pa = posq[a], pb = posq[b];
+    const uint32_t ca = cell_sorted[a], cb = cell_sorted[b];
+    const uint32_t cola = ca / (uint32_t)G.nz, colb = cb / (uint32_t)G.nz;
+    const int cza = (int)(ca - cola * (uint32_t)G.nz), czb = (int)(cb - colb * (uint32_t)G.nz);
+    const bool merged = (b != a) && (cola == colb) && (czb - cza <= 3);
+    const float FAR = 1.0e18f;
+    const int npass = !live ? 0 : ((merged || b == a) ? 1 : 2);
+
+    float2 acc = make_float2(0.f, 0.f);
+    int* const lbase = list + tid;
+    int off = 0, off0 = 0;  // slot * NLIST_THREADS
+#pragma unroll 1
+    for (int p = 0; p < npass; p++) {
+        const bool useA = merged || p == 0, useB = merged || p == 1;
+        const float2 X = make_float2(useA ? pa.x : FAR, useB ? pb.x : FAR);
+        const float2 Y = make_float2(useA ? pa.y : FAR, useB ? pb.y : FAR);
+        const float2 Z = make_float2(useA ? pa.z : FAR, useB ? pb.z : FAR);
+        const uint32_t col = p ? colb : cola;
+        const int czlo = p ? czb : cza, czhi = merged ? czb : czlo;
+        const int cy = (int)(col % (uint32_t)G.ny), cx = (int)(col / (uint32_t)G.ny);
+        const int z0 = czlo > 0 ? czlo - 1 : 0, z1 = czhi < G.nz - 1 ? czhi + 1 : czhi;
+        if (p == 1) off0 = off;
+#pragma unroll 1
+        for (int r = 0; r < 9; r++) {
+            int x = cx + r / 3 - 1, y = cy + r % 3 - 1;
+            if (x < 0 || x >= G.nx || y < 0 || y >= G.ny) continue;
+            int base = (x * G.ny + y) * G.nz;
+            int s = __ldg(&cell_start[base + z0]);
+            int e = __ldg(&cell_start[base + z1 + 1]);
+#pragma unroll 4
+            for (int k = s; k < e; k++) {
+                float4 pj = __ldg(&posq[k]);
+                float2 dx = __fadd2_rn(X, make_float2(-pj.x, -pj.x));
+                float2 dy = __fadd2_rn(Y, make_float2(-pj.y, -pj.y));
+                float2 dz = __fadd2_rn(Z, make_float2(-pj.z, -pj.z));
+                float2 d2 = __fmul2_rn(dx, dx);
+                d2 = __ffma2_rn(dy, dy, d2);
+                d2 = __ffma2_rn(dz, dz, d2);
+                float2 w = __fadd2_rn(make_float2(C.hh, C.hh), make_float2(-d2.x, -d2.y));
+                // branch-free append: store at the current slot, advance only on a pass
+                lbase[min(off, NLIST_CAP * NLIST_THREADS)] = k;
+                off += (fmaxf(w.x, w.y) >= 0.f) ? NLIST_THREADS : 0;
+                w.x = fmaxf(w.x, 0.f);
+                w.y = fmaxf(w.y, 0.f);
+                acc = __ffma2_rn(__fmul2_rn(w, w), w, acc);
+            }
+        }
+    }
+    if (npass == 1) off0 = off;
+    // coalesced flush of the lists: entry e of all threads of the block is one contiguous row
+    const int cnt = off / NLIST_THREADS;
+    const bool fits = cnt <= NLIST_CAP;
+    if (live) ncount[t] = fits ? make_int2(off0 / NLIST_THREADS, cnt) : make_int2(-1, -1);
+    if (fits) {
+        int* dst = nlist + t;
+#pragma unroll 4
+        for (int o = 0, e = 0; o < off; o += NLIST_THREADS, e++) dst[(size_t)e * npairs_pad] = lbase[o];
+    }
+    if (!live) return;
+    float ra = acc.x * C.densK, rb = acc.y * C.densK;
+    float Pa = C.k * (ra - C.p0), Pb = C.k * (rb - C.p0);
+    rho[a] = ra;
+    posq_q[a] = make_float4(pa.x, pa.y, pa.z, Pa / (ra * ra));
+    velv[a].w = C.mass / ra;
+    if (b != a) {
+        rho[b] = rb;
+        posq_q[b] = make_float4(pb.x, pb.y, pb.z, Pb / (rb * rb));
+        velv[b].w = C.mass / rb;
+    }
+}
+
+template <bool DIAG>
+__global__ void __launch_bounds__(NLIST_THREADS) k_force_list(int n, int npairs_pad, const float4* __restrict__ posq_q,
+                                                              const float4* __restrict__ velv, const float* __restrict__ rho,
+                                                              const int* __restrict__ ids, const uint32_t* __restrict__ cell_sorted,
+                                                              const int* __restrict__ cell_start, GridP G, StepC C,
+                                                              const int* __restrict__ nlist, const int2* __restrict__ ncount,
+                                                              float4* __restrict__ posq_out, float4* __restrict__ velv_out, DiagOut D) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int a = 2 * t;
+    if (a >= n) return;
+    const int b = (a + 1 < n) ? a + 1 : a;
+    const float4 pa = posq_q[a], pb = posq_q[b];
+    const float4 va = velv[a], vb = velv[b];
+    const int2 cn = ncount[t];
+    const float inv_sqrt3 = 0.57735026f;
+    const float FAR = 1.0e18f;
+
+    float2 A_x = {0.f, 0.f}, A_y = {0.f, 0.f}, A_z = {0.f, 0.f};
+    float2 F_x = {0.f, 0.f}, F_y = {0.f, 0.f}, F_z = {0.f, 0.f};
+    float2 N_x = {0.f, 0.f}, N_y = {0.f, 0.f}, N_z = {0.f, 0.f};
+    float2 CF = {0.f, 0.f};
+    int maxa = -1, maxb = -1;
+    const float2 Q = make_float2(pa.w, pb.w);
+    const float2 VX = make_float2(va.x, vb.x), VY = make_float2(va.y, vb.y), VZ = make_float2(va.z, vb.z);
+
+    // segment 0 = entries [0, cn.x): targets (a, b) when the pair was merged (cn.x == cn.y), else (a, FAR);
+    // segment 1 = entries [cn.x, cn.y): targets (FAR, b)
+    const bool merged = (cn.x == cn.y);
+    float2 X, Y, Z;
+    int ia, ib;
+    auto body = [&](const int k, const float4 pj, const float4 vj) {
+        float2 dx = __fadd2_rn(X, make_float2(-pj.x, -pj.x));
+        float2 dy = __fadd2_rn(Y, make_float2(-pj.y, -pj.y));
+        float2 dz = __fadd2_rn(Z, make_float2(-pj.z, -pj.z));
+        float2 d2 = __fmul2_rn(dx, dx);
+        d2 = __ffma2_rn(dy, dy, d2);
+        d2 = __ffma2_rn(dz, dz, d2);
+        float2 w = __fadd2_rn(make_float2(C.hh, C.hh), make_float2(-d2.x, -d2.y));
+        w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f);
+        float2 vw = __fmul2_rn(w, make_float2(vj.w, vj.w));
+        float2 t7 = __ffma2_rn(d2, make_float2(-7.0f, -7.0f), make_float2(C.hh3, C.hh3));
+        CF = __ffma2_rn(vw, t7, CF);
+        float2 vww = __fmul2_rn(vw, w);
+        N_x = __ffma2_rn(vww, dx, N_x); N_y = __ffma2_rn(vww, dy, N_y); N_z = __ffma2_rn(vww, dz, N_z);
+        float2 rinv = make_float2(rsqrt_ftz(fmaxf(d2.x, 1e-30f)), rsqrt_ftz(fmaxf(d2.y, 1e-30f)));
+        float2 r = __fmul2_rn(d2, rinv);
+        float2 hm = __fadd2_rn(make_float2(C.h, C.h), make_float2(-r.x, -r.y));
+        hm.x = fmaxf(hm.x, 0.f); hm.y = fmaxf(hm.y, 0.f);
+        float2 tv = __fmul2_rn(hm, make_float2(vj.w, vj.w));
+        float2 dvx = __fadd2_rn(make_float2(vj.x, vj.x), make_float2(-VX.x, -VX.y));
+        float2 dvy = __fadd2_rn(make_float2(vj.y, vj.y), make_float2(-VY.x, -VY.y));
+        float2 dvz = __fadd2_rn(make_float2(vj.z, vj.z), make_float2(-VZ.x, -VZ.y));
+        F_x = __ffma2_rn(tv, dvx, F_x); F_y = __ffma2_rn(tv, dvy, F_y); F_z = __ffma2_rn(tv, dvz, F_z);
+        float2 sq = __fadd2_rn(Q, make_float2(pj.w, pj.w));
+        float2 sc = __fmul2_rn(__fmul2_rn(sq, hm), hm);
+        if (k == ia) sc.x = 0.f;  // pressure excludes j == i (fluid_system.h:142)
+        if (k == ib) sc.y = 0.f;
+        float2 ux = __fmul2_rn(dx, rinv), uy = __fmul2_rn(dy, rinv), uz = __fmul2_rn(dz, rinv);
+        if (fminf(r.x, r.y) <= 1e-4f) {  // coincident pair (fluid_system.h:438-440) or the self entry
+            if (r.x <= 1e-4f) { ux.x = inv_sqrt3; uy.x = inv_sqrt3; uz.x = inv_sqrt3; }
+            if (r.y <= 1e-4f) { ux.y = inv_sqrt3; uy.y = inv_sqrt3; uz.y = inv_sqrt3; }
+        }
+        A_x = __ffma2_rn(sc, ux, A_x); A_y = __ffma2_rn(sc, uy, A_y); A_z = __ffma2_rn(sc, uz, A_z);
+        if (DIAG) {
+            int idk = __ldg(&ids[k]);
+            if (k != ia && ia >= 0 && dist2_exact(pa.x - pj.x, pa.y - pj.y, pa.z - pj.z) <= C.T) maxa = max(maxa, idk);
+            if (k != ib && ib >= 0 && dist2_exact(pb.x - pj.x, pb.y - pj.y, pb.z - pj.z) <= C.T) maxb = max(maxb, idk);
+        }
+    };
+
+    if (cn.y >= 0) {
+        const int* src = nlist + t;
+#pragma unroll 1
+        for (int seg = 0; seg < 2; seg++) {
+            const int e0 = seg ? cn.x : 0, e1 = seg ? cn.y : cn.x;
+            if (e0 >= e1) continue;
+            const bool useA = seg == 0, useB = merged || seg == 1;
+            X = make_float2(useA ? pa.x : FAR, useB ? pb.x : FAR);
+            Y = make_float2(useA ? pa.y : FAR, useB ? pb.y : FAR);
+            Z = make_float2(useA ? pa.z : FAR, useB ? pb.z : FAR);
+            ia = useA ? a : -1; ib = (useB && b != a) ? b : -1;
+            // software pipeline: the next entry's index and gathers are in flight while this one is processed
+            int k = __ldg(&src[(size_t)e0 * npairs_pad]);
+            float4 pj = __ldg(&posq_q[k]);
+            float4 vj = __ldg(&velv[k]);
+#pragma unroll 1
+            for (int e = e0; e < e1; e++) {
+                const int kn = (e + 1 < e1) ? __ldg(&src[(size_t)(e + 1) * npairs_pad]) : k;
+                const float4 pjn = __ldg(&posq_q[kn]);
+                const float4 vjn = __ldg(&velv[kn]);
+                body(k, pj, vj);
+                k = kn; pj = pjn; vj = vjn;
+            }
+        }
+    } else {
+        // list overflowed (strong compression): direct walks with the body under the predicate
+        const uint32_t ca = cell_sorted[a], cb = cell_sorted[b];
+        const uint32_t cola = ca / (uint32_t)G.nz, colb = cb / (uint32_t)G.nz;
+        const int cza = (int)(ca - cola * (uint32_t)G.nz), czb = (int)(cb - colb * (uint32_t)G.nz);
+        const bool mg = (b != a) && (cola == colb) && (czb - cza <= 3);
+        const int npass = (mg || b == a) ? 1 : 2;
+#pragma unroll 1
+        for (int p = 0; p < npass; p++) {
+            const bool useA = mg || p == 0, useB = mg || p == 1;
+            X = make_float2(useA ? pa.x : FAR, useB ? pb.x : FAR);
+            Y = make_float2(useA ? pa.y : FAR, useB ? pb.y : FAR);
+            Z = make_float2(useA ? pa.z : FAR, useB ? pb.z : FAR);
+            ia = useA ? a : -1; ib = (useB && b != a) ? b : -1;
+            const uint32_t col = p ? colb : cola;
+            const int czlo = p ? czb : cza, czhi = mg ? czb : czlo;
+            const int cy = (int)(col % (uint32_t)G.ny), cx = (int)(col / (uint32_t)G.ny);
+            const int z0 = czlo > 0 ? czlo - 1 : 0, z1 = czhi < G.nz - 1 ? czhi + 1 : czhi;
+#pragma unroll 1
+            for (int r = 0; r < 9; r++) {
+                int x = cx + r / 3 - 1, y = cy + r % 3 - 1;
+                if (x < 0 || x >= G.nx || y < 0 || y >= G.ny) continue;
+                int base = (x * G.ny + y) * G.nz;
+                int s = __ldg(&cell_start[base + z0]);
+                int e = __ldg(&cell_start[base + z1 + 1]);
+#pragma unroll 1
+                for (int k = s; k < e; k++) {
+                    float4 pj = __ldg(&posq_q[k]);
+                    float ex = X.x - pj.x, ey = Y.x - pj.y, ez = Z.x - pj.z;
+                    float gx = X.y - pj.x, gy = Y.y - pj.y, gz = Z.y - pj.z;
+                    float da = fmaf(ez, ez, fmaf(ey, ey, ex * ex)), db = fmaf(gz, gz, fmaf(gy, gy, gx * gx));
+                    if (fminf(da, db) <= C.hh) body(k, pj, __ldg(&velv[k]));
+                }
+            }
+        }
+    }
+
+#pragma unroll 1
+    for (int p = 0; p < 2; p++) {
+        if (p == 1 && b == a) break;
+        const int i = p ? b : a;
+        const float4 pi = p ? pb : pa;
+        const float4 vi = p ? vb : va;
+        const float ax = p ? A_x.y : A_x.x, ay = p ? A_y.y : A_y.x, az = p ? A_z.y : A_z.x;
+        const float fx = p ? F_x.y : F_x.x, fy = p ? F_y.y : F_y.x, fz = p ? F_z.y : F_z.x;
+        const float nx = p ? N_x.y : N_x.x, ny = p ? N_y.y : N_y.x, nz = p ? N_z.y : N_z.x;
+        const float cf = p ? CF.y : CF.x;
+        force_epilogue<DIAG>(i, pi, vi, rho[i], ax, ay, az, fx, fy, fz, nx, ny, nz, cf, p ? maxb : maxa, C, ids, posq_out, velv_out, D);
+    }
+}
+
 // ------------------------------------------------------------------ neighbour-list test hooks
 __global__ void __launch_bounds__(128) k_nbr_count(int n, const float4* __restrict__ posq, const uint32_t* __restrict__ cell_sorted,
                                                    const int* __restrict__ cell_start, GridP G, StepC C, int* __restrict__ counts) {
@@ -241,18 +806,43 @@ __global__ void k_slot_of_id(int n, const int* __restrict__ ids, int* __restrict
 // ------------------------------------------------------------------ launch wrappers
 static inline int nblk(int n, int b) { return (n + b - 1) / b; }
 
+int nlist_cap() { return NLIST_CAP; }
+int nlist_pairs_pad(int n) { return (((n + 1) / 2) + 127) & ~127; }
+
 void launch_density(cudaStream_t st, int variant, int n, const float4* posq, float4* posq_q, float4* velv,
-                    const uint32_t* cell_sorted, const int* cell_start, const GridP& G, const StepC& C, float* rho) {
+                    const uint32_t* cell_sorted, const int* cell_start, const GridP& G, const StepC& C, float* rho,
+                    int* nlist, int2* ncount) {
     if (n <= 0) return;
-    (void)variant;
-    k_density_tpp<<<nblk(n, 128), 128, 0, st>>>(n, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho);
+    int pairs = (n + 1) / 2;
+    if (variant == 3) {
+        int pp = nlist_pairs_pad(n);
+        k_density_list<<<pp / NLIST_THREADS, NLIST_THREADS, 0, st>>>(n, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount);
+        return;
+    }
+    if (variant == 1) k_density_pair<1><<<nblk(pairs, 128), 128, 0, st>>>(n, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho);
+    else if (variant == 2) k_density_pair<2><<<nblk(pairs * 2, 128), 128, 0, st>>>(n, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho);
+    else if (variant == 4) k_density_pair<4><<<nblk(pairs * 4, 128), 128, 0, st>>>(n, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho);
+    else if (variant == 8) k_density_pair<8><<<nblk(pairs * 8, 128), 128, 0, st>>>(n, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho);
+    else if (variant == 16) k_density_pair<16><<<nblk(pairs * 16, 128), 128, 0, st>>>(n, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho);
+    else k_density_tpp<<<nblk(n, 128), 128, 0, st>>>(n, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho);
 }
 
 void launch_force(cudaStream_t st, int variant, int n, const float4* posq_q, const float4* velv, const float* rho,
                   const int* ids, const uint32_t* cell_sorted, const int* cell_start, const GridP& G, const StepC& C,
-                  float4* posq_out, float4* velv_out, const DiagOut* diag) {
+                  float4* posq_out, float4* velv_out, const DiagOut* diag, const int* nlist, const int2* ncount) {
     if (n <= 0) return;
-    (void)variant;
+    if (variant == 3) {
+        int pp = nlist_pairs_pad(n);
+        if (diag) k_force_list<true><<<pp / NLIST_THREADS, NLIST_THREADS, 0, st>>>(n, pp, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, nlist, ncount, posq_out, velv_out, *diag);
+        else k_force_list<false><<<pp / NLIST_THREADS, NLIST_THREADS, 0, st>>>(n, pp, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, nlist, ncount, posq_out, velv_out, DiagOut{});
+        return;
+    }
+    if (variant == 1) {
+        int nb = nblk((n + 1) / 2, FORCE_THREADS);
+        if (diag) k_force_pair<true><<<nb, FORCE_THREADS, 0, st>>>(n, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, posq_out, velv_out, *diag);
+        else k_force_pair<false><<<nb, FORCE_THREADS, 0, st>>>(n, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, posq_out, velv_out, DiagOut{});
+        return;
+    }
     if (diag) k_force_tpp<true><<<nblk(n, 128), 128, 0, st>>>(n, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, posq_out, velv_out, *diag);
     else k_force_tpp<false><<<nblk(n, 128), 128, 0, st>>>(n, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, posq_out, velv_out, DiagOut{});
 }

@@ -126,6 +126,11 @@ class FluidSystemSPH:
         capi.check(self._L.sphe_debug_cell_start(self._h, _p(out)))
         return out
 
+    def debug_neighbours_total(self):
+        tot = C.c_longlong(0)
+        capi.check(self._L.sphe_debug_neighbours(self._h, None, None, 0, C.byref(tot)))
+        return tot.value
+
     def debug_neighbours(self):
         n = self.count()
         ns = np.zeros(n + 1, np.int64)

@@ -28,9 +28,20 @@ def close(got, want, what, rtol=RTOL):
     assert err <= rtol * scale, "%s: max err %.3e > %.1e * scale %.3e (rel %.2e)" % (what, err, rtol, scale, err / scale)
 
 
+VARIANT = {"density": 0, "force": 0}
+
+
+@pytest.fixture(autouse=True, params=[(0, 0), (1, 1), (3, 3)], ids=["tpp", "pair", "list"])
+def kernel_variant(request):
+    """Every test runs against both kernel families: thread-per-particle and packed-pair."""
+    VARIANT["density"], VARIANT["force"] = request.param
+    yield
+
+
 def make_sim(P=None, diag=True):
     m = product()
     s = m.FluidSystemSPH()
+    s.set_variant(VARIANT["density"], VARIANT["force"])
     if P is not None:
         q = s.params
         q.mass, q.visc, q.surf_tens, q.p0, q.k, q.h, q.len, q.dt = P.mass, P.visc, P.surf_tens, P.p0, P.k, P.h, P.len, P.dt
