@@ -314,8 +314,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--density-variant", type=int, default=0)
-    ap.add_argument("--force-variant", type=int, default=0)
+    ap.add_argument("--density-variant", type=int, default=3)
+    ap.add_argument("--force-variant", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gravity-unscaled", action="store_true")
     args = ap.parse_args()

@@ -155,7 +155,8 @@ int sphe_debug_neighbours(sphe_sim* s, long long* nbr_start, int* nbr, long long
 enum { SPHE_D_POSQ = 0, SPHE_D_VELV = 1, SPHE_D_IDS = 2, SPHE_D_RHO = 3 };
 void* sphe_device_ptr(sphe_sim* s, int which);
 int sphe_set_stream(sphe_sim* s, void* cuda_stream); /* run on a caller-provided cudaStream_t */
-/* Kernel-variant selector for the two neighbour passes (tuning / ncu A-B runs; 0 = default). */
+/* Kernel-variant selector for the two neighbour passes (tuning / ncu A-B runs).  3 = neighbour lists
+ * (default, must be set for both passes), 1 = packed pair, 0 = thread per particle. */
 int sphe_set_variant(sphe_sim* s, int density_variant, int force_variant);
 
 #ifdef __cplusplus

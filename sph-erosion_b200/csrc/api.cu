@@ -78,7 +78,7 @@ struct sphe_sim {
 
     bool binned = false;  // debug hooks valid
     StepC lastC{};
-    int variant_density = 0, variant_force = 0;
+    int variant_density = 3, variant_force = 3;  // 0 tpp, 1 packed pair, 3 neighbour lists (default)
 
     bool timing = false;
     void* flush_buf = nullptr;

@@ -601,8 +601,11 @@ __global__ void __launch_bounds__(NLIST_THREADS) k_density_list(int n, int npair
     }
 }
 
+#ifndef FL_MINB
+#define FL_MINB 7
+#endif
 template <bool DIAG>
-__global__ void __launch_bounds__(NLIST_THREADS) k_force_list(int n, int npairs_pad, const float4* __restrict__ posq_q,
+__global__ void __launch_bounds__(NLIST_THREADS, FL_MINB) k_force_list(int n, int npairs_pad, const float4* __restrict__ posq_q,
                                                               const float4* __restrict__ velv, const float* __restrict__ rho,
                                                               const int* __restrict__ ids, const uint32_t* __restrict__ cell_sorted,
                                                               const int* __restrict__ cell_start, GridP G, StepC C,
@@ -683,6 +686,7 @@ __global__ void __launch_bounds__(NLIST_THREADS) k_force_list(int n, int npairs_
             Z = make_float2(useA ? pa.z : FAR, useB ? pb.z : FAR);
             ia = useA ? a : -1; ib = (useB && b != a) ? b : -1;
             // software pipeline: the next entry's index and gathers are in flight while this one is processed
+            // (a two-stage version raised the register count to 94 and lost a CTA/SM: slower, measured)
             int k = __ldg(&src[(size_t)e0 * npairs_pad]);
             float4 pj = __ldg(&posq_q[k]);
             float4 vj = __ldg(&velv[k]);

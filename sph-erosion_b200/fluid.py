@@ -65,7 +65,7 @@ class FluidSystemSPH:
     def count(self): return self._L.sphe_count(self._h)
     def sync(self): capi.check(self._L.sphe_sync(self._h))
     def set_diagnostics(self, on=True): capi.check(self._L.sphe_set_diagnostics(self._h, int(on)))
-    def set_variant(self, density=0, force=0): capi.check(self._L.sphe_set_variant(self._h, density, force))
+    def set_variant(self, density=3, force=3): capi.check(self._L.sphe_set_variant(self._h, density, force))
 
     def set_grid_bounds(self, lo, hi):
         lo = np.asarray(lo, np.float32); hi = np.asarray(hi, np.float32)
