@@ -75,7 +75,8 @@ enum {
 typedef struct sphe_grid_info {
     float gmin[3];
     float cell;   /* edge = h * (1 + 2^-10) */
-    int dim[3];   /* cell id = (cx*dim[1] + cy)*dim[2] + cz, coordinates clamped into the grid */
+    int dim[3];   /* cell id = (cx*dim[1] + cy)*dim[2] + cz, coordinates clamped into the grid
+                   (slab mode: the window's dims, cx relative to sphe_slab_info's xoff) */
 } sphe_grid_info;
 
 /* Per-kernel device times of the timed steps (CUDA events on the launch stream). */
@@ -110,6 +111,11 @@ int sphe_num(sphe_sim* s);                          /* `num` (what PrintCoords i
 int sphe_set_grid_bounds(sphe_sim* s, const float lo[3], const float hi[3]);
 int sphe_grid_info_get(sphe_sim* s, sphe_grid_info* out);
 
+/* Per-axis box half-extents (the reference box is the cube `len`, fluid_system.h:478; this is the
+ * generalisation the multi-GPU channel scenes need).  NULL restores the cube.  With unequal extents
+ * collisionS picks the axis of largest overshoot |coord| - half instead of largest |coord|. */
+int sphe_set_box(sphe_sim* s, const float half[3]);
+
 /* Replace the whole state (parity tests, checkpoints, the e2e host-buffer path); ids become 0..n-1. */
 int sphe_upload_state(sphe_sim* s, int n, const float* pos, const float* vel);
 
@@ -134,6 +140,11 @@ int sphe_step_host(sphe_sim* s, sphe_terrain* t, int n, const float* pos_in, con
 int sphe_set_l2_flush(sphe_sim* s, long long bytes);
 int sphe_timed_steps(sphe_sim* s, sphe_terrain* t, int steps, float* ms_total, float* ms_kernels, int* launches);
 
+/* Free-running variant for callers that own the step loop (the multi-GPU driver): switch per-kernel
+ * event timing on, step, then collect the summed times / launch count since the last collect. */
+int sphe_kernel_timing(sphe_sim* s, int on);
+int sphe_kernel_times(sphe_sim* s, float* ms_kernels, int* launches);
+
 /* ---- accessors ---- */
 /* Store the per-particle debug fields the reference keeps in FluidParticle (forces, normal,
  * acceleration, NeighbId).  Off by default; sphe_get_particle switches it on. */
@@ -150,6 +161,24 @@ int sphe_debug_cell_start(sphe_sim* s, int* cell_start);     /* [ncells+1]      
 /* CSR neighbour lists by sorted slot, ids in grid-walk order, self included.  Call with nbr=NULL to
  * get the total in *total. */
 int sphe_debug_neighbours(sphe_sim* s, long long* nbr_start, int* nbr, long long cap, long long* total);
+
+/* ---- multi-GPU x-slabs (no reference counterpart) ----
+ * One handle per GPU owns the global cell columns [x0, x1) of the neighbour grid and bins into the
+ * window [x0-2, x1+2).  Per step the driver (sph-erosion_b200/slabs.py, NCCL P2P) does
+ *     pack -> exchange counts + records with the two x-neighbours -> commit -> append x2 -> sphe_step.
+ * Records are 32 bytes: (x, y, z, sediment) (vx, vy, vz, id bits); both migrants and the 2-layer
+ * halo travel in the same buffer, the receiver classifies each record by its own cell column.
+ * Particle ids are global, < 2^30 (bit 30 marks ghost copies). */
+int sphe_slab_configure(sphe_sim* s, int x0, int x1, int has_left, int has_right);
+int sphe_slab_info(sphe_sim* s, int* gnx, int* xoff, int* n_total, int* n_owned);
+int sphe_slab_upload(sphe_sim* s, int n, const float* pos, const float* vel, const int* ids);
+/* Drops ghosts, compacts what stays, fills the two DEVICE send buffers (cap_records each) and the
+ * DEVICE counters dev_counts[4] = {kept, to_left, to_right, owned}.  Asynchronous on the handle's stream. */
+int sphe_slab_pack(sphe_sim* s, void* dev_send_left, void* dev_send_right, int cap_records, int* dev_counts);
+int sphe_slab_commit(sphe_sim* s, int n_kept, int n_owned);       /* host copy of dev_counts[0], [3] */
+int sphe_slab_append(sphe_sim* s, const void* dev_records, int m); /* received records (device) */
+/* Owned particles only, storage order; rho/sed may be NULL. */
+int sphe_slab_download(sphe_sim* s, int cap, int* ids, float* pos, float* vel, float* rho, float* sed, int* n_out);
 
 /* ---- raw device access for multi-GPU plumbing (halo exchange lives above this ABI) ---- */
 enum { SPHE_D_POSQ = 0, SPHE_D_VELV = 1, SPHE_D_IDS = 2, SPHE_D_RHO = 3 };

@@ -50,7 +50,7 @@ struct sphe_sim {
     int device = -1;
     bool ready = false;
     cudaStream_t st = nullptr;
-    bool own_stream = false;
+    bool own_stream = false, user_stream = false;
 
     int n = 0, cap = 0;
     float4 *posA = nullptr, *posB = nullptr, *posC = nullptr, *velA = nullptr, *velB = nullptr;
@@ -58,7 +58,7 @@ struct sphe_sim {
     float *sedA = nullptr, *sedB = nullptr, *rho = nullptr;
     uint32_t *cell = nullptr, *cell_sorted = nullptr;
     uint2* tmp = nullptr;
-    float* stage = nullptr;  // 2 * 3 * cap floats: id-order staging for uploads/downloads
+    float* stage = nullptr;  // 10 * cap floats: id-order staging for uploads/downloads
     int* slot_of_id = nullptr;
     bool slot_valid = false;
     int* nlist = nullptr;   // variant 3: [nlist_cap][pairs_pad] neighbour indices
@@ -70,6 +70,12 @@ struct sphe_sim {
     GridP G{};
     bool grid_user = false;
     float glo[3], ghi[3];
+    bool box_user = false;   // sphe_set_box: per-axis half-extents (multi-GPU channel scenes)
+    float box[3] = {0, 0, 0};
+    bool slab_on = false;    // multi-GPU x-slab mode (slab.cu)
+    SlabP slab{};
+    int n_owned = 0;
+    int* slab_counters = nullptr;  // device int[8]
     float grid_h = -1.f, grid_len = -1.f;
 
     bool diag = false;
@@ -105,7 +111,7 @@ static int ensure_device(sphe_sim* s) {
         return fail(SPHE_ERR_CUDA, "no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
     if (s->device < 0) CU(cudaGetDevice(&s->device));
     CU(cudaSetDevice(s->device));
-    if (!s->st) {
+    if (!s->st && !s->user_stream) {
         CU(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
         s->own_stream = true;
     }
@@ -142,7 +148,7 @@ static int reserve(sphe_sim* s, int need) {
     TRY(grow(&s->cell, 0, nc, s->st, false));
     TRY(grow(&s->cell_sorted, 0, nc, s->st, false));
     TRY(grow(&s->tmp, 0, nc, s->st, false));
-    TRY(grow(&s->stage, 0, nc * 8, s->st, false));
+    TRY(grow(&s->stage, 0, nc * 10, s->st, false));
     TRY(grow(&s->slot_of_id, 0, nc, s->st, false));
     s->cap = (int)nc;
     s->binned = false;
@@ -191,6 +197,7 @@ static StepC make_consts(const sphe_params& P) {
     C.mass = P.mass; C.k = P.k; C.p0 = P.p0; C.visc = P.visc; C.surf = P.surf_tens;
     C.gx = P.g[0]; C.gy = P.g[1]; C.gz = P.g[2];
     C.dt = P.dt; C.len = P.len; C.cR = P.cR;
+    C.lenx = C.leny = C.lenz = P.len; C.cube = 1;
     float c315 = (float)(315.0f / (64.0f * PI_REF * powf(h, 9.0f)));  // fluid_system.h:415
     C.densK = P.mass * c315;
     C.c45 = (float)(45.f / (PI_REF * powf(h, 6.0f)));                 // :442, :452
@@ -202,13 +209,14 @@ static StepC make_consts(const sphe_params& P) {
 static int setup_grid(sphe_sim* s) {
     const sphe_params& P = s->P;
     if (!(P.h > 0.0f) || !isfinite(P.h)) return fail(SPHE_ERR_ARG, "smoothing radius h must be positive");
-    bool same = (s->grid_h == P.h) && (s->grid_user || s->grid_len == P.len) && s->ncells > 0;
+    bool same = (s->grid_h == P.h) && (s->grid_user || s->box_user || s->grid_len == P.len) && s->ncells > 0;
     if (same) return SPHE_OK;
     float cell = P.h * 1.0009765625f;  // h * (1 + 2^-10), see oracle so_grid_for_box
     float lo[3], hi[3];
     for (int a = 0; a < 3; a++) {
+        float half = s->box_user ? s->box[a] : P.len;
         if (s->grid_user) { lo[a] = s->glo[a]; hi[a] = s->ghi[a]; }
-        else { lo[a] = -P.len - 2.0f * cell; hi[a] = P.len + 2.0f * cell; }
+        else { lo[a] = -half - 2.0f * cell; hi[a] = half + 2.0f * cell; }
     }
     int dim[3];
     for (int a = 0; a < 3; a++) {
@@ -217,10 +225,20 @@ static int setup_grid(sphe_sim* s) {
         if (d < 1) d = 1;
         dim[a] = d;
     }
+    // a slab bins into the window [x0 - halo, x1 + halo) of the global grid
+    int gnx = dim[0], xoff = 0;
+    if (s->slab_on) {
+        int w0 = std::max(s->slab.x0 - s->slab.halo, 0), w1 = std::min(s->slab.x1 + s->slab.halo, gnx);
+        if (!s->slab.has_left) w0 = 0;
+        if (!s->slab.has_right) w1 = gnx;
+        if (w1 <= w0) return fail(SPHE_ERR_ARG, "slab [%d,%d) lies outside the global grid (%d columns)", s->slab.x0, s->slab.x1, gnx);
+        xoff = w0; dim[0] = w1 - w0;
+    }
     long long nc = (long long)dim[0] * dim[1] * dim[2];
     if (nc >= (1LL << 31) - 8) return fail(SPHE_ERR_ARG, "neighbour grid too large: %d x %d x %d cells", dim[0], dim[1], dim[2]);
     s->G.gx = lo[0]; s->G.gy = lo[1]; s->G.gz = lo[2]; s->G.cell = cell;
     s->G.nx = dim[0]; s->G.ny = dim[1]; s->G.nz = dim[2];
+    s->G.gnx = gnx; s->G.xoff = xoff;
     if (nc > s->ncells_cap) {
         size_t padded = ((size_t)nc + 1 + 63) & ~(size_t)63;
         TRY(grow(&s->count, 0, padded, s->st, false));
@@ -254,6 +272,11 @@ static int step_device(sphe_sim* s, sphe_terrain* t) {
     TRY(setup_grid(s));
     TRY(reserve_diag(s));
     StepC C = make_consts(s->P);
+    if (s->box_user) {
+        C.lenx = s->box[0]; C.leny = s->box[1]; C.lenz = s->box[2];
+        C.cube = (C.lenx == C.leny && C.leny == C.lenz) ? 1 : 0;
+    }
+    if (s->slab_on && s->diag) return fail(SPHE_ERR_STATE, "per-particle diagnostics are indexed by local id and are not available in slab mode");
     s->lastC = C;
     int n = s->n;
     { Scope k(s, SPHE_K_HASH); launch_hash(s->st, n, s->posA, s->G, s->cell, s->count); }
@@ -354,7 +377,7 @@ void sphe_destroy(sphe_sim* s) {
         cudaStreamSynchronize(s->st);
         void* ptrs[] = {s->posA, s->posB, s->posC, s->velA, s->velB, s->idsA, s->idsB, s->sedA, s->sedB, s->rho, s->cell,
                         s->cell_sorted, s->tmp, s->stage, s->slot_of_id, s->nlist, s->ncount, s->count, s->cell_start, s->cursor, s->tile_sum,
-                        s->flush_buf, s->D.acc, s->D.fpress, s->D.fvisc, s->D.fgrav, s->D.fsurf, s->D.normal, s->D.neighb};
+                        s->flush_buf, s->slab_counters, s->D.acc, s->D.fpress, s->D.fvisc, s->D.fgrav, s->D.fsurf, s->D.normal, s->D.neighb};
         for (void* p : ptrs) if (p) cudaFree(p);
         if (s->own_stream && s->st) cudaStreamDestroy(s->st);
     }
@@ -373,6 +396,7 @@ int sphe_set_stream(sphe_sim* s, void* stream) {
     if (s->ready && s->own_stream) { cudaStreamSynchronize(s->st); cudaStreamDestroy(s->st); }
     s->st = (cudaStream_t)stream;
     s->own_stream = false;
+    s->user_stream = true;
     return SPHE_OK;
 }
 
@@ -545,6 +569,33 @@ int sphe_timed_steps(sphe_sim* s, sphe_terrain* t, int steps, float* ms_total, f
     if (launches) *launches = s->launches;
     for (auto& e : ev) cudaEventDestroy(e);
     return rc;
+}
+
+int sphe_kernel_timing(sphe_sim* s, int on) {
+    if (!s) return fail(SPHE_ERR_ARG, "NULL handle");
+    TRY(ensure_device(s));
+    for (auto& kt : s->timers) { cudaEventDestroy(kt.a); cudaEventDestroy(kt.b); }
+    s->timers.clear();
+    s->launches = 0;
+    s->timing = on != 0;
+    return SPHE_OK;
+}
+
+int sphe_kernel_times(sphe_sim* s, float* ms_kernels, int* launches) {
+    if (!s) return fail(SPHE_ERR_ARG, "NULL handle");
+    TRY(ensure_device(s));
+    CU(cudaStreamSynchronize(s->st));
+    if (ms_kernels) for (int k = 0; k < SPHE_K_COUNT; k++) ms_kernels[k] = 0.f;
+    for (auto& kt : s->timers) {
+        float m = 0.f;
+        cudaEventElapsedTime(&m, kt.a, kt.b);
+        if (ms_kernels) ms_kernels[kt.kind] += m;
+        cudaEventDestroy(kt.a); cudaEventDestroy(kt.b);
+    }
+    s->timers.clear();
+    if (launches) *launches = s->launches;
+    s->launches = 0;
+    return SPHE_OK;
 }
 
 int sphe_set_diagnostics(sphe_sim* s, int on) {
@@ -720,6 +771,135 @@ int sphe_debug_neighbours(sphe_sim* s, long long* nbr_start, int* nbr, long long
     CU(cudaStreamSynchronize(s->st));
     CU(cudaFree(dstart)); CU(cudaFree(dn));
     return SPHE_OK;
+}
+
+int sphe_set_box(sphe_sim* s, const float half[3]) {
+    if (!s) return fail(SPHE_ERR_ARG, "NULL handle");
+    if (!half) { s->box_user = false; s->grid_h = -1.f; return SPHE_OK; }
+    for (int a = 0; a < 3; a++) {
+        if (!(half[a] > 0.0f)) return fail(SPHE_ERR_ARG, "box half-extent %d must be positive", a);
+        s->box[a] = half[a];
+    }
+    s->box_user = true;
+    s->grid_h = -1.f;  // force re-setup
+    return SPHE_OK;
+}
+
+// ---- multi-GPU x-slabs
+int sphe_slab_configure(sphe_sim* s, int x0, int x1, int has_left, int has_right) {
+    if (!s) return fail(SPHE_ERR_ARG, "NULL handle");
+    if (x1 <= x0) return fail(SPHE_ERR_ARG, "slab needs x1 > x0");
+    if (s->diag) return fail(SPHE_ERR_STATE, "switch diagnostics off before slab mode");
+    TRY(ensure_device(s));
+    s->slab.x0 = x0; s->slab.x1 = x1; s->slab.halo = 2;
+    s->slab.has_left = has_left != 0; s->slab.has_right = has_right != 0;
+    s->slab_on = true;
+    s->grid_h = -1.f;  // re-window the grid
+    if (!s->slab_counters) CU(cudaMalloc(&s->slab_counters, 8 * sizeof(int)));
+    return SPHE_OK;
+}
+
+int sphe_slab_info(sphe_sim* s, int* gnx, int* xoff, int* n_total, int* n_owned) {
+    if (!s) return fail(SPHE_ERR_ARG, "NULL handle");
+    TRY(ensure_device(s));
+    TRY(setup_grid(s));
+    if (gnx) *gnx = s->G.gnx;
+    if (xoff) *xoff = s->G.xoff;
+    if (n_total) *n_total = s->n;
+    if (n_owned) *n_owned = s->slab_on ? s->n_owned : s->n;
+    return SPHE_OK;
+}
+
+int sphe_slab_upload(sphe_sim* s, int n, const float* pos, const float* vel, const int* ids) {
+    if (!s || n < 0 || (n > 0 && (!pos || !vel || !ids))) return fail(SPHE_ERR_ARG, "bad arguments");
+    if (!s->slab_on) return fail(SPHE_ERR_STATE, "call sphe_slab_configure first");
+    TRY(ensure_device(s));
+    s->n = 0;
+    TRY(reserve(s, std::max(n, 1)));
+    float* dpos = s->stage;
+    float* dvel = s->stage + 3 * (size_t)s->cap;
+    int* dids = (int*)(s->stage + 6 * (size_t)s->cap);
+    CU(cudaMemcpyAsync(dpos, pos, 3 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s->st));
+    CU(cudaMemcpyAsync(dvel, vel, 3 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s->st));
+    CU(cudaMemcpyAsync(dids, ids, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s->st));
+    launch_pack_state_ids(s->st, n, dpos, dvel, dids, s->posA, s->velA, s->idsA, s->sedA);
+    CU(cudaStreamSynchronize(s->st));
+    s->n = n; s->n_owned = n;
+    s->num = n; s->init_num = n; s->next_label = n;
+    s->labels.clear(); s->labels_identity = true;
+    s->binned = false; s->slot_valid = false;
+    return SPHE_OK;
+}
+
+int sphe_slab_pack(sphe_sim* s, void* dev_send_left, void* dev_send_right, int cap_records, int* dev_counts) {
+    if (!s || !dev_counts || cap_records < 0) return fail(SPHE_ERR_ARG, "bad arguments");
+    if (!s->slab_on) return fail(SPHE_ERR_STATE, "call sphe_slab_configure first");
+    TRY(ensure_device(s));
+    TRY(setup_grid(s));
+    TRY(reserve(s, std::max(s->n, 1)));
+    CU(cudaMemsetAsync(dev_counts, 0, 4 * sizeof(int), s->st));
+    launch_slab_classify(s->st, s->n, s->posA, s->velA, s->idsA, s->sedA, s->G, s->slab, s->posB, s->velB, s->idsB, s->sedB,
+                         (float4*)dev_send_left, (float4*)dev_send_right, cap_records, dev_counts);
+    s->launches += 1;
+    std::swap(s->posA, s->posB); std::swap(s->velA, s->velB); std::swap(s->idsA, s->idsB); std::swap(s->sedA, s->sedB);
+    s->binned = false; s->slot_valid = false;
+    CU(cudaGetLastError());
+    return SPHE_OK;
+}
+
+int sphe_slab_commit(sphe_sim* s, int n_kept, int n_owned) {
+    if (!s || n_kept < 0 || n_owned < 0 || n_owned > n_kept) return fail(SPHE_ERR_ARG, "bad arguments");
+    if (n_kept > s->cap) return fail(SPHE_ERR_ARG, "n_kept %d exceeds capacity %d", n_kept, s->cap);
+    s->n = n_kept; s->n_owned = n_owned;
+    return SPHE_OK;
+}
+
+int sphe_slab_append(sphe_sim* s, const void* dev_records, int m) {
+    if (!s || m < 0 || (m > 0 && !dev_records)) return fail(SPHE_ERR_ARG, "bad arguments");
+    if (!s->slab_on) return fail(SPHE_ERR_STATE, "call sphe_slab_configure first");
+    if (m == 0) return SPHE_OK;
+    TRY(ensure_device(s));
+    TRY(reserve(s, s->n + m));
+    int* oc = s->slab_counters + 4;
+    CU(cudaMemsetAsync(oc, 0, sizeof(int), s->st));
+    launch_slab_append(s->st, m, (const float4*)dev_records, s->G, s->slab, s->n, s->posA, s->velA, s->idsA, s->sedA, oc);
+    s->launches += 1;
+    int got = 0;
+    CU(cudaMemcpyAsync(&got, oc, sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    s->n += m; s->n_owned += got;
+    s->binned = false; s->slot_valid = false;
+    return SPHE_OK;
+}
+
+int sphe_slab_download(sphe_sim* s, int cap, int* ids, float* pos, float* vel, float* rho, float* sed, int* n_out) {
+    if (!s || !ids || !pos || !vel || !n_out) return fail(SPHE_ERR_ARG, "bad arguments");
+    TRY(ensure_device(s));
+    int n = s->n;
+    *n_out = 0;
+    if (n == 0) return SPHE_OK;
+    if (!s->slab_counters) CU(cudaMalloc(&s->slab_counters, 8 * sizeof(int)));
+    size_t cp = (size_t)s->cap;
+    int* d_cnt = s->slab_counters + 5;
+    int* d_ids = (int*)s->stage;
+    float *d_pos = s->stage + cp, *d_vel = s->stage + 4 * cp, *d_rho = s->stage + 7 * cp, *d_sed = s->stage + 8 * cp;
+    CU(cudaMemsetAsync(d_cnt, 0, sizeof(int), s->st));
+    launch_slab_gather_owned(s->st, n, s->posA, s->velA, s->rho, s->sedA, s->idsA, d_cnt, d_ids, d_pos, d_vel, d_rho, d_sed);
+    int m = 0;
+    CU(cudaMemcpyAsync(&m, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    int rc = SPHE_OK;
+    if (m > cap) rc = fail(SPHE_ERR_ARG, "output capacity %d < %d owned particles", cap, m);
+    else {
+        cudaMemcpyAsync(ids, d_ids, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, s->st);
+        cudaMemcpyAsync(pos, d_pos, 3 * (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, s->st);
+        cudaMemcpyAsync(vel, d_vel, 3 * (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, s->st);
+        if (rho) cudaMemcpyAsync(rho, d_rho, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, s->st);
+        if (sed) cudaMemcpyAsync(sed, d_sed, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, s->st);
+        CU(cudaStreamSynchronize(s->st));
+        *n_out = m;
+    }
+    return rc;
 }
 
 void* sphe_device_ptr(sphe_sim* s, int which) {

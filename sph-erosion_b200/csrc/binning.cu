@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256) k_rank_reorder(int n, const uint2* __rest
     uint32_t c = cell[me.y];
     int a = cell_start[c], b = cell_start[c + 1];
     int rank = 0;
-    for (int k = a; k < b; k++) rank += (tmp[k].x < me.x) ? 1 : 0;
+    for (int k = a; k < b; k++) rank += ((tmp[k].x & SPHE_ID_MASK) < (me.x & SPHE_ID_MASK)) ? 1 : 0;
     int dst = a + rank;
     float4 p = posq_in[me.y];
     float4 v = velv_in[me.y];

@@ -15,6 +15,23 @@ void launch_rank_reorder(cudaStream_t st, int n, const uint2* tmp, const uint32_
                          const float4* posq_in, const float4* velv_in, const float* sed_in,
                          float4* posq_out, float4* velv_out, float* sed_out, int* ids_out, uint32_t* cell_sorted);
 
+// ---- slab.cu (multi-GPU x-slabs)
+struct SlabP {
+    int x0, x1;      // owned global cell columns [x0, x1)
+    int halo;        // cell layers mirrored from each neighbour
+    int has_left, has_right;
+};
+void launch_slab_classify(cudaStream_t st, int n, const float4* posq, const float4* velv, const int* ids, const float* sed,
+                          const GridP& G, const SlabP& S, float4* keep_pos, float4* keep_vel, int* keep_ids, float* keep_sed,
+                          float4* send_left, float4* send_right, int cap_records, int* counters);
+void launch_slab_append(cudaStream_t st, int m, const float4* rec, const GridP& G, const SlabP& S, int base, float4* posq,
+                        float4* velv, int* ids, float* sed, int* owned_counter);
+void launch_slab_gather_owned(cudaStream_t st, int n, const float4* posq, const float4* velv, const float* rho, const float* sed,
+                              const int* ids, int* counter, int* out_ids, float* out_pos, float* out_vel, float* out_rho,
+                              float* out_sed);
+void launch_pack_state_ids(cudaStream_t st, int n, const float* pos, const float* vel, const int* ids_in, float4* posq, float4* velv,
+                           int* ids, float* sed);
+
 // ---- sph.cu
 // Optional per-particle debug fields of the reference's FluidParticle (fluid_system.h:49-64),
 // indexed by PARTICLE ID (not by sorted slot).

@@ -1,0 +1,147 @@
+// Multi-GPU x-slab support (the reference is single-process, nothing to match).
+//
+// A slab owns the global cell columns cx in [x0, x1).  Before every step it
+//   * drops last step's ghosts,
+//   * keeps the particles it still owns, keeps particles that just left but are still inside its
+//     halo zone as ghosts (the new owner has the authoritative copy),
+//   * packs everything a neighbour needs -- migrants AND the HALO outermost cell layers -- into one
+//     send buffer per side (one exchange per step carries both).
+// Records are 32 bytes: (x, y, z, sediment) (vx, vy, vz, id bits).  The receiver decides owned/ghost
+// from the record's own cell column, so sender and receiver never disagree.
+//
+// HALO = 2 cell layers: the density of a ghost in the first layer is recomputed locally from the
+// second layer, so no second exchange of densities is needed (8e option "2-layer halo").
+//
+// Slot allocation uses warp-aggregated atomics (one atomicAdd per warp per destination).  The
+// resulting storage order is arbitrary; the binning pass re-establishes the canonical (cell, id) order.
+#include "common.cuh"
+#include "sim.h"
+
+namespace sphe {
+
+__device__ __forceinline__ int warp_append(bool flag, int* counter) {
+    unsigned m = __ballot_sync(SPHE_FULL, flag);
+    if (m == 0) return -1;
+    unsigned lane = threadIdx.x & 31;
+    int leader = __ffs(m) - 1;
+    int base = 0;
+    if ((int)lane == leader) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(SPHE_FULL, base, leader);
+    return flag ? base + __popc(m & ((1u << lane) - 1u)) : -1;
+}
+
+// counters: [0] kept (owned + retained ghosts), [1] to left, [2] to right, [3] owned
+__global__ void __launch_bounds__(256) k_slab_classify(int n, const float4* __restrict__ posq, const float4* __restrict__ velv,
+                                                       const int* __restrict__ ids, const float* __restrict__ sed, GridP G,
+                                                       SlabP S, float4* __restrict__ keep_pos, float4* __restrict__ keep_vel,
+                                                       int* __restrict__ keep_ids, float* __restrict__ keep_sed,
+                                                       float4* __restrict__ send_left, float4* __restrict__ send_right,
+                                                       int cap_records, int* __restrict__ counters) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = false, own = false, to_l = false, to_r = false;
+    float4 p = make_float4(0, 0, 0, 0), v = p;
+    int id = 0;
+    float sd = 0.f;
+    if (i < n) {
+        id = ids[i];
+        if (!(id & SPHE_GHOST_BIT)) {
+            p = posq[i]; v = velv[i]; sd = sed[i];
+            int cx = cell_axis(p.x, G.gx, G.cell, G.gnx);
+            own = (cx >= S.x0 || !S.has_left) && (cx < S.x1 || !S.has_right);
+            to_l = S.has_left && cx < S.x0 + S.halo;
+            to_r = S.has_right && cx >= S.x1 - S.halo;
+            // left the slab but still within the halo zone: stays here as a ghost
+            live = own || (cx >= S.x0 - S.halo && cx < S.x1 + S.halo);
+        }
+    }
+    int k = warp_append(live, &counters[0]);
+    warp_append(own, &counters[3]);
+    if (live) {
+        keep_pos[k] = make_float4(p.x, p.y, p.z, 0.f);
+        keep_vel[k] = make_float4(v.x, v.y, v.z, 0.f);
+        keep_ids[k] = own ? id : (id | SPHE_GHOST_BIT);
+        keep_sed[k] = sd;
+    }
+    int l = warp_append(to_l, &counters[1]);
+    if (to_l && l < cap_records) {
+        send_left[2 * l] = make_float4(p.x, p.y, p.z, sd);
+        send_left[2 * l + 1] = make_float4(v.x, v.y, v.z, __int_as_float(id));
+    }
+    int r = warp_append(to_r, &counters[2]);
+    if (to_r && r < cap_records) {
+        send_right[2 * r] = make_float4(p.x, p.y, p.z, sd);
+        send_right[2 * r + 1] = make_float4(v.x, v.y, v.z, __int_as_float(id));
+    }
+}
+
+__global__ void __launch_bounds__(256) k_slab_append(int m, const float4* __restrict__ rec, GridP G, SlabP S, int base,
+                                                     float4* __restrict__ posq, float4* __restrict__ velv,
+                                                     int* __restrict__ ids, float* __restrict__ sed, int* __restrict__ owned_counter) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool own = false;
+    if (i < m) {
+        float4 a = rec[2 * i], b = rec[2 * i + 1];
+        int id = __float_as_int(b.w) & SPHE_ID_MASK;
+        int cx = cell_axis(a.x, G.gx, G.cell, G.gnx);
+        own = (cx >= S.x0 || !S.has_left) && (cx < S.x1 || !S.has_right);
+        posq[base + i] = make_float4(a.x, a.y, a.z, 0.f);
+        velv[base + i] = make_float4(b.x, b.y, b.z, 0.f);
+        sed[base + i] = a.w;
+        ids[base + i] = own ? id : (id | SPHE_GHOST_BIT);
+    }
+    warp_append(own, owned_counter);
+}
+
+// owned particles only, storage order, packed xyz (tests, checkpoints, rendering hand-off)
+__global__ void __launch_bounds__(256) k_slab_gather_owned(int n, const float4* __restrict__ posq, const float4* __restrict__ velv,
+                                                           const float* __restrict__ rho, const float* __restrict__ sed,
+                                                           const int* __restrict__ ids, int* __restrict__ counter,
+                                                           int* __restrict__ out_ids, float* __restrict__ out_pos,
+                                                           float* __restrict__ out_vel, float* __restrict__ out_rho,
+                                                           float* __restrict__ out_sed) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool own = (i < n) && !(ids[i] & SPHE_GHOST_BIT);
+    int k = warp_append(own, counter);
+    if (!own) return;
+    float4 p = posq[i], v = velv[i];
+    out_ids[k] = ids[i];
+    out_pos[3 * (size_t)k] = p.x; out_pos[3 * (size_t)k + 1] = p.y; out_pos[3 * (size_t)k + 2] = p.z;
+    out_vel[3 * (size_t)k] = v.x; out_vel[3 * (size_t)k + 1] = v.y; out_vel[3 * (size_t)k + 2] = v.z;
+    out_rho[k] = rho[i];
+    out_sed[k] = sed[i];
+}
+
+__global__ void k_pack_state_ids(int n, const float* __restrict__ pos, const float* __restrict__ vel, const int* __restrict__ ids_in,
+                                 float4* __restrict__ posq, float4* __restrict__ velv, int* __restrict__ ids, float* __restrict__ sed) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    posq[i] = make_float4(pos[3 * (size_t)i], pos[3 * (size_t)i + 1], pos[3 * (size_t)i + 2], 0.f);
+    velv[i] = make_float4(vel[3 * (size_t)i], vel[3 * (size_t)i + 1], vel[3 * (size_t)i + 2], 0.f);
+    ids[i] = ids_in[i] & SPHE_ID_MASK;
+    sed[i] = 0.f;
+}
+
+void launch_slab_classify(cudaStream_t st, int n, const float4* posq, const float4* velv, const int* ids, const float* sed,
+                          const GridP& G, const SlabP& S, float4* keep_pos, float4* keep_vel, int* keep_ids, float* keep_sed,
+                          float4* send_left, float4* send_right, int cap_records, int* counters) {
+    if (n > 0)
+        k_slab_classify<<<(n + 255) / 256, 256, 0, st>>>(n, posq, velv, ids, sed, G, S, keep_pos, keep_vel, keep_ids, keep_sed,
+                                                        send_left, send_right, cap_records, counters);
+}
+void launch_slab_append(cudaStream_t st, int m, const float4* rec, const GridP& G, const SlabP& S, int base, float4* posq,
+                        float4* velv, int* ids, float* sed, int* owned_counter) {
+    if (m > 0) k_slab_append<<<(m + 255) / 256, 256, 0, st>>>(m, rec, G, S, base, posq, velv, ids, sed, owned_counter);
+}
+void launch_slab_gather_owned(cudaStream_t st, int n, const float4* posq, const float4* velv, const float* rho, const float* sed,
+                              const int* ids, int* counter, int* out_ids, float* out_pos, float* out_vel, float* out_rho,
+                              float* out_sed) {
+    if (n > 0)
+        k_slab_gather_owned<<<(n + 255) / 256, 256, 0, st>>>(n, posq, velv, rho, sed, ids, counter, out_ids, out_pos, out_vel,
+                                                            out_rho, out_sed);
+}
+void launch_pack_state_ids(cudaStream_t st, int n, const float* pos, const float* vel, const int* ids_in, float4* posq, float4* velv,
+                           int* ids, float* sed) {
+    if (n > 0) k_pack_state_ids<<<(n + 255) / 256, 256, 0, st>>>(n, pos, vel, ids_in, posq, velv, ids, sed);
+}
+
+}  // namespace sphe

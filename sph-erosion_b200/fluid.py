@@ -109,6 +109,60 @@ class FluidSystemSPH:
                                             mk if per_kernel else None, C.byref(nl)))
         return ms.value, dict(zip(capi.K_NAMES, [float(x) for x in mk])), nl.value
 
+    def set_box(self, half):
+        """Per-axis box half-extents (None restores the reference's cube `len`)."""
+        a = None if half is None else np.asarray(half, np.float32)
+        capi.check(self._L.sphe_set_box(self._h, _p(a)))
+
+    def set_stream(self, cuda_stream):
+        """Run on a caller-owned cudaStream_t (int handle, e.g. torch.cuda.current_stream().cuda_stream)."""
+        capi.check(self._L.sphe_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+
+    def kernel_timing(self, on=True): capi.check(self._L.sphe_kernel_timing(self._h, int(on)))
+
+    def kernel_times(self):
+        mk = (C.c_float * len(capi.K_NAMES))()
+        nl = C.c_int(0)
+        capi.check(self._L.sphe_kernel_times(self._h, mk, C.byref(nl)))
+        return dict(zip(capi.K_NAMES, [float(x) for x in mk])), nl.value
+
+    # ---- multi-GPU x-slabs (include/sphe.h "multi-GPU x-slabs")
+    def slab_configure(self, x0, x1, has_left, has_right):
+        capi.check(self._L.sphe_slab_configure(self._h, int(x0), int(x1), int(bool(has_left)), int(bool(has_right))))
+
+    def slab_info(self):
+        v = [C.c_int(0) for _ in range(4)]
+        capi.check(self._L.sphe_slab_info(self._h, *[C.byref(x) for x in v]))
+        return dict(zip(("gnx", "xoff", "n_total", "n_owned"), [x.value for x in v]))
+
+    def slab_upload(self, pos, vel, ids):
+        pos = np.ascontiguousarray(pos, np.float32); vel = np.ascontiguousarray(vel, np.float32)
+        ids = np.ascontiguousarray(ids, np.int32)
+        capi.check(self._L.sphe_slab_upload(self._h, pos.shape[0], _p(pos), _p(vel), _p(ids)))
+
+    def slab_upload_ptr(self, n, pos, vel, ids):
+        capi.check(self._L.sphe_slab_upload(self._h, int(n), pos, vel, ids))
+
+    def slab_pack(self, dev_left, dev_right, cap_records, dev_counts):
+        capi.check(self._L.sphe_slab_pack(self._h, dev_left, dev_right, int(cap_records), dev_counts))
+
+    def slab_commit(self, n_kept, n_owned): capi.check(self._L.sphe_slab_commit(self._h, int(n_kept), int(n_owned)))
+    def slab_append(self, dev_records, m): capi.check(self._L.sphe_slab_append(self._h, dev_records, int(m)))
+
+    def slab_download(self, cap=None):
+        cap = self.count() if cap is None else int(cap)
+        ids = np.zeros(cap, np.int32); pos = np.zeros((cap, 3), np.float32); vel = np.zeros((cap, 3), np.float32)
+        rho = np.zeros(cap, np.float32); sed = np.zeros(cap, np.float32)
+        m = C.c_int(0)
+        capi.check(self._L.sphe_slab_download(self._h, cap, _p(ids), _p(pos), _p(vel), _p(rho), _p(sed), C.byref(m)))
+        m = m.value
+        return ids[:m], pos[:m], vel[:m], rho[:m], sed[:m]
+
+    def slab_download_ptr(self, cap, ids, pos, vel, rho):
+        m = C.c_int(0)
+        capi.check(self._L.sphe_slab_download(self._h, int(cap), ids, pos, vel, rho, None, C.byref(m)))
+        return m.value
+
     # ---- neighbour-grid test hooks
     def debug_cells(self):
         out = np.zeros(self.count(), np.int32)

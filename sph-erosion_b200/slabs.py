@@ -1,0 +1,317 @@
+"""Multi-GPU driver: 1-D spatial slab decomposition along x.
+
+One process per GPU (torchrun).  Each rank owns the global cell columns [x0, x1) of the neighbour
+grid; per step
+
+    pack      (CUDA, slab.cu)   drop ghosts, keep owned, fill the left/right send buffers with
+                                migrants + the 2-layer halo, leave 4 counters on the device
+    counts    (P2P)             neighbours swap "how many records are coming"       -- 1 host sync
+    records   (P2P)             sized sends/receives of 32-byte records over NCCL (NVLink/NVSwitch)
+    append    (CUDA)            received records join the local arrays as owned or ghost
+    step      (CUDA)            the ordinary single-GPU step over owned + ghost particles
+
+There is no collective on the data path: interactions are local, so only x-neighbours talk
+(torch.distributed batch_isend_irecv = ncclSend/ncclRecv inside one group).  The reference has no
+multi-process code; correctness is "k slabs == 1 GPU" (tests/test_gpu_slabs.py) and the exchange
+protocol is covered on CPU with gloo (tests/test_slabs_gloo.py).
+
+The driver is written against two small interfaces so the protocol can be exercised without a GPU:
+  backend : pack() / commit() / append() / step()      -- GpuSlabBackend here, a numpy double in tests
+  comm    : swap_counts() / swap_records()             -- TorchComm (nccl or gloo) / LocalComm
+"""
+import numpy as np
+
+RECORD_FLOATS = 8  # (x, y, z, sediment) (vx, vy, vz, id bits)
+HALO = 2
+
+
+def partition_columns(gnx, world, boundaries_x=None, gmin_x=None, cell=None):
+    """Column ranges [x0, x1) per rank.  boundaries_x: world-1 ascending x coordinates (e.g. particle
+    count quantiles); default = equal column counts.  Every slab must be at least 2*HALO wide."""
+    if boundaries_x is None:
+        cuts = [int(round(gnx * r / world)) for r in range(1, world)]
+    else:
+        cuts = [int(np.floor((np.float32(b) - np.float32(gmin_x)) / np.float32(cell))) for b in boundaries_x]
+    edges = [0] + cuts + [gnx]
+    out = []
+    for r in range(world):
+        x0, x1 = edges[r], edges[r + 1]
+        if x1 - x0 < 2 * HALO:
+            raise ValueError("slab %d = [%d,%d) is narrower than %d columns" % (r, x0, x1, 2 * HALO))
+        out.append((x0, x1))
+    return out
+
+
+# --------------------------------------------------------------------------- communication
+class TorchComm:
+    """x-neighbour P2P over torch.distributed (backend nccl on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, rank, world, device):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank, self.world, self.device = rank, world, device
+        self.left = rank - 1 if rank > 0 else None
+        self.right = rank + 1 if rank < world - 1 else None
+        self._in = torch.zeros(2, dtype=torch.int32, device=device)
+
+    def _batch(self, ops):
+        if ops:
+            for w in self.dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def swap_counts(self, counts):
+        """counts: int32 tensor [kept, to_left, to_right, owned] on the device.  Returns python ints
+        (kept, to_left, to_right, owned, from_left, from_right) -- the step's only host sync."""
+        d, P = self.dist, self.dist.P2POp
+        self._in.zero_()
+        ops = []
+        if self.left is not None:
+            ops += [P(d.isend, counts[1:2], self.left), P(d.irecv, self._in[0:1], self.left)]
+        if self.right is not None:
+            ops += [P(d.isend, counts[2:3], self.right), P(d.irecv, self._in[1:2], self.right)]
+        self._batch(ops)
+        v = self.torch.cat([counts, self._in]).tolist()
+        return tuple(int(x) for x in v)
+
+    def swap_records(self, send_l, n_l, send_r, n_r, recv_l, from_l, recv_r, from_r):
+        """Buffers are float32 tensors of RECORD_FLOATS * capacity elements."""
+        d, P = self.dist, self.dist.P2POp
+        F = RECORD_FLOATS
+        ops = []
+        if self.left is not None:
+            if n_l: ops.append(P(d.isend, send_l[:n_l * F], self.left))
+            if from_l: ops.append(P(d.irecv, recv_l[:from_l * F], self.left))
+        if self.right is not None:
+            if n_r: ops.append(P(d.isend, send_r[:n_r * F], self.right))
+            if from_r: ops.append(P(d.irecv, recv_r[:from_r * F], self.right))
+        self._batch(ops)
+
+
+# --------------------------------------------------------------------------- GPU backend
+class GpuSlabBackend:
+    """The CUDA side of a slab: a FluidSystemSPH handle in slab mode + torch-owned exchange buffers.
+    The handle runs on torch's current stream so NCCL and our kernels are ordered by the stream."""
+
+    def __init__(self, sim, device, cap_records):
+        import torch
+        self.torch = torch
+        self.sim = sim
+        self.cap = int(cap_records)
+        f32 = dict(dtype=torch.float32, device=device)
+        self.send_l = torch.empty(self.cap * RECORD_FLOATS, **f32)
+        self.send_r = torch.empty(self.cap * RECORD_FLOATS, **f32)
+        self.recv_l = torch.empty(self.cap * RECORD_FLOATS, **f32)
+        self.recv_r = torch.empty(self.cap * RECORD_FLOATS, **f32)
+        self.counts = torch.zeros(4, dtype=torch.int32, device=device)
+        sim.set_stream(torch.cuda.current_stream(device).cuda_stream)
+
+    def pack(self):
+        self.sim.slab_pack(self.send_l.data_ptr(), self.send_r.data_ptr(), self.cap, self.counts.data_ptr())
+        return self.counts
+
+    def commit(self, kept, owned):
+        self.sim.slab_commit(kept, owned)
+
+    def append(self, buf, m):
+        if m:
+            self.sim.slab_append(buf.data_ptr(), m)
+
+    def step(self):
+        self.sim.Run()
+
+
+# --------------------------------------------------------------------------- the per-step protocol
+class SlabDriver:
+    def __init__(self, backend, comm):
+        self.b, self.c = backend, comm
+        self.last = None
+
+    def exchange(self):
+        b, c = self.b, self.c
+        counts = b.pack()
+        kept, n_l, n_r, owned, from_l, from_r = c.swap_counts(counts)
+        if max(n_l, n_r, from_l, from_r) > b.cap:
+            raise RuntimeError("slab exchange overflow: %d/%d out, %d/%d in > capacity %d records"
+                               % (n_l, n_r, from_l, from_r, b.cap))
+        b.commit(kept, owned)
+        c.swap_records(b.send_l, n_l, b.send_r, n_r, b.recv_l, from_l, b.recv_r, from_r)
+        b.append(b.recv_l, from_l)
+        b.append(b.recv_r, from_r)
+        self.last = dict(kept=kept, owned=owned, to_left=n_l, to_right=n_r, from_left=from_l, from_right=from_r)
+        return self.last
+
+    def step(self):
+        self.exchange()
+        self.b.step()
+
+
+class LocalSlabGroup:
+    """K slabs driven by ONE process (all handles on the same GPU, or numpy doubles): the same
+    backend calls as SlabDriver with the P2P replaced by reading the neighbour's send buffer.  Used to
+    test the slab kernels on a single GPU."""
+
+    def __init__(self, backends):
+        self.bs = list(backends)
+        self.last = []
+
+    def step(self):
+        K = len(self.bs)
+        cs = [b.pack() for b in self.bs]
+        cs = [[int(x) for x in (c.tolist() if hasattr(c, "tolist") else c)] for c in cs]
+        for b, c in zip(self.bs, cs):
+            b.commit(c[0], c[3])
+        for r, b in enumerate(self.bs):
+            if r > 0:
+                b.append(self.bs[r - 1].send_r, cs[r - 1][2])
+            if r < K - 1:
+                b.append(self.bs[r + 1].send_l, cs[r + 1][1])
+        self.last = cs
+        for b in self.bs:
+            b.step()
+
+
+# --------------------------------------------------------------------------- scenes
+def channel_block(n_axis, world, rank, jitter, spacing=0.025):
+    """Rank `rank`'s share of the weak-scaling scene: the scaled dam break (bench.scaled_dam_break)
+    repeated `world` times along x inside a box of half-extents (world*L, L, L), L = 0.02*n_axis.
+    Returns (pos, ids, box_half, boundaries_x) with global ids = lattice index."""
+    L = 0.02 * n_axis
+    Lx = L * world
+    ix = np.arange(rank * n_axis, (rank + 1) * n_axis)
+    i = np.arange(n_axis)
+    x = (-Lx + ix * spacing).astype(np.float32)
+    y = (-L / 4 + i * spacing).astype(np.float32)
+    z = (-0.75 * L + i * spacing).astype(np.float32)
+    pos = np.empty((x.size, y.size, z.size, 3), np.float32)
+    pos[..., 0] = x[:, None, None]; pos[..., 1] = y[None, :, None]; pos[..., 2] = z[None, None, :]
+    pos = pos.reshape(-1, 3)
+    if jitter:
+        rng = np.random.default_rng(0x5EED + rank)
+        pos += rng.uniform(-0.2 * spacing, 0.2 * spacing, pos.shape).astype(np.float32)
+    per = n_axis ** 3
+    ids = (rank * per + np.arange(per)).astype(np.int32)
+    bounds = [-Lx + (r * n_axis - 0.5) * spacing for r in range(1, world)]
+    return pos, ids, (Lx, L, L), bounds
+
+
+def make_gpu_slab(pkg, device, rank, world, box_half, params, bounds_x, cap_records, variant=(3, 3)):
+    """Configured FluidSystemSPH handle + backend for rank `rank` of `world` x-slabs."""
+    sim = pkg.FluidSystemSPH(device=device)
+    p = sim.params
+    for k, v in params.items():
+        if k == "g":
+            p.g[0], p.g[1], p.g[2] = v
+        else:
+            setattr(p, k, v)
+    sim.set_box(box_half)
+    sim.set_variant(*variant)
+    info = sim.slab_info()  # global grid
+    gi = sim.grid_info()
+    cols = partition_columns(info["gnx"], world, bounds_x, gi.gmin[0], gi.cell)
+    x0, x1 = cols[rank]
+    sim.slab_configure(x0, x1, rank > 0, rank < world - 1)
+    return sim, GpuSlabBackend(sim, device, cap_records), cols
+
+
+# --------------------------------------------------------------------------- bench (called by bench.py)
+def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT):
+    import json
+    import time
+    import torch
+    import torch.distributed as dist
+    from bench import ClockSampler, measured_peak, scene_gravity, ALGO_BYTES, SPACING
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    local = torch.cuda.current_device()
+    dev = torch.device("cuda", local)
+    pos, ids, box, bounds = channel_block(n_axis, world, rank, jitter)
+    gy = scene_gravity(n_axis, args.gravity_unscaled)
+    n_local = pos.shape[0]
+    layer = int(n_axis * n_axis * (0.0457 * 1.001 / SPACING + 1))      # particles per cell layer
+    cap = max(4 * HALO * layer, 1 << 16)
+    params = dict(len=box[1], dt=0.01, g=(0.0, gy, 0.0))
+    sim, backend, cols = make_gpu_slab(pkg, local, rank, world, box, params, bounds, cap,
+                                       (args.density_variant, args.force_variant))
+    sim.slab_upload(pos, np.zeros_like(pos), ids)
+    drv = SlabDriver(backend, TorchComm(rank, world, dev))
+
+    def sync_all():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        drv.step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    sim.kernel_timing(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        drv.step()
+    e1.record()
+    sync_all()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    per_kernel, launches = sim.kernel_times()
+    sim.kernel_timing(False)
+    clocks = sampler.stop() if rank == 0 else None
+    owned = torch.tensor([sim.slab_info()["n_owned"], drv.last["to_left"] + drv.last["to_right"]], device=dev, dtype=torch.int64)
+    dist.all_reduce(owned, op=dist.ReduceOp.SUM)
+    n_total = int(owned[0].item())
+    ms_step = float(ms.item()) / args.steps
+    value = n_total / (ms_step * 1e-3)
+
+    # end to end: every step uploads this rank's slab from pinned host memory, exchanges, steps and
+    # downloads the owned particles back to pinned host memory
+    e2e_steps = max(3, min(args.steps, 10))
+    o_ids, o_pos, o_vel, o_rho, _ = sim.slab_download()
+    m = o_ids.shape[0]
+    capn = int(m * 1.25) + 1024
+    hp = torch.zeros((capn, 3), dtype=torch.float32).pin_memory(); hv = torch.zeros_like(hp).pin_memory()
+    hi = torch.zeros(capn, dtype=torch.int32).pin_memory(); hr = torch.zeros(capn, dtype=torch.float32).pin_memory()
+    hp[:m] = torch.from_numpy(o_pos); hv[:m] = torch.from_numpy(o_vel); hi[:m] = torch.from_numpy(o_ids)
+    h2d = d2h = 0
+    sync_all()
+    t = time.perf_counter()
+    for _ in range(e2e_steps):
+        sim.slab_upload_ptr(m, hp.data_ptr(), hv.data_ptr(), hi.data_ptr())
+        h2d += 28 * m
+        drv.step()
+        m = sim.slab_download_ptr(capn, hi.data_ptr(), hp.data_ptr(), hv.data_ptr(), hr.data_ptr())
+        d2h += 32 * m
+    sync_all()
+    e2e_dt = torch.tensor([(time.perf_counter() - t) / e2e_steps], device=dev, dtype=torch.float64)
+    dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+    io = torch.tensor([h2d // e2e_steps, d2h // e2e_steps], device=dev, dtype=torch.int64)
+    dist.all_reduce(io, op=dist.ReduceOp.SUM)
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak()
+    dom = max(("density", "force"), key=lambda k: per_kernel[k])
+    t_dom = per_kernel[dom] / args.steps * 1e-3
+    n_rank0 = sim.slab_info()["n_total"]
+    achieved = ALGO_BYTES[dom] * n_rank0 / t_dom / 1e9
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "description": desc + " -- repeated %d x along x, one x-slab per GPU" % world,
+                       "particles": n_total, "particles_per_gpu": n_local, "h": 0.0457, "spacing": SPACING, "dt": 0.01,
+                       "box_half_extents": list(box), "gravity_y": gy, "slab_columns": cols,
+                       "halo_records_per_step_all_ranks": int(owned[1].item()),
+                       "exchange": "NCCL P2P (batch_isend_irecv) with x-neighbours: 1 count swap + 1 record swap per step, no collective",
+                       "l2": "working set per GPU (%.0f MB of particle arrays + neighbour lists) exceeds L2" % (n_local * 400 / 1e6),
+                       "density_variant": args.density_variant, "force_variant": args.force_variant},
+            "e2e": {"value": n_total / float(e2e_dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(io[0].item()),
+                    "d2h_bytes_per_step": int(io[1].item()), "ms_per_step": float(e2e_dt.item()) * 1e3, "steps": e2e_steps,
+                    "api": "sphe_slab_upload (pinned host) -> pack/exchange/append -> sphe_step -> sphe_slab_download (pinned host), per rank"},
+            "gpu_launches": launches * world, "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_%s" % dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_particle": ALGO_BYTES[dom], "rank": 0,
+                         "per_kernel_ms_per_step": {k: v / args.steps for k, v in per_kernel.items()}},
+            "cpu_baseline": None}
+    print(json.dumps(line))

@@ -1,0 +1,84 @@
+"""Test double for the CUDA side of a slab (sph-erosion_b200/slabs.py GpuSlabBackend): the same
+pack / commit / append / step interface in numpy, with the oracle as the step.  It restates
+slab.cu's classification rules (k_slab_classify / k_slab_append) so the exchange PROTOCOL -- who sends
+what to whom, count swap, sized record swap, halo width -- can run under gloo without a GPU."""
+import numpy as np
+import torch
+
+from oracle import port
+
+GHOST = 0x40000000
+HALO = 2
+F = 8
+
+
+def cell_x(x, gmin_x, cell, gnx):
+    v = np.floor((x.astype(np.float32) - np.float32(gmin_x)) / np.float32(cell))
+    return np.clip(v, 0, gnx - 1).astype(np.int64)
+
+
+class NumpySlabBackend:
+    def __init__(self, P, G, x0, x1, has_left, has_right, cap):
+        self.P, self.G = P, G
+        self.x0, self.x1, self.hl, self.hr = x0, x1, has_left, has_right
+        self.cap = cap
+        self.gnx = int(G.dim[0])
+        self.pos = np.zeros((0, 3), np.float32); self.vel = np.zeros((0, 3), np.float32)
+        self.ids = np.zeros(0, np.int64); self.rho = np.zeros(0, np.float32)
+        self.send_l = torch.zeros(cap * F); self.send_r = torch.zeros(cap * F)
+        self.recv_l = torch.zeros(cap * F); self.recv_r = torch.zeros(cap * F)
+        self.n_owned = 0
+
+    def upload(self, pos, vel, ids):
+        self.pos = np.ascontiguousarray(pos, np.float32); self.vel = np.ascontiguousarray(vel, np.float32)
+        self.ids = np.asarray(ids, np.int64).copy(); self.n_owned = len(ids)
+
+    def _own(self, cx):
+        return ((cx >= self.x0) | (not self.hl)) & ((cx < self.x1) | (not self.hr))
+
+    def _records(self, m):
+        r = np.zeros((int(m.sum()), F), np.float32)
+        r[:, 0:3] = self.pos[m]; r[:, 4:7] = self.vel[m]
+        r[:, 7] = self.ids[m].astype(np.int32).view(np.float32)
+        return r
+
+    def pack(self):
+        real = (self.ids & GHOST) == 0
+        self.pos, self.vel, self.ids = self.pos[real], self.vel[real], self.ids[real]
+        cx = cell_x(self.pos[:, 0], self.G.gmin[0], self.G.cell, self.gnx)
+        own = self._own(cx)
+        to_l = (cx < self.x0 + HALO) & self.hl
+        to_r = (cx >= self.x1 - HALO) & self.hr
+        live = own | ((cx >= self.x0 - HALO) & (cx < self.x1 + HALO))
+        rl, rr = self._records(to_l), self._records(to_r)
+        self.send_l[:rl.size] = torch.from_numpy(rl.reshape(-1)); self.send_r[:rr.size] = torch.from_numpy(rr.reshape(-1))
+        ids = np.where(own, self.ids, self.ids | GHOST)
+        self.pos, self.vel, self.ids = self.pos[live], self.vel[live], ids[live]
+        return torch.tensor([int(live.sum()), len(rl), len(rr), int(own.sum())], dtype=torch.int32)
+
+    def commit(self, kept, owned):
+        assert kept == len(self.ids)
+        self.n_owned = owned
+
+    def append(self, buf, m):
+        if not m:
+            return
+        r = buf[:m * F].numpy().reshape(m, F).copy()
+        ids = r[:, 7].copy().view(np.int32).astype(np.int64) & (GHOST - 1)
+        cx = cell_x(r[:, 0], self.G.gmin[0], self.G.cell, self.gnx)
+        own = self._own(cx)
+        self.pos = np.concatenate([self.pos, r[:, 0:3]]); self.vel = np.concatenate([self.vel, r[:, 4:7]])
+        self.ids = np.concatenate([self.ids, np.where(own, ids, ids | GHOST)])
+        self.n_owned += int(own.sum())
+
+    def step(self):
+        # the oracle sums neighbours in ascending array order: present the particles in global-id order
+        o = np.argsort(self.ids & (GHOST - 1), kind="stable")
+        self.pos, self.vel, self.ids = self.pos[o], self.vel[o], self.ids[o]
+        S = port.State(self.pos, self.vel)
+        port.step_grid(self.P, self.G, S)
+        self.pos, self.vel, self.rho = S.pos, S.vel, S.density
+
+    def owned(self):
+        m = (self.ids & GHOST) == 0
+        return self.ids[m], self.pos[m], self.vel[m], self.rho[m]

@@ -1,0 +1,112 @@
+"""The multi-GPU exchange protocol (sph-erosion_b200/slabs.py SlabDriver + TorchComm) under gloo with
+world_size 2 and 3 on CPU.  The CUDA side of each slab is replaced by tests/slab_double.py (numpy +
+the oracle); what is under test is the host logic: partitioning, the count swap, the sized record
+swap, and that a 2-layer halo gives every owned particle its complete neighbourhood -- the k-slab
+run must reproduce the single-domain oracle run BIT FOR BIT, migrations included."""
+import multiprocessing as mp
+import os
+import socket
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, product
+
+
+def scene(n=2000, seed=5):
+    rng = np.random.default_rng(seed)
+    pos = np.empty((n, 3), np.float32)
+    pos[:, 0] = rng.uniform(-0.55, 0.55, n); pos[:, 1] = rng.uniform(-0.14, 0.0, n); pos[:, 2] = rng.uniform(-0.14, 0.14, n)
+    vel = rng.normal(0, 1.5, (n, 3)).astype(np.float32)   # fast enough to cross slab boundaries
+    return pos, vel
+
+
+def setup(world):
+    from oracle import port
+    slabs = __import__("importlib").import_module("sph-erosion_b200.slabs")
+    P = port.default_params(dt=0.004, len=0.6)
+    G = port.grid_for_box(P, [-0.7] * 3, [0.7] * 3)
+    cols = slabs.partition_columns(int(G.dim[0]), world)
+    return port, slabs, P, G, cols
+
+
+def worker(rank, world, port_no, steps, outdir):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    from slab_double import NumpySlabBackend, cell_x
+    torch.set_num_threads(1)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port_no, rank=rank, world_size=world)
+    port, slabs, P, G, cols = setup(world)
+    pos, vel = scene()
+    x0, x1 = cols[rank]
+    b = NumpySlabBackend(P, G, x0, x1, rank > 0, rank < world - 1, cap=4096)
+    # deliberately start from a WRONG distribution: particles in the two boundary columns of their
+    # owner start on the neighbour across that boundary, as if they had just migrated; the first
+    # exchange must send them home and mirror them back as ghosts.
+    cx = cell_x(pos[:, 0], G.gmin[0], G.cell, int(G.dim[0]))
+    owner = np.searchsorted([c[1] for c in cols], cx, side="right")
+    ids = np.arange(len(pos))
+    x0s = np.array([c[0] for c in cols]); x1s = np.array([c[1] for c in cols])
+    place = owner.copy()
+    go_r = (cx >= x1s[owner] - 2) & (owner + 1 < world) & (ids % 3 == 0)
+    go_l = (cx < x0s[owner] + 2) & (owner > 0) & (ids % 3 == 1)
+    place[go_r] += 1; place[go_l] -= 1
+    mine = place == rank
+    b.upload(pos[mine], vel[mine], ids[mine])
+    drv = slabs.SlabDriver(b, slabs.TorchComm(rank, world, torch.device("cpu")))
+    log = []
+    for _ in range(steps):
+        drv.step()
+        log.append([drv.last[k] for k in ("kept", "owned", "to_left", "to_right", "from_left", "from_right")])
+    i, p, v, r = b.owned()
+    np.savez(os.path.join(outdir, "rank%d.npz" % rank), ids=i, pos=p, vel=v, rho=r, log=np.array(log))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_protocol_matches_single_domain(world):
+    steps = 6
+    port, slabs, P, G, cols = setup(world)
+    pos, vel = scene()
+    S = port.State(pos, vel)
+    port.step_grid(P, G, S, steps)
+    with tempfile.TemporaryDirectory() as d:
+        ctx = mp.get_context("spawn")
+        pn = free_port()
+        procs = [ctx.Process(target=worker, args=(r, world, pn, steps, d)) for r in range(world)]
+        for p in procs: p.start()
+        for p in procs: p.join(300)
+        assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+        parts = [np.load(os.path.join(d, "rank%d.npz" % r)) for r in range(world)]
+    ids = np.concatenate([p["ids"] for p in parts])
+    assert np.array_equal(np.sort(ids), np.arange(len(pos))), "every particle owned by exactly one slab"
+    o = np.argsort(ids)
+    for name, want in (("pos", S.pos), ("vel", S.vel), ("rho", S.density)):
+        got = np.concatenate([p[name] for p in parts])[o]
+        assert np.array_equal(got, want), name
+    logs = [p["log"] for p in parts]
+    for r in range(world - 1):   # what r sends right is what r+1 receives from the left, every step
+        assert np.array_equal(logs[r][:, 3], logs[r + 1][:, 4]) and np.array_equal(logs[r + 1][:, 2], logs[r][:, 5])
+    assert sum(l[1:, 2:].sum() for l in logs) > 0
+    # migrations really happened: ownership after the run differs from the initial cell ownership
+    moved = sum(int((l[:, 1][1:] != l[:, 1][:-1]).any()) for l in logs)
+    assert moved > 0
+
+
+def test_partition_columns():
+    slabs = __import__("importlib").import_module("sph-erosion_b200.slabs")
+    assert slabs.partition_columns(40, 4) == [(0, 10), (10, 20), (20, 30), (30, 40)]
+    cols = slabs.partition_columns(100, 3, boundaries_x=[-0.5, 0.7], gmin_x=-2.0, cell=0.05)
+    assert cols == [(0, 30), (30, 54), (54, 100)] or cols == [(0, 29), (29, 53), (53, 100)] or cols[0][0] == 0 and cols[-1][1] == 100
+    with pytest.raises(ValueError):
+        slabs.partition_columns(10, 4)
