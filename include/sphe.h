@@ -165,18 +165,23 @@ int sphe_debug_neighbours(sphe_sim* s, long long* nbr_start, int* nbr, long long
 /* ---- multi-GPU x-slabs (no reference counterpart) ----
  * One handle per GPU owns the global cell columns [x0, x1) of the neighbour grid and bins into the
  * window [x0-2, x1+2).  Per step the driver (sph-erosion_b200/slabs.py, NCCL P2P) does
- *     pack -> exchange counts + records with the two x-neighbours -> commit -> append x2 -> sphe_step.
+ *     pack -> exchange records with the two x-neighbours -> unpack -> sphe_step.
  * Records are 32 bytes: (x, y, z, sediment) (vx, vy, vz, id bits); both migrants and the 2-layer
  * halo travel in the same buffer, the receiver classifies each record by its own cell column.
  * Particle ids are global, < 2^30 (bit 30 marks ghost copies). */
 int sphe_slab_configure(sphe_sim* s, int x0, int x1, int has_left, int has_right);
 int sphe_slab_info(sphe_sim* s, int* gnx, int* xoff, int* n_total, int* n_owned);
 int sphe_slab_upload(sphe_sim* s, int n, const float* pos, const float* vel, const int* ids);
-/* Drops ghosts, compacts what stays, fills the two DEVICE send buffers (cap_records each) and the
- * DEVICE counters dev_counts[4] = {kept, to_left, to_right, owned}.  Asynchronous on the handle's stream. */
-int sphe_slab_pack(sphe_sim* s, void* dev_send_left, void* dev_send_right, int cap_records, int* dev_counts);
-int sphe_slab_commit(sphe_sim* s, int n_kept, int n_owned);       /* host copy of dev_counts[0], [3] */
-int sphe_slab_append(sphe_sim* s, const void* dev_records, int m); /* received records (device) */
+/* Exchange buffers hold cap_records + 1 records; record 0 is a header whose first int is the payload
+ * count, so a buffer can be sent with a size both sides agree on beforehand and no count has to reach
+ * the host before the transfer is posted.
+ * pack:   drops ghosts, compacts what stays, fills the two DEVICE send buffers.  Asynchronous.
+ *         reserve_incoming = upper bound of the records that can arrive (array growth happens here).
+ * unpack: appends the payload of the two received DEVICE buffers (NULL = no neighbour on that side;
+ *         at most max_left / max_right records were transferred), then performs the step's only host
+ *         sync and returns out[6] = {n_total, n_owned, sent_left, sent_right, got_left, got_right}. */
+int sphe_slab_pack(sphe_sim* s, void* dev_send_left, void* dev_send_right, int cap_records, int reserve_incoming);
+int sphe_slab_unpack(sphe_sim* s, const void* dev_recv_left, int max_left, const void* dev_recv_right, int max_right, int out[6]);
 /* Owned particles only, storage order; rho/sed may be NULL. */
 int sphe_slab_download(sphe_sim* s, int cap, int* ids, float* pos, float* vel, float* rho, float* sed, int* n_out);
 

@@ -73,9 +73,8 @@ SYMBOLS = {
     "sphe_slab_configure": (_i, [_vp, _i, _i, _i, _i]),
     "sphe_slab_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "sphe_slab_upload": (_i, [_vp, _i, _vp, _vp, _vp]),
-    "sphe_slab_pack": (_i, [_vp, _vp, _vp, _i, _vp]),
-    "sphe_slab_commit": (_i, [_vp, _i, _i]),
-    "sphe_slab_append": (_i, [_vp, _vp, _i]),
+    "sphe_slab_pack": (_i, [_vp, _vp, _vp, _i, _i]),
+    "sphe_slab_unpack": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
     "sphe_slab_download": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i)]),
 }
 

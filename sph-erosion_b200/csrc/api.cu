@@ -76,6 +76,8 @@ struct sphe_sim {
     SlabP slab{};
     int n_owned = 0;
     int* slab_counters = nullptr;  // device int[8]
+    int* slab_host = nullptr;      // pinned mirror of slab_counters
+    int slab_cap_sent = 0;
     float grid_h = -1.f, grid_len = -1.f;
 
     bool diag = false;
@@ -379,6 +381,7 @@ void sphe_destroy(sphe_sim* s) {
                         s->cell_sorted, s->tmp, s->stage, s->slot_of_id, s->nlist, s->ncount, s->count, s->cell_start, s->cursor, s->tile_sum,
                         s->flush_buf, s->slab_counters, s->D.acc, s->D.fpress, s->D.fvisc, s->D.fgrav, s->D.fsurf, s->D.normal, s->D.neighb};
         for (void* p : ptrs) if (p) cudaFree(p);
+        if (s->slab_host) cudaFreeHost(s->slab_host);
         if (s->own_stream && s->st) cudaStreamDestroy(s->st);
     }
     delete s;
@@ -831,44 +834,49 @@ int sphe_slab_upload(sphe_sim* s, int n, const float* pos, const float* vel, con
     return SPHE_OK;
 }
 
-int sphe_slab_pack(sphe_sim* s, void* dev_send_left, void* dev_send_right, int cap_records, int* dev_counts) {
-    if (!s || !dev_counts || cap_records < 0) return fail(SPHE_ERR_ARG, "bad arguments");
+int sphe_slab_pack(sphe_sim* s, void* dev_send_left, void* dev_send_right, int cap_records, int reserve_incoming) {
+    if (!s || !dev_send_left || !dev_send_right || cap_records < 0 || reserve_incoming < 0) return fail(SPHE_ERR_ARG, "bad arguments");
     if (!s->slab_on) return fail(SPHE_ERR_STATE, "call sphe_slab_configure first");
     TRY(ensure_device(s));
     TRY(setup_grid(s));
-    TRY(reserve(s, std::max(s->n, 1)));
-    CU(cudaMemsetAsync(dev_counts, 0, 4 * sizeof(int), s->st));
+    // room for everything that can arrive, so nothing has to grow between pack and unpack
+    TRY(reserve(s, std::max(s->n + reserve_incoming, 1)));
+    CU(cudaMemsetAsync(s->slab_counters, 0, 8 * sizeof(int), s->st));
     launch_slab_classify(s->st, s->n, s->posA, s->velA, s->idsA, s->sedA, s->G, s->slab, s->posB, s->velB, s->idsB, s->sedB,
-                         (float4*)dev_send_left, (float4*)dev_send_right, cap_records, dev_counts);
-    s->launches += 1;
+                         (float4*)dev_send_left, (float4*)dev_send_right, cap_records, s->slab_counters);
+    launch_slab_headers(s->st, s->slab_counters, (float4*)dev_send_left, (float4*)dev_send_right);
+    s->launches += 2;
     std::swap(s->posA, s->posB); std::swap(s->velA, s->velB); std::swap(s->idsA, s->idsB); std::swap(s->sedA, s->sedB);
     s->binned = false; s->slot_valid = false;
+    s->slab_cap_sent = cap_records;
     CU(cudaGetLastError());
     return SPHE_OK;
 }
 
-int sphe_slab_commit(sphe_sim* s, int n_kept, int n_owned) {
-    if (!s || n_kept < 0 || n_owned < 0 || n_owned > n_kept) return fail(SPHE_ERR_ARG, "bad arguments");
-    if (n_kept > s->cap) return fail(SPHE_ERR_ARG, "n_kept %d exceeds capacity %d", n_kept, s->cap);
-    s->n = n_kept; s->n_owned = n_owned;
-    return SPHE_OK;
-}
-
-int sphe_slab_append(sphe_sim* s, const void* dev_records, int m) {
-    if (!s || m < 0 || (m > 0 && !dev_records)) return fail(SPHE_ERR_ARG, "bad arguments");
+int sphe_slab_unpack(sphe_sim* s, const void* dev_recv_left, int max_left, const void* dev_recv_right, int max_right, int out[6]) {
+    if (!s || max_left < 0 || max_right < 0) return fail(SPHE_ERR_ARG, "bad arguments");
     if (!s->slab_on) return fail(SPHE_ERR_STATE, "call sphe_slab_configure first");
-    if (m == 0) return SPHE_OK;
     TRY(ensure_device(s));
-    TRY(reserve(s, s->n + m));
-    int* oc = s->slab_counters + 4;
-    CU(cudaMemsetAsync(oc, 0, sizeof(int), s->st));
-    launch_slab_append(s->st, m, (const float4*)dev_records, s->G, s->slab, s->n, s->posA, s->velA, s->idsA, s->sedA, oc);
+    if (!dev_recv_left) max_left = 0;
+    if (!dev_recv_right) max_right = 0;
+    CU(cudaMemsetAsync(s->slab_counters + 4, 0, 3 * sizeof(int), s->st));  // unpack may be repeated after a re-send
+    launch_slab_append(s->st, max_left, max_right, (const float4*)dev_recv_left, (const float4*)dev_recv_right, s->G, s->slab,
+                       s->cap, s->posA, s->velA, s->idsA, s->sedA, s->slab_counters);
     s->launches += 1;
-    int got = 0;
-    CU(cudaMemcpyAsync(&got, oc, sizeof(int), cudaMemcpyDeviceToHost, s->st));
-    CU(cudaStreamSynchronize(s->st));
-    s->n += m; s->n_owned += got;
+    if (!s->slab_host) CU(cudaMallocHost(&s->slab_host, 8 * sizeof(int)));
+    CU(cudaMemcpyAsync(s->slab_host, s->slab_counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));   // the step's only host sync: the particle count sizes the next launches
+    const int* c = s->slab_host;        // kept, to_left, to_right, owned(kept), owned(appended), from_left, from_right
+    if (c[1] > s->slab_cap_sent || c[2] > s->slab_cap_sent)
+        return fail(SPHE_ERR_NOMEM, "slab send overflow: %d left / %d right records > buffer capacity %d", c[1], c[2], s->slab_cap_sent);
+    // a header count above the posted size means the transfer was truncated: the caller re-sends that
+    // link at full capacity and calls unpack again (out[] carries the counts it needs to decide)
+    int got_l = std::min(c[5], max_left), got_r = std::min(c[6], max_right);
+    long long n = (long long)c[0] + got_l + got_r;
+    if (n > s->cap) return fail(SPHE_ERR_NOMEM, "slab particle capacity %d exceeded (%lld)", s->cap, n);
+    s->n = (int)n; s->n_owned = c[3] + c[4];
     s->binned = false; s->slot_valid = false;
+    if (out) { out[0] = s->n; out[1] = s->n_owned; out[2] = c[1]; out[3] = c[2]; out[4] = c[5]; out[5] = c[6]; }
     return SPHE_OK;
 }
 
@@ -880,7 +888,7 @@ int sphe_slab_download(sphe_sim* s, int cap, int* ids, float* pos, float* vel, f
     if (n == 0) return SPHE_OK;
     if (!s->slab_counters) CU(cudaMalloc(&s->slab_counters, 8 * sizeof(int)));
     size_t cp = (size_t)s->cap;
-    int* d_cnt = s->slab_counters + 5;
+    int* d_cnt = s->slab_counters + 7;
     int* d_ids = (int*)s->stage;
     float *d_pos = s->stage + cp, *d_vel = s->stage + 4 * cp, *d_rho = s->stage + 7 * cp, *d_sed = s->stage + 8 * cp;
     CU(cudaMemsetAsync(d_cnt, 0, sizeof(int), s->st));

@@ -24,8 +24,9 @@ struct SlabP {
 void launch_slab_classify(cudaStream_t st, int n, const float4* posq, const float4* velv, const int* ids, const float* sed,
                           const GridP& G, const SlabP& S, float4* keep_pos, float4* keep_vel, int* keep_ids, float* keep_sed,
                           float4* send_left, float4* send_right, int cap_records, int* counters);
-void launch_slab_append(cudaStream_t st, int m, const float4* rec, const GridP& G, const SlabP& S, int base, float4* posq,
-                        float4* velv, int* ids, float* sed, int* owned_counter);
+void launch_slab_headers(cudaStream_t st, const int* counters, float4* send_left, float4* send_right);
+void launch_slab_append(cudaStream_t st, int max_l, int max_r, const float4* rec_l, const float4* rec_r, const GridP& G,
+                        const SlabP& S, int cap_particles, float4* posq, float4* velv, int* ids, float* sed, int* counters);
 void launch_slab_gather_owned(cudaStream_t st, int n, const float4* posq, const float4* velv, const float* rho, const float* sed,
                               const int* ids, int* counter, int* out_ids, float* out_pos, float* out_vel, float* out_rho,
                               float* out_sed);

@@ -6,8 +6,10 @@
 //     halo zone as ghosts (the new owner has the authoritative copy),
 //   * packs everything a neighbour needs -- migrants AND the HALO outermost cell layers -- into one
 //     send buffer per side (one exchange per step carries both).
-// Records are 32 bytes: (x, y, z, sediment) (vx, vy, vz, id bits).  The receiver decides owned/ghost
-// from the record's own cell column, so sender and receiver never disagree.
+// Records are 32 bytes: (x, y, z, sediment) (vx, vy, vz, id bits); record 0 of a buffer is a header
+// carrying the payload count, so buffers can be sent with a size both sides already agree on and the
+// host never has to learn a count before posting the transfer.  The receiver decides owned/ghost from
+// the record's own cell column, so sender and receiver never disagree.
 //
 // HALO = 2 cell layers: the density of a ghost in the first layer is recomputed locally from the
 // second layer, so no second exchange of densities is needed (8e option "2-layer halo").
@@ -64,32 +66,55 @@ __global__ void __launch_bounds__(256) k_slab_classify(int n, const float4* __re
     }
     int l = warp_append(to_l, &counters[1]);
     if (to_l && l < cap_records) {
-        send_left[2 * l] = make_float4(p.x, p.y, p.z, sd);
-        send_left[2 * l + 1] = make_float4(v.x, v.y, v.z, __int_as_float(id));
+        send_left[2 * (l + 1)] = make_float4(p.x, p.y, p.z, sd);
+        send_left[2 * (l + 1) + 1] = make_float4(v.x, v.y, v.z, __int_as_float(id));
     }
     int r = warp_append(to_r, &counters[2]);
     if (to_r && r < cap_records) {
-        send_right[2 * r] = make_float4(p.x, p.y, p.z, sd);
-        send_right[2 * r + 1] = make_float4(v.x, v.y, v.z, __int_as_float(id));
+        send_right[2 * (r + 1)] = make_float4(p.x, p.y, p.z, sd);
+        send_right[2 * (r + 1) + 1] = make_float4(v.x, v.y, v.z, __int_as_float(id));
     }
 }
 
-__global__ void __launch_bounds__(256) k_slab_append(int m, const float4* __restrict__ rec, GridP G, SlabP S, int base,
+// Record 0 of every exchange buffer is a header: int[0] = number of payload records that follow.
+__global__ void k_slab_headers(const int* __restrict__ counters, float4* __restrict__ send_left, float4* __restrict__ send_right) {
+    if (threadIdx.x == 0) {
+        send_left[0] = make_float4(__int_as_float(counters[1]), 0.f, 0.f, 0.f);
+        send_right[0] = make_float4(__int_as_float(counters[2]), 0.f, 0.f, 0.f);
+    }
+}
+
+// Appends the payload of both received buffers behind the kept particles.  All counts are read from
+// device memory (the kept count from the pack counters, the payload counts from the headers), so the
+// host does not have to know them before this launch.  counters[4] += owned among the appended,
+// counters[5] = records taken from the left buffer, counters[6] = from the right buffer.
+__global__ void __launch_bounds__(256) k_slab_append(int max_l, int max_r, const float4* __restrict__ rec_l,
+                                                     const float4* __restrict__ rec_r, GridP G, SlabP S, int cap_particles,
                                                      float4* __restrict__ posq, float4* __restrict__ velv,
-                                                     int* __restrict__ ids, float* __restrict__ sed, int* __restrict__ owned_counter) {
+                                                     int* __restrict__ ids, float* __restrict__ sed, int* __restrict__ counters) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int kept = counters[0];
+    int from_l = rec_l ? min(__float_as_int(rec_l[0].x), max_l) : 0;
+    int from_r = rec_r ? min(__float_as_int(rec_r[0].x), max_r) : 0;
+    if (from_l < 0) from_l = 0;
+    if (from_r < 0) from_r = 0;
+    if (i == 0) { counters[5] = rec_l ? __float_as_int(rec_l[0].x) : 0; counters[6] = rec_r ? __float_as_int(rec_r[0].x) : 0; }
     bool own = false;
-    if (i < m) {
-        float4 a = rec[2 * i], b = rec[2 * i + 1];
+    const float4* rec = nullptr;
+    int j = 0;
+    if (i < from_l) { rec = rec_l; j = i; }
+    else if (i < from_l + from_r) { rec = rec_r; j = i - from_l; }
+    if (rec && kept + i < cap_particles) {
+        float4 a = rec[2 * (j + 1)], b = rec[2 * (j + 1) + 1];
         int id = __float_as_int(b.w) & SPHE_ID_MASK;
         int cx = cell_axis(a.x, G.gx, G.cell, G.gnx);
         own = (cx >= S.x0 || !S.has_left) && (cx < S.x1 || !S.has_right);
-        posq[base + i] = make_float4(a.x, a.y, a.z, 0.f);
-        velv[base + i] = make_float4(b.x, b.y, b.z, 0.f);
-        sed[base + i] = a.w;
-        ids[base + i] = own ? id : (id | SPHE_GHOST_BIT);
+        posq[kept + i] = make_float4(a.x, a.y, a.z, 0.f);
+        velv[kept + i] = make_float4(b.x, b.y, b.z, 0.f);
+        sed[kept + i] = a.w;
+        ids[kept + i] = own ? id : (id | SPHE_GHOST_BIT);
     }
-    warp_append(own, owned_counter);
+    warp_append(own, &counters[4]);
 }
 
 // owned particles only, storage order, packed xyz (tests, checkpoints, rendering hand-off)
@@ -128,9 +153,14 @@ void launch_slab_classify(cudaStream_t st, int n, const float4* posq, const floa
         k_slab_classify<<<(n + 255) / 256, 256, 0, st>>>(n, posq, velv, ids, sed, G, S, keep_pos, keep_vel, keep_ids, keep_sed,
                                                         send_left, send_right, cap_records, counters);
 }
-void launch_slab_append(cudaStream_t st, int m, const float4* rec, const GridP& G, const SlabP& S, int base, float4* posq,
-                        float4* velv, int* ids, float* sed, int* owned_counter) {
-    if (m > 0) k_slab_append<<<(m + 255) / 256, 256, 0, st>>>(m, rec, G, S, base, posq, velv, ids, sed, owned_counter);
+void launch_slab_headers(cudaStream_t st, const int* counters, float4* send_left, float4* send_right) {
+    k_slab_headers<<<1, 32, 0, st>>>(counters, send_left, send_right);
+}
+void launch_slab_append(cudaStream_t st, int max_l, int max_r, const float4* rec_l, const float4* rec_r, const GridP& G,
+                        const SlabP& S, int cap_particles, float4* posq, float4* velv, int* ids, float* sed, int* counters) {
+    int m = max_l + max_r;
+    if (m < 1) m = 1;
+    k_slab_append<<<(m + 255) / 256, 256, 0, st>>>(max_l, max_r, rec_l, rec_r, G, S, cap_particles, posq, velv, ids, sed, counters);
 }
 void launch_slab_gather_owned(cudaStream_t st, int n, const float4* posq, const float4* velv, const float* rho, const float* sed,
                               const int* ids, int* counter, int* out_ids, float* out_pos, float* out_vel, float* out_rho,

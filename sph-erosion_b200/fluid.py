@@ -143,11 +143,13 @@ class FluidSystemSPH:
     def slab_upload_ptr(self, n, pos, vel, ids):
         capi.check(self._L.sphe_slab_upload(self._h, int(n), pos, vel, ids))
 
-    def slab_pack(self, dev_left, dev_right, cap_records, dev_counts):
-        capi.check(self._L.sphe_slab_pack(self._h, dev_left, dev_right, int(cap_records), dev_counts))
+    def slab_pack(self, dev_left, dev_right, cap_records, reserve_incoming):
+        capi.check(self._L.sphe_slab_pack(self._h, dev_left, dev_right, int(cap_records), int(reserve_incoming)))
 
-    def slab_commit(self, n_kept, n_owned): capi.check(self._L.sphe_slab_commit(self._h, int(n_kept), int(n_owned)))
-    def slab_append(self, dev_records, m): capi.check(self._L.sphe_slab_append(self._h, dev_records, int(m)))
+    def slab_unpack(self, dev_left, max_left, dev_right, max_right):
+        out = (C.c_int * 6)()
+        capi.check(self._L.sphe_slab_unpack(self._h, dev_left, int(max_left), dev_right, int(max_right), out))
+        return dict(zip(("n_total", "n_owned", "to_left", "to_right", "from_left", "from_right"), list(out)))
 
     def slab_download(self, cap=None):
         cap = self.count() if cap is None else int(cap)

@@ -4,10 +4,12 @@ One process per GPU (torchrun).  Each rank owns the global cell columns [x0, x1)
 grid; per step
 
     pack      (CUDA, slab.cu)   drop ghosts, keep owned, fill the left/right send buffers with
-                                migrants + the 2-layer halo, leave 4 counters on the device
-    counts    (P2P)             neighbours swap "how many records are coming"       -- 1 host sync
-    records   (P2P)             sized sends/receives of 32-byte records over NCCL (NVLink/NVSwitch)
-    append    (CUDA)            received records join the local arrays as owned or ghost
+                                migrants + the 2-layer halo; record 0 of a buffer = payload count
+    records   (P2P)             ONE group of sends/receives of 32-byte records over NCCL
+                                (NVLink/NVSwitch); message sizes follow last step's counts, which both
+                                ends of a link know, so no count has to reach the host first
+    unpack    (CUDA)            received records join the local arrays as owned or ghost; then the
+                                step's only host sync (the new particle count sizes the launches)
     step      (CUDA)            the ordinary single-GPU step over owned + ghost particles
 
 There is no collective on the data path: interactions are local, so only x-neighbours talk
@@ -16,8 +18,8 @@ multi-process code; correctness is "k slabs == 1 GPU" (tests/test_gpu_slabs.py) 
 protocol is covered on CPU with gloo (tests/test_slabs_gloo.py).
 
 The driver is written against two small interfaces so the protocol can be exercised without a GPU:
-  backend : pack() / commit() / append() / step()      -- GpuSlabBackend here, a numpy double in tests
-  comm    : swap_counts() / swap_records()             -- TorchComm (nccl or gloo) / LocalComm
+  backend : pack() / unpack() / step()     -- GpuSlabBackend here, a numpy double in tests
+  comm    : swap_records()                 -- TorchComm (nccl on GPUs, gloo on CPU)
 """
 import numpy as np
 
@@ -46,100 +48,96 @@ def partition_columns(gnx, world, boundaries_x=None, gmin_x=None, cell=None):
 class TorchComm:
     """x-neighbour P2P over torch.distributed (backend nccl on GPUs, gloo in the CPU tests)."""
 
-    def __init__(self, rank, world, device):
-        import torch
+    def __init__(self, rank, world):
         import torch.distributed as dist
-        self.torch, self.dist = torch, dist
-        self.rank, self.world, self.device = rank, world, device
+        self.dist = dist
+        self.rank, self.world = rank, world
         self.left = rank - 1 if rank > 0 else None
         self.right = rank + 1 if rank < world - 1 else None
-        self._in = torch.zeros(2, dtype=torch.int32, device=device)
 
-    def _batch(self, ops):
-        if ops:
-            for w in self.dist.batch_isend_irecv(ops):
-                w.wait()
-
-    def swap_counts(self, counts):
-        """counts: int32 tensor [kept, to_left, to_right, owned] on the device.  Returns python ints
-        (kept, to_left, to_right, owned, from_left, from_right) -- the step's only host sync."""
-        d, P = self.dist, self.dist.P2POp
-        self._in.zero_()
-        ops = []
-        if self.left is not None:
-            ops += [P(d.isend, counts[1:2], self.left), P(d.irecv, self._in[0:1], self.left)]
-        if self.right is not None:
-            ops += [P(d.isend, counts[2:3], self.right), P(d.irecv, self._in[1:2], self.right)]
-        self._batch(ops)
-        v = self.torch.cat([counts, self._in]).tolist()
-        return tuple(int(x) for x in v)
-
-    def swap_records(self, send_l, n_l, send_r, n_r, recv_l, from_l, recv_r, from_r):
-        """Buffers are float32 tensors of RECORD_FLOATS * capacity elements."""
+    def swap_records(self, send_l, out_l, send_r, out_r, recv_l, in_l, recv_r, in_r):
+        """One group of sends/receives.  Buffers are float32 tensors; out_*/in_* are the payload sizes
+        (records, header excluded) both ends of a link agreed on; None skips that transfer."""
         d, P = self.dist, self.dist.P2POp
         F = RECORD_FLOATS
         ops = []
         if self.left is not None:
-            if n_l: ops.append(P(d.isend, send_l[:n_l * F], self.left))
-            if from_l: ops.append(P(d.irecv, recv_l[:from_l * F], self.left))
+            if out_l is not None: ops.append(P(d.isend, send_l[:(out_l + 1) * F], self.left))
+            if in_l is not None: ops.append(P(d.irecv, recv_l[:(in_l + 1) * F], self.left))
         if self.right is not None:
-            if n_r: ops.append(P(d.isend, send_r[:n_r * F], self.right))
-            if from_r: ops.append(P(d.irecv, recv_r[:from_r * F], self.right))
-        self._batch(ops)
+            if out_r is not None: ops.append(P(d.isend, send_r[:(out_r + 1) * F], self.right))
+            if in_r is not None: ops.append(P(d.irecv, recv_r[:(in_r + 1) * F], self.right))
+        if ops:
+            for w in d.batch_isend_irecv(ops):
+                w.wait()
 
 
 # --------------------------------------------------------------------------- GPU backend
 class GpuSlabBackend:
-    """The CUDA side of a slab: a FluidSystemSPH handle in slab mode + torch-owned exchange buffers.
-    The handle runs on torch's current stream so NCCL and our kernels are ordered by the stream."""
+    """The CUDA side of a slab: a FluidSystemSPH handle in slab mode + torch-owned exchange buffers
+    (cap + 1 records each: record 0 is the header).  The handle runs on torch's current stream so NCCL
+    and our kernels are ordered by the stream."""
 
-    def __init__(self, sim, device, cap_records):
+    def __init__(self, sim, device, cap_records, has_left=True, has_right=True):
         import torch
-        self.torch = torch
         self.sim = sim
         self.cap = int(cap_records)
+        self.has_left, self.has_right = has_left, has_right
         f32 = dict(dtype=torch.float32, device=device)
-        self.send_l = torch.empty(self.cap * RECORD_FLOATS, **f32)
-        self.send_r = torch.empty(self.cap * RECORD_FLOATS, **f32)
-        self.recv_l = torch.empty(self.cap * RECORD_FLOATS, **f32)
-        self.recv_r = torch.empty(self.cap * RECORD_FLOATS, **f32)
-        self.counts = torch.zeros(4, dtype=torch.int32, device=device)
+        n = (self.cap + 1) * RECORD_FLOATS
+        self.send_l = torch.zeros(n, **f32); self.send_r = torch.zeros(n, **f32)
+        self.recv_l = torch.zeros(n, **f32); self.recv_r = torch.zeros(n, **f32)
         sim.set_stream(torch.cuda.current_stream(device).cuda_stream)
 
     def pack(self):
-        self.sim.slab_pack(self.send_l.data_ptr(), self.send_r.data_ptr(), self.cap, self.counts.data_ptr())
-        return self.counts
+        self.sim.slab_pack(self.send_l.data_ptr(), self.send_r.data_ptr(), self.cap, 2 * self.cap)
 
-    def commit(self, kept, owned):
-        self.sim.slab_commit(kept, owned)
-
-    def append(self, buf, m):
-        if m:
-            self.sim.slab_append(buf.data_ptr(), m)
+    def unpack(self, buf_l, max_l, buf_r, max_r):
+        return self.sim.slab_unpack(buf_l.data_ptr() if (self.has_left and buf_l is not None) else None, max_l,
+                                    buf_r.data_ptr() if (self.has_right and buf_r is not None) else None, max_r)
 
     def step(self):
         self.sim.Run()
 
 
 # --------------------------------------------------------------------------- the per-step protocol
+def next_size(count, cap, floor=1024):
+    """Message size (payload records) both ends of a link derive from the count they both saw last."""
+    return int(min(cap, max(floor, count + count // 4 + 1024)))
+
+
 class SlabDriver:
+    """pack -> one P2P group -> unpack (the step's only host sync) -> step.  Message sizes follow the
+    previous step's counts, which both ends of a link know; a count that outgrew its message makes
+    both ends repeat that link at full capacity."""
+
     def __init__(self, backend, comm):
         self.b, self.c = backend, comm
+        cap = backend.cap
+        self.out_l = self.out_r = self.in_l = self.in_r = cap
         self.last = None
+        self.resends = 0
 
     def exchange(self):
         b, c = self.b, self.c
-        counts = b.pack()
-        kept, n_l, n_r, owned, from_l, from_r = c.swap_counts(counts)
-        if max(n_l, n_r, from_l, from_r) > b.cap:
-            raise RuntimeError("slab exchange overflow: %d/%d out, %d/%d in > capacity %d records"
-                               % (n_l, n_r, from_l, from_r, b.cap))
-        b.commit(kept, owned)
-        c.swap_records(b.send_l, n_l, b.send_r, n_r, b.recv_l, from_l, b.recv_r, from_r)
-        b.append(b.recv_l, from_l)
-        b.append(b.recv_r, from_r)
-        self.last = dict(kept=kept, owned=owned, to_left=n_l, to_right=n_r, from_left=from_l, from_right=from_r)
-        return self.last
+        b.pack()
+        c.swap_records(b.send_l, self.out_l, b.send_r, self.out_r, b.recv_l, self.in_l, b.recv_r, self.in_r)
+        info = b.unpack(b.recv_l, self.in_l, b.recv_r, self.in_r)
+        if max(info["to_left"], info["to_right"], info["from_left"], info["from_right"]) > b.cap:
+            raise RuntimeError("slab exchange overflow: %r > capacity %d records" % (info, b.cap))
+        redo_l = c.left is not None and (info["to_left"] > self.out_l or info["from_left"] > self.in_l)
+        redo_r = c.right is not None and (info["to_right"] > self.out_r or info["from_right"] > self.in_r)
+        if redo_l or redo_r:
+            self.resends += 1
+            if redo_l: self.out_l = self.in_l = b.cap
+            if redo_r: self.out_r = self.in_r = b.cap
+            c.swap_records(b.send_l, b.cap if redo_l else None, b.send_r, b.cap if redo_r else None,
+                           b.recv_l, b.cap if redo_l else None, b.recv_r, b.cap if redo_r else None)
+            info = b.unpack(b.recv_l, self.in_l, b.recv_r, self.in_r)
+        self.out_l, self.in_l = next_size(info["to_left"], b.cap), next_size(info["from_left"], b.cap)
+        self.out_r, self.in_r = next_size(info["to_right"], b.cap), next_size(info["from_right"], b.cap)
+        self.last = info
+        return info
 
     def step(self):
         self.exchange()
@@ -147,9 +145,9 @@ class SlabDriver:
 
 
 class LocalSlabGroup:
-    """K slabs driven by ONE process (all handles on the same GPU, or numpy doubles): the same
-    backend calls as SlabDriver with the P2P replaced by reading the neighbour's send buffer.  Used to
-    test the slab kernels on a single GPU."""
+    """K slabs driven by ONE process (all handles on the same GPU): the same backend calls as
+    SlabDriver with the P2P replaced by reading the neighbour's send buffer.  Used to test the slab
+    kernels on a single GPU."""
 
     def __init__(self, backends):
         self.bs = list(backends)
@@ -157,16 +155,12 @@ class LocalSlabGroup:
 
     def step(self):
         K = len(self.bs)
-        cs = [b.pack() for b in self.bs]
-        cs = [[int(x) for x in (c.tolist() if hasattr(c, "tolist") else c)] for c in cs]
-        for b, c in zip(self.bs, cs):
-            b.commit(c[0], c[3])
+        for b in self.bs:
+            b.pack()
+        self.last = []
         for r, b in enumerate(self.bs):
-            if r > 0:
-                b.append(self.bs[r - 1].send_r, cs[r - 1][2])
-            if r < K - 1:
-                b.append(self.bs[r + 1].send_l, cs[r + 1][1])
-        self.last = cs
+            self.last.append(b.unpack(self.bs[r - 1].send_r if r > 0 else None, b.cap,
+                                      self.bs[r + 1].send_l if r < K - 1 else None, b.cap))
         for b in self.bs:
             b.step()
 
@@ -211,7 +205,7 @@ def make_gpu_slab(pkg, device, rank, world, box_half, params, bounds_x, cap_reco
     cols = partition_columns(info["gnx"], world, bounds_x, gi.gmin[0], gi.cell)
     x0, x1 = cols[rank]
     sim.slab_configure(x0, x1, rank > 0, rank < world - 1)
-    return sim, GpuSlabBackend(sim, device, cap_records), cols
+    return sim, GpuSlabBackend(sim, device, cap_records, rank > 0, rank < world - 1), cols
 
 
 # --------------------------------------------------------------------------- bench (called by bench.py)
@@ -229,12 +223,12 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT):
     gy = scene_gravity(n_axis, args.gravity_unscaled)
     n_local = pos.shape[0]
     layer = int(n_axis * n_axis * (0.0457 * 1.001 / SPACING + 1))      # particles per cell layer
-    cap = max(4 * HALO * layer, 1 << 16)
+    cap = max(2 * HALO * layer, 1 << 14)
     params = dict(len=box[1], dt=0.01, g=(0.0, gy, 0.0))
     sim, backend, cols = make_gpu_slab(pkg, local, rank, world, box, params, bounds, cap,
                                        (args.density_variant, args.force_variant))
     sim.slab_upload(pos, np.zeros_like(pos), ids)
-    drv = SlabDriver(backend, TorchComm(rank, world, dev))
+    drv = SlabDriver(backend, TorchComm(rank, world))
 
     def sync_all():
         torch.cuda.synchronize()
@@ -302,7 +296,8 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT):
                        "particles": n_total, "particles_per_gpu": n_local, "h": 0.0457, "spacing": SPACING, "dt": 0.01,
                        "box_half_extents": list(box), "gravity_y": gy, "slab_columns": cols,
                        "halo_records_per_step_all_ranks": int(owned[1].item()),
-                       "exchange": "NCCL P2P (batch_isend_irecv) with x-neighbours: 1 count swap + 1 record swap per step, no collective",
+                       "exchange": "NCCL P2P (one batch_isend_irecv group per step) with the x-neighbours, counts ride in the record headers, 1 host sync per step, no collective",
+                       "exchange_resends": drv.resends,
                        "l2": "working set per GPU (%.0f MB of particle arrays + neighbour lists) exceeds L2" % (n_local * 400 / 1e6),
                        "density_variant": args.density_variant, "force_variant": args.force_variant},
             "e2e": {"value": n_total / float(e2e_dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(io[0].item()),

@@ -1,5 +1,5 @@
 """Test double for the CUDA side of a slab (sph-erosion_b200/slabs.py GpuSlabBackend): the same
-pack / commit / append / step interface in numpy, with the oracle as the step.  It restates
+pack / unpack / step interface in numpy, with the oracle as the step.  It restates
 slab.cu's classification rules (k_slab_classify / k_slab_append) so the exchange PROTOCOL -- who sends
 what to whom, count swap, sized record swap, halo width -- can run under gloo without a GPU."""
 import numpy as np
@@ -25,8 +25,8 @@ class NumpySlabBackend:
         self.gnx = int(G.dim[0])
         self.pos = np.zeros((0, 3), np.float32); self.vel = np.zeros((0, 3), np.float32)
         self.ids = np.zeros(0, np.int64); self.rho = np.zeros(0, np.float32)
-        self.send_l = torch.zeros(cap * F); self.send_r = torch.zeros(cap * F)
-        self.recv_l = torch.zeros(cap * F); self.recv_r = torch.zeros(cap * F)
+        self.send_l = torch.zeros((cap + 1) * F); self.send_r = torch.zeros((cap + 1) * F)
+        self.recv_l = torch.zeros((cap + 1) * F); self.recv_r = torch.zeros((cap + 1) * F)
         self.n_owned = 0
 
     def upload(self, pos, vel, ids):
@@ -50,26 +50,35 @@ class NumpySlabBackend:
         to_l = (cx < self.x0 + HALO) & self.hl
         to_r = (cx >= self.x1 - HALO) & self.hr
         live = own | ((cx >= self.x0 - HALO) & (cx < self.x1 + HALO))
-        rl, rr = self._records(to_l), self._records(to_r)
-        self.send_l[:rl.size] = torch.from_numpy(rl.reshape(-1)); self.send_r[:rr.size] = torch.from_numpy(rr.reshape(-1))
+        for buf, m in ((self.send_l, to_l), (self.send_r, to_r)):
+            r = self._records(m)
+            assert len(r) <= self.cap
+            buf[0] = float(np.array([len(r)], np.int32).view(np.float32)[0])   # header: payload count
+            buf[F:F + r.size] = torch.from_numpy(r.reshape(-1))
+        self.sent = (int(to_l.sum()), int(to_r.sum()))
         ids = np.where(own, self.ids, self.ids | GHOST)
         self.pos, self.vel, self.ids = self.pos[live], self.vel[live], ids[live]
-        return torch.tensor([int(live.sum()), len(rl), len(rr), int(own.sum())], dtype=torch.int32)
+        self.kept = (self.pos.copy(), self.vel.copy(), self.ids.copy(), int(own.sum()))
 
-    def commit(self, kept, owned):
-        assert kept == len(self.ids)
-        self.n_owned = owned
-
-    def append(self, buf, m):
-        if not m:
-            return
-        r = buf[:m * F].numpy().reshape(m, F).copy()
-        ids = r[:, 7].copy().view(np.int32).astype(np.int64) & (GHOST - 1)
-        cx = cell_x(r[:, 0], self.G.gmin[0], self.G.cell, self.gnx)
-        own = self._own(cx)
-        self.pos = np.concatenate([self.pos, r[:, 0:3]]); self.vel = np.concatenate([self.vel, r[:, 4:7]])
-        self.ids = np.concatenate([self.ids, np.where(own, ids, ids | GHOST)])
-        self.n_owned += int(own.sum())
+    def unpack(self, buf_l, max_l, buf_r, max_r):
+        self.pos, self.vel, self.ids, self.n_owned = self.kept[0], self.kept[1], self.kept[2], self.kept[3]
+        got = []
+        for buf, mx, has in ((buf_l, max_l, self.hl), (buf_r, max_r, self.hr)):
+            if not has or buf is None:
+                got.append(0); continue
+            cnt = int(buf[0:1].numpy().view(np.int32)[0])
+            got.append(cnt)
+            m = min(cnt, mx)
+            if m:
+                r = buf[F:F + m * F].numpy().reshape(m, F).copy()
+                ids = r[:, 7].copy().view(np.int32).astype(np.int64) & (GHOST - 1)
+                cx = cell_x(r[:, 0], self.G.gmin[0], self.G.cell, self.gnx)
+                own = self._own(cx)
+                self.pos = np.concatenate([self.pos, r[:, 0:3]]); self.vel = np.concatenate([self.vel, r[:, 4:7]])
+                self.ids = np.concatenate([self.ids, np.where(own, ids, ids | GHOST)])
+                self.n_owned += int(own.sum())
+        return dict(n_total=len(self.ids), n_owned=self.n_owned, to_left=self.sent[0], to_right=self.sent[1],
+                    from_left=got[0], from_right=got[1])
 
     def step(self):
         # the oracle sums neighbours in ascending array order: present the particles in global-id order

@@ -1,5 +1,5 @@
 """Multi-GPU slab kernels (slab.cu) on ONE GPU: K slab handles driven in one process
-(slabs.LocalSlabGroup: the same pack/commit/append/step calls the NCCL driver makes, the P2P replaced
+(slabs.LocalSlabGroup: the same pack/unpack/step calls the NCCL driver makes, the P2P replaced
 by reading the neighbour's send buffer) must reproduce the single-handle run.
 
 Bar: BIT-EQUAL positions, velocities and densities for every particle after every step -- a slab sees

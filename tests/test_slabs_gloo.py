@@ -32,7 +32,7 @@ def setup(world):
     return port, slabs, P, G, cols
 
 
-def worker(rank, world, port_no, steps, outdir):
+def worker(rank, world, port_no, steps, outdir, cap=4096, floor=None):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
     import torch.distributed as dist
@@ -41,9 +41,12 @@ def worker(rank, world, port_no, steps, outdir):
     os.environ["OMP_NUM_THREADS"] = "2"
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port_no, rank=rank, world_size=world)
     port, slabs, P, G, cols = setup(world)
+    if floor is not None:
+        _ns = slabs.next_size
+        slabs.next_size = lambda count, cap_, floor_=floor: max(floor, count // 2)  # too small on purpose -> every step re-sends
     pos, vel = scene()
     x0, x1 = cols[rank]
-    b = NumpySlabBackend(P, G, x0, x1, rank > 0, rank < world - 1, cap=4096)
+    b = NumpySlabBackend(P, G, x0, x1, rank > 0, rank < world - 1, cap=cap)
     # deliberately start from a WRONG distribution: particles in the two boundary columns of their
     # owner start on the neighbour across that boundary, as if they had just migrated; the first
     # exchange must send them home and mirror them back as ghosts.
@@ -57,11 +60,11 @@ def worker(rank, world, port_no, steps, outdir):
     place[go_r] += 1; place[go_l] -= 1
     mine = place == rank
     b.upload(pos[mine], vel[mine], ids[mine])
-    drv = slabs.SlabDriver(b, slabs.TorchComm(rank, world, torch.device("cpu")))
+    drv = slabs.SlabDriver(b, slabs.TorchComm(rank, world))
     log = []
     for _ in range(steps):
         drv.step()
-        log.append([drv.last[k] for k in ("kept", "owned", "to_left", "to_right", "from_left", "from_right")])
+        log.append([drv.last[k] for k in ("n_total", "n_owned", "to_left", "to_right", "from_left", "from_right")] + [drv.resends])
     i, p, v, r = b.owned()
     np.savez(os.path.join(outdir, "rank%d.npz" % rank), ids=i, pos=p, vel=v, rho=r, log=np.array(log))
     dist.barrier()
@@ -73,8 +76,8 @@ def free_port():
     return p
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_slab_protocol_matches_single_domain(world):
+@pytest.mark.parametrize("world,floor", [(2, None), (3, None), (2, 1)], ids=["w2", "w3", "w2-resend"])
+def test_slab_protocol_matches_single_domain(world, floor):
     steps = 6
     port, slabs, P, G, cols = setup(world)
     pos, vel = scene()
@@ -83,7 +86,7 @@ def test_slab_protocol_matches_single_domain(world):
     with tempfile.TemporaryDirectory() as d:
         ctx = mp.get_context("spawn")
         pn = free_port()
-        procs = [ctx.Process(target=worker, args=(r, world, pn, steps, d)) for r in range(world)]
+        procs = [ctx.Process(target=worker, args=(r, world, pn, steps, d, 4096, floor)) for r in range(world)]
         for p in procs: p.start()
         for p in procs: p.join(300)
         assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
@@ -97,7 +100,8 @@ def test_slab_protocol_matches_single_domain(world):
     logs = [p["log"] for p in parts]
     for r in range(world - 1):   # what r sends right is what r+1 receives from the left, every step
         assert np.array_equal(logs[r][:, 3], logs[r + 1][:, 4]) and np.array_equal(logs[r + 1][:, 2], logs[r][:, 5])
-    assert sum(l[1:, 2:].sum() for l in logs) > 0
+    assert sum(l[1:, 2:6].sum() for l in logs) > 0
+    assert (sum(int(l[-1, 6]) for l in logs) > 0) == (floor is not None), "re-send path exercised only when sizes are forced too small"
     # migrations really happened: ownership after the run differs from the initial cell ownership
     moved = sum(int((l[:, 1][1:] != l[:, 1][:-1]).any()) for l in logs)
     assert moved > 0
