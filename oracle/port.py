@@ -32,7 +32,7 @@ class _State(C.Structure):
 
 
 def build(force=False):
-    src = [os.path.join(_HERE, f) for f in ("sph_oracle.c", "sph_oracle.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("sph_oracle.c", "sph_oracle.h", "terrain_oracle.c", "terrain_oracle.h", "Makefile")]
     if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in src):
         subprocess.check_call(["make", "-s", "-C", _HERE, "oracle"])
     return _LIB
@@ -54,6 +54,12 @@ def lib():
         L.so_neighbours.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
         L.so_neighbours.restype = C.c_long
         L.so_default_params.argtypes = [C.c_void_p]
+        L.so_terrain_collision.argtypes = [C.c_void_p] * 6
+        L.so_terrain_surface.argtypes = [C.c_void_p, C.c_void_p]
+        L.so_terrain_indices.argtypes = [C.c_void_p, C.c_void_p]
+        L.so_terrain_indices.restype = C.c_long
+        L.so_terrain_stage.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_float, C.c_float, C.c_void_p]
         _lib = L
     return _lib
 
@@ -146,3 +152,75 @@ def neighbours(P, G, pos, order, cell_start):
 
 def omp_threads():
     return lib().so_omp_threads()
+
+
+# ----------------------------------------------------------------------------- terrain (terrain_oracle.c)
+FX = 4096  # fixed-point scale of heights and sediment
+
+
+class _Terrain(C.Structure):
+    _fields_ = [("rows", C.c_int), ("cols", C.c_int), ("dimx", C.c_int), ("dimy", C.c_int), ("dimz", C.c_int),
+                ("h", C.c_void_p), ("hfx", C.c_void_p)]
+
+
+class Erosion(C.Structure):
+    _fields_ = [("enabled", C.c_int), ("origin", C.c_float * 3), ("scale", C.c_float), ("Kc", C.c_float),
+                ("Ke", C.c_float), ("Kd", C.c_float), ("hmin_fx", C.c_int), ("max_pickup_fx", C.c_int)]
+
+
+def erosion_params(enabled=True, origin=(0.0, 0.0, 0.0), scale=1.0, Kc=0.05, Ke=0.3, Kd=0.3, hmin=0.0, max_pickup=0.25):
+    E = Erosion()
+    E.enabled = int(enabled); E.origin[:] = list(origin); E.scale = scale
+    E.Kc, E.Ke, E.Kd = Kc, Ke, Kd
+    E.hmin_fx = int(round(hmin * FX)); E.max_pickup_fx = int(round(max_pickup * FX))
+    return E
+
+
+class Terrain:
+    """Heightfield (rows x cols, H(x, z) = h[x, z]) + Grid dims, as Erosion/grid.h holds them."""
+
+    def __init__(self, heights, dims):
+        h = np.ascontiguousarray(heights, np.float32)
+        self.hfx = np.ascontiguousarray(np.rint(h.astype(np.float64) * FX), np.int32)
+        self.h = (self.hfx.astype(np.float32) * np.float32(1.0 / FX)).astype(np.float32)
+        self.dims = tuple(int(d) for d in dims)
+
+    def _c(self):
+        t = _Terrain()
+        t.rows, t.cols = self.h.shape
+        t.dimx, t.dimy, t.dimz = self.dims
+        t.h = _p(self.h); t.hfx = _p(self.hfx)
+        return t
+
+    def collision(self, pc, pn, vn):
+        pc = np.ascontiguousarray(pc, np.float32); pn = np.ascontiguousarray(pn, np.float32)
+        vn = np.ascontiguousarray(vn, np.float32)
+        n = pc.shape[0]
+        hit = np.zeros(n, np.int32); cp = np.zeros((n, 3), np.float32); nrm = np.zeros((n, 3), np.float32)
+        t = self._c()
+        f = lib().so_terrain_collision
+        for i in range(n):
+            hit[i] = f(C.byref(t), _p(pc[i]), _p(pn[i]), _p(vn[i]), _p(cp[i]), _p(nrm[i]))
+        return hit, cp, nrm
+
+    def surface(self):
+        out = np.zeros(self.dims[0] * self.dims[2] * 6, np.float32)
+        t = self._c()
+        lib().so_terrain_surface(C.byref(t), _p(out))
+        return out
+
+    def indices(self):
+        t = self._c()
+        k = lib().so_terrain_indices(C.byref(t), None)
+        out = np.zeros(k, np.uint32)
+        lib().so_terrain_indices(C.byref(t), _p(out))
+        return out
+
+    def stage(self, E, pos_curr, pos_next, vel_next, sediment, dt, cR=0.5):
+        """Terrain stage of the step (contact response + erosion); arrays are updated in place."""
+        n = pos_curr.shape[0]
+        hit = np.zeros(n, np.int32)
+        t = self._c()
+        lib().so_terrain_stage(C.byref(t), C.byref(E), n, _p(pos_curr), _p(pos_next), _p(vel_next), _p(sediment),
+                               C.c_float(dt), C.c_float(cR), _p(hit))
+        return hit

@@ -96,7 +96,51 @@ def add_particles():
     print("add_particles ok", s.count())
 
 
+def terrain_trials(rng, img, n, pen, step, lo=2.5, hi=46.5):
+    """Particle moves ending near the heightfield surface (cells stay inside [1, 47]: at the border the
+    reference reads heights at index -1, undefined behaviour)."""
+    x = rng.uniform(lo, hi, n); z = rng.uniform(lo, hi, n)
+    hloc = img[np.floor(x).astype(int), np.floor(z).astype(int)].astype(np.float32)
+    vdir = rng.normal(0, 1, (n, 3)); vdir[:, 1] = -np.abs(vdir[:, 1]) * 2 - 0.2
+    vdir /= np.linalg.norm(vdir, axis=1)[:, None]
+    pn = np.stack([x, hloc - rng.uniform(0, pen, n) + rng.uniform(-3, 3, n), z], 1)
+    pc = pn - vdir * np.minimum(rng.uniform(0.01, step, n), 1.4)[:, None]
+    vn = vdir * rng.uniform(0.1, 5, n)[:, None]
+    return pc.astype(np.float32), pn.astype(np.float32), vn.astype(np.float32)
+
+
+def terrain():
+    """Grid::collision (grid.h:462-805) and UpdateGrid/genIndices (grid.h:118-176) of the unmodified
+    reference on lena_gray.png, Grid(50, 255, 50) as in main.cpp:100-105.  Only the top-left 64 x 64
+    texels matter for these inputs; they are stored so the test needs no PNG decoder."""
+    from PIL import Image
+    img = np.array(Image.open("/root/reference/Erosion/lena_gray.png"))
+    assert img.shape == (512, 512) and img.dtype == np.uint8
+    g = ref.RefGrid(50, 255, 50); g.load_heightfield(img); g.update(50, 255, 50)
+    rng = np.random.default_rng(0x7E44A1)
+    out = {"hf64": img[:64, :64].copy(), "dims": np.array([50, 255, 50], np.int32)}
+    pcs, pns, vns = [], [], []
+    for pen, step in [(0.02, 0.05), (0.5, 0.5), (3, 1.5), (8, 3.0), (0.1, 1.2)]:
+        pc, pn, vn = terrain_trials(rng, img, 1600, pen, step)
+        pcs.append(pc); pns.append(pn); vns.append(vn)
+    # degenerate inputs: zero velocity (NaN direction), vertical drop onto a vertex, a move along a cell edge
+    pcs.append(np.array([[10.5, 200.0, 10.5], [12.0, 200.0, 12.0], [20.0, float(img[20, 20]) + 0.4, 20.25]], np.float32))
+    pns.append(np.array([[10.5, 10.0, 10.5], [12.0, float(img[12, 12]) - 0.5, 12.0], [20.0, float(img[20, 20]) - 0.3, 20.75]], np.float32))
+    vns.append(np.array([[0, 0, 0], [0, -3, 0], [0, -1, 1]], np.float32))
+    pc, pn, vn = np.concatenate(pcs), np.concatenate(pns), np.concatenate(vns)
+    hit, cp, nrm = g.collision(pc, pn, vn)
+    out.update(pc=pc, pn=pn, vn=vn, hit=hit, cp=cp, nrm=nrm)
+    out["surface"] = g.surface(); out["indices"] = g.indices()
+    out["heights_probe"] = np.array([g.height_at(x, z) for x, z in [(0, 0), (5, 7), (49, 49), (63, 1)]], np.int32)
+    out["voxel_probe"] = np.array([[g.voxel_type(x, int(img[x, z]), z), g.voxel_type(x, int(img[x, z]) - 1, z)] for x, z in [(3, 4), (20, 31)]], np.int32)
+    np.savez_compressed(os.path.join(OUT, "terrain.npz"), **out)
+    print("terrain ok: %d trials, %d hits (%.1f%%), surface %d floats, %d indices" % (len(hit), hit.sum(), 100 * hit.mean(), out["surface"].size, out["indices"].size))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "terrain":
+        terrain(); sys.exit(0)
     default_scene()
     random_state()
     add_particles()
+    terrain()
