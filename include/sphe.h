@@ -185,6 +185,48 @@ int sphe_slab_unpack(sphe_sim* s, const void* dev_recv_left, int max_left, const
 /* Owned particles only, storage order; rho/sed may be NULL. */
 int sphe_slab_download(sphe_sim* s, int cap, int* ids, float* pos, float* vel, float* rho, float* sed, int* n_out);
 
+/* ---- terrain: replacement of the reference's Grid (Erosion/grid.h) ----
+ * Heightfield storage is rows x cols with H(x, z) = map[cols * x + z] (GetHeightfieldAt, grid.h:104-107;
+ * the reference hard-codes 512 x 512, grid.h:78-81); dimx/dimy/dimz are the Grid dimensions used for the
+ * range checks of collision() and for the render mesh (main.cpp:100-105 uses 50, 255, 50).
+ * Heights live on the device in fixed point (1/4096) so that erosion is exactly conservative.
+ * World <-> terrain coordinates: world = origin + scale * terrain (uniform; default identity, like the
+ * reference where 1 cell = 1 world unit). */
+typedef struct sphe_erosion {   /* this project's erosion model (no reference code exists) */
+    int enabled;        /* 0 (default): contact response only */
+    float Kc;           /* carrying capacity per unit tangential speed   [height units / (world unit / s)] */
+    float Ke, Kd;       /* pick-up and deposit rates per step, 0..1 */
+    float hmin;         /* bedrock height: nothing is picked up below it */
+    float max_pickup;   /* per particle per step, height units */
+} sphe_erosion;
+
+int sphe_terrain_create(sphe_terrain** out, int dimx, int dimy, int dimz);              /* Grid(int,int,int) grid.h:72-82 */
+void sphe_terrain_destroy(sphe_terrain* t);
+int sphe_terrain_load_heightfield(sphe_terrain* t, const unsigned char* img_512x512);   /* LoadHeightfield grid.h:98-102 */
+int sphe_terrain_load_heightfield_ex(sphe_terrain* t, const unsigned char* img, int rows, int cols);
+int sphe_terrain_set_heights(sphe_terrain* t, const float* h, int rows, int cols);
+int sphe_terrain_get_heights(sphe_terrain* t, float* h);                                /* rows*cols floats */
+int sphe_terrain_get_heights_fx(sphe_terrain* t, int* hfx);                             /* exact fixed-point heights */
+int sphe_terrain_size(sphe_terrain* t, int* rows, int* cols, int dims[3]);
+int sphe_terrain_height_at(sphe_terrain* t, int x, int y);                              /* GetHeightfieldAt grid.h:104-107; -1 on error */
+int sphe_terrain_update_grid(sphe_terrain* t, int dimx, int dimy, int dimz);            /* UpdateGrid grid.h:138-176 */
+long long sphe_terrain_surface_size(sphe_terrain* t);                                   /* GetSurfacePartsSize grid.h:827 */
+long long sphe_terrain_indices_size(sphe_terrain* t);                                   /* GetIndicesSize grid.h:812 */
+int sphe_terrain_get_surface(sphe_terrain* t, float* out);                              /* GetSurfaceParts grid.h:822: x y z nx ny nz per vertex */
+int sphe_terrain_get_indices(sphe_terrain* t, unsigned* out);                           /* GetIndices grid.h:807 */
+/* Grid::collision (grid.h:462-805), batched: arrays of n packed xyz in TERRAIN coordinates. */
+int sphe_terrain_collision(sphe_terrain* t, int n, const float* pos_curr, const float* pos_next, const float* vel_next,
+                           int* hit, float* contact, float* normal);
+int sphe_terrain_set_transform(sphe_terrain* t, const float origin[3], float scale);
+sphe_erosion* sphe_terrain_erosion_ptr(sphe_terrain* t);   /* host-resident, re-read by every step (like sphe_params_ptr) */
+/* The terrain stage of sphe_step on caller-provided arrays (world coordinates; sediment fixed point):
+ * contact response (the call commented out at fluid_system.h:335-340) + erosion, no box collision. */
+int sphe_terrain_stage_host(sphe_terrain* t, int n, const float* pos_curr, float* pos_next, float* vel_next, int* sediment,
+                            float dt, float cR, int* hit);
+int sphe_terrain_total_fx(sphe_terrain* t, long long* sum);     /* sum of all heights, fixed point */
+int sphe_sediment_total_fx(sphe_sim* s, long long* sum);        /* sum of carried sediment (owned particles), fixed point */
+int sphe_set_sediment_fx(sphe_sim* s, const int* sediment_by_id);
+
 /* ---- raw device access for multi-GPU plumbing (halo exchange lives above this ABI) ---- */
 enum { SPHE_D_POSQ = 0, SPHE_D_VELV = 1, SPHE_D_IDS = 2, SPHE_D_RHO = 3 };
 void* sphe_device_ptr(sphe_sim* s, int which);

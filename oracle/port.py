@@ -50,6 +50,9 @@ def lib():
         L.so_step_allpairs.argtypes = [C.c_void_p, C.c_void_p]
         L.so_step_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.so_grid_for_box.argtypes = [C.c_void_p] * 4
+        L.so_forces_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.so_integrate.argtypes = [C.c_void_p] * 4
+        L.so_box.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.so_bin.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
         L.so_neighbours.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
         L.so_neighbours.restype = C.c_long
@@ -129,6 +132,20 @@ def step_grid(P, G, S, steps=1):
     cs = S._c()
     for _ in range(steps):
         lib().so_step_grid(C.byref(P), C.byref(G), C.byref(cs))
+
+
+def step_grid_terrain(P, G, S, T, E, sediment, cR=0.5):
+    """One step with a terrain attached: passes 1-3, integration, terrain stage (contact response +
+    erosion, oracle/terrain_oracle.c), then the box collision -- the order of fluid_system.h:335-347
+    with the commented call live.  sediment: int32 fixed point, updated in place.  Returns hit flags."""
+    cs = S._c()
+    lib().so_forces_grid(C.byref(P), C.byref(G), C.byref(cs))
+    pn = np.zeros_like(S.pos); vn = np.zeros_like(S.vel)
+    lib().so_integrate(C.byref(P), C.byref(cs), _p(pn), _p(vn))
+    hit = T.stage(E, S.pos, pn, vn, sediment, P.dt, cR)
+    lib().so_box(C.byref(P), S.n, _p(pn), _p(vn))
+    S.pos[:] = pn; S.vel[:] = vn
+    return hit
 
 
 def bin_particles(G, pos):

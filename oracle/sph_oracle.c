@@ -139,24 +139,41 @@ static int collisionS(float len, v3 pos, v3* contactP, v3* normal) {
     return 1;
 }
 
-/* advance(), fluid_system.h:306-353 */
-static void advance_one(const so_params* P, so_state* S, int i) {
+/* advance(), fluid_system.h:306-353, split in two so that the terrain stage (the commented call at
+ * :335-340) can run between the integration and the box collision. */
+static void integrate_one(const so_params* P, so_state* S, int i, v3* posNext, v3* velNext) {
     v3 fInternal = add3(ld3(S->fpress, i), ld3(S->fvisc, i));
     v3 fExternal = add3(ld3(S->fgrav, i), ld3(S->fsurf, i));
     v3 F = add3(fInternal, fExternal);
     v3 acc = div3s(F, S->density[i]);
     st3(S->acc, i, acc);
     float deltaT = P->dt;
-    v3 velNext = add3(ld3(S->vel, i), mul3s(acc, deltaT));
-    v3 posNext = add3(ld3(S->pos, i), mul3s(velNext, deltaT));
+    *velNext = add3(ld3(S->vel, i), mul3s(acc, deltaT));
+    *posNext = add3(ld3(S->pos, i), mul3s(*velNext, deltaT));
+}
+static void box_one(const so_params* P, v3* posNext, v3* velNext) {
+    float deltaT = P->dt;
     v3 contactP = mk3(0, 0, 0), norm = mk3(0, 0, 0);
-    if (collisionS(P->len, posNext, &contactP, &norm) && deltaT != 0) {
-        float d = len3(sub3(posNext, contactP));
-        velNext = sub3(velNext, mul3s(mul3s(norm, (float)(1 + 0.5f * d / (deltaT * len3(velNext)))), dot3(velNext, norm)));
-        posNext = contactP;
+    if (collisionS(P->len, *posNext, &contactP, &norm) && deltaT != 0) {
+        float d = len3(sub3(*posNext, contactP));
+        *velNext = sub3(*velNext, mul3s(mul3s(norm, (float)(1 + 0.5f * d / (deltaT * len3(*velNext)))), dot3(*velNext, norm)));
+        *posNext = contactP;
     }
+}
+static void advance_one(const so_params* P, so_state* S, int i) {
+    v3 posNext, velNext;
+    integrate_one(P, S, i, &posNext, &velNext);
+    box_one(P, &posNext, &velNext);
     st3(S->vel, i, velNext);
     st3(S->pos, i, posNext);
+}
+
+/* the two halves for callers that insert the terrain stage (tests of sphe_step with a terrain) */
+void so_integrate(const so_params* P, so_state* S, float* pos_next, float* vel_next) {
+    for (int i = 0; i < S->n; i++) { v3 p, v; integrate_one(P, S, i, &p, &v); st3(pos_next, i, p); st3(vel_next, i, v); }
+}
+void so_box(const so_params* P, int n, float* pos_next, float* vel_next) {
+    for (int i = 0; i < n; i++) { v3 p = ld3(pos_next, i), v = ld3(vel_next, i); box_one(P, &p, &v); st3(pos_next, i, p); st3(vel_next, i, v); }
 }
 
 void so_step_allpairs(const so_params* P, so_state* S) {
@@ -268,7 +285,7 @@ static void isort(int* a, int m) {
     for (int i = 1; i < m; i++) { int v = a[i], k = i - 1; while (k >= 0 && a[k] > v) { a[k + 1] = a[k]; k--; } a[k + 1] = v; }
 }
 
-void so_step_grid(const so_params* P, const so_grid* G, so_state* S) {
+void so_forces_grid(const so_params* P, const so_grid* G, so_state* S) {
     int n = S->n;
     long ncells = (long)G->dim[0] * G->dim[1] * G->dim[2];
     int* cell_of = (int*)malloc((size_t)n * sizeof(int));
@@ -324,10 +341,14 @@ void so_step_grid(const so_params* P, const so_grid* G, so_state* S) {
         for (long q = ns[i]; q < ns[i + 1]; q++) p3_pair(P, S, i, nb[q], &cfl);
         st3(S->fsurf, i, smul3(-P->surf_tens * cfl, ld3(S->normal, i)));
     }
+    free(nb); free(cnt); free(ns); free(cell_start); free(order); free(cell_of);
+}
+
+void so_step_grid(const so_params* P, const so_grid* G, so_state* S) {
+    int n = S->n;
+    so_forces_grid(P, G, S);
 #pragma omp parallel for schedule(static)
     for (int i = 0; i < n; i++) advance_one(P, S, i);
-
-    free(nb); free(cnt); free(ns); free(cell_start); free(order); free(cell_of);
 }
 
 int so_omp_threads(void) {

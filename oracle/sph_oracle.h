@@ -66,6 +66,12 @@ long so_neighbours(const so_params* P, const so_grid* G, int n, const float* pos
  * order so every sum is bit-identical to the all-pairs loops.  OpenMP over particles. */
 void so_step_grid(const so_params* P, const so_grid* G, so_state* S);
 
+/* so_step_grid in pieces: passes 1-3 only; integration without the box; the box collision alone.
+ * so_step_grid == so_forces_grid + so_integrate + so_box + store. */
+void so_forces_grid(const so_params* P, const so_grid* G, so_state* S);
+void so_integrate(const so_params* P, so_state* S, float* pos_next, float* vel_next);
+void so_box(const so_params* P, int n, float* pos_next, float* vel_next);
+
 int so_omp_threads(void);
 
 #ifdef __cplusplus

@@ -32,6 +32,10 @@ def needs_build():
     return any(os.path.getmtime(f) > t for f in _deps())
 
 
+# per-file extra flags: the terrain contact search must round every multiply/add separately (terrain.cu)
+EXTRA = {"terrain.cu": ["-fmad=false"]}
+
+
 def build_library(force=False, verbose=False):
     """nvcc -gencode arch=compute_100a,code=sm_100a ... -> sph-erosion_b200/lib/libsphe_b200.so"""
     if not force and not needs_build():
@@ -40,8 +44,19 @@ def build_library(force=False, verbose=False):
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found and %s is missing or stale" % LIB)
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
-    subprocess.check_call(cmd, cwd=HERE)
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    procs, objs = [], []
+    for src in sources():
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        cmd = [nvcc] + compile_flags + EXTRA.get(os.path.basename(src), []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        procs.append((cmd, subprocess.Popen(cmd, cwd=HERE)))
+    for cmd, p in procs:
+        if p.wait() != 0:
+            raise subprocess.CalledProcessError(p.returncode, cmd)
+    subprocess.check_call([nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs, cwd=HERE)
     return LIB
 
 

@@ -26,6 +26,11 @@ class Particle(C.Structure):
                 ("surface_normal", C.c_float * 3), ("neighb_id", C.c_int)]
 
 
+class Erosion(C.Structure):
+    _fields_ = [("enabled", C.c_int), ("Kc", C.c_float), ("Ke", C.c_float), ("Kd", C.c_float), ("hmin", C.c_float),
+                ("max_pickup", C.c_float)]
+
+
 class GridInfo(C.Structure):
     _fields_ = [("gmin", C.c_float * 3), ("cell", C.c_float), ("dim", C.c_int * 3)]
 
@@ -68,6 +73,27 @@ SYMBOLS = {
     "sphe_set_stream": (_i, [_vp, _vp]),
     "sphe_set_variant": (_i, [_vp, _i, _i]),
     "sphe_set_box": (_i, [_vp, _vp]),
+    "sphe_terrain_create": (_i, [C.POINTER(_vp), _i, _i, _i]),
+    "sphe_terrain_destroy": (None, [_vp]),
+    "sphe_terrain_load_heightfield": (_i, [_vp, _vp]),
+    "sphe_terrain_load_heightfield_ex": (_i, [_vp, _vp, _i, _i]),
+    "sphe_terrain_set_heights": (_i, [_vp, _vp, _i, _i]),
+    "sphe_terrain_get_heights": (_i, [_vp, _vp]),
+    "sphe_terrain_get_heights_fx": (_i, [_vp, _vp]),
+    "sphe_terrain_size": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), _vp]),
+    "sphe_terrain_height_at": (_i, [_vp, _i, _i]),
+    "sphe_terrain_update_grid": (_i, [_vp, _i, _i, _i]),
+    "sphe_terrain_surface_size": (_ll, [_vp]),
+    "sphe_terrain_indices_size": (_ll, [_vp]),
+    "sphe_terrain_get_surface": (_i, [_vp, _vp]),
+    "sphe_terrain_get_indices": (_i, [_vp, _vp]),
+    "sphe_terrain_collision": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sphe_terrain_set_transform": (_i, [_vp, _vp, _f]),
+    "sphe_terrain_erosion_ptr": (C.POINTER(Erosion), [_vp]),
+    "sphe_terrain_stage_host": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _f, _f, _vp]),
+    "sphe_terrain_total_fx": (_i, [_vp, C.POINTER(_ll)]),
+    "sphe_sediment_total_fx": (_i, [_vp, C.POINTER(_ll)]),
+    "sphe_set_sediment_fx": (_i, [_vp, _vp]),
     "sphe_kernel_timing": (_i, [_vp, _i]),
     "sphe_kernel_times": (_i, [_vp, C.POINTER(_f), C.POINTER(_i)]),
     "sphe_slab_configure": (_i, [_vp, _i, _i, _i, _i]),

@@ -40,6 +40,23 @@ struct KTimer {
     cudaEvent_t a, b;
 };
 
+struct sphe_terrain {
+    int dimx, dimy, dimz;          // Grid dims (grid.h:29-32)
+    int rows = 512, cols = 512;    // heightfield storage; the reference hard-codes 512 x 512 (grid.h:78-81)
+    int device = -1;
+    bool ready = false;
+    int *hfx = nullptr, *want = nullptr, *delta = nullptr, *hmax = nullptr;
+    size_t cells_cap = 0;
+    float origin[3] = {0.f, 0.f, 0.f};
+    float scale = 1.0f;
+    sphe_erosion E;
+    float* d_surface = nullptr;
+    unsigned* d_indices = nullptr;
+    long long surface_floats = 0, index_count = 0;
+    long long* d_sum = nullptr;
+    sphe_terrain() { E.enabled = 0; E.Kc = 0.05f; E.Ke = 0.3f; E.Kd = 0.3f; E.hmin = 0.0f; E.max_pickup = 0.25f; }
+};
+
 struct sphe_sim {
     sphe_params P;
     float origin[3] = {0, 0, 0};
@@ -60,6 +77,7 @@ struct sphe_sim {
     uint2* tmp = nullptr;
     float* stage = nullptr;  // 10 * cap floats: id-order staging for uploads/downloads
     int* slot_of_id = nullptr;
+    int *req_vertex = nullptr, *req_amount = nullptr;  // terrain stage: pending pick-up requests per particle
     bool slot_valid = false;
     int* nlist = nullptr;   // variant 3: [nlist_cap][pairs_pad] neighbour indices
     int2* ncount = nullptr;
@@ -152,6 +170,8 @@ static int reserve(sphe_sim* s, int need) {
     TRY(grow(&s->tmp, 0, nc, s->st, false));
     TRY(grow(&s->stage, 0, nc * 10, s->st, false));
     TRY(grow(&s->slot_of_id, 0, nc, s->st, false));
+    TRY(grow(&s->req_vertex, 0, nc, s->st, false));
+    TRY(grow(&s->req_amount, 0, nc, s->st, false));
     s->cap = (int)nc;
     s->binned = false;
     s->slot_valid = false;
@@ -199,7 +219,7 @@ static StepC make_consts(const sphe_params& P) {
     C.mass = P.mass; C.k = P.k; C.p0 = P.p0; C.visc = P.visc; C.surf = P.surf_tens;
     C.gx = P.g[0]; C.gy = P.g[1]; C.gz = P.g[2];
     C.dt = P.dt; C.len = P.len; C.cR = P.cR;
-    C.lenx = C.leny = C.lenz = P.len; C.cube = 1;
+    C.lenx = C.leny = C.lenz = P.len; C.cube = 1; C.box = 1;
     float c315 = (float)(315.0f / (64.0f * PI_REF * powf(h, 9.0f)));  // fluid_system.h:415
     C.densK = P.mass * c315;
     C.c45 = (float)(45.f / (PI_REF * powf(h, 6.0f)));                 // :442, :452
@@ -267,9 +287,12 @@ struct Scope {
 };
 
 // ------------------------------------------------------------------ the step
+static int terrain_ready(sphe_terrain* t);
+static TerrainDev terrain_view(const sphe_terrain* t);
+
 static int step_device(sphe_sim* s, sphe_terrain* t) {
-    (void)t;
     TRY(ensure_device(s));
+    if (t) TRY(terrain_ready(t));
     if (s->n == 0) return SPHE_OK;
     TRY(setup_grid(s));
     TRY(reserve_diag(s));
@@ -279,6 +302,7 @@ static int step_device(sphe_sim* s, sphe_terrain* t) {
         C.cube = (C.lenx == C.leny && C.leny == C.lenz) ? 1 : 0;
     }
     if (s->slab_on && s->diag) return fail(SPHE_ERR_STATE, "per-particle diagnostics are indexed by local id and are not available in slab mode");
+    if (t) C.box = 0;  // with a terrain the box collision runs after the terrain contact (fluid_system.h:335-347)
     s->lastC = C;
     int n = s->n;
     { Scope k(s, SPHE_K_HASH); launch_hash(s->st, n, s->posA, s->G, s->cell, s->count); }
@@ -302,6 +326,11 @@ static int step_device(sphe_sim* s, sphe_terrain* t) {
     { Scope k(s, SPHE_K_FORCE);
       launch_force(s->st, s->variant_force, n, s->posC, s->velB, s->rho, s->idsB, s->cell_sorted, s->cell_start, s->G, C,
                    s->posA, s->velA, s->diag ? &s->D : nullptr, s->nlist, s->ncount); }
+    if (t) {
+        TerrainDev T = terrain_view(t);
+        Scope k(s, SPHE_K_TERRAIN, terrain_stage_launches(C, T));
+        launch_terrain_stage(s->st, n, s->posC, s->posA, s->velA, (int*)s->sedB, C, T, 1, s->req_vertex, s->req_amount, nullptr);
+    }
     std::swap(s->idsA, s->idsB);
     std::swap(s->sedA, s->sedB);
     s->binned = true;
@@ -378,7 +407,7 @@ void sphe_destroy(sphe_sim* s) {
         cudaSetDevice(s->device);
         cudaStreamSynchronize(s->st);
         void* ptrs[] = {s->posA, s->posB, s->posC, s->velA, s->velB, s->idsA, s->idsB, s->sedA, s->sedB, s->rho, s->cell,
-                        s->cell_sorted, s->tmp, s->stage, s->slot_of_id, s->nlist, s->ncount, s->count, s->cell_start, s->cursor, s->tile_sum,
+                        s->cell_sorted, s->tmp, s->stage, s->slot_of_id, s->req_vertex, s->req_amount, s->nlist, s->ncount, s->count, s->cell_start, s->cursor, s->tile_sum,
                         s->flush_buf, s->slab_counters, s->D.acc, s->D.fpress, s->D.fvisc, s->D.fgrav, s->D.fsurf, s->D.normal, s->D.neighb};
         for (void* p : ptrs) if (p) cudaFree(p);
         if (s->slab_host) cudaFreeHost(s->slab_host);
@@ -648,10 +677,16 @@ int sphe_download(sphe_sim* s, int field, void* out) {
         for (int i = 0; i < n; i++) f[i] = s->lastC.k * (f[i] - s->lastC.p0);
         break;
     }
-    case SPHE_F_SEDIMENT:
+    case SPHE_F_SEDIMENT: {
+        // carried sediment is fixed point (1/4096 height units) on the device
         launch_unsort_f1(s->st, n, s->sedA, s->idsA, stage);
         CU(cudaMemcpyAsync(out, stage, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->st));
+        CU(cudaStreamSynchronize(s->st));
+        float* f = (float*)out;
+        const int* q = (const int*)out;
+        for (int i = 0; i < n; i++) f[i] = (float)q[i] * (1.0f / 4096.0f);
         break;
+    }
     case SPHE_F_ID: {
         int* o = (int*)out;
         if (s->labels.empty()) for (int i = 0; i < n; i++) o[i] = i;
@@ -919,6 +954,295 @@ void* sphe_device_ptr(sphe_sim* s, int which) {
     case SPHE_D_RHO: return s->rho;
     }
     return nullptr;
+}
+
+}  // extern "C"
+
+// ================================================================== terrain (replacement of Grid)
+static int terrain_alloc(sphe_terrain* t, int rows, int cols) {
+    size_t cells = (size_t)rows * cols;
+    if (cells > t->cells_cap) {
+        cudaFree(t->hfx); cudaFree(t->want); cudaFree(t->delta);
+        t->hfx = t->want = t->delta = nullptr;
+        cudaError_t e = cudaMalloc(&t->hfx, cells * sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc(&t->want, cells * sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc(&t->delta, cells * sizeof(int));
+        if (e != cudaSuccess) return fail(SPHE_ERR_NOMEM, "terrain %d x %d: %s", rows, cols, cudaGetErrorString(e));
+        t->cells_cap = cells;
+    }
+    t->rows = rows; t->cols = cols;
+    CU(cudaMemset(t->hfx, 0, cells * sizeof(int)));
+    CU(cudaMemset(t->want, 0, cells * sizeof(int)));
+    CU(cudaMemset(t->delta, 0, cells * sizeof(int)));
+    CU(cudaMemset(t->hmax, 0, sizeof(int)));
+    return SPHE_OK;
+}
+
+static int terrain_ready(sphe_terrain* t) {
+    if (!t) return fail(SPHE_ERR_ARG, "NULL terrain");
+    if (t->ready) { CU(cudaSetDevice(t->device)); return SPHE_OK; }
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt == 0)
+        return fail(SPHE_ERR_CUDA, "no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    if (t->device < 0) CU(cudaGetDevice(&t->device));
+    CU(cudaSetDevice(t->device));
+    CU(cudaMalloc(&t->hmax, sizeof(int)));
+    CU(cudaMalloc(&t->d_sum, sizeof(long long)));
+    TRY(terrain_alloc(t, t->rows, t->cols));  // Grid(): 512 x 512 heightfield, zeroed (grid.h:78-81)
+    t->ready = true;
+    return SPHE_OK;
+}
+
+static TerrainDev terrain_view(const sphe_terrain* t) {
+    TerrainDev T;
+    T.rows = t->rows; T.cols = t->cols; T.dimx = t->dimx; T.dimy = t->dimy; T.dimz = t->dimz;
+    T.hfx = t->hfx; T.hfx_rw = t->hfx; T.want = t->want; T.delta = t->delta; T.hmax_fx = t->hmax; T.hmax_rw = t->hmax;
+    T.ox = t->origin[0]; T.oy = t->origin[1]; T.oz = t->origin[2]; T.scale = t->scale; T.inv_scale = 1.0f / t->scale;
+    T.Kc = t->E.Kc; T.Ke = t->E.Ke; T.Kd = t->E.Kd;
+    T.hmin_fx = (int)lrint((double)t->E.hmin * 4096.0); T.max_pickup_fx = (int)lrint((double)t->E.max_pickup * 4096.0);
+    T.erosion = t->E.enabled ? 1 : 0;
+    return T;
+}
+
+extern "C" {
+
+int sphe_terrain_create(sphe_terrain** out, int dimx, int dimy, int dimz) {
+    if (!out || dimx < 1 || dimy < 1 || dimz < 1) return fail(SPHE_ERR_ARG, "bad terrain dimensions");
+    sphe_terrain* t = new sphe_terrain();
+    t->dimx = dimx; t->dimy = dimy; t->dimz = dimz;
+    *out = t;
+    return SPHE_OK;
+}
+
+void sphe_terrain_destroy(sphe_terrain* t) {
+    if (!t) return;
+    if (t->ready) {
+        cudaSetDevice(t->device);
+        cudaDeviceSynchronize();
+        void* ptrs[] = {t->hfx, t->want, t->delta, t->hmax, t->d_surface, t->d_indices, t->d_sum};
+        for (void* p : ptrs) if (p) cudaFree(p);
+    }
+    delete t;
+}
+
+int sphe_terrain_load_heightfield_ex(sphe_terrain* t, const unsigned char* img, int rows, int cols) {
+    if (!t || !img || rows < 2 || cols < 2) return fail(SPHE_ERR_ARG, "bad arguments");
+    TRY(terrain_ready(t));
+    CU(cudaDeviceSynchronize());
+    TRY(terrain_alloc(t, rows, cols));
+    size_t cells = (size_t)rows * cols;
+    unsigned char* d = nullptr;
+    CU(cudaMalloc(&d, cells));
+    CU(cudaMemcpy(d, img, cells, cudaMemcpyHostToDevice));  // the caller keeps ownership of img (main.cpp:102-103)
+    launch_heights_from_u8(0, (int)cells, d, t->hfx, t->hmax);
+    CU(cudaDeviceSynchronize());
+    CU(cudaFree(d));
+    return SPHE_OK;
+}
+
+int sphe_terrain_load_heightfield(sphe_terrain* t, const unsigned char* img) {
+    return sphe_terrain_load_heightfield_ex(t, img, 512, 512);  // LoadHeightfield, grid.h:98-102
+}
+
+int sphe_terrain_set_heights(sphe_terrain* t, const float* h, int rows, int cols) {
+    if (!t || !h || rows < 2 || cols < 2) return fail(SPHE_ERR_ARG, "bad arguments");
+    TRY(terrain_ready(t));
+    CU(cudaDeviceSynchronize());
+    TRY(terrain_alloc(t, rows, cols));
+    size_t cells = (size_t)rows * cols;
+    float* d = nullptr;
+    CU(cudaMalloc(&d, cells * sizeof(float)));
+    CU(cudaMemcpy(d, h, cells * sizeof(float), cudaMemcpyHostToDevice));
+    launch_heights_from_f32(0, (int)cells, d, t->hfx, t->hmax);
+    CU(cudaDeviceSynchronize());
+    CU(cudaFree(d));
+    return SPHE_OK;
+}
+
+int sphe_terrain_get_heights(sphe_terrain* t, float* h) {
+    if (!t || !h) return fail(SPHE_ERR_ARG, "bad arguments");
+    TRY(terrain_ready(t));
+    CU(cudaDeviceSynchronize());
+    size_t cells = (size_t)t->rows * t->cols;
+    float* d = nullptr;
+    CU(cudaMalloc(&d, cells * sizeof(float)));
+    launch_heights_to_f32(0, (int)cells, t->hfx, d);
+    CU(cudaMemcpy(h, d, cells * sizeof(float), cudaMemcpyDeviceToHost));
+    CU(cudaFree(d));
+    return SPHE_OK;
+}
+
+int sphe_terrain_get_heights_fx(sphe_terrain* t, int* hfx) {
+    if (!t || !hfx) return fail(SPHE_ERR_ARG, "bad arguments");
+    TRY(terrain_ready(t));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(hfx, t->hfx, (size_t)t->rows * t->cols * sizeof(int), cudaMemcpyDeviceToHost));
+    return SPHE_OK;
+}
+
+int sphe_terrain_size(sphe_terrain* t, int* rows, int* cols, int dims[3]) {
+    if (!t) return fail(SPHE_ERR_ARG, "NULL terrain");
+    if (rows) *rows = t->rows;
+    if (cols) *cols = t->cols;
+    if (dims) { dims[0] = t->dimx; dims[1] = t->dimy; dims[2] = t->dimz; }
+    return SPHE_OK;
+}
+
+int sphe_terrain_height_at(sphe_terrain* t, int x, int y) {
+    if (!t || x < 0 || y < 0 || x >= t->rows || y >= t->cols) { fail(SPHE_ERR_ARG, "height index out of range"); return -1; }
+    if (terrain_ready(t) != SPHE_OK) return -1;
+    int v = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(&v, t->hfx + (size_t)t->cols * x + y, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        fail(SPHE_ERR_CUDA, "height read failed");
+        return -1;
+    }
+    v >>= 12;  // GetHeightfieldAt returns unsigned char (grid.h:104-107): integer part, saturated
+    return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+int sphe_terrain_set_transform(sphe_terrain* t, const float origin[3], float scale) {
+    if (!t || !origin || !(scale > 0.0f)) return fail(SPHE_ERR_ARG, "bad arguments");
+    memcpy(t->origin, origin, sizeof t->origin);
+    t->scale = scale;
+    return SPHE_OK;
+}
+
+sphe_erosion* sphe_terrain_erosion_ptr(sphe_terrain* t) { return t ? &t->E : nullptr; }
+
+int sphe_terrain_update_grid(sphe_terrain* t, int dimx, int dimy, int dimz) {
+    if (!t || dimx < 1 || dimy < 1 || dimz < 1) return fail(SPHE_ERR_ARG, "bad terrain dimensions");
+    TRY(terrain_ready(t));
+    CU(cudaDeviceSynchronize());
+    t->dimx = dimx; t->dimy = dimy; t->dimz = dimz;
+    long long nv = (long long)dimx * dimz, nq = (long long)(dimx - 1) * (dimz - 1);
+    cudaFree(t->d_surface); cudaFree(t->d_indices);
+    t->d_surface = nullptr; t->d_indices = nullptr;
+    CU(cudaMalloc(&t->d_surface, (size_t)std::max<long long>(nv * 6, 1) * sizeof(float)));
+    CU(cudaMalloc(&t->d_indices, (size_t)std::max<long long>(nq * 6, 1) * sizeof(unsigned)));
+    TerrainDev T = terrain_view(t);
+    launch_terrain_surface(0, T, t->d_surface);
+    launch_terrain_indices(0, dimx, dimz, t->d_indices);
+    CU(cudaDeviceSynchronize());
+    t->surface_floats = nv * 6; t->index_count = nq * 6;
+    return SPHE_OK;
+}
+
+long long sphe_terrain_surface_size(sphe_terrain* t) { return t ? t->surface_floats : 0; }
+long long sphe_terrain_indices_size(sphe_terrain* t) { return t ? t->index_count : 0; }
+
+int sphe_terrain_get_surface(sphe_terrain* t, float* out) {
+    if (!t || !out) return fail(SPHE_ERR_ARG, "bad arguments");
+    if (!t->d_surface) return fail(SPHE_ERR_STATE, "call sphe_terrain_update_grid first");
+    CU(cudaSetDevice(t->device));
+    CU(cudaMemcpy(out, t->d_surface, (size_t)t->surface_floats * sizeof(float), cudaMemcpyDeviceToHost));
+    return SPHE_OK;
+}
+
+int sphe_terrain_get_indices(sphe_terrain* t, unsigned* out) {
+    if (!t || !out) return fail(SPHE_ERR_ARG, "bad arguments");
+    if (!t->d_indices) return fail(SPHE_ERR_STATE, "call sphe_terrain_update_grid first");
+    CU(cudaSetDevice(t->device));
+    CU(cudaMemcpy(out, t->d_indices, (size_t)t->index_count * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    return SPHE_OK;
+}
+
+int sphe_terrain_collision(sphe_terrain* t, int n, const float* pos_curr, const float* pos_next, const float* vel_next,
+                           int* hit, float* contact, float* normal) {
+    if (!t || n < 0 || (n > 0 && (!pos_curr || !pos_next || !vel_next || !hit || !contact || !normal)))
+        return fail(SPHE_ERR_ARG, "bad arguments");
+    if (n == 0) return SPHE_OK;
+    TRY(terrain_ready(t));
+    CU(cudaDeviceSynchronize());
+    float* d = nullptr;
+    int* dh = nullptr;
+    size_t v = 3 * (size_t)n;
+    CU(cudaMalloc(&d, 5 * v * sizeof(float)));
+    CU(cudaMalloc(&dh, (size_t)n * sizeof(int)));
+    CU(cudaMemcpy(d, pos_curr, v * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d + v, pos_next, v * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d + 2 * v, vel_next, v * sizeof(float), cudaMemcpyHostToDevice));
+    launch_terrain_collide(0, n, d, d + v, d + 2 * v, terrain_view(t), dh, d + 3 * v, d + 4 * v);
+    CU(cudaMemcpy(hit, dh, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(contact, d + 3 * v, v * sizeof(float), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(normal, d + 4 * v, v * sizeof(float), cudaMemcpyDeviceToHost));
+    CU(cudaFree(d)); CU(cudaFree(dh));
+    return SPHE_OK;
+}
+
+int sphe_terrain_stage_host(sphe_terrain* t, int n, const float* pos_curr, float* pos_next, float* vel_next, int* sediment,
+                            float dt, float cR, int* hit) {
+    if (!t || n <= 0 || !pos_curr || !pos_next || !vel_next || !sediment) return fail(SPHE_ERR_ARG, "bad arguments");
+    TRY(terrain_ready(t));
+    CU(cudaDeviceSynchronize());
+    float4 *po = nullptr, *pn = nullptr, *vn = nullptr;
+    int *sd = nullptr, *rq = nullptr, *dh = nullptr;
+    CU(cudaMalloc(&po, (size_t)n * sizeof(float4))); CU(cudaMalloc(&pn, (size_t)n * sizeof(float4)));
+    CU(cudaMalloc(&vn, (size_t)n * sizeof(float4))); CU(cudaMalloc(&sd, (size_t)n * sizeof(int)));
+    CU(cudaMalloc(&rq, 2 * (size_t)n * sizeof(int))); CU(cudaMalloc(&dh, (size_t)n * sizeof(int)));
+    std::vector<float4> a((size_t)n), b((size_t)n), c((size_t)n);
+    for (int i = 0; i < n; i++) {
+        a[i] = make_float4(pos_curr[3 * i], pos_curr[3 * i + 1], pos_curr[3 * i + 2], 0.f);
+        b[i] = make_float4(pos_next[3 * i], pos_next[3 * i + 1], pos_next[3 * i + 2], 0.f);
+        c[i] = make_float4(vel_next[3 * i], vel_next[3 * i + 1], vel_next[3 * i + 2], 0.f);
+    }
+    CU(cudaMemcpy(po, a.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(pn, b.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(vn, c.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(sd, sediment, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+    StepC C{};
+    C.dt = dt; C.cR = cR; C.box = 0; C.cube = 1; C.lenx = C.leny = C.lenz = C.len = 3.0e38f;
+    launch_terrain_stage(0, n, po, pn, vn, sd, C, terrain_view(t), 0, rq, rq + n, dh);
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(b.data(), pn, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(c.data(), vn, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(sediment, sd, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+    if (hit) CU(cudaMemcpy(hit, dh, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) {
+        pos_next[3 * i] = b[i].x; pos_next[3 * i + 1] = b[i].y; pos_next[3 * i + 2] = b[i].z;
+        vel_next[3 * i] = c[i].x; vel_next[3 * i + 1] = c[i].y; vel_next[3 * i + 2] = c[i].z;
+    }
+    cudaFree(po); cudaFree(pn); cudaFree(vn); cudaFree(sd); cudaFree(rq); cudaFree(dh);
+    return SPHE_OK;
+}
+
+int sphe_terrain_total_fx(sphe_terrain* t, long long* sum) {
+    if (!t || !sum) return fail(SPHE_ERR_ARG, "bad arguments");
+    TRY(terrain_ready(t));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemset(t->d_sum, 0, sizeof(long long)));
+    launch_sum_i32(0, t->rows * t->cols, t->hfx, nullptr, t->d_sum);
+    CU(cudaMemcpy(sum, t->d_sum, sizeof(long long), cudaMemcpyDeviceToHost));
+    return SPHE_OK;
+}
+
+int sphe_sediment_total_fx(sphe_sim* s, long long* sum) {
+    if (!s || !sum) return fail(SPHE_ERR_ARG, "bad arguments");
+    TRY(ensure_device(s));
+    *sum = 0;
+    if (s->n == 0) return SPHE_OK;
+    long long* d = nullptr;
+    CU(cudaMalloc(&d, sizeof(long long)));
+    CU(cudaMemsetAsync(d, 0, sizeof(long long), s->st));
+    launch_sum_i32(s->st, s->n, (const int*)s->sedA, s->slab_on ? s->idsA : nullptr, d);
+    CU(cudaMemcpyAsync(sum, d, sizeof(long long), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    CU(cudaFree(d));
+    return SPHE_OK;
+}
+
+int sphe_set_sediment_fx(sphe_sim* s, const int* sediment_by_id) {
+    if (!s || !sediment_by_id) return fail(SPHE_ERR_ARG, "bad arguments");
+    if (s->slab_on) return fail(SPHE_ERR_STATE, "not available in slab mode");
+    TRY(ensure_device(s));
+    if (s->n == 0) return SPHE_OK;
+    std::vector<int> ids((size_t)s->n), out((size_t)s->n);
+    CU(cudaMemcpyAsync(ids.data(), s->idsA, (size_t)s->n * sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    for (int i = 0; i < s->n; i++) out[i] = sediment_by_id[ids[i]];
+    CU(cudaMemcpyAsync(s->sedA, out.data(), (size_t)s->n * sizeof(int), cudaMemcpyHostToDevice, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    return SPHE_OK;
 }
 
 }  // extern "C"

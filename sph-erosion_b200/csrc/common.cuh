@@ -31,6 +31,7 @@ struct StepC {
     float gx, gy, gz;
     float dt, len, cR;
     float lenx, leny, lenz;   // per-axis box half-extents (all = len unless sphe_set_box was called)
+    int box;                  // 0: the box collision is applied by the terrain stage instead (terrain.cu)
     int cube;                 // 1: the reference's cubic box, compare |coord| directly (fluid_system.h:362-371)
     float densK;              // mass * 315/(64 PI h^9)
     float c45;                // 45/(PI h^6)
@@ -57,4 +58,34 @@ __device__ __forceinline__ void cell_coords(const GridP& G, float x, float y, fl
 // every operation rounded separately (no FMA contraction), vendor/glm func_geometric.inl:47-55.
 __device__ __forceinline__ float dist2_exact(float dx, float dy, float dz) {
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// Box collision + response, fluid_system.h:342-347 + collisionS :355-407.  Shared by the force kernels
+// (sph.cu) and the terrain stage (terrain.cu, built without FMA contraction): written with explicitly
+// rounded operations so both translation units produce the same bits.
+// The reference box is a cube of half-extent len: the violated axis is the one with the largest
+// |coordinate| (ties x -> y -> z by strict <, :362-371).  sphe_set_box generalises it to per-axis
+// half-extents for the multi-GPU channel scenes; then the axis with the largest overshoot wins.
+__device__ __forceinline__ void box_collide(const StepC& C, float& px, float& py, float& pz, float& vx, float& vy, float& vz) {
+    float ax = fabsf(px), ay = fabsf(py), az = fabsf(pz);
+    if (ax < C.lenx && ay < C.leny && az < C.lenz) return;
+    if (C.dt == 0.0f) return;
+    if (!C.cube) { ax = __fsub_rn(ax, C.lenx); ay = __fsub_rn(ay, C.leny); az = __fsub_rn(az, C.lenz); }
+    int axis = 0;
+    float m = ax;
+    if (m < ay) { axis = 1; m = ay; }
+    if (m < az) { axis = 2; m = az; }
+    float cx = px, cy = py, cz = pz, nx = 0.0f, ny = 0.0f, nz = 0.0f;
+    if (axis == 0) { if (px < -C.lenx) { cx = -C.lenx; nx = 1.0f; } else { cx = C.lenx; nx = -1.0f; } }
+    else if (axis == 1) { if (py < -C.leny) { cy = -C.leny; ny = 1.0f; } else { cy = C.leny; ny = -1.0f; } }
+    else { if (pz < -C.lenz) { cz = -C.lenz; nz = 1.0f; } else { cz = C.lenz; nz = -1.0f; } }
+    float ex = __fsub_rn(px, cx), ey = __fsub_rn(py, cy), ez = __fsub_rn(pz, cz);
+    float d = __fsqrt_rn(dist2_exact(ex, ey, ez));
+    float vlen = __fsqrt_rn(dist2_exact(vx, vy, vz));
+    float sc = __fadd_rn(1.0f, __fdiv_rn(__fmul_rn(0.5f, d), __fmul_rn(C.dt, vlen)));
+    float vn = __fadd_rn(__fadd_rn(__fmul_rn(vx, nx), __fmul_rn(vy, ny)), __fmul_rn(vz, nz));
+    vx = __fsub_rn(vx, __fmul_rn(__fmul_rn(nx, sc), vn));
+    vy = __fsub_rn(vy, __fmul_rn(__fmul_rn(ny, sc), vn));
+    vz = __fsub_rn(vz, __fmul_rn(__fmul_rn(nz, sc), vn));
+    px = cx; py = cy; pz = cz;
 }

@@ -15,6 +15,34 @@ void launch_rank_reorder(cudaStream_t st, int n, const uint2* tmp, const uint32_
                          const float4* posq_in, const float4* velv_in, const float* sed_in,
                          float4* posq_out, float4* velv_out, float* sed_out, int* ids_out, uint32_t* cell_sorted);
 
+// ---- terrain.cu
+// Device view of a terrain (replacement of the reference's Grid, Erosion/grid.h:26-51).
+struct TerrainDev {
+    int rows, cols;          // heightfield storage, H(x, z) = hfx[cols * x + z] / 4096
+    int dimx, dimy, dimz;    // Grid dimensions (range checks, render mesh)
+    const int* hfx;          // heights, fixed point 1/4096
+    int* hfx_rw;
+    int* want;               // per-vertex sum of pick-up requests of the current step
+    int* delta;              // per-vertex deposits - grants of the current step
+    const int* hmax_fx;      // upper bound of all heights (contact culling)
+    int* hmax_rw;
+    float ox, oy, oz, scale, inv_scale;   // world = origin + scale * terrain coordinates
+    float Kc, Ke, Kd;
+    int hmin_fx, max_pickup_fx;
+    int erosion;
+};
+void launch_terrain_stage(cudaStream_t st, int n, const float4* pos_old, float4* posq, float4* velv, int* sediment,
+                          const StepC& C, const TerrainDev& T, int apply_box, int* req_vertex, int* req_amount, int* hit_out);
+int terrain_stage_launches(const StepC& C, const TerrainDev& T);
+void launch_terrain_surface(cudaStream_t st, const TerrainDev& T, float* out);
+void launch_terrain_indices(cudaStream_t st, int dimx, int dimz, unsigned* out);
+void launch_terrain_collide(cudaStream_t st, int n, const float* pc, const float* pn, const float* vn, const TerrainDev& T,
+                            int* hit, float* cp, float* nrm);
+void launch_heights_from_u8(cudaStream_t st, int cells, const unsigned char* img, int* hfx, int* hmax);
+void launch_heights_from_f32(cudaStream_t st, int cells, const float* src, int* hfx, int* hmax);
+void launch_heights_to_f32(cudaStream_t st, int cells, const int* hfx, float* dst);
+void launch_sum_i32(cudaStream_t st, int n, const int* a, const int* ghost_ids, long long* out);
+
 // ---- slab.cu (multi-GPU x-slabs)
 struct SlabP {
     int x0, x1;      // owned global cell columns [x0, x1)
@@ -46,7 +74,6 @@ struct DiagOut {
     int* neighb;
 };
 
-struct TerrainDev;  // terrain.cu
 
 void launch_density(cudaStream_t st, int variant, int n, const float4* posq, float4* posq_q, float4* velv,
                     const uint32_t* cell_sorted, const int* cell_start, const GridP& G, const StepC& C, float* rho,

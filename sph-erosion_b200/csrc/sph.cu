@@ -172,27 +172,6 @@ __global__ void __launch_bounds__(128) k_density_pair(int n, const float4* __res
     }
 }
 
-// ------------------------------------------------------------------ box collision, fluid_system.h:355-407
-// The reference box is a cube of half-extent len: the violated axis is the one with the largest |coordinate|
-// (ties x -> y -> z by strict <, :362-371).  sphe_set_box generalises it to per-axis half-extents for the
-// multi-GPU channel scenes; then the axis with the largest overshoot |coordinate| - l_axis is chosen.
-__device__ __forceinline__ bool collision_box(const StepC& C, float x, float y, float z, float& cx, float& cy, float& cz,
-                                              float& nx, float& ny, float& nz) {
-    float ax = fabsf(x), ay = fabsf(y), az = fabsf(z);
-    if (ax < C.lenx && ay < C.leny && az < C.lenz) return false;
-    if (!C.cube) { ax -= C.lenx; ay -= C.leny; az -= C.lenz; }
-    int axis = 0;
-    float m = ax;
-    if (m < ay) { axis = 1; m = ay; }
-    if (m < az) { axis = 2; m = az; }
-    cx = x; cy = y; cz = z;
-    nx = ny = nz = 0.0f;
-    if (axis == 0) { if (x < -C.lenx) { cx = -C.lenx; nx = 1.0f; } else { cx = C.lenx; nx = -1.0f; } }
-    else if (axis == 1) { if (y < -C.leny) { cy = -C.leny; ny = 1.0f; } else { cy = C.leny; ny = -1.0f; } }
-    else { if (z < -C.lenz) { cz = -C.lenz; nz = 1.0f; } else { cz = C.lenz; nz = -1.0f; } }
-    return true;
-}
-
 // ------------------------------------------------------------------ force -> integrate -> collide (per particle)
 // PressureForce = -(fPress*rho_i), fPress = -mass*c45*A (fluid_system.h:145,151); ViscosityForce = c45*visc*F
 // (:146,153); SurfaceNormal = -c945*N (:147,154); colorFieldLapl = -c945*cf, SurfaceForce = -surf_tens*cfl*n
@@ -216,16 +195,7 @@ __device__ __forceinline__ void force_epilogue(int i, float4 pi, float4 vi, floa
     float dt = C.dt;
     float vx = fmaf(acx, dt, vi.x), vy = fmaf(acy, dt, vi.y), vz = fmaf(acz, dt, vi.z);
     float px = fmaf(vx, dt, pi.x), py = fmaf(vy, dt, pi.y), pz = fmaf(vz, dt, pi.z);
-    float cx, cy, cz, bx, by, bz;
-    if (collision_box(C, px, py, pz, cx, cy, cz, bx, by, bz) && dt != 0.0f) {
-        float ex = px - cx, ey = py - cy, ez = pz - cz;
-        float d = sqrtf(ex * ex + ey * ey + ez * ez);
-        float vlen = sqrtf(vx * vx + vy * vy + vz * vz);
-        float sc = 1.0f + 0.5f * d / (dt * vlen);
-        float vn = vx * bx + vy * by + vz * bz;
-        vx -= bx * sc * vn; vy -= by * sc * vn; vz -= bz * sc * vn;
-        px = cx; py = cy; pz = cz;
-    }
+    if (C.box) box_collide(C, px, py, pz, vx, vy, vz);
     posq_out[i] = make_float4(px, py, pz, 0.0f);
     velv_out[i] = make_float4(vx, vy, vz, 0.0f);
     if (DIAG) {
@@ -309,16 +279,7 @@ __global__ void __launch_bounds__(128) k_force_tpp(int n, const float4* __restri
     float vx = fmaf(acx, dt, vi.x), vy = fmaf(acy, dt, vi.y), vz = fmaf(acz, dt, vi.z);
     float px = fmaf(vx, dt, pi.x), py = fmaf(vy, dt, pi.y), pz = fmaf(vz, dt, pi.z);
 
-    float cx, cy, cz, bx, by, bz;
-    if (collision_box(C, px, py, pz, cx, cy, cz, bx, by, bz) && dt != 0.0f) {
-        float ex = px - cx, ey = py - cy, ez = pz - cz;
-        float d = sqrtf(ex * ex + ey * ey + ez * ez);
-        float vlen = sqrtf(vx * vx + vy * vy + vz * vz);
-        float sc = 1.0f + 0.5f * d / (dt * vlen);
-        float vn = vx * bx + vy * by + vz * bz;
-        vx -= bx * sc * vn; vy -= by * sc * vn; vz -= bz * sc * vn;
-        px = cx; py = cy; pz = cz;
-    }
+    if (C.box) box_collide(C, px, py, pz, vx, vy, vz);
     posq_out[i] = make_float4(px, py, pz, 0.0f);
     velv_out[i] = make_float4(vx, vy, vz, 0.0f);
 

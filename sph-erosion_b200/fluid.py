@@ -109,6 +109,16 @@ class FluidSystemSPH:
                                             mk if per_kernel else None, C.byref(nl)))
         return ms.value, dict(zip(capi.K_NAMES, [float(x) for x in mk])), nl.value
 
+    def sediment_total_fx(self):
+        v = C.c_longlong(0)
+        capi.check(self._L.sphe_sediment_total_fx(self._h, C.byref(v)))
+        return v.value
+
+    def set_sediment_fx(self, sed_by_id):
+        a = np.ascontiguousarray(sed_by_id, np.int32)
+        assert a.shape[0] == self.count()
+        capi.check(self._L.sphe_set_sediment_fx(self._h, _p(a)))
+
     def set_box(self, half):
         """Per-axis box half-extents (None restores the reference's cube `len`)."""
         a = None if half is None else np.asarray(half, np.float32)
