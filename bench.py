@@ -25,7 +25,7 @@ METRIC = "sph_particle_updates_per_sec"
 UNIT = "particle-updates/s"
 SPACING = 0.025
 # algorithmic HBM bytes per particle per launch (SURVEY.md section 8d / DESIGN.md "kernels")
-ALGO_BYTES = {"hash": 20, "scatter": 16, "reorder": 92, "density": 44, "force": 72}
+ALGO_BYTES = {"hash": 20, "scatter": 16, "reorder": 92, "density": 44, "force": 72, "terrain": 92}
 
 
 # ----------------------------------------------------------------------------- scenes
@@ -63,8 +63,50 @@ WORKLOADS = {
     # name: (n_axis, jitter, terrain, description)
     "small": (32, False, False, "32^3 = 32,768-particle dam break (smoke-sized)"),
     "c2": (100, False, False, "BASELINE configs[1]: 1M-particle dam break in a box, no terrain (n=100 -> 1,000,000)"),
-    "c3": (160, True, False, "BASELINE configs[2] particle scene: 4.096M-particle dam break (n=160), terrain/erosion stage not yet attached"),
+    "c3": (160, True, True, "BASELINE configs[2]: 4.096M-particle SPH erosion (n=160) over a 1024x1024 heightmap terrain, sediment pickup/deposit enabled"),
+    "c3-noterrain": (160, True, False, "the c3 particle scene without the terrain stage (4.096M-particle dam break, n=160)"),
 }
+
+
+def synthetic_heightmap(size=1024, seed=0x7E44A1):
+    """8-bit heightmap in the style of the reference's photographs (lena_gray.png: min 34, max 246, mean
+    125, rough at the pixel scale): five octaves of bilinear value noise plus pixel noise.  The PNGs are
+    reference assets and do not travel to the GPU box, so the scene generates its own."""
+    rng = np.random.default_rng(seed)
+    h = np.zeros((size, size), np.float64)
+    amp, total = 1.0, 0.0
+    for cells in (4, 8, 16, 64, 256):
+        g = rng.uniform(0, 1, (cells + 1, cells + 1))
+        t = np.linspace(0, cells, size, endpoint=False)
+        i = t.astype(int); f = t - i
+        f = f * f * (3 - 2 * f)
+        row = g[i][:, i] * (1 - f)[None, :] + g[i][:, i + 1] * f[None, :]
+        row1 = g[i + 1][:, i] * (1 - f)[None, :] + g[i + 1][:, i + 1] * f[None, :]
+        h += amp * (row * (1 - f)[:, None] + row1 * f[:, None])
+        total += amp; amp *= 0.5
+    h = h / total + rng.normal(0, 0.01, h.shape)
+    h = (h - h.min()) / (h.max() - h.min())
+    return np.clip(np.rint(34 + h * (246 - 34)), 0, 255).astype(np.uint8)
+
+
+def attach_terrain(pkg, L, n_axis):
+    """1024 x 1024 terrain under the whole box floor: cell = 2L/1024 world units (uniform scale), heights
+    0..255 levels scaled to 0..0.25*block height so the relief is a fraction of the fluid depth, terrain
+    top just under the block so the fluid lands on it during the settle phase."""
+    img = synthetic_heightmap()
+    cell = 2.0 * L / 1024.0
+    relief = 0.1 * L                                    # world units between the lowest and highest vertex
+    heights = img.astype(np.float32) * np.float32(relief / 255.0 / cell)   # in cells
+    g = pkg.Grid(1024, 255, 1024)
+    g.set_heights(heights)
+    top = float(heights.max()) * cell
+    origin = (-L, -L / 4 - 0.5 * SPACING - top, -L)     # highest vertex half a lattice spacing under the block
+    g.set_transform(origin, cell)
+    e = g.erosion
+    e.enabled = 1; e.Kc = 2.0; e.Ke = 0.3; e.Kd = 0.3; e.hmin = 0.0; e.max_pickup = 0.25
+    return g, {"heightmap": "synthetic 1024x1024 8-bit value noise (lena_gray statistics), seed 0x7E44A1",
+               "terrain_cell": cell, "terrain_relief": relief, "terrain_origin": list(origin),
+               "erosion": {"Kc": 2.0, "Ke": 0.3, "Kd": 0.3, "hmin": 0.0, "max_pickup": 0.25}}
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -145,9 +187,10 @@ def dist_env():
 
 
 # ----------------------------------------------------------------------------- CPU arms
-def cpu_port_baseline(pos, L, gy=-9.82, budget_s=20.0):
+def cpu_port_baseline(pos, L, gy=-9.82, budget_s=20.0, terrain=None, vel=None):
     """Times oracle/sph_oracle.c so_step_grid (OpenMP, all host cores) on a bounded sample of the
-    same scene.  kind = "port": the cell-grid restatement, bit-identical to the reference's sums."""
+    same scene.  kind = "port": the cell-grid restatement, bit-identical to the reference's sums.
+    terrain = (heights_in_cells, origin, cell, erosion dict): the terrain stage of the oracle runs too."""
     from oracle import port
     n = pos.shape[0]
     sample_n = n
@@ -159,15 +202,27 @@ def cpu_port_baseline(pos, L, gy=-9.82, budget_s=20.0):
     order = np.argsort(pos[:, 0], kind="stable")[:sample_n]
     sp = np.ascontiguousarray(pos[order])
     P = port.default_params(dt=0.01, len=L, g=(0.0, gy, 0.0))
-    S = port.State(sp)
+    S = port.State(sp, None if vel is None else vel[order])
     G = port.grid_for_box(P, [-L - 0.1] * 3, [L + 0.1] * 3)
-    port.step_grid(P, G, S)  # warm (page faults, thread pool)
-    t = time.perf_counter()
     steps = 2
-    port.step_grid(P, G, S, steps)
+    if terrain is None:
+        port.step_grid(P, G, S)  # warm (page faults, thread pool)
+        t = time.perf_counter()
+        port.step_grid(P, G, S, steps)
+        what = "oracle so_step_grid (OpenMP cell grid, sums bit-identical to the reference)"
+    else:
+        heights, origin, cell, ero = terrain
+        T = port.Terrain(heights, (heights.shape[0], 255, heights.shape[1]))
+        E = port.erosion_params(enabled=True, origin=origin, scale=cell, **ero)
+        sed = np.zeros(S.n, np.int32)
+        port.step_grid_terrain(P, G, S, T, E, sed)
+        t = time.perf_counter()
+        for _ in range(steps):
+            port.step_grid_terrain(P, G, S, T, E, sed)
+        what = "oracle so_forces_grid + so_terrain_stage + so_box (OpenMP cell grid + terrain contact/erosion restatement)"
     dt = (time.perf_counter() - t) / steps
     return {"value": sample_n / dt, "unit": UNIT, "cores": port.omp_threads(), "kind": "port",
-            "sample": "%d of %d particles (x-slab of the same scene), %d steps of oracle so_step_grid (OpenMP cell grid, sums bit-identical to the reference), %.2f s/step" % (sample_n, n, steps, dt)}
+            "sample": "%d of %d particles (x-slab of the same scene), %d steps of %s, %.2f s/step" % (sample_n, n, steps, what, dt)}
 
 
 def run_reference_arm(args):
@@ -248,14 +303,26 @@ def run_gpu_arm(args):
     sim.upload_state(pos, np.zeros_like(pos))
     flush_bytes = 256 << 20
     sim.set_l2_flush(flush_bytes)
+    grid, tinfo = (attach_terrain(pkg, L, n_axis) if terrain else (None, {}))
+    if grid is not None:
+        # untimed settle phase: let the block land on the terrain so the timed steps exercise contacts
+        sim.timed_steps(args.settle, grid=grid, per_kernel=False)
+        tinfo["settle_steps"] = args.settle
+        tot0 = grid.total_fx() + sim.sediment_total_fx()
 
-    sim.timed_steps(args.warmup, per_kernel=False)
+    sim.timed_steps(args.warmup, grid=grid, per_kernel=False)
+    if grid is not None:
+        grid.contacts(reset=True)
     sampler = ClockSampler(local)
     sampler.start()
     torch.cuda.synchronize()
-    ms, per_kernel, launches = sim.timed_steps(args.steps, per_kernel=True)
+    ms, per_kernel, launches = sim.timed_steps(args.steps, grid=grid, per_kernel=True)
     torch.cuda.synchronize()
     clocks = sampler.stop()
+    if grid is not None:
+        tinfo["terrain_contacts_per_step"] = grid.contacts() / args.steps
+        tinfo["sediment_in_flight_fx"] = sim.sediment_total_fx()
+        tinfo["conservation_exact"] = bool(grid.total_fx() + sim.sediment_total_fx() == tot0)
     ms_step = ms / args.steps
     value = n / (ms_step * 1e-3)
 
@@ -267,11 +334,14 @@ def run_gpu_arm(args):
     sim2 = pkg.FluidSystemSPH(device=local)
     sim2.params.len = L; sim2.params.g[1] = gy; sim2.SetDeltaTime(0.01)
     sim2.set_variant(args.density_variant, args.force_variant)
+    if grid is not None:
+        # start the end-to-end loop from the settled state so it, too, runs with terrain contacts
+        hp.copy_(torch.from_numpy(sim.download("pos"))); hv.copy_(torch.from_numpy(sim.download("vel")))
     for _ in range(3):
-        sim2.step_host_ptr(n, hp.data_ptr(), hv.data_ptr(), op.data_ptr(), ov.data_ptr(), orho.data_ptr())
+        sim2.step_host_ptr(n, hp.data_ptr(), hv.data_ptr(), op.data_ptr(), ov.data_ptr(), orho.data_ptr(), grid=grid)
     t = time.perf_counter()
     for _ in range(e2e_steps):
-        sim2.step_host_ptr(n, hp.data_ptr(), hv.data_ptr(), op.data_ptr(), ov.data_ptr(), orho.data_ptr())
+        sim2.step_host_ptr(n, hp.data_ptr(), hv.data_ptr(), op.data_ptr(), ov.data_ptr(), orho.data_ptr(), grid=grid)
         hp, op = op, hp
         hv, ov = ov, hv
     e2e_dt = (time.perf_counter() - t) / e2e_steps
@@ -280,7 +350,7 @@ def run_gpu_arm(args):
            "api": "sphe_step_host (pinned host pos/vel in, pos/vel/density out, id order)"}
 
     peak, peak_src = measured_peak()
-    dom = max(("density", "force"), key=lambda k: per_kernel[k])
+    dom = max(("density", "force", "terrain"), key=lambda k: per_kernel[k])
     t_dom = per_kernel[dom] / args.steps * 1e-3
     achieved = ALGO_BYTES[dom] * n / t_dom / 1e9
     roofline = {"bound": "hbm", "kernel": "k_%s" % dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -291,7 +361,15 @@ def run_gpu_arm(args):
                 "per_kernel_ms_per_step": {k: v / args.steps for k, v in per_kernel.items()},
                 "per_kernel_hbm_frac": {k: (ALGO_BYTES[k] * n / (per_kernel[k] / args.steps * 1e-3) / 1e9 / peak)
                                         for k in ALGO_BYTES if per_kernel.get(k, 0) > 0}}
-    cb = cpu_port_baseline(pos, L, gy) if not args.no_cpu_baseline else None
+    cb = None
+    if not args.no_cpu_baseline:
+        if grid is not None:
+            # the settled state, so the CPU baseline also has particles in contact with the terrain
+            th = grid.heights()
+            cb = cpu_port_baseline(sim.download("pos"), L, gy, terrain=(th, tinfo["terrain_origin"], tinfo["terrain_cell"], tinfo["erosion"]),
+                                   vel=sim.download("vel"))
+        else:
+            cb = cpu_port_baseline(pos, L, gy)
     ns_total = None
     if n <= 4200000:
         ns_total = int(sim.debug_neighbours_total())
@@ -302,7 +380,7 @@ def run_gpu_arm(args):
                        "dt": 0.01, "box_half_extent": L, "gravity_y": gy,
                        "gravity_note": "g scaled by 10/n_axis: dynamic similarity with the reference default scene (see bench.scene_gravity)" if not args.gravity_unscaled else "unscaled g",
                        "mean_neighbours_after_run": (ns_total / n) if ns_total else None, "l2": "flushed between timed steps (%d MiB memset, outside the event brackets)" % (flush_bytes >> 20),
-                       "density_variant": args.density_variant, "force_variant": args.force_variant},
+                       "density_variant": args.density_variant, "force_variant": args.force_variant, **tinfo},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cb}
     print(json.dumps(line))
 
@@ -317,6 +395,7 @@ def main():
     ap.add_argument("--density-variant", type=int, default=3)
     ap.add_argument("--force-variant", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--settle", type=int, default=150, help="untimed steps before warm-up when the workload has a terrain")
     ap.add_argument("--gravity-unscaled", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

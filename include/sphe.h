@@ -224,6 +224,7 @@ sphe_erosion* sphe_terrain_erosion_ptr(sphe_terrain* t);   /* host-resident, re-
 int sphe_terrain_stage_host(sphe_terrain* t, int n, const float* pos_curr, float* pos_next, float* vel_next, int* sediment,
                             float dt, float cR, int* hit);
 int sphe_terrain_total_fx(sphe_terrain* t, long long* sum);     /* sum of all heights, fixed point */
+int sphe_terrain_contacts(sphe_terrain* t, long long* total, int reset); /* particle-terrain contacts since the last reset */
 int sphe_sediment_total_fx(sphe_sim* s, long long* sum);        /* sum of carried sediment (owned particles), fixed point */
 int sphe_set_sediment_fx(sphe_sim* s, const int* sediment_by_id);
 

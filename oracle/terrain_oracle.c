@@ -294,9 +294,13 @@ void so_terrain_stage(so_terrain* T, const so_erosion* E, int n, const float* po
     long long* delta = (long long*)calloc(cells, sizeof(long long));
     int* req_cell = (int*)malloc((size_t)n * sizeof(int));
     int* req_amt = (int*)malloc((size_t)n * sizeof(int));
+    int* dep_cell = (int*)malloc((size_t)n * sizeof(int));
+    int* dep_amt = (int*)malloc((size_t)n * sizeof(int));
     float inv = 1.0f / E->scale;
+    /* per-particle part (independent, OpenMP for the timed CPU baseline); the per-vertex sums follow serially */
+#pragma omp parallel for schedule(dynamic, 1024)
     for (int i = 0; i < n; i++) {
-        req_cell[i] = -1; req_amt[i] = 0;
+        req_cell[i] = -1; req_amt[i] = 0; dep_cell[i] = -1; dep_amt[i] = 0;
         if (hit_out) hit_out[i] = 0;
         float pc[3], pn[3], vn[3], cp[3] = { 0, 0, 0 }, nn[3] = { 0, 0, 0 };
         for (int a = 0; a < 3; a++) {
@@ -328,12 +332,16 @@ void so_terrain_stage(so_terrain* T, const so_erosion* E, int n, const float* po
         if (s > cap) {
             int q = rint_fx((s - cap) * E->Kd);
             if (q > sediment[i]) q = sediment[i];
-            if (q > 0) { sediment[i] -= q; delta[c] += q; }
+            if (q > 0) { sediment[i] -= q; dep_cell[i] = c; dep_amt[i] = q; }
         } else if (s < cap) {
             int q = rint_fx((cap - s) * E->Ke);
             if (q > E->max_pickup_fx) q = E->max_pickup_fx;
-            if (q > 0) { req_cell[i] = c; req_amt[i] = q; want[c] += q; }
+            if (q > 0) { req_cell[i] = c; req_amt[i] = q; }
         }
+    }
+    for (int i = 0; i < n; i++) {
+        if (dep_cell[i] >= 0) delta[dep_cell[i]] += dep_amt[i];
+        if (req_cell[i] >= 0) want[req_cell[i]] += req_amt[i];
     }
     for (int i = 0; i < n; i++) {
         int c = req_cell[i];
@@ -346,5 +354,5 @@ void so_terrain_stage(so_terrain* T, const so_erosion* E, int n, const float* po
     }
     for (size_t c = 0; c < cells; c++)
         if (delta[c]) { T->hfx[c] += (int)delta[c]; T->h[c] = (float)T->hfx[c] * (1.0f / 4096.0f); }
-    free(want); free(delta); free(req_cell); free(req_amt);
+    free(want); free(delta); free(req_cell); free(req_amt); free(dep_cell); free(dep_amt);
 }

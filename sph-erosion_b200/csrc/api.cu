@@ -53,7 +53,7 @@ struct sphe_terrain {
     float* d_surface = nullptr;
     unsigned* d_indices = nullptr;
     long long surface_floats = 0, index_count = 0;
-    long long* d_sum = nullptr;
+    long long* d_sum = nullptr;   // [0] scratch sum, [1] cumulative contact count
     sphe_terrain() { E.enabled = 0; E.Kc = 0.05f; E.Ke = 0.3f; E.Kd = 0.3f; E.hmin = 0.0f; E.max_pickup = 0.25f; }
 };
 
@@ -988,7 +988,8 @@ static int terrain_ready(sphe_terrain* t) {
     if (t->device < 0) CU(cudaGetDevice(&t->device));
     CU(cudaSetDevice(t->device));
     CU(cudaMalloc(&t->hmax, sizeof(int)));
-    CU(cudaMalloc(&t->d_sum, sizeof(long long)));
+    CU(cudaMalloc(&t->d_sum, 2 * sizeof(long long)));
+    CU(cudaMemset(t->d_sum, 0, 2 * sizeof(long long)));
     TRY(terrain_alloc(t, t->rows, t->cols));  // Grid(): 512 x 512 heightfield, zeroed (grid.h:78-81)
     t->ready = true;
     return SPHE_OK;
@@ -1002,6 +1003,7 @@ static TerrainDev terrain_view(const sphe_terrain* t) {
     T.Kc = t->E.Kc; T.Ke = t->E.Ke; T.Kd = t->E.Kd;
     T.hmin_fx = (int)lrint((double)t->E.hmin * 4096.0); T.max_pickup_fx = (int)lrint((double)t->E.max_pickup * 4096.0);
     T.erosion = t->E.enabled ? 1 : 0;
+    T.contacts = (unsigned long long*)(t->d_sum + 1);
     return T;
 }
 
@@ -1213,6 +1215,15 @@ int sphe_terrain_total_fx(sphe_terrain* t, long long* sum) {
     CU(cudaMemset(t->d_sum, 0, sizeof(long long)));
     launch_sum_i32(0, t->rows * t->cols, t->hfx, nullptr, t->d_sum);
     CU(cudaMemcpy(sum, t->d_sum, sizeof(long long), cudaMemcpyDeviceToHost));
+    return SPHE_OK;
+}
+
+int sphe_terrain_contacts(sphe_terrain* t, long long* total, int reset) {
+    if (!t || !total) return fail(SPHE_ERR_ARG, "bad arguments");
+    TRY(terrain_ready(t));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(total, t->d_sum + 1, sizeof(long long), cudaMemcpyDeviceToHost));
+    if (reset) CU(cudaMemset(t->d_sum + 1, 0, sizeof(long long)));
     return SPHE_OK;
 }
 

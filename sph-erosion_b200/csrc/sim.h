@@ -26,6 +26,7 @@ struct TerrainDev {
     int* delta;              // per-vertex deposits - grants of the current step
     const int* hmax_fx;      // upper bound of all heights (contact culling)
     int* hmax_rw;
+    unsigned long long* contacts;  // cumulative number of particle-terrain contacts
     float ox, oy, oz, scale, inv_scale;   // world = origin + scale * terrain coordinates
     float Kc, Ke, Kd;
     int hmin_fx, max_pickup_fx;

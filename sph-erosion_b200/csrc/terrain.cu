@@ -256,6 +256,8 @@ __global__ void __launch_bounds__(128) k_terrain_contact(int n, const float4* __
             }
         }
     }
+    unsigned m_hit = __ballot_sync(SPHE_FULL, hit);
+    if (m_hit && (threadIdx.x & 31) == 0) atomicAdd(T.contacts, (unsigned long long)__popc(m_hit));
     unsigned m_dep = __ballot_sync(SPHE_FULL, dep), m_want = __ballot_sync(SPHE_FULL, want);
     vertex_add(m_dep, dep, T.delta, dep_vertex, dep_amount);
     vertex_add(m_want, want, T.want, want_vertex, want_amount);

@@ -106,6 +106,11 @@ class Grid:
         capi.check(self._L.sphe_terrain_total_fx(self._t, C.byref(v)))
         return v.value
 
+    def contacts(self, reset=False):
+        v = C.c_longlong(0)
+        capi.check(self._L.sphe_terrain_contacts(self._t, C.byref(v), int(reset)))
+        return v.value
+
     def stage(self, pos_curr, pos_next, vel_next, sediment, dt, cR=0.5):
         """Terrain stage on caller arrays (updated in place); returns the hit flags."""
         n = pos_curr.shape[0]
