@@ -395,6 +395,7 @@ def main():
     ap.add_argument("--density-variant", type=int, default=3)
     ap.add_argument("--force-variant", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--slab-lag", type=int, default=2, help="multi-GPU: steps the host may run ahead (0 = one host sync per step)")
     ap.add_argument("--settle", type=int, default=150, help="untimed steps before warm-up when the workload has a terrain")
     ap.add_argument("--gravity-unscaled", action="store_true")
     args = ap.parse_args()

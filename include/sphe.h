@@ -182,6 +182,14 @@ int sphe_slab_upload(sphe_sim* s, int n, const float* pos, const float* vel, con
  *         sync and returns out[6] = {n_total, n_owned, sent_left, sent_right, got_left, got_right}. */
 int sphe_slab_pack(sphe_sim* s, void* dev_send_left, void* dev_send_right, int cap_records, int reserve_incoming);
 int sphe_slab_unpack(sphe_sim* s, const void* dev_recv_left, int max_left, const void* dev_recv_right, int max_right, int out[6]);
+/* Asynchronous form: no host sync at all.  The append kernel leaves the exact particle count in device
+ * memory, the following sphe_step launches with an upper bound and its kernels read the exact count
+ * there; the counters travel to pinned host memory behind an event.  sphe_slab_result(ticket) returns the
+ * same out[6] later (wait = 0: returns 1 if the step has not finished yet).  At most 6 tickets may be
+ * outstanding; every accessor that needs the exact count settles them first. */
+int sphe_slab_unpack_async(sphe_sim* s, const void* dev_recv_left, int max_left, const void* dev_recv_right, int max_right,
+                           long long* ticket);
+int sphe_slab_result(sphe_sim* s, long long ticket, int wait, int out[6]);
 /* Owned particles only, storage order; rho/sed may be NULL. */
 int sphe_slab_download(sphe_sim* s, int cap, int* ids, float* pos, float* vel, float* rho, float* sed, int* n_out);
 

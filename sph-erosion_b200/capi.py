@@ -102,6 +102,8 @@ SYMBOLS = {
     "sphe_slab_upload": (_i, [_vp, _i, _vp, _vp, _vp]),
     "sphe_slab_pack": (_i, [_vp, _vp, _vp, _i, _i]),
     "sphe_slab_unpack": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
+    "sphe_slab_unpack_async": (_i, [_vp, _vp, _i, _vp, _i, C.POINTER(_ll)]),
+    "sphe_slab_result": (_i, [_vp, _ll, _i, _vp]),
     "sphe_slab_download": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i)]),
 }
 

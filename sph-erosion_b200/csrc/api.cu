@@ -94,8 +94,18 @@ struct sphe_sim {
     SlabP slab{};
     int n_owned = 0;
     int* slab_counters = nullptr;  // device int[8]
-    int* slab_host = nullptr;      // pinned mirror of slab_counters
+    int* slab_host = nullptr;      // pinned ring of counter snapshots, SLAB_RING x 8 ints
     int slab_cap_sent = 0;
+    bool slab_unpacked = false;    // unpack already ran since the last pack (a repeat must clear its counters)
+    int* d_n = nullptr;            // device word: exact particle count after the last unpack
+    // asynchronous unpack: results of the last SLAB_RING steps, read back without stalling the stream
+    static const int SLAB_RING = 8;
+    cudaEvent_t slab_ev[SLAB_RING] = {};
+    long long slab_seq = 0;        // tickets issued
+    long long slab_done = 0;       // tickets whose result has been folded into n
+    int slab_add[SLAB_RING] = {};  // upper bound of the records appended by each ticket
+    int slab_max[SLAB_RING][2] = {};
+    int slab_pending = 0;          // > 0: s->n is an upper bound, kernels read the exact count from d_n
     float grid_h = -1.f, grid_len = -1.f;
 
     bool diag = false;
@@ -160,7 +170,7 @@ static int reserve(sphe_sim* s, int need) {
     TRY(grow(&s->idsA, live, nc, s->st, true));
     TRY(grow(&s->sedA, live, nc, s->st, true));
     TRY(grow(&s->posB, 0, nc, s->st, false));
-    TRY(grow(&s->posC, 0, nc, s->st, false));
+    TRY(grow(&s->posC, 0, 2 * nc, s->st, false));  // 2x: doubles as the interleaved record array of variant 4
     TRY(grow(&s->velB, 0, nc, s->st, false));
     TRY(grow(&s->idsB, 0, nc, s->st, false));
     TRY(grow(&s->sedB, 0, nc, s->st, false));
@@ -288,6 +298,7 @@ struct Scope {
 
 // ------------------------------------------------------------------ the step
 static int terrain_ready(sphe_terrain* t);
+extern "C" { static int slab_settle(sphe_sim* s); }
 static TerrainDev terrain_view(const sphe_terrain* t);
 
 static int step_device(sphe_sim* s, sphe_terrain* t) {
@@ -305,14 +316,15 @@ static int step_device(sphe_sim* s, sphe_terrain* t) {
     if (t) C.box = 0;  // with a terrain the box collision runs after the terrain contact (fluid_system.h:335-347)
     s->lastC = C;
     int n = s->n;
-    { Scope k(s, SPHE_K_HASH); launch_hash(s->st, n, s->posA, s->G, s->cell, s->count); }
-    { Scope k(s, SPHE_K_SCAN, 3); launch_scan(s->st, s->ncells, n, s->count, s->tile_sum, s->cell_start, s->cursor); }
-    { Scope k(s, SPHE_K_SCATTER); launch_scatter(s->st, n, s->cell, s->idsA, s->cursor, s->tmp); }
+    const int* nd = s->slab_pending ? s->d_n : nullptr;  // exact count on the device while unpack results are in flight
+    { Scope k(s, SPHE_K_HASH); launch_hash(s->st, n, nd, s->posA, s->G, s->cell, s->count); }
+    { Scope k(s, SPHE_K_SCAN, 3); launch_scan(s->st, s->ncells, n, nd, s->count, s->tile_sum, s->cell_start, s->cursor); }
+    { Scope k(s, SPHE_K_SCATTER); launch_scatter(s->st, n, nd, s->cell, s->idsA, s->cursor, s->tmp); }
     { Scope k(s, SPHE_K_REORDER);
-      launch_rank_reorder(s->st, n, s->tmp, s->cell, s->cell_start, s->posA, s->velA, s->sedA, s->posB, s->velB, s->sedB,
+      launch_rank_reorder(s->st, n, nd, s->tmp, s->cell, s->cell_start, s->posA, s->velA, s->sedA, s->posB, s->velB, s->sedB,
                           s->idsB, s->cell_sorted); }
-    if (s->variant_density == 3 || s->variant_force == 3) {
-        if (s->variant_density != s->variant_force) return fail(SPHE_ERR_ARG, "variant 3 (neighbour lists) must be selected for both passes");
+    if (s->variant_density >= 3 || s->variant_force >= 3) {
+        if (s->variant_density != s->variant_force) return fail(SPHE_ERR_ARG, "variants 3/4 (neighbour lists) must be selected for both passes");
         size_t pp = (size_t)nlist_pairs_pad(s->cap);
         if (pp > s->nlist_pairs) {
             TRY(grow(&s->nlist, 0, pp * (size_t)nlist_cap(), s->st, false));
@@ -321,15 +333,15 @@ static int step_device(sphe_sim* s, sphe_terrain* t) {
         }
     }
     { Scope k(s, SPHE_K_DENSITY);
-      launch_density(s->st, s->variant_density, n, s->posB, s->posC, s->velB, s->cell_sorted, s->cell_start, s->G, C, s->rho,
+      launch_density(s->st, s->variant_density, n, nd, s->posB, s->posC, s->velB, s->cell_sorted, s->cell_start, s->G, C, s->rho,
                      s->nlist, s->ncount); }
     { Scope k(s, SPHE_K_FORCE);
-      launch_force(s->st, s->variant_force, n, s->posC, s->velB, s->rho, s->idsB, s->cell_sorted, s->cell_start, s->G, C,
+      launch_force(s->st, s->variant_force, n, nd, s->posC, s->velB, s->rho, s->idsB, s->cell_sorted, s->cell_start, s->G, C,
                    s->posA, s->velA, s->diag ? &s->D : nullptr, s->nlist, s->ncount); }
     if (t) {
         TerrainDev T = terrain_view(t);
         Scope k(s, SPHE_K_TERRAIN, terrain_stage_launches(C, T));
-        launch_terrain_stage(s->st, n, s->posC, s->posA, s->velA, (int*)s->sedB, C, T, 1, s->req_vertex, s->req_amount, nullptr);
+        launch_terrain_stage(s->st, n, nd, s->posB, s->posA, s->velA, (int*)s->sedB, C, T, 1, s->req_vertex, s->req_amount, nullptr);
     }
     std::swap(s->idsA, s->idsB);
     std::swap(s->sedA, s->sedB);
@@ -411,6 +423,8 @@ void sphe_destroy(sphe_sim* s) {
                         s->flush_buf, s->slab_counters, s->D.acc, s->D.fpress, s->D.fvisc, s->D.fgrav, s->D.fsurf, s->D.normal, s->D.neighb};
         for (void* p : ptrs) if (p) cudaFree(p);
         if (s->slab_host) cudaFreeHost(s->slab_host);
+        if (s->d_n) cudaFree(s->d_n);
+        for (auto& e : s->slab_ev) if (e) cudaEventDestroy(e);
         if (s->own_stream && s->st) cudaStreamDestroy(s->st);
     }
     delete s;
@@ -834,6 +848,9 @@ int sphe_slab_configure(sphe_sim* s, int x0, int x1, int has_left, int has_right
     s->slab_on = true;
     s->grid_h = -1.f;  // re-window the grid
     if (!s->slab_counters) CU(cudaMalloc(&s->slab_counters, 8 * sizeof(int)));
+    if (!s->d_n) CU(cudaMalloc(&s->d_n, sizeof(int)));
+    if (!s->slab_host) CU(cudaMallocHost(&s->slab_host, sphe_sim::SLAB_RING * 8 * sizeof(int)));
+    for (auto& e : s->slab_ev) if (!e) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     return SPHE_OK;
 }
 
@@ -841,6 +858,7 @@ int sphe_slab_info(sphe_sim* s, int* gnx, int* xoff, int* n_total, int* n_owned)
     if (!s) return fail(SPHE_ERR_ARG, "NULL handle");
     TRY(ensure_device(s));
     TRY(setup_grid(s));
+    TRY(slab_settle(s));
     if (gnx) *gnx = s->G.gnx;
     if (xoff) *xoff = s->G.xoff;
     if (n_total) *n_total = s->n;
@@ -863,6 +881,7 @@ int sphe_slab_upload(sphe_sim* s, int n, const float* pos, const float* vel, con
     launch_pack_state_ids(s->st, n, dpos, dvel, dids, s->posA, s->velA, s->idsA, s->sedA);
     CU(cudaStreamSynchronize(s->st));
     s->n = n; s->n_owned = n;
+    s->slab_done = s->slab_seq; s->slab_pending = 0;
     s->num = n; s->init_num = n; s->next_label = n;
     s->labels.clear(); s->labels_identity = true;
     s->binned = false; s->slot_valid = false;
@@ -877,47 +896,106 @@ int sphe_slab_pack(sphe_sim* s, void* dev_send_left, void* dev_send_right, int c
     // room for everything that can arrive, so nothing has to grow between pack and unpack
     TRY(reserve(s, std::max(s->n + reserve_incoming, 1)));
     CU(cudaMemsetAsync(s->slab_counters, 0, 8 * sizeof(int), s->st));
-    launch_slab_classify(s->st, s->n, s->posA, s->velA, s->idsA, s->sedA, s->G, s->slab, s->posB, s->velB, s->idsB, s->sedB,
+    launch_slab_classify(s->st, s->n, s->slab_pending ? s->d_n : nullptr, s->posA, s->velA, s->idsA, s->sedA, s->G, s->slab, s->posB, s->velB, s->idsB, s->sedB,
                          (float4*)dev_send_left, (float4*)dev_send_right, cap_records, s->slab_counters);
     launch_slab_headers(s->st, s->slab_counters, (float4*)dev_send_left, (float4*)dev_send_right);
     s->launches += 2;
     std::swap(s->posA, s->posB); std::swap(s->velA, s->velB); std::swap(s->idsA, s->idsB); std::swap(s->sedA, s->sedB);
     s->binned = false; s->slot_valid = false;
     s->slab_cap_sent = cap_records;
+    s->slab_unpacked = false;
     CU(cudaGetLastError());
     return SPHE_OK;
 }
 
-int sphe_slab_unpack(sphe_sim* s, const void* dev_recv_left, int max_left, const void* dev_recv_right, int max_right, int out[6]) {
+// Folds the result of ticket `t` (which must have completed) into the host-side bookkeeping.
+static int slab_fold(sphe_sim* s, long long t, int out[6]) {
+    const int slot = (int)(t % sphe_sim::SLAB_RING);
+    const int* c = s->slab_host + 8 * slot;  // kept, to_left, to_right, owned(kept), owned(appended), from_left, from_right
+    if (c[1] > s->slab_cap_sent || c[2] > s->slab_cap_sent)
+        return fail(SPHE_ERR_NOMEM, "slab send overflow: %d left / %d right records > buffer capacity %d", c[1], c[2], s->slab_cap_sent);
+    int got_l = std::min(c[5], s->slab_max[slot][0]), got_r = std::min(c[6], s->slab_max[slot][1]);
+    long long n = (long long)c[0] + got_l + got_r;
+    if (n > s->cap) return fail(SPHE_ERR_NOMEM, "slab particle capacity %d exceeded (%lld)", s->cap, n);
+    if (t + 1 > s->slab_done) {
+        // exact count at ticket t + what later tickets may have added since
+        long long hi = n;
+        for (long long u = t + 1; u < s->slab_seq; u++) hi += s->slab_add[u % sphe_sim::SLAB_RING];
+        s->n = (int)std::min<long long>(hi, s->cap);
+        s->n_owned = c[3] + c[4];
+        s->slab_done = t + 1;
+        s->slab_pending = (int)(s->slab_seq - s->slab_done);
+    }
+    if (out) { out[0] = (int)n; out[1] = c[3] + c[4]; out[2] = c[1]; out[3] = c[2]; out[4] = c[5]; out[5] = c[6]; }
+    return SPHE_OK;
+}
+
+// Blocks until every issued ticket has completed and s->n is exact again.
+static int slab_settle(sphe_sim* s) {
+    if (!s->slab_on || s->slab_seq == s->slab_done) return SPHE_OK;
+    long long t = s->slab_seq - 1;
+    CU(cudaEventSynchronize(s->slab_ev[t % sphe_sim::SLAB_RING]));
+    return slab_fold(s, t, nullptr);
+}
+
+int sphe_slab_unpack_async(sphe_sim* s, const void* dev_recv_left, int max_left, const void* dev_recv_right, int max_right,
+                           long long* ticket) {
     if (!s || max_left < 0 || max_right < 0) return fail(SPHE_ERR_ARG, "bad arguments");
     if (!s->slab_on) return fail(SPHE_ERR_STATE, "call sphe_slab_configure first");
     TRY(ensure_device(s));
     if (!dev_recv_left) max_left = 0;
     if (!dev_recv_right) max_right = 0;
-    CU(cudaMemsetAsync(s->slab_counters + 4, 0, 3 * sizeof(int), s->st));  // unpack may be repeated after a re-send
+    // never let the ring wrap over a result that has not been folded yet
+    if (s->slab_seq - s->slab_done >= sphe_sim::SLAB_RING - 1) {
+        long long t = s->slab_seq - 2;
+        CU(cudaEventSynchronize(s->slab_ev[t % sphe_sim::SLAB_RING]));
+        TRY(slab_fold(s, t, nullptr));
+    }
+    const long long t = s->slab_seq;
+    const int slot = (int)(t % sphe_sim::SLAB_RING);
+    if (s->slab_unpacked) CU(cudaMemsetAsync(s->slab_counters + 4, 0, 3 * sizeof(int), s->st));  // repeated after a re-send
+    s->slab_unpacked = true;
     launch_slab_append(s->st, max_left, max_right, (const float4*)dev_recv_left, (const float4*)dev_recv_right, s->G, s->slab,
-                       s->cap, s->posA, s->velA, s->idsA, s->sedA, s->slab_counters);
+                       s->cap, s->posA, s->velA, s->idsA, s->sedA, s->slab_counters, s->d_n);
     s->launches += 1;
-    if (!s->slab_host) CU(cudaMallocHost(&s->slab_host, 8 * sizeof(int)));
-    CU(cudaMemcpyAsync(s->slab_host, s->slab_counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, s->st));
-    CU(cudaStreamSynchronize(s->st));   // the step's only host sync: the particle count sizes the next launches
-    const int* c = s->slab_host;        // kept, to_left, to_right, owned(kept), owned(appended), from_left, from_right
-    if (c[1] > s->slab_cap_sent || c[2] > s->slab_cap_sent)
-        return fail(SPHE_ERR_NOMEM, "slab send overflow: %d left / %d right records > buffer capacity %d", c[1], c[2], s->slab_cap_sent);
-    // a header count above the posted size means the transfer was truncated: the caller re-sends that
-    // link at full capacity and calls unpack again (out[] carries the counts it needs to decide)
-    int got_l = std::min(c[5], max_left), got_r = std::min(c[6], max_right);
-    long long n = (long long)c[0] + got_l + got_r;
-    if (n > s->cap) return fail(SPHE_ERR_NOMEM, "slab particle capacity %d exceeded (%lld)", s->cap, n);
-    s->n = (int)n; s->n_owned = c[3] + c[4];
+    CU(cudaMemcpyAsync(s->slab_host + 8 * slot, s->slab_counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaEventRecord(s->slab_ev[slot], s->st));
+    s->slab_add[slot] = max_left + max_right;
+    s->slab_max[slot][0] = max_left; s->slab_max[slot][1] = max_right;
+    s->slab_seq = t + 1;
+    s->slab_pending = (int)(s->slab_seq - s->slab_done);
+    // until the result is folded, n is an upper bound (pack made room for it) and kernels read d_n
+    s->n = (int)std::min<long long>((long long)s->n + max_left + max_right, s->cap);
     s->binned = false; s->slot_valid = false;
-    if (out) { out[0] = s->n; out[1] = s->n_owned; out[2] = c[1]; out[3] = c[2]; out[4] = c[5]; out[5] = c[6]; }
+    if (ticket) *ticket = t;
+    CU(cudaGetLastError());
     return SPHE_OK;
+}
+
+int sphe_slab_result(sphe_sim* s, long long ticket, int wait, int out[6]) {
+    if (!s || ticket < 0 || ticket >= s->slab_seq) return fail(SPHE_ERR_ARG, "unknown ticket");
+    if (s->slab_seq - ticket > sphe_sim::SLAB_RING) return fail(SPHE_ERR_STATE, "ticket %lld is too old", ticket);
+    TRY(ensure_device(s));
+    cudaEvent_t ev = s->slab_ev[ticket % sphe_sim::SLAB_RING];
+    if (wait) CU(cudaEventSynchronize(ev));
+    else {
+        cudaError_t e = cudaEventQuery(ev);
+        if (e == cudaErrorNotReady) return 1;  // not an error: result not available yet
+        CU(e);
+    }
+    return slab_fold(s, ticket, out);
+}
+
+int sphe_slab_unpack(sphe_sim* s, const void* dev_recv_left, int max_left, const void* dev_recv_right, int max_right, int out[6]) {
+    long long t = 0;
+    TRY(sphe_slab_unpack_async(s, dev_recv_left, max_left, dev_recv_right, max_right, &t));
+    return sphe_slab_result(s, t, 1, out);   // the synchronous form: one host sync per step
 }
 
 int sphe_slab_download(sphe_sim* s, int cap, int* ids, float* pos, float* vel, float* rho, float* sed, int* n_out) {
     if (!s || !ids || !pos || !vel || !n_out) return fail(SPHE_ERR_ARG, "bad arguments");
     TRY(ensure_device(s));
+    TRY(slab_settle(s));
     int n = s->n;
     *n_out = 0;
     if (n == 0) return SPHE_OK;
@@ -1194,7 +1272,7 @@ int sphe_terrain_stage_host(sphe_terrain* t, int n, const float* pos_curr, float
     CU(cudaMemcpy(sd, sediment, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
     StepC C{};
     C.dt = dt; C.cR = cR; C.box = 0; C.cube = 1; C.lenx = C.leny = C.lenz = C.len = 3.0e38f;
-    launch_terrain_stage(0, n, po, pn, vn, sd, C, terrain_view(t), 0, rq, rq + n, dh);
+    launch_terrain_stage(0, n, nullptr, po, pn, vn, sd, C, terrain_view(t), 0, rq, rq + n, dh);
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(b.data(), pn, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(c.data(), vn, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost));
@@ -1230,6 +1308,7 @@ int sphe_terrain_contacts(sphe_terrain* t, long long* total, int reset) {
 int sphe_sediment_total_fx(sphe_sim* s, long long* sum) {
     if (!s || !sum) return fail(SPHE_ERR_ARG, "bad arguments");
     TRY(ensure_device(s));
+    TRY(slab_settle(s));
     *sum = 0;
     if (s->n == 0) return SPHE_OK;
     long long* d = nullptr;

@@ -13,8 +13,9 @@ namespace sphe {
 // One thread per particle (storage order).  Storage order is last step's sorted order, so
 // consecutive lanes mostly share a cell: counts are aggregated per run of equal cells inside the
 // warp (shfl + ballot) and only the run head issues the atomic.
-__global__ void __launch_bounds__(256) k_hash(int n, const float4* __restrict__ posq, GridP G,
+__global__ void __launch_bounds__(256) k_hash(int n_hi, const int* __restrict__ n_dev, const float4* __restrict__ posq, GridP G,
                                               uint32_t* __restrict__ cell, int* __restrict__ count) {
+    const int n = n_dev ? __ldg(n_dev) : n_hi;  // exact count from the device in slab mode, else the launch bound
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned lane = threadIdx.x & 31;
     uint32_t c = 0xffffffffu;
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(int ntiles, int* __restrict
     }
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(long long ncells, int n_total, int* __restrict__ count,
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(long long ncells, int n_total, const int* __restrict__ n_dev, int* __restrict__ count,
                                                              const int* __restrict__ tile_off,
                                                              int* __restrict__ cell_start, int* __restrict__ cursor) {
     long long base = (long long)blockIdx.x * SCAN_TILE;
@@ -152,14 +153,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(long long ncells, i
             if (e0 + k < ncells) { cell_start[e0 + k] = run; cursor[e0 + k] = run; count[e0 + k] = 0; run += v[k]; }
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) cell_start[ncells] = n_total;
+    if (blockIdx.x == 0 && threadIdx.x == 0) cell_start[ncells] = n_dev ? __ldg(n_dev) : n_total;
 }
 
 // ---------------------------------------------------------------- counting-sort scatter
 // slot = cursor[cell]++ (run-aggregated).  The order INSIDE a cell is whatever the atomics give;
 // k_rank_reorder makes it canonical.
-__global__ void __launch_bounds__(256) k_scatter(int n, const uint32_t* __restrict__ cell, const int* __restrict__ ids,
+__global__ void __launch_bounds__(256) k_scatter(int n_hi, const int* __restrict__ n_dev, const uint32_t* __restrict__ cell, const int* __restrict__ ids,
                                                  int* __restrict__ cursor, uint2* __restrict__ tmp) {
+    const int n = n_dev ? __ldg(n_dev) : n_hi;  // exact count from the device in slab mode, else the launch bound
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned lane = threadIdx.x & 31;
     uint32_t c = (i < n) ? cell[i] : 0xffffffffu;
@@ -183,13 +185,14 @@ __global__ void __launch_bounds__(256) k_scatter(int n, const uint32_t* __restri
 // ---------------------------------------------------------------- rank inside the cell + reorder
 // One thread per scattered slot.  rank = number of particles of the same cell with a smaller id;
 // destination = cell_start + rank.  Then gather the particle's state from its old storage slot.
-__global__ void __launch_bounds__(256) k_rank_reorder(int n, const uint2* __restrict__ tmp, const uint32_t* __restrict__ cell,
+__global__ void __launch_bounds__(256) k_rank_reorder(int n_hi, const int* __restrict__ n_dev, const uint2* __restrict__ tmp, const uint32_t* __restrict__ cell,
                                                       const int* __restrict__ cell_start,
                                                       const float4* __restrict__ posq_in, const float4* __restrict__ velv_in,
                                                       const float* __restrict__ sed_in,
                                                       float4* __restrict__ posq_out, float4* __restrict__ velv_out,
                                                       float* __restrict__ sed_out, int* __restrict__ ids_out,
                                                       uint32_t* __restrict__ cell_sorted) {
+    const int n = n_dev ? __ldg(n_dev) : n_hi;  // exact count from the device in slab mode, else the launch bound
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     uint2 me = tmp[s];
@@ -208,30 +211,30 @@ __global__ void __launch_bounds__(256) k_rank_reorder(int n, const uint2* __rest
 }
 
 // ---------------------------------------------------------------- launch wrappers
-void launch_hash(cudaStream_t st, int n, const float4* posq, const GridP& G, uint32_t* cell, int* count) {
+void launch_hash(cudaStream_t st, int n, const int* n_dev, const float4* posq, const GridP& G, uint32_t* cell, int* count) {
     if (n <= 0) return;
-    k_hash<<<(n + 255) / 256, 256, 0, st>>>(n, posq, G, cell, count);
+    k_hash<<<(n + 255) / 256, 256, 0, st>>>(n, n_dev, posq, G, cell, count);
 }
 
 int scan_tiles_for(long long ncells) { return (int)((ncells + SCAN_TILE - 1) / SCAN_TILE); }
 
-void launch_scan(cudaStream_t st, long long ncells, int n_total, int* count, int* tile_sum, int* cell_start, int* cursor) {
+void launch_scan(cudaStream_t st, long long ncells, int n_total, const int* n_dev, int* count, int* tile_sum, int* cell_start, int* cursor) {
     int ntiles = scan_tiles_for(ncells);
     k_scan_reduce<<<ntiles, SCAN_THREADS, 0, st>>>(ncells, count, tile_sum);
     k_scan_tiles<<<1, 1024, 0, st>>>(ntiles, tile_sum);
-    k_scan_final<<<ntiles, SCAN_THREADS, 0, st>>>(ncells, n_total, count, tile_sum, cell_start, cursor);
+    k_scan_final<<<ntiles, SCAN_THREADS, 0, st>>>(ncells, n_total, n_dev, count, tile_sum, cell_start, cursor);
 }
 
-void launch_scatter(cudaStream_t st, int n, const uint32_t* cell, const int* ids, int* cursor, uint2* tmp) {
+void launch_scatter(cudaStream_t st, int n, const int* n_dev, const uint32_t* cell, const int* ids, int* cursor, uint2* tmp) {
     if (n <= 0) return;
-    k_scatter<<<(n + 255) / 256, 256, 0, st>>>(n, cell, ids, cursor, tmp);
+    k_scatter<<<(n + 255) / 256, 256, 0, st>>>(n, n_dev, cell, ids, cursor, tmp);
 }
 
-void launch_rank_reorder(cudaStream_t st, int n, const uint2* tmp, const uint32_t* cell, const int* cell_start,
+void launch_rank_reorder(cudaStream_t st, int n, const int* n_dev, const uint2* tmp, const uint32_t* cell, const int* cell_start,
                          const float4* posq_in, const float4* velv_in, const float* sed_in,
                          float4* posq_out, float4* velv_out, float* sed_out, int* ids_out, uint32_t* cell_sorted) {
     if (n <= 0) return;
-    k_rank_reorder<<<(n + 255) / 256, 256, 0, st>>>(n, tmp, cell, cell_start, posq_in, velv_in, sed_in,
+    k_rank_reorder<<<(n + 255) / 256, 256, 0, st>>>(n, n_dev, tmp, cell, cell_start, posq_in, velv_in, sed_in,
                                                     posq_out, velv_out, sed_out, ids_out, cell_sorted);
 }
 

@@ -1,4 +1,7 @@
 // Internal declarations shared by the .cu translation units (not part of the C ABI).
+// Launchers of the per-step kernels take the particle count twice: `n` sizes the grid (an upper bound is
+// enough) and `n_dev`, when not NULL, is a device word holding the exact count -- in slab mode the host
+// launches a step before it knows how many halo records arrived.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -7,11 +10,11 @@
 namespace sphe {
 
 // ---- binning.cu
-void launch_hash(cudaStream_t st, int n, const float4* posq, const GridP& G, uint32_t* cell, int* count);
+void launch_hash(cudaStream_t st, int n, const int* n_dev, const float4* posq, const GridP& G, uint32_t* cell, int* count);
 int scan_tiles_for(long long ncells);
-void launch_scan(cudaStream_t st, long long ncells, int n_total, int* count, int* tile_sum, int* cell_start, int* cursor);
-void launch_scatter(cudaStream_t st, int n, const uint32_t* cell, const int* ids, int* cursor, uint2* tmp);
-void launch_rank_reorder(cudaStream_t st, int n, const uint2* tmp, const uint32_t* cell, const int* cell_start,
+void launch_scan(cudaStream_t st, long long ncells, int n_total, const int* n_dev, int* count, int* tile_sum, int* cell_start, int* cursor);
+void launch_scatter(cudaStream_t st, int n, const int* n_dev, const uint32_t* cell, const int* ids, int* cursor, uint2* tmp);
+void launch_rank_reorder(cudaStream_t st, int n, const int* n_dev, const uint2* tmp, const uint32_t* cell, const int* cell_start,
                          const float4* posq_in, const float4* velv_in, const float* sed_in,
                          float4* posq_out, float4* velv_out, float* sed_out, int* ids_out, uint32_t* cell_sorted);
 
@@ -32,7 +35,7 @@ struct TerrainDev {
     int hmin_fx, max_pickup_fx;
     int erosion;
 };
-void launch_terrain_stage(cudaStream_t st, int n, const float4* pos_old, float4* posq, float4* velv, int* sediment,
+void launch_terrain_stage(cudaStream_t st, int n, const int* n_dev, const float4* pos_old, float4* posq, float4* velv, int* sediment,
                           const StepC& C, const TerrainDev& T, int apply_box, int* req_vertex, int* req_amount, int* hit_out);
 int terrain_stage_launches(const StepC& C, const TerrainDev& T);
 void launch_terrain_surface(cudaStream_t st, const TerrainDev& T, float* out);
@@ -50,12 +53,12 @@ struct SlabP {
     int halo;        // cell layers mirrored from each neighbour
     int has_left, has_right;
 };
-void launch_slab_classify(cudaStream_t st, int n, const float4* posq, const float4* velv, const int* ids, const float* sed,
+void launch_slab_classify(cudaStream_t st, int n, const int* n_dev, const float4* posq, const float4* velv, const int* ids, const float* sed,
                           const GridP& G, const SlabP& S, float4* keep_pos, float4* keep_vel, int* keep_ids, float* keep_sed,
                           float4* send_left, float4* send_right, int cap_records, int* counters);
-void launch_slab_headers(cudaStream_t st, const int* counters, float4* send_left, float4* send_right);
+void launch_slab_headers(cudaStream_t st, int* counters, float4* send_left, float4* send_right);
 void launch_slab_append(cudaStream_t st, int max_l, int max_r, const float4* rec_l, const float4* rec_r, const GridP& G,
-                        const SlabP& S, int cap_particles, float4* posq, float4* velv, int* ids, float* sed, int* counters);
+                        const SlabP& S, int cap_particles, float4* posq, float4* velv, int* ids, float* sed, int* counters, int* n_out);
 void launch_slab_gather_owned(cudaStream_t st, int n, const float4* posq, const float4* velv, const float* rho, const float* sed,
                               const int* ids, int* counter, int* out_ids, float* out_pos, float* out_vel, float* out_rho,
                               float* out_sed);
@@ -76,12 +79,12 @@ struct DiagOut {
 };
 
 
-void launch_density(cudaStream_t st, int variant, int n, const float4* posq, float4* posq_q, float4* velv,
+void launch_density(cudaStream_t st, int variant, int n, const int* n_dev, const float4* posq, float4* posq_q, float4* velv,
                     const uint32_t* cell_sorted, const int* cell_start, const GridP& G, const StepC& C, float* rho,
                     int* nlist, int2* ncount);
 int nlist_cap();
 int nlist_pairs_pad(int n);
-void launch_force(cudaStream_t st, int variant, int n, const float4* posq, const float4* velv, const float* rho,
+void launch_force(cudaStream_t st, int variant, int n, const int* n_dev, const float4* posq, const float4* velv, const float* rho,
                   const int* ids, const uint32_t* cell_sorted, const int* cell_start, const GridP& G, const StepC& C,
                   float4* posq_out, float4* velv_out, const DiagOut* diag, const int* nlist, const int2* ncount);
 void launch_neighbour_count(cudaStream_t st, int n, const float4* posq, const uint32_t* cell_sorted, const int* cell_start,

@@ -47,10 +47,11 @@ __device__ __forceinline__ void walk27(const GridP& G, const int* __restrict__ c
 // ------------------------------------------------------------------ pass 1: density + pressure
 // Writes rho, and packs what pass 2 needs per neighbour into the arrays it will stream anyway:
 //   posq_q[i] = (x, y, z, P_i / rho_i^2)      velv[i].w = mass / rho_i
-__global__ void __launch_bounds__(128) k_density_tpp(int n, const float4* __restrict__ posq, float4* __restrict__ posq_q,
+__global__ void __launch_bounds__(128) k_density_tpp(int n_hi, const int* __restrict__ n_dev, const float4* __restrict__ posq, float4* __restrict__ posq_q,
                                                      float4* __restrict__ velv, const uint32_t* __restrict__ cell_sorted,
                                                      const int* __restrict__ cell_start, GridP G, StepC C,
                                                      float* __restrict__ rho) {
+    const int n = n_dev ? __ldg(n_dev) : n_hi;  // exact count from the device in slab mode, else the launch bound
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 pi = posq[i];
@@ -123,10 +124,11 @@ __device__ __forceinline__ float2 density_walk_pair(const GridP& G, const int* _
 // leaves fewer distinct cells per warp (less trip-count divergence).  Partial sums are combined with
 // __shfl_xor.
 template <int S>
-__global__ void __launch_bounds__(128) k_density_pair(int n, const float4* __restrict__ posq, float4* __restrict__ posq_q,
+__global__ void __launch_bounds__(128) k_density_pair(int n_hi, const int* __restrict__ n_dev, const float4* __restrict__ posq, float4* __restrict__ posq_q,
                                                       float4* __restrict__ velv, const uint32_t* __restrict__ cell_sorted,
                                                       const int* __restrict__ cell_start, GridP G, StepC C,
                                                       float* __restrict__ rho) {
+    const int n = n_dev ? __ldg(n_dev) : n_hi;  // exact count from the device in slab mode, else the launch bound
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int slice = gt % S;
     int a = 2 * (gt / S);
@@ -212,11 +214,12 @@ __device__ __forceinline__ void force_epilogue(int i, float4 pi, float4 vi, floa
 
 // ------------------------------------------------------------------ passes 2+3 + integrate + collide
 template <bool DIAG>
-__global__ void __launch_bounds__(128) k_force_tpp(int n, const float4* __restrict__ posq_q, const float4* __restrict__ velv,
+__global__ void __launch_bounds__(128) k_force_tpp(int n_hi, const int* __restrict__ n_dev, const float4* __restrict__ posq_q, const float4* __restrict__ velv,
                                                    const float* __restrict__ rho, const int* __restrict__ ids,
                                                    const uint32_t* __restrict__ cell_sorted,
                                                    const int* __restrict__ cell_start, GridP G, StepC C,
                                                    float4* __restrict__ posq_out, float4* __restrict__ velv_out, DiagOut D) {
+    const int n = n_dev ? __ldg(n_dev) : n_hi;  // exact count from the device in slab mode, else the launch bound
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 pi = posq_q[i];
@@ -314,11 +317,12 @@ constexpr int FORCE_LIST_CAP = 48;
 constexpr int FORCE_THREADS = 128;
 
 template <bool DIAG>
-__global__ void __launch_bounds__(FORCE_THREADS) k_force_pair(int n, const float4* __restrict__ posq_q, const float4* __restrict__ velv,
+__global__ void __launch_bounds__(FORCE_THREADS) k_force_pair(int n_hi, const int* __restrict__ n_dev, const float4* __restrict__ posq_q, const float4* __restrict__ velv,
                                                     const float* __restrict__ rho, const int* __restrict__ ids,
                                                     const uint32_t* __restrict__ cell_sorted,
                                                     const int* __restrict__ cell_start, GridP G, StepC C,
                                                     float4* __restrict__ posq_out, float4* __restrict__ velv_out, DiagOut D) {
+    const int n = n_dev ? __ldg(n_dev) : n_hi;  // exact count from the device in slab mode, else the launch bound
     __shared__ int list[(FORCE_LIST_CAP + 1) * FORCE_THREADS];  // +1: trash slot for saturated appends
     const int tid = threadIdx.x;
     int a = 2 * (blockIdx.x * blockDim.x + tid);
@@ -482,12 +486,17 @@ __global__ void __launch_bounds__(FORCE_THREADS) k_force_pair(int n, const float
 constexpr int NLIST_CAP = 64;       // entries per pair (both split passes together)
 constexpr int NLIST_THREADS = 128;
 
-__global__ void __launch_bounds__(NLIST_THREADS) k_density_list(int n, int npairs_pad, const float4* __restrict__ posq,
+// REC = true (variant 4): instead of (posC, vel.w) the pass writes ONE interleaved 32-byte record per particle,
+// rec[2i] = (x, y, z, P/rho^2), rec[2i+1] = (vx, vy, vz, m/rho), so the force pass fetches everything it needs
+// about a neighbour with a single 256-bit gather (LDG.E.256, new on sm_100) instead of two 128-bit ones.
+template <bool REC>
+__global__ void __launch_bounds__(NLIST_THREADS) k_density_list(int n_hi, const int* __restrict__ n_dev, int npairs_pad, const float4* __restrict__ posq,
                                                                 float4* __restrict__ posq_q, float4* __restrict__ velv,
                                                                 const uint32_t* __restrict__ cell_sorted,
                                                                 const int* __restrict__ cell_start, GridP G, StepC C,
                                                                 float* __restrict__ rho, int* __restrict__ nlist,
                                                                 int2* __restrict__ ncount) {
+    const int n = n_dev ? __ldg(n_dev) : n_hi;  // exact count from the device in slab mode, else the launch bound
     __shared__ int list[(NLIST_CAP + 1) * NLIST_THREADS];  // +1: trash slot for saturated appends
     const int tid = threadIdx.x;
     const int t = blockIdx.x * blockDim.x + tid;
@@ -557,31 +566,53 @@ __global__ void __launch_bounds__(NLIST_THREADS) k_density_list(int n, int npair
     float ra = acc.x * C.densK, rb = acc.y * C.densK;
     float Pa = C.k * (ra - C.p0), Pb = C.k * (rb - C.p0);
     rho[a] = ra;
-    posq_q[a] = make_float4(pa.x, pa.y, pa.z, Pa / (ra * ra));
-    velv[a].w = C.mass / ra;
+    if (REC) {
+        // posq_q doubles as the record array (2n float4)
+        const float4 va = velv[a];
+        posq_q[2 * a] = make_float4(pa.x, pa.y, pa.z, Pa / (ra * ra));
+        posq_q[2 * a + 1] = make_float4(va.x, va.y, va.z, C.mass / ra);
+    } else {
+        posq_q[a] = make_float4(pa.x, pa.y, pa.z, Pa / (ra * ra));
+        velv[a].w = C.mass / ra;
+    }
     if (b != a) {
         rho[b] = rb;
-        posq_q[b] = make_float4(pb.x, pb.y, pb.z, Pb / (rb * rb));
-        velv[b].w = C.mass / rb;
+        if (REC) {
+            const float4 vb = velv[b];
+            posq_q[2 * b] = make_float4(pb.x, pb.y, pb.z, Pb / (rb * rb));
+            posq_q[2 * b + 1] = make_float4(vb.x, vb.y, vb.z, C.mass / rb);
+        } else {
+            posq_q[b] = make_float4(pb.x, pb.y, pb.z, Pb / (rb * rb));
+            velv[b].w = C.mass / rb;
+        }
     }
+}
+
+// one 256-bit read-only gather of an interleaved particle record
+__device__ __forceinline__ void ldg_rec(const float4* __restrict__ rec, int k, float4& p, float4& v) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(p.x), "=f"(p.y), "=f"(p.z), "=f"(p.w), "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+        : "l"(rec + 2 * (size_t)k));
 }
 
 #ifndef FL_MINB
 #define FL_MINB 7
 #endif
-template <bool DIAG>
-__global__ void __launch_bounds__(NLIST_THREADS, FL_MINB) k_force_list(int n, int npairs_pad, const float4* __restrict__ posq_q,
+template <bool DIAG, bool REC>
+__global__ void __launch_bounds__(NLIST_THREADS, FL_MINB) k_force_list(int n_hi, const int* __restrict__ n_dev, int npairs_pad, const float4* __restrict__ posq_q,
                                                               const float4* __restrict__ velv, const float* __restrict__ rho,
                                                               const int* __restrict__ ids, const uint32_t* __restrict__ cell_sorted,
                                                               const int* __restrict__ cell_start, GridP G, StepC C,
                                                               const int* __restrict__ nlist, const int2* __restrict__ ncount,
                                                               float4* __restrict__ posq_out, float4* __restrict__ velv_out, DiagOut D) {
+    const int n = n_dev ? __ldg(n_dev) : n_hi;  // exact count from the device in slab mode, else the launch bound
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int a = 2 * t;
     if (a >= n) return;
     const int b = (a + 1 < n) ? a + 1 : a;
-    const float4 pa = posq_q[a], pb = posq_q[b];
-    const float4 va = velv[a], vb = velv[b];
+    float4 pa, pb, va, vb;
+    if (REC) { ldg_rec(posq_q, a, pa, va); ldg_rec(posq_q, b, pb, vb); }
+    else { pa = posq_q[a]; pb = posq_q[b]; va = velv[a]; vb = velv[b]; }
     const int2 cn = ncount[t];
     const float inv_sqrt3 = 0.57735026f;
     const float FAR = 1.0e18f;
@@ -653,13 +684,13 @@ __global__ void __launch_bounds__(NLIST_THREADS, FL_MINB) k_force_list(int n, in
             // software pipeline: the next entry's index and gathers are in flight while this one is processed
             // (a two-stage version raised the register count to 94 and lost a CTA/SM: slower, measured)
             int k = __ldg(&src[(size_t)e0 * npairs_pad]);
-            float4 pj = __ldg(&posq_q[k]);
-            float4 vj = __ldg(&velv[k]);
+            float4 pj, vj;
+            if (REC) ldg_rec(posq_q, k, pj, vj); else { pj = __ldg(&posq_q[k]); vj = __ldg(&velv[k]); }
 #pragma unroll 1
             for (int e = e0; e < e1; e++) {
                 const int kn = (e + 1 < e1) ? __ldg(&src[(size_t)(e + 1) * npairs_pad]) : k;
-                const float4 pjn = __ldg(&posq_q[kn]);
-                const float4 vjn = __ldg(&velv[kn]);
+                float4 pjn, vjn;
+                if (REC) ldg_rec(posq_q, kn, pjn, vjn); else { pjn = __ldg(&posq_q[kn]); vjn = __ldg(&velv[kn]); }
                 body(k, pj, vj);
                 k = kn; pj = pjn; vj = vjn;
             }
@@ -691,11 +722,12 @@ __global__ void __launch_bounds__(NLIST_THREADS, FL_MINB) k_force_list(int n, in
                 int e = __ldg(&cell_start[base + z1 + 1]);
 #pragma unroll 1
                 for (int k = s; k < e; k++) {
-                    float4 pj = __ldg(&posq_q[k]);
+                    float4 pj, vj;
+                    if (REC) ldg_rec(posq_q, k, pj, vj); else { pj = __ldg(&posq_q[k]); vj = __ldg(&velv[k]); }
                     float ex = X.x - pj.x, ey = Y.x - pj.y, ez = Z.x - pj.z;
                     float gx = X.y - pj.x, gy = Y.y - pj.y, gz = Z.y - pj.z;
                     float da = fmaf(ez, ez, fmaf(ey, ey, ex * ex)), db = fmaf(gz, gz, fmaf(gy, gy, gx * gx));
-                    if (fminf(da, db) <= C.hh) body(k, pj, __ldg(&velv[k]));
+                    if (fminf(da, db) <= C.hh) body(k, pj, vj);
                 }
             }
         }
@@ -778,42 +810,49 @@ static inline int nblk(int n, int b) { return (n + b - 1) / b; }
 int nlist_cap() { return NLIST_CAP; }
 int nlist_pairs_pad(int n) { return (((n + 1) / 2) + 127) & ~127; }
 
-void launch_density(cudaStream_t st, int variant, int n, const float4* posq, float4* posq_q, float4* velv,
+void launch_density(cudaStream_t st, int variant, int n, const int* n_dev, const float4* posq, float4* posq_q, float4* velv,
                     const uint32_t* cell_sorted, const int* cell_start, const GridP& G, const StepC& C, float* rho,
                     int* nlist, int2* ncount) {
     if (n <= 0) return;
     int pairs = (n + 1) / 2;
-    if (variant == 3) {
+    if (variant == 3 || variant == 4) {
         int pp = nlist_pairs_pad(n);
-        k_density_list<<<pp / NLIST_THREADS, NLIST_THREADS, 0, st>>>(n, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount);
+        if (variant == 4) k_density_list<true><<<pp / NLIST_THREADS, NLIST_THREADS, 0, st>>>(n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount);
+        else k_density_list<false><<<pp / NLIST_THREADS, NLIST_THREADS, 0, st>>>(n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount);
         return;
     }
-    if (variant == 1) k_density_pair<1><<<nblk(pairs, 128), 128, 0, st>>>(n, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho);
-    else if (variant == 2) k_density_pair<2><<<nblk(pairs * 2, 128), 128, 0, st>>>(n, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho);
-    else if (variant == 4) k_density_pair<4><<<nblk(pairs * 4, 128), 128, 0, st>>>(n, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho);
-    else if (variant == 8) k_density_pair<8><<<nblk(pairs * 8, 128), 128, 0, st>>>(n, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho);
-    else if (variant == 16) k_density_pair<16><<<nblk(pairs * 16, 128), 128, 0, st>>>(n, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho);
-    else k_density_tpp<<<nblk(n, 128), 128, 0, st>>>(n, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho);
+    if (variant == 1) k_density_pair<1><<<nblk(pairs, 128), 128, 0, st>>>(n, n_dev, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho);
+    else if (variant == 2) k_density_pair<2><<<nblk(pairs * 2, 128), 128, 0, st>>>(n, n_dev, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho);
+    else if (variant == 4) k_density_pair<4><<<nblk(pairs * 4, 128), 128, 0, st>>>(n, n_dev, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho);
+    else if (variant == 8) k_density_pair<8><<<nblk(pairs * 8, 128), 128, 0, st>>>(n, n_dev, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho);
+    else if (variant == 16) k_density_pair<16><<<nblk(pairs * 16, 128), 128, 0, st>>>(n, n_dev, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho);
+    else k_density_tpp<<<nblk(n, 128), 128, 0, st>>>(n, n_dev, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho);
 }
 
-void launch_force(cudaStream_t st, int variant, int n, const float4* posq_q, const float4* velv, const float* rho,
+void launch_force(cudaStream_t st, int variant, int n, const int* n_dev, const float4* posq_q, const float4* velv, const float* rho,
                   const int* ids, const uint32_t* cell_sorted, const int* cell_start, const GridP& G, const StepC& C,
                   float4* posq_out, float4* velv_out, const DiagOut* diag, const int* nlist, const int2* ncount) {
     if (n <= 0) return;
-    if (variant == 3) {
+    if (variant == 3 || variant == 4) {
         int pp = nlist_pairs_pad(n);
-        if (diag) k_force_list<true><<<pp / NLIST_THREADS, NLIST_THREADS, 0, st>>>(n, pp, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, nlist, ncount, posq_out, velv_out, *diag);
-        else k_force_list<false><<<pp / NLIST_THREADS, NLIST_THREADS, 0, st>>>(n, pp, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, nlist, ncount, posq_out, velv_out, DiagOut{});
+        dim3 g(pp / NLIST_THREADS), b(NLIST_THREADS);
+        if (variant == 4) {
+            if (diag) k_force_list<true, true><<<g, b, 0, st>>>(n, n_dev, pp, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, nlist, ncount, posq_out, velv_out, *diag);
+            else k_force_list<false, true><<<g, b, 0, st>>>(n, n_dev, pp, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, nlist, ncount, posq_out, velv_out, DiagOut{});
+        } else {
+            if (diag) k_force_list<true, false><<<g, b, 0, st>>>(n, n_dev, pp, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, nlist, ncount, posq_out, velv_out, *diag);
+            else k_force_list<false, false><<<g, b, 0, st>>>(n, n_dev, pp, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, nlist, ncount, posq_out, velv_out, DiagOut{});
+        }
         return;
     }
     if (variant == 1) {
         int nb = nblk((n + 1) / 2, FORCE_THREADS);
-        if (diag) k_force_pair<true><<<nb, FORCE_THREADS, 0, st>>>(n, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, posq_out, velv_out, *diag);
-        else k_force_pair<false><<<nb, FORCE_THREADS, 0, st>>>(n, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, posq_out, velv_out, DiagOut{});
+        if (diag) k_force_pair<true><<<nb, FORCE_THREADS, 0, st>>>(n, n_dev, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, posq_out, velv_out, *diag);
+        else k_force_pair<false><<<nb, FORCE_THREADS, 0, st>>>(n, n_dev, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, posq_out, velv_out, DiagOut{});
         return;
     }
-    if (diag) k_force_tpp<true><<<nblk(n, 128), 128, 0, st>>>(n, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, posq_out, velv_out, *diag);
-    else k_force_tpp<false><<<nblk(n, 128), 128, 0, st>>>(n, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, posq_out, velv_out, DiagOut{});
+    if (diag) k_force_tpp<true><<<nblk(n, 128), 128, 0, st>>>(n, n_dev, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, posq_out, velv_out, *diag);
+    else k_force_tpp<false><<<nblk(n, 128), 128, 0, st>>>(n, n_dev, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, posq_out, velv_out, DiagOut{});
 }
 
 void launch_neighbour_count(cudaStream_t st, int n, const float4* posq, const uint32_t* cell_sorted, const int* cell_start,

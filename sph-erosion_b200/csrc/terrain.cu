@@ -204,10 +204,11 @@ __device__ __forceinline__ void vertex_add(unsigned participants, bool active, i
 // pos_old: positions before the step (sorted slot order, .xyz); posq / velv: the integrated state the
 // force kernel wrote WITHOUT the box collision (StepC.box == 0 when a terrain is attached); both are
 // updated in place.  req_vertex[i] = vertex of a pending pick-up request (or -1), req_amount[i] its size.
-__global__ void __launch_bounds__(128) k_terrain_contact(int n, const float4* __restrict__ pos_old, float4* __restrict__ posq,
+__global__ void __launch_bounds__(128) k_terrain_contact(int n_hi, const int* __restrict__ n_dev, const float4* __restrict__ pos_old, float4* __restrict__ posq,
                                                          float4* __restrict__ velv, int* __restrict__ sediment, StepC C,
                                                          TerrainDev T, int apply_box, int* __restrict__ req_vertex,
                                                          int* __restrict__ req_amount, int* __restrict__ hit_out) {
+    const int n = n_dev ? __ldg(n_dev) : n_hi;  // exact count from the device in slab mode, else the launch bound
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool live = i < n;
     float4 po = make_float4(0, 0, 0, 0), p4 = po, v4 = po;
@@ -270,8 +271,9 @@ __global__ void __launch_bounds__(128) k_terrain_contact(int n, const float4* __
 }
 
 // ------------------------------------------------------------------ share what is above bedrock
-__global__ void __launch_bounds__(256) k_terrain_grant(int n, const int* __restrict__ req_vertex, const int* __restrict__ req_amount,
+__global__ void __launch_bounds__(256) k_terrain_grant(int n_hi, const int* __restrict__ n_dev, const int* __restrict__ req_vertex, const int* __restrict__ req_amount,
                                                        int* __restrict__ sediment, TerrainDev T) {
+    const int n = n_dev ? __ldg(n_dev) : n_hi;  // exact count from the device in slab mode, else the launch bound
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int c = (i < n) ? req_vertex[i] : -1;
     bool act = c >= 0;
@@ -376,12 +378,12 @@ __global__ void __launch_bounds__(256) k_sum_i32(int n, const int* __restrict__ 
 // ------------------------------------------------------------------ launch wrappers
 static inline int nb(int n, int b) { return (n + b - 1) / b; }
 
-void launch_terrain_stage(cudaStream_t st, int n, const float4* pos_old, float4* posq, float4* velv, int* sediment,
+void launch_terrain_stage(cudaStream_t st, int n, const int* n_dev, const float4* pos_old, float4* posq, float4* velv, int* sediment,
                           const StepC& C, const TerrainDev& T, int apply_box, int* req_vertex, int* req_amount, int* hit_out) {
     if (n <= 0) return;
-    k_terrain_contact<<<nb(n, 128), 128, 0, st>>>(n, pos_old, posq, velv, sediment, C, T, apply_box, req_vertex, req_amount, hit_out);
+    k_terrain_contact<<<nb(n, 128), 128, 0, st>>>(n, n_dev, pos_old, posq, velv, sediment, C, T, apply_box, req_vertex, req_amount, hit_out);
     if (T.erosion && C.dt != 0.0f) {
-        k_terrain_grant<<<nb(n, 256), 256, 0, st>>>(n, req_vertex, req_amount, sediment, T);
+        k_terrain_grant<<<nb(n, 256), 256, 0, st>>>(n, n_dev, req_vertex, req_amount, sediment, T);
         k_terrain_apply<<<nb(T.rows * T.cols, 256), 256, 0, st>>>(T.rows * T.cols, T);
     }
 }

@@ -161,6 +161,19 @@ class FluidSystemSPH:
         capi.check(self._L.sphe_slab_unpack(self._h, dev_left, int(max_left), dev_right, int(max_right), out))
         return dict(zip(("n_total", "n_owned", "to_left", "to_right", "from_left", "from_right"), list(out)))
 
+    def slab_unpack_async(self, dev_left, max_left, dev_right, max_right):
+        t = C.c_longlong(0)
+        capi.check(self._L.sphe_slab_unpack_async(self._h, dev_left, int(max_left), dev_right, int(max_right), C.byref(t)))
+        return t.value
+
+    def slab_result(self, ticket, wait=True):
+        out = (C.c_int * 6)()
+        rc = self._L.sphe_slab_result(self._h, int(ticket), int(bool(wait)), out)
+        if rc == 1:
+            return None
+        capi.check(rc)
+        return dict(zip(("n_total", "n_owned", "to_left", "to_right", "from_left", "from_right"), list(out)))
+
     def slab_download(self, cap=None):
         cap = self.count() if cap is None else int(cap)
         ids = np.zeros(cap, np.int32); pos = np.zeros((cap, 3), np.float32); vel = np.zeros((cap, 3), np.float32)

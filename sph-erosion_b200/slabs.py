@@ -96,6 +96,14 @@ class GpuSlabBackend:
         return self.sim.slab_unpack(buf_l.data_ptr() if (self.has_left and buf_l is not None) else None, max_l,
                                     buf_r.data_ptr() if (self.has_right and buf_r is not None) else None, max_r)
 
+    def unpack_async(self, buf_l, max_l, buf_r, max_r):
+        """No host sync: returns a ticket; result(ticket) gives the counts once that step has finished."""
+        return self.sim.slab_unpack_async(buf_l.data_ptr() if (self.has_left and buf_l is not None) else None, max_l,
+                                          buf_r.data_ptr() if (self.has_right and buf_r is not None) else None, max_r)
+
+    def result(self, ticket, wait=True):
+        return self.sim.slab_result(ticket, wait)
+
     def step(self):
         self.sim.Run()
 
@@ -103,30 +111,57 @@ class GpuSlabBackend:
 # --------------------------------------------------------------------------- the per-step protocol
 def next_size(count, cap, floor=1024):
     """Message size (payload records) both ends of a link derive from the count they both saw last."""
-    return int(min(cap, max(floor, count + count // 4 + 1024)))
+    return int(min(cap, max(floor, count + count // 2 + 2048)))
 
 
 class SlabDriver:
-    """pack -> one P2P group -> unpack (the step's only host sync) -> step.  Message sizes follow the
-    previous step's counts, which both ends of a link know; a count that outgrew its message makes
-    both ends repeat that link at full capacity."""
+    """pack -> one P2P group -> unpack -> step.
 
-    def __init__(self, backend, comm):
+    lag = 0 (synchronous): unpack ends with the step's only host sync; message sizes follow the previous
+    step's counts, which both ends of a link know; a count that outgrew its message makes both ends
+    repeat that link at full capacity.
+
+    lag >= 1 (asynchronous, the bench default): NO host sync in the step.  unpack leaves the exact particle
+    count on the device and returns a ticket; the counts of step k are only read back at step k + lag
+    (by then long finished), and the message sizes of step k derive from the counts of step k - lag --
+    still something both ends of a link know, so they keep agreeing without talking.  The first
+    `sync_steps` steps run synchronously (the initial distribution migrates particles in bulk).  The host runs
+    ahead of the GPU by up to `lag` steps, which hides launch and NCCL enqueue latency.  The price: an
+    overflow (halo grew by more than the 50 % + 2048 slack within `lag` steps) is detected after the
+    fact and is an error instead of a re-send."""
+
+    def __init__(self, backend, comm, lag=0, sync_steps=4):
         self.b, self.c = backend, comm
         cap = backend.cap
+        self.lag = int(lag)
+        self.sync_left = int(sync_steps) if lag else 0   # start-up transients (initial migration) run synchronously
         self.out_l = self.out_r = self.in_l = self.in_r = cap
         self.last = None
         self.resends = 0
+        self.pending = []   # (ticket, out_l, out_r, in_l, in_r) of steps whose counts are not folded yet
+
+    def _check(self, info, out_l, out_r, in_l, in_r):
+        b, c = self.b, self.c
+        if max(info["to_left"], info["to_right"], info["from_left"], info["from_right"]) > b.cap:
+            raise RuntimeError("slab exchange overflow: %r > capacity %d records" % (info, b.cap))
+        redo_l = c.left is not None and (info["to_left"] > out_l or info["from_left"] > in_l)
+        redo_r = c.right is not None and (info["to_right"] > out_r or info["from_right"] > in_r)
+        return redo_l, redo_r
+
+    def _resize(self, info):
+        b = self.b
+        self.out_l, self.in_l = next_size(info["to_left"], b.cap), next_size(info["from_left"], b.cap)
+        self.out_r, self.in_r = next_size(info["to_right"], b.cap), next_size(info["from_right"], b.cap)
 
     def exchange(self):
         b, c = self.b, self.c
+        if self.lag and self.sync_left <= 0:
+            return self._exchange_async()
+        self.sync_left -= 1
         b.pack()
         c.swap_records(b.send_l, self.out_l, b.send_r, self.out_r, b.recv_l, self.in_l, b.recv_r, self.in_r)
         info = b.unpack(b.recv_l, self.in_l, b.recv_r, self.in_r)
-        if max(info["to_left"], info["to_right"], info["from_left"], info["from_right"]) > b.cap:
-            raise RuntimeError("slab exchange overflow: %r > capacity %d records" % (info, b.cap))
-        redo_l = c.left is not None and (info["to_left"] > self.out_l or info["from_left"] > self.in_l)
-        redo_r = c.right is not None and (info["to_right"] > self.out_r or info["from_right"] > self.in_r)
+        redo_l, redo_r = self._check(info, self.out_l, self.out_r, self.in_l, self.in_r)
         if redo_l or redo_r:
             self.resends += 1
             if redo_l: self.out_l = self.in_l = b.cap
@@ -134,10 +169,38 @@ class SlabDriver:
             c.swap_records(b.send_l, b.cap if redo_l else None, b.send_r, b.cap if redo_r else None,
                            b.recv_l, b.cap if redo_l else None, b.recv_r, b.cap if redo_r else None)
             info = b.unpack(b.recv_l, self.in_l, b.recv_r, self.in_r)
-        self.out_l, self.in_l = next_size(info["to_left"], b.cap), next_size(info["from_left"], b.cap)
-        self.out_r, self.in_r = next_size(info["to_right"], b.cap), next_size(info["from_right"], b.cap)
+        self._resize(info)
         self.last = info
         return info
+
+    def _exchange_async(self):
+        b, c = self.b, self.c
+        # fold the step that is `lag` steps old: its counts size this step's messages on both ends
+        if len(self.pending) >= self.lag:
+            t, ol, orr, il, ir = self.pending.pop(0)
+            info = b.result(t, True)
+            redo_l, redo_r = self._check(info, ol, orr, il, ir)
+            if redo_l or redo_r:
+                raise RuntimeError("slab halo outgrew its message within %d steps (%r vs sizes %d/%d/%d/%d): "
+                                   "use lag=0 or more slack" % (self.lag, info, ol, orr, il, ir))
+            self._resize(info)
+            self.last = info
+        b.pack()
+        c.swap_records(b.send_l, self.out_l, b.send_r, self.out_r, b.recv_l, self.in_l, b.recv_r, self.in_r)
+        t = b.unpack_async(b.recv_l, self.in_l, b.recv_r, self.in_r)
+        self.pending.append((t, self.out_l, self.out_r, self.in_l, self.in_r))
+        return self.last
+
+    def drain(self):
+        """Fold every outstanding ticket (end of a run, before reading state)."""
+        while self.pending:
+            t, ol, orr, il, ir = self.pending.pop(0)
+            info = self.b.result(t, True)
+            if any(self._check(info, ol, orr, il, ir)):
+                raise RuntimeError("slab halo outgrew its message (%r)" % (info,))
+            self._resize(info)
+            self.last = info
+        return self.last
 
     def step(self):
         self.exchange()
@@ -147,11 +210,13 @@ class SlabDriver:
 class LocalSlabGroup:
     """K slabs driven by ONE process (all handles on the same GPU): the same backend calls as
     SlabDriver with the P2P replaced by reading the neighbour's send buffer.  Used to test the slab
-    kernels on a single GPU."""
+    kernels on a single GPU.  async_=True uses unpack_async (no host sync between steps)."""
 
-    def __init__(self, backends):
+    def __init__(self, backends, async_=False):
         self.bs = list(backends)
+        self.async_ = async_
         self.last = []
+        self.tickets = []
 
     def step(self):
         K = len(self.bs)
@@ -159,10 +224,19 @@ class LocalSlabGroup:
             b.pack()
         self.last = []
         for r, b in enumerate(self.bs):
-            self.last.append(b.unpack(self.bs[r - 1].send_r if r > 0 else None, b.cap,
-                                      self.bs[r + 1].send_l if r < K - 1 else None, b.cap))
+            left = self.bs[r - 1].send_r if r > 0 else None
+            right = self.bs[r + 1].send_l if r < K - 1 else None
+            if self.async_:
+                self.tickets.append((b, b.unpack_async(left, b.cap, right, b.cap)))
+            else:
+                self.last.append(b.unpack(left, b.cap, right, b.cap))
         for b in self.bs:
             b.step()
+
+    def drain(self):
+        out = [b.result(t, True) for b, t in self.tickets[-len(self.bs):]]
+        self.tickets = []
+        return out
 
 
 # --------------------------------------------------------------------------- scenes
@@ -228,7 +302,7 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT):
     sim, backend, cols = make_gpu_slab(pkg, local, rank, world, box, params, bounds, cap,
                                        (args.density_variant, args.force_variant))
     sim.slab_upload(pos, np.zeros_like(pos), ids)
-    drv = SlabDriver(backend, TorchComm(rank, world))
+    drv = SlabDriver(backend, TorchComm(rank, world), lag=args.slab_lag)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -250,6 +324,7 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT):
     sync_all()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    drv.drain()
     per_kernel, launches = sim.kernel_times()
     sim.kernel_timing(False)
     clocks = sampler.stop() if rank == 0 else None
@@ -275,6 +350,7 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT):
         sim.slab_upload_ptr(m, hp.data_ptr(), hv.data_ptr(), hi.data_ptr())
         h2d += 28 * m
         drv.step()
+        drv.drain()
         m = sim.slab_download_ptr(capn, hi.data_ptr(), hp.data_ptr(), hv.data_ptr(), hr.data_ptr())
         d2h += 32 * m
     sync_all()
@@ -297,7 +373,7 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT):
                        "box_half_extents": list(box), "gravity_y": gy, "slab_columns": cols,
                        "halo_records_per_step_all_ranks": int(owned[1].item()),
                        "exchange": "NCCL P2P (one batch_isend_irecv group per step) with the x-neighbours, counts ride in the record headers, 1 host sync per step, no collective",
-                       "exchange_resends": drv.resends,
+                       "exchange_resends": drv.resends, "exchange_lag": args.slab_lag,
                        "l2": "working set per GPU (%.0f MB of particle arrays + neighbour lists) exceeds L2" % (n_local * 400 / 1e6),
                        "density_variant": args.density_variant, "force_variant": args.force_variant},
             "e2e": {"value": n_total / float(e2e_dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(io[0].item()),

@@ -77,8 +77,17 @@ class NumpySlabBackend:
                 self.pos = np.concatenate([self.pos, r[:, 0:3]]); self.vel = np.concatenate([self.vel, r[:, 4:7]])
                 self.ids = np.concatenate([self.ids, np.where(own, ids, ids | GHOST)])
                 self.n_owned += int(own.sum())
-        return dict(n_total=len(self.ids), n_owned=self.n_owned, to_left=self.sent[0], to_right=self.sent[1],
-                    from_left=got[0], from_right=got[1])
+        self.last_info = dict(n_total=len(self.ids), n_owned=self.n_owned, to_left=self.sent[0], to_right=self.sent[1],
+                              from_left=got[0], from_right=got[1])
+        return self.last_info
+
+    def unpack_async(self, buf_l, max_l, buf_r, max_r):
+        self._results = getattr(self, "_results", [])
+        self._results.append(self.unpack(buf_l, max_l, buf_r, max_r))
+        return len(self._results) - 1
+
+    def result(self, ticket, wait=True):
+        return self._results[ticket]
 
     def step(self):
         # the oracle sums neighbours in ascending array order: present the particles in global-id order

@@ -31,7 +31,7 @@ def close(got, want, what, rtol=RTOL):
 VARIANT = {"density": 0, "force": 0}
 
 
-@pytest.fixture(autouse=True, params=[(0, 0), (1, 1), (3, 3)], ids=["tpp", "pair", "list"])
+@pytest.fixture(autouse=True, params=[(0, 0), (1, 1), (3, 3), (4, 4)], ids=["tpp", "pair", "list", "list256"])
 def kernel_variant(request):
     """Every test runs against both kernel families: thread-per-particle and packed-pair."""
     VARIANT["density"], VARIANT["force"] = request.param

@@ -32,7 +32,7 @@ def setup(world):
     return port, slabs, P, G, cols
 
 
-def worker(rank, world, port_no, steps, outdir, cap=4096, floor=None):
+def worker(rank, world, port_no, steps, outdir, cap=4096, floor=None, lag=0):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
     import torch.distributed as dist
@@ -60,11 +60,13 @@ def worker(rank, world, port_no, steps, outdir, cap=4096, floor=None):
     place[go_r] += 1; place[go_l] -= 1
     mine = place == rank
     b.upload(pos[mine], vel[mine], ids[mine])
-    drv = slabs.SlabDriver(b, slabs.TorchComm(rank, world))
+    drv = slabs.SlabDriver(b, slabs.TorchComm(rank, world), lag=lag, sync_steps=1)
     log = []
     for _ in range(steps):
         drv.step()
-        log.append([drv.last[k] for k in ("n_total", "n_owned", "to_left", "to_right", "from_left", "from_right")] + [drv.resends])
+        info = b.last_info
+        log.append([info[k] for k in ("n_total", "n_owned", "to_left", "to_right", "from_left", "from_right")] + [drv.resends])
+    drv.drain()
     i, p, v, r = b.owned()
     np.savez(os.path.join(outdir, "rank%d.npz" % rank), ids=i, pos=p, vel=v, rho=r, log=np.array(log))
     dist.barrier()
@@ -76,8 +78,9 @@ def free_port():
     return p
 
 
-@pytest.mark.parametrize("world,floor", [(2, None), (3, None), (2, 1)], ids=["w2", "w3", "w2-resend"])
-def test_slab_protocol_matches_single_domain(world, floor):
+@pytest.mark.parametrize("world,floor,lag", [(2, None, 0), (3, None, 0), (2, 1, 0), (2, None, 2), (3, None, 1)],
+                         ids=["w2", "w3", "w2-resend", "w2-async2", "w3-async1"])
+def test_slab_protocol_matches_single_domain(world, floor, lag):
     steps = 6
     port, slabs, P, G, cols = setup(world)
     pos, vel = scene()
@@ -86,7 +89,7 @@ def test_slab_protocol_matches_single_domain(world, floor):
     with tempfile.TemporaryDirectory() as d:
         ctx = mp.get_context("spawn")
         pn = free_port()
-        procs = [ctx.Process(target=worker, args=(r, world, pn, steps, d, 4096, floor)) for r in range(world)]
+        procs = [ctx.Process(target=worker, args=(r, world, pn, steps, d, 4096, floor, lag)) for r in range(world)]
         for p in procs: p.start()
         for p in procs: p.join(300)
         assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
