@@ -168,12 +168,13 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(kernel):
-    """dram read+write bytes per launch from the committed ncu summary, if one exists."""
+def ncu_traffic(kernel, workload="c2"):
+    """dram read+write bytes per launch of `kernel` on `workload` from the committed ncu summaries
+    (profiles/ncu_traffic.json), or None when that kernel/workload pair has not been captured."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(kernel)
+            return json.load(open(p)).get(workload, {}).get(kernel)
         except Exception:
             return None
     return None
@@ -354,7 +355,7 @@ def run_gpu_arm(args):
     t_dom = per_kernel[dom] / args.steps * 1e-3
     achieved = ALGO_BYTES[dom] * n / t_dom / 1e9
     roofline = {"bound": "hbm", "kernel": "k_%s" % dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic(dom), "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": ncu_traffic(dom, args.workload), "peak_source": peak_src,
                 "algorithmic_bytes_per_particle": ALGO_BYTES[dom],
                 "note": "neighbour passes are fp32-issue/LSU bound, not HBM bound (DESIGN.md); "
                         "frac is reported against HBM as the contract asks",

@@ -45,7 +45,7 @@ struct sphe_terrain {
     int rows = 512, cols = 512;    // heightfield storage; the reference hard-codes 512 x 512 (grid.h:78-81)
     int device = -1;
     bool ready = false;
-    int *hfx = nullptr, *want = nullptr, *delta = nullptr, *hmax = nullptr;
+    int *hfx = nullptr, *want = nullptr, *delta = nullptr, *hmax = nullptr, *lmax = nullptr;
     size_t cells_cap = 0;
     float origin[3] = {0.f, 0.f, 0.f};
     float scale = 1.0f;
@@ -77,7 +77,8 @@ struct sphe_sim {
     uint2* tmp = nullptr;
     float* stage = nullptr;  // 10 * cap floats: id-order staging for uploads/downloads
     int* slot_of_id = nullptr;
-    int *req_vertex = nullptr, *req_amount = nullptr;  // terrain stage: pending pick-up requests per particle
+    int *req_vertex = nullptr, *req_amount = nullptr;  // terrain stage: pending pick-up requests per survivor
+    int *surv = nullptr, *surv_count = nullptr;        // terrain stage: survivors of the contact cull
     bool slot_valid = false;
     int* nlist = nullptr;   // variant 3: [nlist_cap][pairs_pad] neighbour indices
     int2* ncount = nullptr;
@@ -182,6 +183,8 @@ static int reserve(sphe_sim* s, int need) {
     TRY(grow(&s->slot_of_id, 0, nc, s->st, false));
     TRY(grow(&s->req_vertex, 0, nc, s->st, false));
     TRY(grow(&s->req_amount, 0, nc, s->st, false));
+    TRY(grow(&s->surv, 0, nc, s->st, false));
+    if (!s->surv_count) CU(cudaMalloc(&s->surv_count, sizeof(int)));
     s->cap = (int)nc;
     s->binned = false;
     s->slot_valid = false;
@@ -230,6 +233,7 @@ static StepC make_consts(const sphe_params& P) {
     C.gx = P.g[0]; C.gy = P.g[1]; C.gz = P.g[2];
     C.dt = P.dt; C.len = P.len; C.cR = P.cR;
     C.lenx = C.leny = C.lenz = P.len; C.cube = 1; C.box = 1;
+    C.t_lmax = nullptr; C.t_surv = nullptr; C.t_count = nullptr;
     float c315 = (float)(315.0f / (64.0f * PI_REF * powf(h, 9.0f)));  // fluid_system.h:415
     C.densK = P.mass * c315;
     C.c45 = (float)(45.f / (PI_REF * powf(h, 6.0f)));                 // :442, :452
@@ -313,7 +317,14 @@ static int step_device(sphe_sim* s, sphe_terrain* t) {
         C.cube = (C.lenx == C.leny && C.leny == C.lenz) ? 1 : 0;
     }
     if (s->slab_on && s->diag) return fail(SPHE_ERR_STATE, "per-particle diagnostics are indexed by local id and are not available in slab mode");
-    if (t) C.box = 0;  // with a terrain the box collision runs after the terrain contact (fluid_system.h:335-347)
+    C.t_lmax = nullptr;
+    if (t) {
+        // exact contact cull in the force epilogue; survivors skip the box there and get it after the contact search
+        C.t_lmax = t->lmax; C.t_surv = s->surv; C.t_count = s->surv_count;
+        C.t_rows = t->rows; C.t_cols = t->cols; C.t_dimx = t->dimx; C.t_dimz = t->dimz;
+        C.t_ox = t->origin[0]; C.t_oy = t->origin[1]; C.t_oz = t->origin[2]; C.t_inv = 1.0f / t->scale;
+        CU(cudaMemsetAsync(s->surv_count, 0, sizeof(int), s->st));
+    }
     s->lastC = C;
     int n = s->n;
     const int* nd = s->slab_pending ? s->d_n : nullptr;  // exact count on the device while unpack results are in flight
@@ -341,7 +352,7 @@ static int step_device(sphe_sim* s, sphe_terrain* t) {
     if (t) {
         TerrainDev T = terrain_view(t);
         Scope k(s, SPHE_K_TERRAIN, terrain_stage_launches(C, T));
-        launch_terrain_stage(s->st, n, nd, s->posB, s->posA, s->velA, (int*)s->sedB, C, T, 1, s->req_vertex, s->req_amount, nullptr);
+        launch_terrain_stage(s->st, s->surv, s->surv_count, s->posB, s->posA, s->velA, (int*)s->sedB, C, T, 1, s->req_vertex, s->req_amount, nullptr);
     }
     std::swap(s->idsA, s->idsB);
     std::swap(s->sedA, s->sedB);
@@ -419,7 +430,7 @@ void sphe_destroy(sphe_sim* s) {
         cudaSetDevice(s->device);
         cudaStreamSynchronize(s->st);
         void* ptrs[] = {s->posA, s->posB, s->posC, s->velA, s->velB, s->idsA, s->idsB, s->sedA, s->sedB, s->rho, s->cell,
-                        s->cell_sorted, s->tmp, s->stage, s->slot_of_id, s->req_vertex, s->req_amount, s->nlist, s->ncount, s->count, s->cell_start, s->cursor, s->tile_sum,
+                        s->cell_sorted, s->tmp, s->stage, s->slot_of_id, s->req_vertex, s->req_amount, s->surv, s->surv_count, s->nlist, s->ncount, s->count, s->cell_start, s->cursor, s->tile_sum,
                         s->flush_buf, s->slab_counters, s->D.acc, s->D.fpress, s->D.fvisc, s->D.fgrav, s->D.fsurf, s->D.normal, s->D.neighb};
         for (void* p : ptrs) if (p) cudaFree(p);
         if (s->slab_host) cudaFreeHost(s->slab_host);
@@ -1040,11 +1051,12 @@ void* sphe_device_ptr(sphe_sim* s, int which) {
 static int terrain_alloc(sphe_terrain* t, int rows, int cols) {
     size_t cells = (size_t)rows * cols;
     if (cells > t->cells_cap) {
-        cudaFree(t->hfx); cudaFree(t->want); cudaFree(t->delta);
-        t->hfx = t->want = t->delta = nullptr;
+        cudaFree(t->hfx); cudaFree(t->want); cudaFree(t->delta); cudaFree(t->lmax);
+        t->hfx = t->want = t->delta = t->lmax = nullptr;
         cudaError_t e = cudaMalloc(&t->hfx, cells * sizeof(int));
         if (e == cudaSuccess) e = cudaMalloc(&t->want, cells * sizeof(int));
         if (e == cudaSuccess) e = cudaMalloc(&t->delta, cells * sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc(&t->lmax, cells * sizeof(int));
         if (e != cudaSuccess) return fail(SPHE_ERR_NOMEM, "terrain %d x %d: %s", rows, cols, cudaGetErrorString(e));
         t->cells_cap = cells;
     }
@@ -1052,6 +1064,7 @@ static int terrain_alloc(sphe_terrain* t, int rows, int cols) {
     CU(cudaMemset(t->hfx, 0, cells * sizeof(int)));
     CU(cudaMemset(t->want, 0, cells * sizeof(int)));
     CU(cudaMemset(t->delta, 0, cells * sizeof(int)));
+    CU(cudaMemset(t->lmax, 0, cells * sizeof(int)));
     CU(cudaMemset(t->hmax, 0, sizeof(int)));
     return SPHE_OK;
 }
@@ -1076,7 +1089,7 @@ static int terrain_ready(sphe_terrain* t) {
 static TerrainDev terrain_view(const sphe_terrain* t) {
     TerrainDev T;
     T.rows = t->rows; T.cols = t->cols; T.dimx = t->dimx; T.dimy = t->dimy; T.dimz = t->dimz;
-    T.hfx = t->hfx; T.hfx_rw = t->hfx; T.want = t->want; T.delta = t->delta; T.hmax_fx = t->hmax; T.hmax_rw = t->hmax;
+    T.hfx = t->hfx; T.hfx_rw = t->hfx; T.want = t->want; T.delta = t->delta; T.hmax_fx = t->hmax; T.hmax_rw = t->hmax; T.lmax = t->lmax; T.lmax_rw = t->lmax;
     T.ox = t->origin[0]; T.oy = t->origin[1]; T.oz = t->origin[2]; T.scale = t->scale; T.inv_scale = 1.0f / t->scale;
     T.Kc = t->E.Kc; T.Ke = t->E.Ke; T.Kd = t->E.Kd;
     T.hmin_fx = (int)lrint((double)t->E.hmin * 4096.0); T.max_pickup_fx = (int)lrint((double)t->E.max_pickup * 4096.0);
@@ -1100,7 +1113,7 @@ void sphe_terrain_destroy(sphe_terrain* t) {
     if (t->ready) {
         cudaSetDevice(t->device);
         cudaDeviceSynchronize();
-        void* ptrs[] = {t->hfx, t->want, t->delta, t->hmax, t->d_surface, t->d_indices, t->d_sum};
+        void* ptrs[] = {t->hfx, t->want, t->delta, t->hmax, t->lmax, t->d_surface, t->d_indices, t->d_sum};
         for (void* p : ptrs) if (p) cudaFree(p);
     }
     delete t;
@@ -1116,6 +1129,7 @@ int sphe_terrain_load_heightfield_ex(sphe_terrain* t, const unsigned char* img, 
     CU(cudaMalloc(&d, cells));
     CU(cudaMemcpy(d, img, cells, cudaMemcpyHostToDevice));  // the caller keeps ownership of img (main.cpp:102-103)
     launch_heights_from_u8(0, (int)cells, d, t->hfx, t->hmax);
+    launch_terrain_lmax(0, terrain_view(t));
     CU(cudaDeviceSynchronize());
     CU(cudaFree(d));
     return SPHE_OK;
@@ -1135,6 +1149,7 @@ int sphe_terrain_set_heights(sphe_terrain* t, const float* h, int rows, int cols
     CU(cudaMalloc(&d, cells * sizeof(float)));
     CU(cudaMemcpy(d, h, cells * sizeof(float), cudaMemcpyHostToDevice));
     launch_heights_from_f32(0, (int)cells, d, t->hfx, t->hmax);
+    launch_terrain_lmax(0, terrain_view(t));
     CU(cudaDeviceSynchronize());
     CU(cudaFree(d));
     return SPHE_OK;
@@ -1259,7 +1274,8 @@ int sphe_terrain_stage_host(sphe_terrain* t, int n, const float* pos_curr, float
     int *sd = nullptr, *rq = nullptr, *dh = nullptr;
     CU(cudaMalloc(&po, (size_t)n * sizeof(float4))); CU(cudaMalloc(&pn, (size_t)n * sizeof(float4)));
     CU(cudaMalloc(&vn, (size_t)n * sizeof(float4))); CU(cudaMalloc(&sd, (size_t)n * sizeof(int)));
-    CU(cudaMalloc(&rq, 2 * (size_t)n * sizeof(int))); CU(cudaMalloc(&dh, (size_t)n * sizeof(int)));
+    CU(cudaMalloc(&rq, (3 * (size_t)n + 1) * sizeof(int))); CU(cudaMalloc(&dh, (size_t)n * sizeof(int)));
+    CU(cudaMemset(dh, 0, (size_t)n * sizeof(int)));
     std::vector<float4> a((size_t)n), b((size_t)n), c((size_t)n);
     for (int i = 0; i < n; i++) {
         a[i] = make_float4(pos_curr[3 * i], pos_curr[3 * i + 1], pos_curr[3 * i + 2], 0.f);
@@ -1272,7 +1288,8 @@ int sphe_terrain_stage_host(sphe_terrain* t, int n, const float* pos_curr, float
     CU(cudaMemcpy(sd, sediment, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
     StepC C{};
     C.dt = dt; C.cR = cR; C.box = 0; C.cube = 1; C.lenx = C.leny = C.lenz = C.len = 3.0e38f;
-    launch_terrain_stage(0, n, nullptr, po, pn, vn, sd, C, terrain_view(t), 0, rq, rq + n, dh);
+    launch_iota(0, n, rq + 2 * (size_t)n, rq + 3 * (size_t)n);   // no cull in front of the hook: everyone is a survivor
+    launch_terrain_stage(0, rq + 2 * (size_t)n, rq + 3 * (size_t)n, po, pn, vn, sd, C, terrain_view(t), 0, rq, rq + n, dh);
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(b.data(), pn, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(c.data(), vn, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost));

@@ -37,7 +37,28 @@ struct StepC {
     float c45;                // 45/(PI h^6)
     float c945;               // 945/(32 PI h^9)
     float hh3;                // 3*h*h
+    // Terrain attached: the force kernels' epilogue runs the exact contact cull (terrain.cu) on the state
+    // it has in registers and appends the survivors to t_surv; only those go through the contact search.
+    const int* t_lmax;        // NULL: no terrain
+    int* t_surv;              // survivor slots
+    int* t_count;             // number of survivors
+    int t_rows, t_cols, t_dimx, t_dimz;
+    float t_ox, t_oy, t_oz, t_inv;
 };
+
+// Exact contact culling (see k_terrain_contact): nothing above the local maxima of the cells of posCurr and
+// posNext can touch the heightfield.  Same arithmetic in sph.cu (FMA contraction allowed) and terrain.cu
+// (not allowed): (p - o) * inv has nothing to contract.
+__device__ __forceinline__ bool terrain_may_touch(const StepC& C, float ox_, float oy_, float oz_, float px, float py, float pz) {
+    float cx = floorf((ox_ - C.t_ox) * C.t_inv), cz = floorf((oz_ - C.t_oz) * C.t_inv);
+    float nx = floorf((px - C.t_ox) * C.t_inv), nz = floorf((pz - C.t_oz) * C.t_inv);
+    float mx = (float)(C.t_dimx - 1), mz = (float)(C.t_dimz - 1);
+    if (cx < 0.0f || cx >= mx || cz < 0.0f || cz >= mz || nx < 0.0f || nx >= mx || nz < 0.0f || nz >= mz) return false;
+    int ia = min((int)cx, C.t_rows - 1) * C.t_cols + min((int)cz, C.t_cols - 1);
+    int ib = min((int)nx, C.t_rows - 1) * C.t_cols + min((int)nz, C.t_cols - 1);
+    int top = max(__ldg(&C.t_lmax[ia]), __ldg(&C.t_lmax[ib]));
+    return (py - C.t_oy) * C.t_inv <= (float)top * (1.0f / 4096.0f) + 0.01f;
+}
 
 __device__ __forceinline__ int cell_axis(float p, float gmin, float cell, int dim) {
     // bit-identical to oracle/sph_oracle.c cell_axis(): IEEE sub, div, floor; clamp; NaN -> 0
@@ -66,10 +87,10 @@ __device__ __forceinline__ float dist2_exact(float dx, float dy, float dz) {
 // The reference box is a cube of half-extent len: the violated axis is the one with the largest
 // |coordinate| (ties x -> y -> z by strict <, :362-371).  sphe_set_box generalises it to per-axis
 // half-extents for the multi-GPU channel scenes; then the axis with the largest overshoot wins.
-__device__ __forceinline__ void box_collide(const StepC& C, float& px, float& py, float& pz, float& vx, float& vy, float& vz) {
+__device__ __forceinline__ bool box_collide(const StepC& C, float& px, float& py, float& pz, float& vx, float& vy, float& vz) {
     float ax = fabsf(px), ay = fabsf(py), az = fabsf(pz);
-    if (ax < C.lenx && ay < C.leny && az < C.lenz) return;
-    if (C.dt == 0.0f) return;
+    if (ax < C.lenx && ay < C.leny && az < C.lenz) return false;
+    if (C.dt == 0.0f) return false;
     if (!C.cube) { ax = __fsub_rn(ax, C.lenx); ay = __fsub_rn(ay, C.leny); az = __fsub_rn(az, C.lenz); }
     int axis = 0;
     float m = ax;
@@ -88,4 +109,5 @@ __device__ __forceinline__ void box_collide(const StepC& C, float& px, float& py
     vy = __fsub_rn(vy, __fmul_rn(__fmul_rn(ny, sc), vn));
     vz = __fsub_rn(vz, __fmul_rn(__fmul_rn(nz, sc), vn));
     px = cx; py = cy; pz = cz;
+    return true;
 }

@@ -29,15 +29,20 @@ struct TerrainDev {
     int* delta;              // per-vertex deposits - grants of the current step
     const int* hmax_fx;      // upper bound of all heights (contact culling)
     int* hmax_rw;
+    const int* lmax;         // per cell: max height of the 4x4 vertex neighbourhood (exact contact culling)
+    int* lmax_rw;
     unsigned long long* contacts;  // cumulative number of particle-terrain contacts
     float ox, oy, oz, scale, inv_scale;   // world = origin + scale * terrain coordinates
     float Kc, Ke, Kd;
     int hmin_fx, max_pickup_fx;
     int erosion;
 };
-void launch_terrain_stage(cudaStream_t st, int n, const int* n_dev, const float4* pos_old, float4* posq, float4* velv, int* sediment,
-                          const StepC& C, const TerrainDev& T, int apply_box, int* req_vertex, int* req_amount, int* hit_out);
+void launch_terrain_stage(cudaStream_t st, const int* surv, const int* surv_count, const float4* pos_old, float4* posq, float4* velv,
+                          int* sediment, const StepC& C, const TerrainDev& T, int apply_box, int* req_vertex, int* req_amount,
+                          int* hit_out);
+void launch_iota(cudaStream_t st, int n, int* a, int* count);
 int terrain_stage_launches(const StepC& C, const TerrainDev& T);
+void launch_terrain_lmax(cudaStream_t st, const TerrainDev& T);
 void launch_terrain_surface(cudaStream_t st, const TerrainDev& T, float* out);
 void launch_terrain_indices(cudaStream_t st, int dimx, int dimz, unsigned* out);
 void launch_terrain_collide(cudaStream_t st, int n, const float* pc, const float* pn, const float* vn, const TerrainDev& T,

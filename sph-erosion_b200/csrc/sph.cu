@@ -197,7 +197,21 @@ __device__ __forceinline__ void force_epilogue(int i, float4 pi, float4 vi, floa
     float dt = C.dt;
     float vx = fmaf(acx, dt, vi.x), vy = fmaf(acy, dt, vi.y), vz = fmaf(acz, dt, vi.z);
     float px = fmaf(vx, dt, pi.x), py = fmaf(vy, dt, pi.y), pz = fmaf(vz, dt, pi.z);
-    if (C.box) box_collide(C, px, py, pz, vx, vy, vz);
+    // With a terrain, particles that may touch it keep their un-boxed state: the contact search
+    // (k_terrain_contact) runs on them first and applies the box afterwards (fluid_system.h:335-347).
+    bool surv = false;
+    if (C.t_lmax) {
+        surv = dt != 0.0f && terrain_may_touch(C, pi.x, pi.y, pi.z, px, py, pz);
+        unsigned act = __activemask();
+        unsigned m = __ballot_sync(act, surv);
+        if (m) {
+            int lane = threadIdx.x & 31, leader = __ffs(m) - 1, base = 0;
+            if (lane == leader) base = atomicAdd(C.t_count, __popc(m));
+            base = __shfl_sync(act, base, leader);
+            if (surv) C.t_surv[base + __popc(m & ((1u << lane) - 1u))] = i;
+        }
+    }
+    if (C.box && !surv) box_collide(C, px, py, pz, vx, vy, vz);
     posq_out[i] = make_float4(px, py, pz, 0.0f);
     velv_out[i] = make_float4(vx, vy, vz, 0.0f);
     if (DIAG) {
@@ -260,42 +274,7 @@ __global__ void __launch_bounds__(128) k_force_tpp(int n_hi, const int* __restri
         }
     });
 
-    // PressureForce = -(fPress * rho_i), fPress = -mass*c45 * A        (fluid_system.h:145,151)
-    float kp = rho_i * C.mass * C.c45;
-    float Fpx = kp * ax, Fpy = kp * ay, Fpz = kp * az;
-    // ViscosityForce = fVisc * visc, fVisc = c45 * F                    (:146,153)
-    float kv = C.visc * C.c45;
-    float Fvx = kv * fx, Fvy = kv * fy, Fvz = kv * fz;
-    // SurfaceNormal = -c945 * N                                         (:147,154)
-    float Nx = -C.c945 * nx, Ny = -C.c945 * ny, Nz = -C.c945 * nz;
-    // colorFieldLapl = -c945 * cf ; SurfaceForce = -surf_tens * cfl * n (:171,177)
-    float cfl = -C.c945 * cf;
-    float ks = -C.surf * cfl;
-    float Fsx = ks * Nx, Fsy = ks * Ny, Fsz = ks * Nz;
-    // GravityForce = rho_i * g                                          (:163)
-    float Fgx = rho_i * C.gx, Fgy = rho_i * C.gy, Fgz = rho_i * C.gz;
-
-    // advance(), fluid_system.h:318-350
-    float Fx = (Fpx + Fvx) + (Fgx + Fsx), Fy = (Fpy + Fvy) + (Fgy + Fsy), Fz = (Fpz + Fvz) + (Fgz + Fsz);
-    float acx = Fx / rho_i, acy = Fy / rho_i, acz = Fz / rho_i;
-    float dt = C.dt;
-    float vx = fmaf(acx, dt, vi.x), vy = fmaf(acy, dt, vi.y), vz = fmaf(acz, dt, vi.z);
-    float px = fmaf(vx, dt, pi.x), py = fmaf(vy, dt, pi.y), pz = fmaf(vz, dt, pi.z);
-
-    if (C.box) box_collide(C, px, py, pz, vx, vy, vz);
-    posq_out[i] = make_float4(px, py, pz, 0.0f);
-    velv_out[i] = make_float4(vx, vy, vz, 0.0f);
-
-    if (DIAG) {
-        int id = ids[i];
-        D.acc[id] = make_float4(acx, acy, acz, 0.f);
-        D.fpress[id] = make_float4(Fpx, Fpy, Fpz, 0.f);
-        D.fvisc[id] = make_float4(Fvx, Fvy, Fvz, 0.f);
-        D.fgrav[id] = make_float4(Fgx, Fgy, Fgz, 0.f);
-        D.fsurf[id] = make_float4(Fsx, Fsy, Fsz, 0.f);
-        D.normal[id] = make_float4(Nx, Ny, Nz, 0.f);
-        if (maxid >= 0) D.neighb[id] = maxid;  // last neighbour in ascending-id order (:144)
-    }
+    force_epilogue<DIAG>(i, pi, vi, rho_i, ax, ay, az, fx, fy, fz, nx, ny, nz, cf, maxid, C, ids, posq_out, velv_out, D);
 }
 
 __device__ __forceinline__ float rsqrt_ftz(float x) {

@@ -5,11 +5,14 @@
 //
 //   collide()          Grid::collision + helpers, Erosion/grid.h:178-805: contact point and normal of a
 //                      moving particle against the two-triangles-per-cell heightfield surface.
+//   (cull)             in the force kernels' epilogue (common.cuh terrain_may_touch): only particles at or below the
+//                      local maximum of the heightfield round their cells reach the contact search.
 //   k_terrain_contact  the call the reference has commented out in advance() (fluid_system.h:335-340):
 //                      contact response, then the box collision (:342-347), + this project's erosion
 //                      requests (the reference has no erosion code; model in DESIGN.md).
 //   k_terrain_grant    shares the material available above bedrock among the pick-up requests.
-//   k_terrain_apply    heights += deposits - grants; clears the per-vertex accumulators; max height.
+//   k_terrain_apply    heights += deposits - grants; clears the per-vertex accumulators.
+//   k_terrain_lmax     per-cell maximum of the 4x4 vertex neighbourhood the contact search can touch (the cull bound).
 //   k_terrain_surface  UpdateGrid (grid.h:138-176) vertices + normals;  k_terrain_indices  genIndices (:118-136).
 //
 // Heights are fixed point (int32, 1/4096 of a height unit): every per-vertex accumulation is an integer
@@ -201,106 +204,131 @@ __device__ __forceinline__ void vertex_add(unsigned participants, bool active, i
 }  // namespace
 
 // ------------------------------------------------------------------ contact response + erosion requests
-// pos_old: positions before the step (sorted slot order, .xyz); posq / velv: the integrated state the
-// force kernel wrote WITHOUT the box collision (StepC.box == 0 when a terrain is attached); both are
-// updated in place.  req_vertex[i] = vertex of a pending pick-up request (or -1), req_amount[i] its size.
-__global__ void __launch_bounds__(128) k_terrain_contact(int n_hi, const int* __restrict__ n_dev, const float4* __restrict__ pos_old, float4* __restrict__ posq,
+// Runs over the SURVIVORS of the exact cull only (a few per cent of the particles): surv[j] is the sorted
+// slot of survivor j, *surv_count their number (device word: the host never learns it; the grid is a fixed
+// persistent one and every warp strides over the list).  pos_old: positions before the step (.xyz);
+// posq / velv: the integrated, un-boxed state the force kernel wrote for survivors; updated in place,
+// then the box collision.  req_vertex[j] = vertex of survivor j's pending pick-up request (or -1).
+__global__ void __launch_bounds__(128) k_terrain_contact(const int* __restrict__ surv, const int* __restrict__ surv_count,
+                                                         const float4* __restrict__ pos_old, float4* __restrict__ posq,
                                                          float4* __restrict__ velv, int* __restrict__ sediment, StepC C,
                                                          TerrainDev T, int apply_box, int* __restrict__ req_vertex,
                                                          int* __restrict__ req_amount, int* __restrict__ hit_out) {
-    const int n = n_dev ? __ldg(n_dev) : n_hi;  // exact count from the device in slab mode, else the launch bound
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool live = i < n;
-    float4 po = make_float4(0, 0, 0, 0), p4 = po, v4 = po;
-    bool hit = false;
-    V3 cp = mk(0, 0, 0), nn = mk(0, 0, 0);
-    if (live) {
-        po = pos_old[i]; p4 = posq[i]; v4 = velv[i];
-        if (C.dt != 0.0f) {
-            float ty = (p4.y - T.oy) * T.inv_scale;
-            // a contact needs posNext below some facet along an upward direction (every facet normal has
-            // n.y > 0), so nothing above the highest vertex can be in contact
-            if (ty <= (float)__ldg(T.hmax_fx) * (1.0f / 4096.0f) + 0.01f) {
-                V3 pc = mk((po.x - T.ox) * T.inv_scale, (po.y - T.oy) * T.inv_scale, (po.z - T.oz) * T.inv_scale);
-                V3 pn = mk((p4.x - T.ox) * T.inv_scale, ty, (p4.z - T.oz) * T.inv_scale);
-                V3 vn = mk(v4.x * T.inv_scale, v4.y * T.inv_scale, v4.z * T.inv_scale);
-                hit = collide(T, pc, pn, vn, cp, nn);
+    const int count = __ldg(surv_count);
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int base = warp * 32; base < count; base += nwarps * 32) {
+        const int j = base + lane;
+        const bool live = j < count;
+        int i = 0;
+        float4 po = make_float4(0, 0, 0, 0), p4 = po, v4 = po;
+        bool hit = false;
+        V3 cp = mk(0, 0, 0), nn = mk(0, 0, 0);
+        if (live) {
+            i = surv[j];
+            po = pos_old[i]; p4 = posq[i]; v4 = velv[i];
+            V3 pc = mk((po.x - T.ox) * T.inv_scale, (po.y - T.oy) * T.inv_scale, (po.z - T.oz) * T.inv_scale);
+            V3 pn = mk((p4.x - T.ox) * T.inv_scale, (p4.y - T.oy) * T.inv_scale, (p4.z - T.oz) * T.inv_scale);
+            V3 vn = mk(v4.x * T.inv_scale, v4.y * T.inv_scale, v4.z * T.inv_scale);
+            hit = C.dt != 0.0f && collide(T, pc, pn, vn, cp, nn);
+        }
+        int dep_vertex = 0, dep_amount = 0, want_vertex = 0, want_amount = 0;
+        bool dep = false, want = false;
+        if (hit) {
+            // fluid_system.h:337-339 (world units)
+            V3 v = mk(v4.x, v4.y, v4.z);
+            V3 cw = mk(cp.x * T.scale + T.ox, cp.y * T.scale + T.oy, cp.z * T.scale + T.oz);
+            float d = norm3(mk(p4.x, p4.y, p4.z) - cw);
+            float vn_ = dot(v, nn);
+            float k = 1.0f + C.cR * (d / (C.dt * norm3(v)));
+            float vtl = norm3(v - vn_ * nn);
+            V3 v2 = v - (k * vn_) * nn;
+            v4.x = v2.x; v4.y = v2.y; v4.z = v2.z;
+            p4.x = cw.x; p4.y = cw.y; p4.z = cw.z;
+            if (T.erosion) {
+                int vx = min(max((int)floorf(cp.x + 0.5f), 0), T.rows - 1);
+                int vz = min(max((int)floorf(cp.z + 0.5f), 0), T.cols - 1);
+                int c = vx * T.cols + vz;
+                int s_fx = sediment[i];
+                float cap = T.Kc * vtl;
+                float s = (float)s_fx * (1.0f / 4096.0f);
+                if (s > cap) {
+                    int q = min(__float2int_rn((s - cap) * T.Kd * 4096.0f), s_fx);
+                    if (q > 0) { dep = true; dep_vertex = c; dep_amount = q; sediment[i] = s_fx - q; }
+                } else if (s < cap) {
+                    int q = min(__float2int_rn((cap - s) * T.Ke * 4096.0f), T.max_pickup_fx);
+                    if (q > 0) { want = true; want_vertex = c; want_amount = q; }
+                }
             }
         }
+        unsigned m_hit = __ballot_sync(SPHE_FULL, hit);
+        if (m_hit && lane == 0) atomicAdd(T.contacts, (unsigned long long)__popc(m_hit));
+        unsigned m_dep = __ballot_sync(SPHE_FULL, dep), m_want = __ballot_sync(SPHE_FULL, want);
+        vertex_add(m_dep, dep, T.delta, dep_vertex, dep_amount);
+        vertex_add(m_want, want, T.want, want_vertex, want_amount);
+        if (!live) continue;
+        req_vertex[j] = want ? want_vertex : -1;
+        req_amount[j] = want_amount;
+        if (hit_out) hit_out[i] = hit ? 1 : 0;
+        bool boxed = apply_box && box_collide(C, p4.x, p4.y, p4.z, v4.x, v4.y, v4.z);  // fluid_system.h:342-347
+        if (hit || boxed) { posq[i] = p4; velv[i] = v4; }
     }
-    int dep_vertex = 0, dep_amount = 0, want_vertex = 0, want_amount = 0;
-    bool dep = false, want = false;
-    if (hit) {
-        // fluid_system.h:337-339 (world units)
-        V3 v = mk(v4.x, v4.y, v4.z);
-        V3 cw = mk(cp.x * T.scale + T.ox, cp.y * T.scale + T.oy, cp.z * T.scale + T.oz);
-        float d = norm3(mk(p4.x, p4.y, p4.z) - cw);
-        float vn_ = dot(v, nn);
-        float k = 1.0f + C.cR * (d / (C.dt * norm3(v)));
-        float vtl = norm3(v - vn_ * nn);
-        V3 v2 = v - (k * vn_) * nn;
-        v4.x = v2.x; v4.y = v2.y; v4.z = v2.z;
-        p4.x = cw.x; p4.y = cw.y; p4.z = cw.z;
-        if (T.erosion) {
-            int vx = min(max((int)floorf(cp.x + 0.5f), 0), T.rows - 1);
-            int vz = min(max((int)floorf(cp.z + 0.5f), 0), T.cols - 1);
-            int c = vx * T.cols + vz;
-            int s_fx = sediment[i];
-            float cap = T.Kc * vtl;
-            float s = (float)s_fx * (1.0f / 4096.0f);
-            if (s > cap) {
-                int q = min(__float2int_rn((s - cap) * T.Kd * 4096.0f), s_fx);
-                if (q > 0) { dep = true; dep_vertex = c; dep_amount = q; sediment[i] = s_fx - q; }
-            } else if (s < cap) {
-                int q = min(__float2int_rn((cap - s) * T.Ke * 4096.0f), T.max_pickup_fx);
-                if (q > 0) { want = true; want_vertex = c; want_amount = q; }
-            }
-        }
-    }
-    unsigned m_hit = __ballot_sync(SPHE_FULL, hit);
-    if (m_hit && (threadIdx.x & 31) == 0) atomicAdd(T.contacts, (unsigned long long)__popc(m_hit));
-    unsigned m_dep = __ballot_sync(SPHE_FULL, dep), m_want = __ballot_sync(SPHE_FULL, want);
-    vertex_add(m_dep, dep, T.delta, dep_vertex, dep_amount);
-    vertex_add(m_want, want, T.want, want_vertex, want_amount);
-    if (!live) return;
-    req_vertex[i] = want ? want_vertex : -1;
-    req_amount[i] = want_amount;
-    if (hit_out) hit_out[i] = hit ? 1 : 0;
-    if (apply_box) box_collide(C, p4.x, p4.y, p4.z, v4.x, v4.y, v4.z);  // fluid_system.h:342-347
-    if (hit || apply_box) { posq[i] = p4; velv[i] = v4; }
 }
 
 // ------------------------------------------------------------------ share what is above bedrock
-__global__ void __launch_bounds__(256) k_terrain_grant(int n_hi, const int* __restrict__ n_dev, const int* __restrict__ req_vertex, const int* __restrict__ req_amount,
+__global__ void __launch_bounds__(128) k_terrain_grant(const int* __restrict__ surv, const int* __restrict__ surv_count,
+                                                       const int* __restrict__ req_vertex, const int* __restrict__ req_amount,
                                                        int* __restrict__ sediment, TerrainDev T) {
-    const int n = n_dev ? __ldg(n_dev) : n_hi;  // exact count from the device in slab mode, else the launch bound
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int c = (i < n) ? req_vertex[i] : -1;
-    bool act = c >= 0;
-    int g = 0;
-    if (act) {
-        long long avail = (long long)T.hfx_rw[c] - T.hmin_fx;
-        if (avail < 0) avail = 0;
-        long long w = T.want[c];
-        int q = req_amount[i];
-        g = (w <= avail) ? q : (int)(((long long)q * avail) / w);
-        sediment[i] += g;
+    const int count = __ldg(surv_count);
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int base = warp * 32; base < count; base += nwarps * 32) {
+        const int j = base + lane;
+        int c = (j < count) ? req_vertex[j] : -1;
+        bool act = c >= 0;
+        int g = 0;
+        if (act) {
+            long long avail = (long long)T.hfx_rw[c] - T.hmin_fx;
+            if (avail < 0) avail = 0;
+            long long w = T.want[c];
+            int q = req_amount[j];
+            g = (w <= avail) ? q : (int)(((long long)q * avail) / w);
+            sediment[surv[j]] += g;
+        }
+        unsigned m = __ballot_sync(SPHE_FULL, act);
+        vertex_add(m, act, T.delta, c, -g);
     }
-    unsigned m = __ballot_sync(SPHE_FULL, act);
-    vertex_add(m, act, T.delta, c, -g);
 }
 
 __global__ void __launch_bounds__(256) k_terrain_apply(int cells, TerrainDev T) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
-    int h = -0x7fffffff;
-    if (c < cells) {
-        int d = T.delta[c];
-        h = T.hfx_rw[c];
-        if (d) { h += d; T.hfx_rw[c] = h; T.delta[c] = 0; }
-        if (T.want[c]) T.want[c] = 0;
-    }
-    h = __reduce_max_sync(SPHE_FULL, h);
-    if ((threadIdx.x & 31) == 0 && h > -0x7fffffff) atomicMax(T.hmax_rw, h);
+    if (c >= cells) return;
+    int d = T.delta[c];
+    if (d) { T.hfx_rw[c] += d; T.delta[c] = 0; }
+    if (T.want[c]) T.want[c] = 0;
+}
+
+// every slot is a survivor (the test hook sphe_terrain_stage_host has no force kernel in front of it)
+__global__ void k_iota(int n, int* __restrict__ a, int* __restrict__ count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = i;
+    if (i == 0) *count = n;
+}
+
+// lmax[x, z] = max height over the vertices [x-1, x+2] x [z-1, z+2]: everything collide() can touch from cell (x, z)
+__global__ void __launch_bounds__(256) k_terrain_lmax(TerrainDev T, int* __restrict__ lmax) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= T.rows * T.cols) return;
+    int x = c / T.cols, z = c - x * T.cols;
+    int m = -0x7fffffff;
+#pragma unroll
+    for (int dx = -1; dx <= 2; dx++)
+#pragma unroll
+        for (int dz = -1; dz <= 2; dz++) {
+            int xx = min(max(x + dx, 0), T.rows - 1), zz = min(max(z + dz, 0), T.cols - 1);
+            m = max(m, T.hfx_rw[xx * T.cols + zz]);
+        }
+    lmax[c] = m;
 }
 
 // ------------------------------------------------------------------ render mesh (UpdateGrid, grid.h:138-176)
@@ -378,16 +406,24 @@ __global__ void __launch_bounds__(256) k_sum_i32(int n, const int* __restrict__ 
 // ------------------------------------------------------------------ launch wrappers
 static inline int nb(int n, int b) { return (n + b - 1) / b; }
 
-void launch_terrain_stage(cudaStream_t st, int n, const int* n_dev, const float4* pos_old, float4* posq, float4* velv, int* sediment,
-                          const StepC& C, const TerrainDev& T, int apply_box, int* req_vertex, int* req_amount, int* hit_out) {
-    if (n <= 0) return;
-    k_terrain_contact<<<nb(n, 128), 128, 0, st>>>(n, n_dev, pos_old, posq, velv, sediment, C, T, apply_box, req_vertex, req_amount, hit_out);
+// persistent grid: 148 SMs x 4 blocks of 128 threads stride over the survivor list
+void launch_terrain_stage(cudaStream_t st, const int* surv, const int* surv_count, const float4* pos_old, float4* posq, float4* velv,
+                          int* sediment, const StepC& C, const TerrainDev& T, int apply_box, int* req_vertex, int* req_amount,
+                          int* hit_out) {
+    k_terrain_contact<<<148 * 4, 128, 0, st>>>(surv, surv_count, pos_old, posq, velv, sediment, C, T, apply_box, req_vertex, req_amount, hit_out);
     if (T.erosion && C.dt != 0.0f) {
-        k_terrain_grant<<<nb(n, 256), 256, 0, st>>>(n, n_dev, req_vertex, req_amount, sediment, T);
+        k_terrain_grant<<<148 * 4, 128, 0, st>>>(surv, surv_count, req_vertex, req_amount, sediment, T);
         k_terrain_apply<<<nb(T.rows * T.cols, 256), 256, 0, st>>>(T.rows * T.cols, T);
+        k_terrain_lmax<<<nb(T.rows * T.cols, 256), 256, 0, st>>>(T, T.lmax_rw);
     }
 }
-int terrain_stage_launches(const StepC& C, const TerrainDev& T) { return (T.erosion && C.dt != 0.0f) ? 3 : 1; }
+int terrain_stage_launches(const StepC& C, const TerrainDev& T) { return (T.erosion && C.dt != 0.0f) ? 4 : 1; }
+void launch_iota(cudaStream_t st, int n, int* a, int* count) {
+    if (n > 0) k_iota<<<nb(n, 256), 256, 0, st>>>(n, a, count);
+}
+void launch_terrain_lmax(cudaStream_t st, const TerrainDev& T) {
+    k_terrain_lmax<<<nb(T.rows * T.cols, 256), 256, 0, st>>>(T, T.lmax_rw);
+}
 
 void launch_terrain_surface(cudaStream_t st, const TerrainDev& T, float* out) {
     int m = T.dimx * T.dimz;
