@@ -336,10 +336,11 @@ static int step_device(sphe_sim* s, sphe_terrain* t) {
                           s->idsB, s->cell_sorted); }
     if (s->variant_density >= 3 || s->variant_force >= 3) {
         if (s->variant_density != s->variant_force) return fail(SPHE_ERR_ARG, "variants 3/4 (neighbour lists) must be selected for both passes");
-        size_t pp = (size_t)nlist_pairs_pad(s->cap);
+        // capacity for every list variant: S sub-lists of slist_entries(S) entries per pair, S <= 8 -> <= 96 ints per pair
+        size_t pp = (size_t)nlist_pairs_pad(s->cap) + 128;
         if (pp > s->nlist_pairs) {
-            TRY(grow(&s->nlist, 0, pp * (size_t)nlist_cap(), s->st, false));
-            TRY(grow(&s->ncount, 0, pp, s->st, false));
+            TRY(grow(&s->nlist, 0, pp * 96, s->st, false));
+            TRY(grow(&s->ncount, 0, pp * 8, s->st, false));
             s->nlist_pairs = pp;
         }
     }

@@ -468,7 +468,11 @@ constexpr int NLIST_THREADS = 128;
 // REC = true (variant 4): instead of (posC, vel.w) the pass writes ONE interleaved 32-byte record per particle,
 // rec[2i] = (x, y, z, P/rho^2), rec[2i+1] = (vx, vy, vz, m/rho), so the force pass fetches everything it needs
 // about a neighbour with a single 256-bit gather (LDG.E.256, new on sm_100) instead of two 128-bit ones.
-template <bool REC>
+// PF = true (variant 6): software-pipelined candidate stream.  ncu source view of the plain kernel: 45 % of the
+// stall samples sit on the first use of the gathered positions and 9 % on the run bounds (cell_start) -- the
+// kernel waits on its own loads.  Here the next group of four candidates and the next run's bounds are
+// already in flight while the current group is processed.
+template <bool REC, bool PF>
 __global__ void __launch_bounds__(NLIST_THREADS) k_density_list(int n_hi, const int* __restrict__ n_dev, int npairs_pad, const float4* __restrict__ posq,
                                                                 float4* __restrict__ posq_q, float4* __restrict__ velv,
                                                                 const uint32_t* __restrict__ cell_sorted,
@@ -505,29 +509,57 @@ __global__ void __launch_bounds__(NLIST_THREADS) k_density_list(int n_hi, const 
         const int cy = (int)(col % (uint32_t)G.ny), cx = (int)(col / (uint32_t)G.ny);
         const int z0 = czlo > 0 ? czlo - 1 : 0, z1 = czhi < G.nz - 1 ? czhi + 1 : czhi;
         if (p == 1) off0 = off;
-#pragma unroll 1
-        for (int r = 0; r < 9; r++) {
+        auto test = [&](const int k, const float4 pj) {
+            float2 dx = __fadd2_rn(X, make_float2(-pj.x, -pj.x));
+            float2 dy = __fadd2_rn(Y, make_float2(-pj.y, -pj.y));
+            float2 dz = __fadd2_rn(Z, make_float2(-pj.z, -pj.z));
+            float2 d2 = __fmul2_rn(dx, dx);
+            d2 = __ffma2_rn(dy, dy, d2);
+            d2 = __ffma2_rn(dz, dz, d2);
+            float2 w = __fadd2_rn(make_float2(C.hh, C.hh), make_float2(-d2.x, -d2.y));
+            // branch-free append: store at the current slot, advance only on a pass
+            lbase[min(off, NLIST_CAP * NLIST_THREADS)] = k;
+            off += (fmaxf(w.x, w.y) >= 0.f) ? NLIST_THREADS : 0;
+            w.x = fmaxf(w.x, 0.f);
+            w.y = fmaxf(w.y, 0.f);
+            acc = __ffma2_rn(__fmul2_rn(w, w), w, acc);
+        };
+        auto bounds = [&](const int r, int& s, int& e) {
             int x = cx + r / 3 - 1, y = cy + r % 3 - 1;
-            if (x < 0 || x >= G.nx || y < 0 || y >= G.ny) continue;
-            int base = (x * G.ny + y) * G.nz;
-            int s = __ldg(&cell_start[base + z0]);
-            int e = __ldg(&cell_start[base + z1 + 1]);
+            bool ok = r < 9 && x >= 0 && x < G.nx && y >= 0 && y < G.ny;
+            int base = ok ? (x * G.ny + y) * G.nz : 0;
+            s = __ldg(&cell_start[base + z0]);
+            e = ok ? __ldg(&cell_start[base + z1 + 1]) : s;   // empty range for a column outside the grid
+        };
+        if (!PF) {
+#pragma unroll 1
+            for (int r = 0; r < 9; r++) {
+                int s, e;
+                bounds(r, s, e);
 #pragma unroll 4
-            for (int k = s; k < e; k++) {
-                float4 pj = __ldg(&posq[k]);
-                float2 dx = __fadd2_rn(X, make_float2(-pj.x, -pj.x));
-                float2 dy = __fadd2_rn(Y, make_float2(-pj.y, -pj.y));
-                float2 dz = __fadd2_rn(Z, make_float2(-pj.z, -pj.z));
-                float2 d2 = __fmul2_rn(dx, dx);
-                d2 = __ffma2_rn(dy, dy, d2);
-                d2 = __ffma2_rn(dz, dz, d2);
-                float2 w = __fadd2_rn(make_float2(C.hh, C.hh), make_float2(-d2.x, -d2.y));
-                // branch-free append: store at the current slot, advance only on a pass
-                lbase[min(off, NLIST_CAP * NLIST_THREADS)] = k;
-                off += (fmaxf(w.x, w.y) >= 0.f) ? NLIST_THREADS : 0;
-                w.x = fmaxf(w.x, 0.f);
-                w.y = fmaxf(w.y, 0.f);
-                acc = __ffma2_rn(__fmul2_rn(w, w), w, acc);
+                for (int k = s; k < e; k++) test(k, __ldg(&posq[k]));
+            }
+        } else {
+            int s, e, sn, en;
+            bounds(0, s, e);
+#pragma unroll 1
+            for (int r = 0; r < 9; r++) {
+                bounds(r + 1, sn, en);   // next run's bounds in flight (r + 1 == 9 yields an empty range)
+                int k = s;
+                if (k + 4 <= e) {
+                    float4 q0 = __ldg(&posq[k]), q1 = __ldg(&posq[k + 1]), q2 = __ldg(&posq[k + 2]), q3 = __ldg(&posq[k + 3]);
+#pragma unroll 1
+                    for (; k + 8 <= e; k += 4) {
+                        const float4 n0 = __ldg(&posq[k + 4]), n1 = __ldg(&posq[k + 5]), n2 = __ldg(&posq[k + 6]), n3 = __ldg(&posq[k + 7]);
+                        test(k, q0); test(k + 1, q1); test(k + 2, q2); test(k + 3, q3);
+                        q0 = n0; q1 = n1; q2 = n2; q3 = n3;
+                    }
+                    test(k, q0); test(k + 1, q1); test(k + 2, q2); test(k + 3, q3);
+                    k += 4;
+                }
+#pragma unroll 1
+                for (; k < e; k++) test(k, __ldg(&posq[k]));
+                s = sn; e = en;
             }
         }
     }
@@ -577,7 +609,10 @@ __device__ __forceinline__ void ldg_rec(const float4* __restrict__ rec, int k, f
 #ifndef FL_MINB
 #define FL_MINB 7
 #endif
-template <bool DIAG, bool REC>
+// PF = true (variant 6): the list index is fetched TWO entries ahead.  ncu source view of the plain kernel: 38 % of
+// the stall samples sit on the address computation of the next gather, i.e. on the index load it depends on
+// (index -> gather is a dependent chain; the lists stream from HBM).  One more register hides it.
+template <bool DIAG, bool REC, bool PF>
 __global__ void __launch_bounds__(NLIST_THREADS, FL_MINB) k_force_list(int n_hi, const int* __restrict__ n_dev, int npairs_pad, const float4* __restrict__ posq_q,
                                                               const float4* __restrict__ velv, const float* __restrict__ rho,
                                                               const int* __restrict__ ids, const uint32_t* __restrict__ cell_sorted,
@@ -664,14 +699,27 @@ __global__ void __launch_bounds__(NLIST_THREADS, FL_MINB) k_force_list(int n_hi,
             // (a two-stage version raised the register count to 94 and lost a CTA/SM: slower, measured)
             int k = __ldg(&src[(size_t)e0 * npairs_pad]);
             float4 pj, vj;
-            if (REC) ldg_rec(posq_q, k, pj, vj); else { pj = __ldg(&posq_q[k]); vj = __ldg(&velv[k]); }
+            if (!PF) {
+                if (REC) ldg_rec(posq_q, k, pj, vj); else { pj = __ldg(&posq_q[k]); vj = __ldg(&velv[k]); }
 #pragma unroll 1
-            for (int e = e0; e < e1; e++) {
-                const int kn = (e + 1 < e1) ? __ldg(&src[(size_t)(e + 1) * npairs_pad]) : k;
-                float4 pjn, vjn;
-                if (REC) ldg_rec(posq_q, kn, pjn, vjn); else { pjn = __ldg(&posq_q[kn]); vjn = __ldg(&velv[kn]); }
-                body(k, pj, vj);
-                k = kn; pj = pjn; vj = vjn;
+                for (int e = e0; e < e1; e++) {
+                    const int kn = (e + 1 < e1) ? __ldg(&src[(size_t)(e + 1) * npairs_pad]) : k;
+                    float4 pjn, vjn;
+                    if (REC) ldg_rec(posq_q, kn, pjn, vjn); else { pjn = __ldg(&posq_q[kn]); vjn = __ldg(&velv[kn]); }
+                    body(k, pj, vj);
+                    k = kn; pj = pjn; vj = vjn;
+                }
+            } else {
+                int k1 = (e0 + 1 < e1) ? __ldg(&src[(size_t)(e0 + 1) * npairs_pad]) : k;
+                if (REC) ldg_rec(posq_q, k, pj, vj); else { pj = __ldg(&posq_q[k]); vj = __ldg(&velv[k]); }
+#pragma unroll 1
+                for (int e = e0; e < e1; e++) {
+                    const int k2 = (e + 2 < e1) ? __ldg(&src[(size_t)(e + 2) * npairs_pad]) : k1;   // index two ahead
+                    float4 pjn, vjn;                                                                // gathers one ahead
+                    if (REC) ldg_rec(posq_q, k1, pjn, vjn); else { pjn = __ldg(&posq_q[k1]); vjn = __ldg(&velv[k1]); }
+                    body(k, pj, vj);
+                    k = k1; k1 = k2; pj = pjn; vj = vjn;
+                }
             }
         }
     } else {
@@ -724,6 +772,293 @@ __global__ void __launch_bounds__(NLIST_THREADS, FL_MINB) k_force_list(int n_hi,
         const float cf = p ? CF.y : CF.x;
         force_epilogue<DIAG>(i, pi, vi, rho[i], ax, ay, az, fx, fy, fz, nx, ny, nz, cf, p ? maxb : maxa, C, ids, posq_out, velv_out, D);
     }
+}
+
+// ------------------------------------------------------------------ variant 5x: S lanes per target pair
+// ncu on the list kernels (profiles/r01_ncu_density_list_c2.txt, r01_ncu_force_list_c2.txt): both sit on the
+// L1 data pipe (lsu wavefronts 80 % / 65 % of peak, issue active 55 % / 45 %).  The pipe delivers one 128-byte
+// line per cycle per SM, and with one pair per lane a warp spans ~10 cells, so every gather request touches
+// ~10-20 distinct lines.  Here S consecutive lanes share one target pair and stride the candidates
+// (lane % S, step S): a warp spans 32/S pairs (~3 cells at S = 4), the S lanes of a pair read S consecutive
+// candidates (one line), pairs of the same cell read the same addresses -> 3-4x fewer lines per request at
+// the same number of lane-candidates per request.  Each lane keeps its own sub-list (entry-major in HBM as
+// before); the force pass walks the sub-list it is given and the S partial sums are combined with
+// __shfl_xor (20 values, log2 S levels: ~3 % of the body work).  Shared memory per CTA drops with S
+// (shorter sub-lists), which also lifts the occupancy limit of the S = 1 kernel.
+template <int S> struct SList { static constexpr int CAP = S == 1 ? 64 : (S == 2 ? 36 : (S == 4 ? 20 : 12)); };
+
+template <int S>
+__global__ void __launch_bounds__(NLIST_THREADS) k_density_slist(int n_hi, const int* __restrict__ n_dev, int stride,
+                                                                 const float4* __restrict__ posq, float4* __restrict__ posq_q,
+                                                                 float4* __restrict__ velv, const uint32_t* __restrict__ cell_sorted,
+                                                                 const int* __restrict__ cell_start, GridP G, StepC C,
+                                                                 float* __restrict__ rho, int* __restrict__ nlist,
+                                                                 int2* __restrict__ ncount) {
+    constexpr int CAP = SList<S>::CAP;
+    const int n = n_dev ? __ldg(n_dev) : n_hi;
+    __shared__ int list[(CAP + 1) * NLIST_THREADS];  // +1: trash slot for saturated appends
+    const int tid = threadIdx.x;
+    const int gt = blockIdx.x * blockDim.x + tid;
+    const int slice = gt % S;
+    int a = 2 * (gt / S);
+    const bool live = a < n;
+    if (!live) a = 0;
+    const int b = (a + 1 < n) ? a + 1 : a;
+    const float4 pa = posq[a], pb = posq[b];
+    const uint32_t ca = cell_sorted[a], cb = cell_sorted[b];
+    const uint32_t cola = ca / (uint32_t)G.nz, colb = cb / (uint32_t)G.nz;
+    const int cza = (int)(ca - cola * (uint32_t)G.nz), czb = (int)(cb - colb * (uint32_t)G.nz);
+    const bool merged = (b != a) && (cola == colb) && (czb - cza <= 3);
+    const float FAR = 1.0e18f;
+    const int npass = !live ? 0 : ((merged || b == a) ? 1 : 2);
+
+    float2 acc = make_float2(0.f, 0.f);
+    int* const lbase = list + tid;
+    int off = 0, off0 = 0;  // slot * NLIST_THREADS
+#pragma unroll 1
+    for (int p = 0; p < npass; p++) {
+        const bool useA = merged || p == 0, useB = merged || p == 1;
+        const float2 X = make_float2(useA ? pa.x : FAR, useB ? pb.x : FAR);
+        const float2 Y = make_float2(useA ? pa.y : FAR, useB ? pb.y : FAR);
+        const float2 Z = make_float2(useA ? pa.z : FAR, useB ? pb.z : FAR);
+        const uint32_t col = p ? colb : cola;
+        const int czlo = p ? czb : cza, czhi = merged ? czb : czlo;
+        const int cy = (int)(col % (uint32_t)G.ny), cx = (int)(col / (uint32_t)G.ny);
+        const int z0 = czlo > 0 ? czlo - 1 : 0, z1 = czhi < G.nz - 1 ? czhi + 1 : czhi;
+        if (p == 1) off0 = off;
+#pragma unroll 1
+        for (int r = 0; r < 9; r++) {
+            int x = cx + r / 3 - 1, y = cy + r % 3 - 1;
+            if (x < 0 || x >= G.nx || y < 0 || y >= G.ny) continue;
+            int base = (x * G.ny + y) * G.nz;
+            int s = __ldg(&cell_start[base + z0]);
+            int e = __ldg(&cell_start[base + z1 + 1]);
+#pragma unroll 4
+            for (int k = s + slice; k < e; k += S) {
+                float4 pj = __ldg(&posq[k]);
+                float2 dx = __fadd2_rn(X, make_float2(-pj.x, -pj.x));
+                float2 dy = __fadd2_rn(Y, make_float2(-pj.y, -pj.y));
+                float2 dz = __fadd2_rn(Z, make_float2(-pj.z, -pj.z));
+                float2 d2 = __fmul2_rn(dx, dx);
+                d2 = __ffma2_rn(dy, dy, d2);
+                d2 = __ffma2_rn(dz, dz, d2);
+                float2 w = __fadd2_rn(make_float2(C.hh, C.hh), make_float2(-d2.x, -d2.y));
+                lbase[min(off, CAP * NLIST_THREADS)] = k;  // branch-free append
+                off += (fmaxf(w.x, w.y) >= 0.f) ? NLIST_THREADS : 0;
+                w.x = fmaxf(w.x, 0.f);
+                w.y = fmaxf(w.y, 0.f);
+                acc = __ffma2_rn(__fmul2_rn(w, w), w, acc);
+            }
+        }
+    }
+    if (npass == 1) off0 = off;
+    const int cnt = off / NLIST_THREADS;
+    // the S sub-lists of a pair are used together: if one overflowed, all of them fall back
+    int fits = cnt <= CAP;
+#pragma unroll
+    for (int o = 1; o < S; o <<= 1) {
+        fits &= __shfl_xor_sync(SPHE_FULL, fits, o);
+        acc.x += __shfl_xor_sync(SPHE_FULL, acc.x, o);
+        acc.y += __shfl_xor_sync(SPHE_FULL, acc.y, o);
+    }
+    if (live) ncount[gt] = fits ? make_int2(off0 / NLIST_THREADS, cnt) : make_int2(-1, -1);
+    if (fits) {
+        int* dst = nlist + gt;
+#pragma unroll 4
+        for (int o = 0, e = 0; o < off; o += NLIST_THREADS, e++) dst[(size_t)e * stride] = lbase[o];
+    }
+    if (!live || slice != 0) return;
+    float ra = acc.x * C.densK, rb = acc.y * C.densK;
+    float Pa = C.k * (ra - C.p0), Pb = C.k * (rb - C.p0);
+    rho[a] = ra;
+    posq_q[a] = make_float4(pa.x, pa.y, pa.z, Pa / (ra * ra));
+    velv[a].w = C.mass / ra;
+    if (b != a) {
+        rho[b] = rb;
+        posq_q[b] = make_float4(pb.x, pb.y, pb.z, Pb / (rb * rb));
+        velv[b].w = C.mass / rb;
+    }
+}
+
+template <bool DIAG, int S>
+__global__ void __launch_bounds__(NLIST_THREADS, FL_MINB) k_force_slist(int n_hi, const int* __restrict__ n_dev, int stride,
+                                                               const float4* __restrict__ posq_q, const float4* __restrict__ velv,
+                                                               const float* __restrict__ rho, const int* __restrict__ ids,
+                                                               const uint32_t* __restrict__ cell_sorted,
+                                                               const int* __restrict__ cell_start, GridP G, StepC C,
+                                                               const int* __restrict__ nlist, const int2* __restrict__ ncount,
+                                                               float4* __restrict__ posq_out, float4* __restrict__ velv_out, DiagOut D) {
+    const int n = n_dev ? __ldg(n_dev) : n_hi;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int slice = gt % S;
+    int a = 2 * (gt / S);
+    const bool live = a < n;   // dead lanes stay for the shuffles (a whole S-group is dead or alive together)
+    if (!live) a = 0;
+    const int b = (a + 1 < n) ? a + 1 : a;
+    const float4 pa = posq_q[a], pb = posq_q[b];
+    const float4 va = velv[a], vb = velv[b];
+    const int2 cn = live ? ncount[gt] : make_int2(0, 0);
+    const float inv_sqrt3 = 0.57735026f;
+    const float FAR = 1.0e18f;
+
+    float2 A_x = {0.f, 0.f}, A_y = {0.f, 0.f}, A_z = {0.f, 0.f};
+    float2 F_x = {0.f, 0.f}, F_y = {0.f, 0.f}, F_z = {0.f, 0.f};
+    float2 N_x = {0.f, 0.f}, N_y = {0.f, 0.f}, N_z = {0.f, 0.f};
+    float2 CF = {0.f, 0.f};
+    int maxa = -1, maxb = -1;
+    const float2 Q = make_float2(pa.w, pb.w);
+    const float2 VX = make_float2(va.x, vb.x), VY = make_float2(va.y, vb.y), VZ = make_float2(va.z, vb.z);
+
+    // the pair's own geometry decides merged/split (all S lanes agree; a sub-list may be empty)
+    const uint32_t ca = cell_sorted[a], cb = cell_sorted[b];
+    const uint32_t cola = ca / (uint32_t)G.nz, colb = cb / (uint32_t)G.nz;
+    const int cza = (int)(ca - cola * (uint32_t)G.nz), czb = (int)(cb - colb * (uint32_t)G.nz);
+    const bool merged = (b != a) && (cola == colb) && (czb - cza <= 3);
+    float2 X, Y, Z;
+    int ia, ib;
+    auto body = [&](const int k, const float4 pj, const float4 vj) {
+        float2 dx = __fadd2_rn(X, make_float2(-pj.x, -pj.x));
+        float2 dy = __fadd2_rn(Y, make_float2(-pj.y, -pj.y));
+        float2 dz = __fadd2_rn(Z, make_float2(-pj.z, -pj.z));
+        float2 d2 = __fmul2_rn(dx, dx);
+        d2 = __ffma2_rn(dy, dy, d2);
+        d2 = __ffma2_rn(dz, dz, d2);
+        float2 w = __fadd2_rn(make_float2(C.hh, C.hh), make_float2(-d2.x, -d2.y));
+        w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f);
+        float2 vw = __fmul2_rn(w, make_float2(vj.w, vj.w));
+        float2 t7 = __ffma2_rn(d2, make_float2(-7.0f, -7.0f), make_float2(C.hh3, C.hh3));
+        CF = __ffma2_rn(vw, t7, CF);
+        float2 vww = __fmul2_rn(vw, w);
+        N_x = __ffma2_rn(vww, dx, N_x); N_y = __ffma2_rn(vww, dy, N_y); N_z = __ffma2_rn(vww, dz, N_z);
+        float2 rinv = make_float2(rsqrt_ftz(fmaxf(d2.x, 1e-30f)), rsqrt_ftz(fmaxf(d2.y, 1e-30f)));
+        float2 r = __fmul2_rn(d2, rinv);
+        float2 hm = __fadd2_rn(make_float2(C.h, C.h), make_float2(-r.x, -r.y));
+        hm.x = fmaxf(hm.x, 0.f); hm.y = fmaxf(hm.y, 0.f);
+        float2 tv = __fmul2_rn(hm, make_float2(vj.w, vj.w));
+        float2 dvx = __fadd2_rn(make_float2(vj.x, vj.x), make_float2(-VX.x, -VX.y));
+        float2 dvy = __fadd2_rn(make_float2(vj.y, vj.y), make_float2(-VY.x, -VY.y));
+        float2 dvz = __fadd2_rn(make_float2(vj.z, vj.z), make_float2(-VZ.x, -VZ.y));
+        F_x = __ffma2_rn(tv, dvx, F_x); F_y = __ffma2_rn(tv, dvy, F_y); F_z = __ffma2_rn(tv, dvz, F_z);
+        float2 sq = __fadd2_rn(Q, make_float2(pj.w, pj.w));
+        float2 sc = __fmul2_rn(__fmul2_rn(sq, hm), hm);
+        if (k == ia) sc.x = 0.f;  // pressure excludes j == i (fluid_system.h:142)
+        if (k == ib) sc.y = 0.f;
+        float2 ux = __fmul2_rn(dx, rinv), uy = __fmul2_rn(dy, rinv), uz = __fmul2_rn(dz, rinv);
+        if (fminf(r.x, r.y) <= 1e-4f) {  // coincident pair (fluid_system.h:438-440) or the self entry
+            if (r.x <= 1e-4f) { ux.x = inv_sqrt3; uy.x = inv_sqrt3; uz.x = inv_sqrt3; }
+            if (r.y <= 1e-4f) { ux.y = inv_sqrt3; uy.y = inv_sqrt3; uz.y = inv_sqrt3; }
+        }
+        A_x = __ffma2_rn(sc, ux, A_x); A_y = __ffma2_rn(sc, uy, A_y); A_z = __ffma2_rn(sc, uz, A_z);
+        if (DIAG) {
+            int idk = __ldg(&ids[k]);
+            if (k != ia && ia >= 0 && dist2_exact(pa.x - pj.x, pa.y - pj.y, pa.z - pj.z) <= C.T) maxa = max(maxa, idk);
+            if (k != ib && ib >= 0 && dist2_exact(pb.x - pj.x, pb.y - pj.y, pb.z - pj.z) <= C.T) maxb = max(maxb, idk);
+        }
+    };
+
+    if (live && cn.y >= 0) {
+        const int* src = nlist + gt;
+#pragma unroll 1
+        for (int seg = 0; seg < 2; seg++) {
+            // segment 0 = entries [0, cn.x): targets (a, b) when merged, else (a, FAR); segment 1 = [cn.x, cn.y): (FAR, b)
+            const int e0 = seg ? cn.x : 0, e1 = seg ? cn.y : cn.x;
+            if (e0 >= e1) continue;
+            const bool useA = seg == 0, useB = merged || seg == 1;
+            X = make_float2(useA ? pa.x : FAR, useB ? pb.x : FAR);
+            Y = make_float2(useA ? pa.y : FAR, useB ? pb.y : FAR);
+            Z = make_float2(useA ? pa.z : FAR, useB ? pb.z : FAR);
+            ia = useA ? a : -1; ib = (useB && b != a) ? b : -1;
+            int k = __ldg(&src[(size_t)e0 * stride]);
+            float4 pj = __ldg(&posq_q[k]);
+            float4 vj = __ldg(&velv[k]);
+#pragma unroll 1
+            for (int e = e0; e < e1; e++) {
+                const int kn = (e + 1 < e1) ? __ldg(&src[(size_t)(e + 1) * stride]) : k;
+                const float4 pjn = __ldg(&posq_q[kn]);
+                const float4 vjn = __ldg(&velv[kn]);
+                body(k, pj, vj);
+                k = kn; pj = pjn; vj = vjn;
+            }
+        }
+    } else if (live) {
+        // a sub-list overflowed (strong compression): direct walks, the S lanes stride the candidates
+        const int npass = (merged || b == a) ? 1 : 2;
+#pragma unroll 1
+        for (int p = 0; p < npass; p++) {
+            const bool useA = merged || p == 0, useB = merged || p == 1;
+            X = make_float2(useA ? pa.x : FAR, useB ? pb.x : FAR);
+            Y = make_float2(useA ? pa.y : FAR, useB ? pb.y : FAR);
+            Z = make_float2(useA ? pa.z : FAR, useB ? pb.z : FAR);
+            ia = useA ? a : -1; ib = (useB && b != a) ? b : -1;
+            const uint32_t col = p ? colb : cola;
+            const int czlo = p ? czb : cza, czhi = merged ? czb : czlo;
+            const int cy = (int)(col % (uint32_t)G.ny), cx = (int)(col / (uint32_t)G.ny);
+            const int z0 = czlo > 0 ? czlo - 1 : 0, z1 = czhi < G.nz - 1 ? czhi + 1 : czhi;
+#pragma unroll 1
+            for (int r = 0; r < 9; r++) {
+                int x = cx + r / 3 - 1, y = cy + r % 3 - 1;
+                if (x < 0 || x >= G.nx || y < 0 || y >= G.ny) continue;
+                int base = (x * G.ny + y) * G.nz;
+                int s = __ldg(&cell_start[base + z0]);
+                int e = __ldg(&cell_start[base + z1 + 1]);
+#pragma unroll 1
+                for (int k = s + slice; k < e; k += S) {
+                    float4 pj = __ldg(&posq_q[k]);
+                    float ex = X.x - pj.x, ey = Y.x - pj.y, ez = Z.x - pj.z;
+                    float gx = X.y - pj.x, gy = Y.y - pj.y, gz = Z.y - pj.z;
+                    float da = fmaf(ez, ez, fmaf(ey, ey, ex * ex)), db = fmaf(gz, gz, fmaf(gy, gy, gx * gx));
+                    if (fminf(da, db) <= C.hh) body(k, pj, __ldg(&velv[k]));
+                }
+            }
+        }
+    }
+
+    // combine the S partial sums of the pair
+#pragma unroll
+    for (int o = 1; o < S; o <<= 1) {
+#define SPHE_RED2(v) v.x += __shfl_xor_sync(SPHE_FULL, v.x, o); v.y += __shfl_xor_sync(SPHE_FULL, v.y, o);
+        SPHE_RED2(A_x) SPHE_RED2(A_y) SPHE_RED2(A_z) SPHE_RED2(F_x) SPHE_RED2(F_y) SPHE_RED2(F_z)
+        SPHE_RED2(N_x) SPHE_RED2(N_y) SPHE_RED2(N_z) SPHE_RED2(CF)
+#undef SPHE_RED2
+        if (DIAG) { maxa = max(maxa, __shfl_xor_sync(SPHE_FULL, maxa, o)); maxb = max(maxb, __shfl_xor_sync(SPHE_FULL, maxb, o)); }
+    }
+    if (!live) return;
+    // lane 0 of the group finishes target a, lane 1 (if any) target b
+#pragma unroll 1
+    for (int p = 0; p < 2; p++) {
+        if (p == 1 && b == a) break;
+        if (S > 1 && slice != p) continue;
+        if (S == 1 || slice == p) {
+            const int i = p ? b : a;
+            const float4 pi = p ? pb : pa;
+            const float4 vi = p ? vb : va;
+            const float ax = p ? A_x.y : A_x.x, ay = p ? A_y.y : A_y.x, az = p ? A_z.y : A_z.x;
+            const float fx = p ? F_x.y : F_x.x, fy = p ? F_y.y : F_y.x, fz = p ? F_z.y : F_z.x;
+            const float nx = p ? N_x.y : N_x.x, ny = p ? N_y.y : N_y.x, nz = p ? N_z.y : N_z.x;
+            const float cf = p ? CF.y : CF.x;
+            force_epilogue<DIAG>(i, pi, vi, rho[i], ax, ay, az, fx, fy, fz, nx, ny, nz, cf, p ? maxb : maxa, C, ids, posq_out, velv_out, D);
+        }
+    }
+}
+
+int slist_threads_pad(int n, int S) { return ((((n + 1) / 2) * S) + NLIST_THREADS - 1) / NLIST_THREADS * NLIST_THREADS; }
+int slist_entries(int S) { return S == 1 ? 64 : (S == 2 ? 36 : (S == 4 ? 20 : 12)); }
+
+template <int S>
+static void launch_density_s(cudaStream_t st, int n, const int* n_dev, const float4* posq, float4* posq_q, float4* velv,
+                             const uint32_t* cell_sorted, const int* cell_start, const GridP& G, const StepC& C, float* rho,
+                             int* nlist, int2* ncount) {
+    int tp = slist_threads_pad(n, S);
+    k_density_slist<S><<<tp / NLIST_THREADS, NLIST_THREADS, 0, st>>>(n, n_dev, tp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount);
+}
+template <int S>
+static void launch_force_s(cudaStream_t st, int n, const int* n_dev, const float4* posq_q, const float4* velv, const float* rho,
+                           const int* ids, const uint32_t* cell_sorted, const int* cell_start, const GridP& G, const StepC& C,
+                           float4* posq_out, float4* velv_out, const DiagOut* diag, const int* nlist, const int2* ncount) {
+    int tp = slist_threads_pad(n, S);
+    dim3 g(tp / NLIST_THREADS), b(NLIST_THREADS);
+    if (diag) k_force_slist<true, S><<<g, b, 0, st>>>(n, n_dev, tp, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, nlist, ncount, posq_out, velv_out, *diag);
+    else k_force_slist<false, S><<<g, b, 0, st>>>(n, n_dev, tp, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, nlist, ncount, posq_out, velv_out, DiagOut{});
 }
 
 // ------------------------------------------------------------------ neighbour-list test hooks
@@ -794,10 +1129,14 @@ void launch_density(cudaStream_t st, int variant, int n, const int* n_dev, const
                     int* nlist, int2* ncount) {
     if (n <= 0) return;
     int pairs = (n + 1) / 2;
-    if (variant == 3 || variant == 4) {
+    if (variant == 52) return launch_density_s<2>(st, n, n_dev, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount);
+    if (variant == 54) return launch_density_s<4>(st, n, n_dev, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount);
+    if (variant == 58) return launch_density_s<8>(st, n, n_dev, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount);
+    if (variant == 3 || variant == 4 || variant == 6) {
         int pp = nlist_pairs_pad(n);
-        if (variant == 4) k_density_list<true><<<pp / NLIST_THREADS, NLIST_THREADS, 0, st>>>(n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount);
-        else k_density_list<false><<<pp / NLIST_THREADS, NLIST_THREADS, 0, st>>>(n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount);
+        if (variant == 4) k_density_list<true, false><<<pp / NLIST_THREADS, NLIST_THREADS, 0, st>>>(n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount);
+        else if (variant == 6) k_density_list<false, true><<<pp / NLIST_THREADS, NLIST_THREADS, 0, st>>>(n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount);
+        else k_density_list<false, false><<<pp / NLIST_THREADS, NLIST_THREADS, 0, st>>>(n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount);
         return;
     }
     if (variant == 1) k_density_pair<1><<<nblk(pairs, 128), 128, 0, st>>>(n, n_dev, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho);
@@ -812,16 +1151,17 @@ void launch_force(cudaStream_t st, int variant, int n, const int* n_dev, const f
                   const int* ids, const uint32_t* cell_sorted, const int* cell_start, const GridP& G, const StepC& C,
                   float4* posq_out, float4* velv_out, const DiagOut* diag, const int* nlist, const int2* ncount) {
     if (n <= 0) return;
-    if (variant == 3 || variant == 4) {
+    if (variant == 52) return launch_force_s<2>(st, n, n_dev, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, posq_out, velv_out, diag, nlist, ncount);
+    if (variant == 54) return launch_force_s<4>(st, n, n_dev, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, posq_out, velv_out, diag, nlist, ncount);
+    if (variant == 58) return launch_force_s<8>(st, n, n_dev, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, posq_out, velv_out, diag, nlist, ncount);
+    if (variant == 3 || variant == 4 || variant == 6) {
         int pp = nlist_pairs_pad(n);
         dim3 g(pp / NLIST_THREADS), b(NLIST_THREADS);
-        if (variant == 4) {
-            if (diag) k_force_list<true, true><<<g, b, 0, st>>>(n, n_dev, pp, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, nlist, ncount, posq_out, velv_out, *diag);
-            else k_force_list<false, true><<<g, b, 0, st>>>(n, n_dev, pp, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, nlist, ncount, posq_out, velv_out, DiagOut{});
-        } else {
-            if (diag) k_force_list<true, false><<<g, b, 0, st>>>(n, n_dev, pp, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, nlist, ncount, posq_out, velv_out, *diag);
-            else k_force_list<false, false><<<g, b, 0, st>>>(n, n_dev, pp, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, nlist, ncount, posq_out, velv_out, DiagOut{});
-        }
+#define SPHE_FL(DG, RC, PFv, dg) k_force_list<DG, RC, PFv><<<g, b, 0, st>>>(n, n_dev, pp, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, nlist, ncount, posq_out, velv_out, dg)
+        if (variant == 4) { if (diag) SPHE_FL(true, true, false, *diag); else SPHE_FL(false, true, false, DiagOut{}); }
+        else if (variant == 6) { if (diag) SPHE_FL(true, false, true, *diag); else SPHE_FL(false, false, true, DiagOut{}); }
+        else { if (diag) SPHE_FL(true, false, false, *diag); else SPHE_FL(false, false, false, DiagOut{}); }
+#undef SPHE_FL
         return;
     }
     if (variant == 1) {
