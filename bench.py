@@ -89,22 +89,23 @@ def synthetic_heightmap(size=1024, seed=0x7E44A1):
     return np.clip(np.rint(34 + h * (246 - 34)), 0, 255).astype(np.uint8)
 
 
-def attach_terrain(pkg, L, n_axis):
+def attach_terrain(pkg, L, n_axis, nx_mult=1):
     """1024 x 1024 terrain under the whole box floor: cell = 2L/1024 world units (uniform scale), heights
     0..255 levels scaled to 0..0.25*block height so the relief is a fraction of the fluid depth, terrain
-    top just under the block so the fluid lands on it during the settle phase."""
-    img = synthetic_heightmap()
+    top just under the block so the fluid lands on it during the settle phase.  nx_mult > 1 (multi-GPU weak
+    scaling): the heightmap is repeated nx_mult times along x under the (nx_mult*L, L, L) channel."""
+    img = np.tile(synthetic_heightmap(), (nx_mult, 1))
     cell = 2.0 * L / 1024.0
     relief = 0.1 * L                                    # world units between the lowest and highest vertex
     heights = img.astype(np.float32) * np.float32(relief / 255.0 / cell)   # in cells
-    g = pkg.Grid(1024, 255, 1024)
+    g = pkg.Grid(1024 * nx_mult, 255, 1024)
     g.set_heights(heights)
     top = float(heights.max()) * cell
-    origin = (-L, -L / 4 - 0.5 * SPACING - top, -L)     # highest vertex half a lattice spacing under the block
+    origin = (-L * nx_mult, -L / 4 - 0.5 * SPACING - top, -L)     # highest vertex half a lattice spacing under the block
     g.set_transform(origin, cell)
     e = g.erosion
     e.enabled = 1; e.Kc = 2.0; e.Ke = 0.3; e.Kd = 0.3; e.hmin = 0.0; e.max_pickup = 0.25
-    return g, {"heightmap": "synthetic 1024x1024 8-bit value noise (lena_gray statistics), seed 0x7E44A1",
+    return g, {"heightmap": "synthetic 1024x1024 8-bit value noise (lena_gray statistics), seed 0x7E44A1" + (", repeated %d x along x" % nx_mult if nx_mult > 1 else ""),
                "terrain_cell": cell, "terrain_relief": relief, "terrain_origin": list(origin),
                "erosion": {"Kc": 2.0, "Ke": 0.3, "Kd": 0.3, "hmin": 0.0, "max_pickup": 0.25}}
 
@@ -245,7 +246,7 @@ def run_reference_arm(args):
         line.update({"value": cb["value"], "ms_per_step": None, "cpu_baseline": cb,
                      "config": {"workload": args.workload, "description": desc, "note": "oracle/_ref absent: timed the C port"},
                      "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-        print(json.dumps(line))
+        emit(line)
         return
     os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
     sample_axis = 22
@@ -272,7 +273,7 @@ def run_reference_arm(args):
     line.update({"value": n / dt, "ms_per_step": dt * 1e3, "cpu_baseline": cb,
                  "config": {"workload": args.workload, "description": desc, "reference_sample_particles": n},
                  "e2e": {"value": n / dt, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -291,7 +292,7 @@ def run_gpu_arm(args):
     if world > 1:
         from importlib import import_module
         slabs = import_module("sph-erosion_b200.slabs")
-        return slabs.bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT)
+        return slabs.bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT, terrain)
 
     pos, L = scaled_dam_break(n_axis, jitter)
     n = pos.shape[0]
@@ -383,10 +384,30 @@ def run_gpu_arm(args):
                        "mean_neighbours_after_run": (ns_total / n) if ns_total else None, "l2": "flushed between timed steps (%d MiB memset, outside the event brackets)" % (flush_bytes >> 20),
                        "density_variant": args.density_variant, "force_variant": args.force_variant, **tinfo},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cb}
-    print(json.dumps(line))
+    emit(line)
+
+
+def quiet_stdout():
+    """STDOUT must carry ONE JSON line, but libraries write banners there (NCCL prints its version on fd 1):
+    point fd 1 at stderr for the whole run and keep the real stdout for emit().  The saved descriptor lives
+    in the environment because slabs.py imports this file as a second module (`bench` vs `__main__`)."""
+    if "SPHE_BENCH_JSON_FD" not in os.environ:
+        sys.stdout.flush()
+        os.environ["SPHE_BENCH_JSON_FD"] = str(os.dup(1))
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    fd = os.environ.get("SPHE_BENCH_JSON_FD")
+    if fd is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(int(fd), data)
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -396,6 +417,8 @@ def main():
     ap.add_argument("--density-variant", type=int, default=3)
     ap.add_argument("--force-variant", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU halo/migration transport: peer = pack kernel stores into the neighbours' mailboxes over NVLink (default); nccl = NCCL P2P group")
     ap.add_argument("--slab-lag", type=int, default=2, help="multi-GPU: steps the host may run ahead (0 = one host sync per step)")
     ap.add_argument("--settle", type=int, default=150, help="untimed steps before warm-up when the workload has a terrain")
     ap.add_argument("--gravity-unscaled", action="store_true")

@@ -190,6 +190,26 @@ int sphe_slab_unpack(sphe_sim* s, const void* dev_recv_left, int max_left, const
 int sphe_slab_unpack_async(sphe_sim* s, const void* dev_recv_left, int max_left, const void* dev_recv_right, int max_right,
                            long long* ticket);
 int sphe_slab_result(sphe_sim* s, long long ticket, int wait, int out[6]);
+/* Peer-memory exchange (the multi-GPU default): no transport library on the data path.  Every slab owns a
+ * MAILBOX in its GPU's memory (4 record buffers -- from the left / from the right neighbour, double buffered
+ * by exchange parity -- and 4 flags).  sphe_slab_send runs the pack kernel with the NEIGHBOURS' mailboxes as
+ * its output (stores over NVLink, peer memory mapped with cudaIpcOpenMemHandle) and then publishes the
+ * record counts and a sequence flag (release, system scope); sphe_slab_recv launches the append kernel, which
+ * waits ON THE DEVICE for its own mailbox flags (acquire) and appends the payload.  Neither call syncs the
+ * host; sphe_slab_result(ticket) returns the counts later.  A flag that does not arrive within the timeout
+ * (default 4e9 clock cycles) is reported as an error by sphe_slab_result instead of hanging the GPU.
+ *   setup:   allocates the mailbox for cap_records payload records per buffer (same on every slab) and
+ *            reserves particle storage (so the arrays never grow mid-run);
+ *   handle:  64-byte cudaIpcMemHandle of the mailbox, to be handed to the two neighbour processes;
+ *   connect: maps the neighbours' mailboxes (NULL = no neighbour on that side);
+ *   connect_local: the same for slabs that live in ONE process on one GPU (tests). */
+int sphe_slab_peer_setup(sphe_sim* s, int cap_records, int reserve_particles);
+int sphe_slab_peer_handle(sphe_sim* s, void* handle64);
+int sphe_slab_peer_connect(sphe_sim* s, const void* left_handle64, const void* right_handle64);
+int sphe_slab_peer_connect_local(sphe_sim* s, sphe_sim* left, sphe_sim* right);
+int sphe_slab_peer_timeout(sphe_sim* s, long long clock_cycles);
+int sphe_slab_send(sphe_sim* s);
+int sphe_slab_recv(sphe_sim* s, long long* ticket);
 /* Owned particles only, storage order; rho/sed may be NULL. */
 int sphe_slab_download(sphe_sim* s, int cap, int* ids, float* pos, float* vel, float* rho, float* sed, int* n_out);
 
@@ -231,6 +251,13 @@ sphe_erosion* sphe_terrain_erosion_ptr(sphe_terrain* t);   /* host-resident, re-
  * contact response (the call commented out at fluid_system.h:335-340) + erosion, no box collision. */
 int sphe_terrain_stage_host(sphe_terrain* t, int n, const float* pos_curr, float* pos_next, float* vel_next, int* sediment,
                             float dt, float cR, int* hit);
+/* Slabs eroding ONE terrain (every rank holds a replica): run the step in phases and sum the integer
+ * accumulators over the ranks in between -- phase 0 (binning .. forces, contact response, erosion requests of
+ * OWNED particles; ghost copies never enter the terrain stage), sum `want`, phase 1 (grants), sum `delta`,
+ * phase 2 (apply + cull map).  All sums are integers: the replicas stay bit-identical and equal to a
+ * single-GPU run.  sphe_terrain_accumulators returns the two DEVICE arrays (rows*cols int32 each). */
+int sphe_step_phase(sphe_sim* s, sphe_terrain* t, int phase);
+int sphe_terrain_accumulators(sphe_terrain* t, void** want, void** delta, long long* cells);
 int sphe_terrain_total_fx(sphe_terrain* t, long long* sum);     /* sum of all heights, fixed point */
 int sphe_terrain_contacts(sphe_terrain* t, long long* total, int reset); /* particle-terrain contacts since the last reset */
 int sphe_sediment_total_fx(sphe_sim* s, long long* sum);        /* sum of carried sediment (owned particles), fixed point */

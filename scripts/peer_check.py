@@ -1,0 +1,78 @@
+"""Multi-PROCESS check of the peer-memory slab exchange (run under torchrun, one rank per GPU; with
+SPHE_ONE_GPU=1 all ranks share cuda:0, which exercises the same CUDA-IPC mapping on a single-GPU box).
+
+Every rank steps its x-slab with PeerSlabDriver (mailbox stores over NVLink / IPC, device-side flag waits,
+terrain accumulators summed with NCCL or gloo all-reduce); rank 0 also runs the whole scene on one handle.
+Bar: positions, velocities, densities, carried sediment and terrain heights BIT-EQUAL to the single-handle
+run, sum(heights) + sum(sediment) exactly conserved."""
+import importlib, os, sys
+import numpy as np, torch, torch.distributed as dist
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
+one_gpu = os.environ.get("SPHE_ONE_GPU") == "1"
+devno = 0 if one_gpu else local
+torch.cuda.set_device(devno)
+dev = torch.device("cuda", devno)
+if one_gpu:
+    dist.init_process_group("gloo")      # NCCL refuses two ranks on one device; the exchange itself does not use it
+    def reduce(t):
+        h = t.cpu(); dist.all_reduce(h); t.copy_(h)
+else:
+    dist.init_process_group("nccl", device_id=dev)
+    def reduce(t):
+        dist.all_reduce(t)
+pkg = importlib.import_module("sph-erosion_b200"); slabs = importlib.import_module("sph-erosion_b200.slabs")
+import test_gpu_slabs as T
+
+steps = int(os.environ.get("STEPS", "12"))
+box = (1.2, 0.3, 0.3)
+params = dict(len=0.3, dt=0.004, g=(0.0, -9.82, 0.0))
+grid, pos, vel = T._terrain_scene(pkg)
+n = pos.shape[0]
+cap = 1 << 15
+sim, backend, cols = slabs.make_gpu_slab(pkg, devno, rank, world, box, params, None, cap, (3, 3))
+order = np.argsort(pos[:, 0], kind="stable")
+part = np.array_split(order, world)[rank]
+sim.slab_upload(pos[part], vel[part], part.astype(np.int32))
+if one_gpu:
+    sim.slab_peer_timeout(400_000_000_000)   # ranks time-slice one GPU: a waiting kernel can sit out whole time slices
+total0 = grid.total_fx()
+drv = slabs.PeerSlabDriver(sim, rank, world, cap, n + 4 * cap, slabs.TerrainShare(grid, dev, reduce))
+drv.connect(dist)
+for _ in range(steps):
+    drv.step()
+info = drv.drain()
+ids, p, v, rho, sed = sim.slab_download()
+sed_fx = sim.sediment_total_fx()
+gathered = [None] * world
+dist.all_gather_object(gathered, (ids, p, v, rho, sed_fx, grid.heights_fx(), grid.contacts(), info))
+ok = True
+if rank == 0:
+    one = T._single(pkg, box, params, (3, 3), pos, vel)
+    g1, _, _ = T._terrain_scene(pkg)
+    for _ in range(steps):
+        one.Run(g1)
+    allids = np.concatenate([g[0] for g in gathered]); o = np.argsort(allids)
+    assert np.array_equal(allids[o], np.arange(n)), "every particle owned exactly once"
+    for j, name in ((1, "pos"), (2, "vel"), (3, "density")):
+        a = np.concatenate([g[j] for g in gathered])[o]
+        b = one.download(name)
+        same = np.array_equal(a, b)
+        ok &= same
+        print("%-8s bit-equal: %s" % (name, same))
+    for r, g in enumerate(gathered):
+        same = np.array_equal(g[5], g1.heights_fx())
+        ok &= same
+        print("terrain replica of rank %d bit-equal to the single-GPU terrain: %s" % (r, same))
+    sed_k = sum(g[4] for g in gathered)
+    cons = gathered[0][5].astype(np.int64).sum() + sed_k == total0
+    ok &= bool(cons) and sed_k == one.sediment_total_fx() and sed_k > 0
+    print("sediment in flight %d (single GPU %d), conservation exact: %s" % (sed_k, one.sediment_total_fx(), cons))
+    contacts = sum(g[6] for g in gathered)
+    ok &= contacts == g1.contacts() and contacts > 1000
+    print("contacts %d (single GPU %d); exchange counts per rank: %s" % (contacts, g1.contacts(), [g[7] for g in gathered]))
+    print("PEER_CHECK %s world=%d one_gpu=%s" % ("OK" if ok else "FAILED", world, one_gpu))
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)

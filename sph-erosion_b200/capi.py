@@ -105,6 +105,15 @@ SYMBOLS = {
     "sphe_slab_unpack_async": (_i, [_vp, _vp, _i, _vp, _i, C.POINTER(_ll)]),
     "sphe_slab_result": (_i, [_vp, _ll, _i, _vp]),
     "sphe_slab_download": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i)]),
+    "sphe_slab_peer_setup": (_i, [_vp, _i, _i]),
+    "sphe_slab_peer_handle": (_i, [_vp, _vp]),
+    "sphe_slab_peer_connect": (_i, [_vp, _vp, _vp]),
+    "sphe_slab_peer_connect_local": (_i, [_vp, _vp, _vp]),
+    "sphe_slab_peer_timeout": (_i, [_vp, _ll]),
+    "sphe_slab_send": (_i, [_vp]),
+    "sphe_slab_recv": (_i, [_vp, C.POINTER(_ll)]),
+    "sphe_step_phase": (_i, [_vp, _vp, _i]),
+    "sphe_terrain_accumulators": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_ll)]),
 }
 
 _lib = None

@@ -107,6 +107,14 @@ struct sphe_sim {
     int slab_add[SLAB_RING] = {};  // upper bound of the records appended by each ticket
     int slab_max[SLAB_RING][2] = {};
     int slab_pending = 0;          // > 0: s->n is an upper bound, kernels read the exact count from d_n
+    // peer-memory exchange (NVLink): this slab's mailbox and the two neighbours' mailboxes
+    char* mbox = nullptr;          // cudaMalloc'd: 4 record buffers [side][parity] + 4 flags
+    size_t mbox_buf = 0;           // bytes of one record buffer
+    int mbox_cap = 0;              // payload records per buffer
+    char* peer_mbox[2] = {nullptr, nullptr};   // left / right neighbour's mailbox, mapped into this process
+    bool peer_ipc[2] = {false, false};         // opened with cudaIpcOpenMemHandle (close on destroy)
+    int peer_seq = 0;              // exchanges sent so far; sequence number of the current one
+    long long peer_timeout = 4000000000LL;     // clock cycles a consumer waits for its flags (~2 s)
     float grid_h = -1.f, grid_len = -1.f;
 
     bool diag = false;
@@ -305,7 +313,7 @@ static int terrain_ready(sphe_terrain* t);
 extern "C" { static int slab_settle(sphe_sim* s); }
 static TerrainDev terrain_view(const sphe_terrain* t);
 
-static int step_device(sphe_sim* s, sphe_terrain* t) {
+static int step_device(sphe_sim* s, sphe_terrain* t, int terrain_phases = 7) {
     TRY(ensure_device(s));
     if (t) TRY(terrain_ready(t));
     if (s->n == 0) return SPHE_OK;
@@ -353,7 +361,8 @@ static int step_device(sphe_sim* s, sphe_terrain* t) {
     if (t) {
         TerrainDev T = terrain_view(t);
         Scope k(s, SPHE_K_TERRAIN, terrain_stage_launches(C, T));
-        launch_terrain_stage(s->st, s->surv, s->surv_count, s->posB, s->posA, s->velA, (int*)s->sedB, C, T, 1, s->req_vertex, s->req_amount, nullptr);
+        launch_terrain_stage(s->st, s->surv, s->surv_count, s->posB, s->posA, s->velA, (int*)s->sedB, C, T, 1, s->req_vertex, s->req_amount, nullptr,
+                             terrain_phases);
     }
     std::swap(s->idsA, s->idsB);
     std::swap(s->sedA, s->sedB);
@@ -434,6 +443,8 @@ void sphe_destroy(sphe_sim* s) {
                         s->cell_sorted, s->tmp, s->stage, s->slot_of_id, s->req_vertex, s->req_amount, s->surv, s->surv_count, s->nlist, s->ncount, s->count, s->cell_start, s->cursor, s->tile_sum,
                         s->flush_buf, s->slab_counters, s->D.acc, s->D.fpress, s->D.fvisc, s->D.fgrav, s->D.fsurf, s->D.normal, s->D.neighb};
         for (void* p : ptrs) if (p) cudaFree(p);
+        for (int k = 0; k < 2; k++) if (s->peer_mbox[k] && s->peer_ipc[k]) cudaIpcCloseMemHandle(s->peer_mbox[k]);
+        if (s->mbox) cudaFree(s->mbox);
         if (s->slab_host) cudaFreeHost(s->slab_host);
         if (s->d_n) cudaFree(s->d_n);
         for (auto& e : s->slab_ev) if (e) cudaEventDestroy(e);
@@ -923,7 +934,8 @@ int sphe_slab_pack(sphe_sim* s, void* dev_send_left, void* dev_send_right, int c
 // Folds the result of ticket `t` (which must have completed) into the host-side bookkeeping.
 static int slab_fold(sphe_sim* s, long long t, int out[6]) {
     const int slot = (int)(t % sphe_sim::SLAB_RING);
-    const int* c = s->slab_host + 8 * slot;  // kept, to_left, to_right, owned(kept), owned(appended), from_left, from_right
+    const int* c = s->slab_host + 8 * slot;  // kept, to_left, to_right, owned(kept), owned(appended), from_left, from_right, error
+    if (c[7]) return fail(SPHE_ERR_STATE, "peer exchange: a neighbour's records did not arrive within %lld clock cycles", s->peer_timeout);
     if (c[1] > s->slab_cap_sent || c[2] > s->slab_cap_sent)
         return fail(SPHE_ERR_NOMEM, "slab send overflow: %d left / %d right records > buffer capacity %d", c[1], c[2], s->slab_cap_sent);
     int got_l = std::min(c[5], s->slab_max[slot][0]), got_r = std::min(c[6], s->slab_max[slot][1]);
@@ -1033,6 +1045,196 @@ int sphe_slab_download(sphe_sim* s, int cap, int* ids, float* pos, float* vel, f
         *n_out = m;
     }
     return rc;
+}
+
+
+// ---- peer-memory exchange: records are stored straight into the neighbour's mailbox over NVLink
+// Mailbox layout (one cudaMalloc, exportable as ONE cudaIpcMemHandle):
+//   buffer(side, parity) at (2*side + parity) * mbox_buf, side 0 = records coming from the LEFT neighbour,
+//   side 1 = from the RIGHT; each buffer = header record + mbox_cap payload records of 32 bytes;
+//   flag(side, parity)   at 4 * mbox_buf + (2*side + parity) * 128: sequence number of the exchange whose
+//   payload is complete in that buffer.
+// Exchange q uses parity q & 1.  A producer may only overwrite buffer parity p at exchange q + 2 after it has
+// itself consumed exchange q + 1 of the same neighbour, which that neighbour published after finishing its
+// own append of exchange q (stream order) -- so two buffers per direction are enough and nobody ever waits
+// for a consumer.
+static inline float4* mbox_buffer(char* base, size_t buf, int side, int parity) { return (float4*)(base + (size_t)(2 * side + parity) * buf); }
+static inline int* mbox_flag(char* base, size_t buf, int side, int parity) { return (int*)(base + 4 * buf + (size_t)(2 * side + parity) * 128); }
+
+int sphe_slab_peer_setup(sphe_sim* s, int cap_records, int reserve_particles) {
+    if (!s || cap_records < 1) return fail(SPHE_ERR_ARG, "bad arguments");
+    if (!s->slab_on) return fail(SPHE_ERR_STATE, "call sphe_slab_configure first");
+    TRY(ensure_device(s));
+    CU(cudaStreamSynchronize(s->st));
+    for (int k = 0; k < 2; k++) {
+        if (s->peer_mbox[k] && s->peer_ipc[k]) cudaIpcCloseMemHandle(s->peer_mbox[k]);
+        s->peer_mbox[k] = nullptr; s->peer_ipc[k] = false;
+    }
+    if (s->mbox) { CU(cudaFree(s->mbox)); s->mbox = nullptr; }
+    s->mbox_cap = cap_records;
+    s->mbox_buf = (((size_t)cap_records + 1) * 32 + 255) & ~(size_t)255;
+    size_t bytes = 4 * s->mbox_buf + 4 * 128;
+    cudaError_t e = cudaMalloc(&s->mbox, bytes);
+    if (e != cudaSuccess) return fail(SPHE_ERR_NOMEM, "mailbox of %zu bytes: %s", bytes, cudaGetErrorString(e));
+    CU(cudaMemset(s->mbox, 0, bytes));
+    s->peer_seq = 0;
+    if (reserve_particles > 0) TRY(reserve(s, reserve_particles));
+    return SPHE_OK;
+}
+
+int sphe_slab_peer_handle(sphe_sim* s, void* handle64) {
+    if (!s || !handle64) return fail(SPHE_ERR_ARG, "bad arguments");
+    if (!s->mbox) return fail(SPHE_ERR_STATE, "call sphe_slab_peer_setup first");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    TRY(ensure_device(s));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, s->mbox));
+    memcpy(handle64, &h, sizeof h);
+    return SPHE_OK;
+}
+
+// left / right: the 64-byte handles of the neighbours' mailboxes (another process, any GPU of the node), NULL
+// where there is no neighbour.  Their mailboxes must have been set up with the same cap_records.
+int sphe_slab_peer_connect(sphe_sim* s, const void* left_handle64, const void* right_handle64) {
+    if (!s) return fail(SPHE_ERR_ARG, "NULL handle");
+    if (!s->mbox) return fail(SPHE_ERR_STATE, "call sphe_slab_peer_setup first");
+    TRY(ensure_device(s));
+    const void* hs[2] = {left_handle64, right_handle64};
+    for (int k = 0; k < 2; k++) {
+        if (s->peer_mbox[k] && s->peer_ipc[k]) cudaIpcCloseMemHandle(s->peer_mbox[k]);
+        s->peer_mbox[k] = nullptr; s->peer_ipc[k] = false;
+        if (!hs[k]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, hs[k], sizeof h);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(SPHE_ERR_CUDA, "cudaIpcOpenMemHandle(%s neighbour): %s", k ? "right" : "left", cudaGetErrorString(e));
+        }
+        s->peer_mbox[k] = (char*)p; s->peer_ipc[k] = true;
+    }
+    return SPHE_OK;
+}
+
+// Same-process form (several slabs driven by one process on one GPU: tests, single-GPU domain splitting).
+int sphe_slab_peer_connect_local(sphe_sim* s, sphe_sim* left, sphe_sim* right) {
+    if (!s) return fail(SPHE_ERR_ARG, "NULL handle");
+    if (!s->mbox) return fail(SPHE_ERR_STATE, "call sphe_slab_peer_setup first");
+    sphe_sim* ns[2] = {left, right};
+    for (int k = 0; k < 2; k++) {
+        if (s->peer_mbox[k] && s->peer_ipc[k]) cudaIpcCloseMemHandle(s->peer_mbox[k]);
+        s->peer_mbox[k] = nullptr; s->peer_ipc[k] = false;
+        if (!ns[k]) continue;
+        if (!ns[k]->mbox || ns[k]->mbox_cap != s->mbox_cap) return fail(SPHE_ERR_STATE, "neighbour mailbox missing or of a different capacity");
+        if (ns[k]->device != s->device) return fail(SPHE_ERR_ARG, "sphe_slab_peer_connect_local needs both slabs on one device");
+        s->peer_mbox[k] = ns[k]->mbox;
+    }
+    return SPHE_OK;
+}
+
+int sphe_slab_peer_timeout(sphe_sim* s, long long clock_cycles) {
+    if (!s || clock_cycles < 1) return fail(SPHE_ERR_ARG, "bad arguments");
+    s->peer_timeout = clock_cycles;
+    return SPHE_OK;
+}
+
+// folds every finished ticket without blocking, so the launch bound s->n stays close to the exact count
+static int slab_fold_ready(sphe_sim* s) {
+    while (s->slab_done < s->slab_seq) {
+        long long t = s->slab_done;
+        cudaError_t e = cudaEventQuery(s->slab_ev[t % sphe_sim::SLAB_RING]);
+        if (e == cudaErrorNotReady) break;
+        CU(e);
+        TRY(slab_fold(s, t, nullptr));
+    }
+    return SPHE_OK;
+}
+
+// Exchange, producer half: drop ghosts, compact, and store migrants + halo straight into the neighbours'
+// mailboxes (k_slab_classify<true>), then publish counts and flags.  Never waits for anybody.
+int sphe_slab_send(sphe_sim* s) {
+    if (!s) return fail(SPHE_ERR_ARG, "NULL handle");
+    if (!s->slab_on || !s->mbox) return fail(SPHE_ERR_STATE, "call sphe_slab_configure and sphe_slab_peer_setup first");
+    if ((s->slab.has_left && !s->peer_mbox[0]) || (s->slab.has_right && !s->peer_mbox[1]))
+        return fail(SPHE_ERR_STATE, "neighbour mailbox not connected");
+    TRY(ensure_device(s));
+    TRY(slab_fold_ready(s));
+    const int incoming = 2 * s->mbox_cap;
+    if ((long long)s->n + incoming > s->cap) TRY(slab_settle(s));   // exact count before deciding to grow
+    TRY(reserve(s, std::max(s->n + incoming, 1)));
+    const int q = ++s->peer_seq, par = q & 1;
+    // what goes LEFT lands in the left neighbour's "from the right" buffer, and vice versa
+    float4* dl = s->slab.has_left ? mbox_buffer(s->peer_mbox[0], s->mbox_buf, 1, par) : nullptr;
+    float4* dr = s->slab.has_right ? mbox_buffer(s->peer_mbox[1], s->mbox_buf, 0, par) : nullptr;
+    int* fl = s->slab.has_left ? mbox_flag(s->peer_mbox[0], s->mbox_buf, 1, par) : nullptr;
+    int* fr = s->slab.has_right ? mbox_flag(s->peer_mbox[1], s->mbox_buf, 0, par) : nullptr;
+    CU(cudaMemsetAsync(s->slab_counters, 0, 8 * sizeof(int), s->st));
+    launch_slab_classify(s->st, s->n, s->slab_pending ? s->d_n : nullptr, s->posA, s->velA, s->idsA, s->sedA, s->G, s->slab, s->posB, s->velB,
+                         s->idsB, s->sedB, dl, dr, s->mbox_cap, s->slab_counters, true);
+    launch_slab_headers(s->st, s->slab_counters, dl, dr, fl, fr, q);
+    s->launches += 2;
+    std::swap(s->posA, s->posB); std::swap(s->velA, s->velB); std::swap(s->idsA, s->idsB); std::swap(s->sedA, s->sedB);
+    s->binned = false; s->slot_valid = false;
+    s->slab_cap_sent = s->mbox_cap;
+    s->slab_unpacked = false;
+    CU(cudaGetLastError());
+    return SPHE_OK;
+}
+
+// Exchange, consumer half: k_slab_append<true> waits on the device for this exchange's flags and appends the
+// mailbox payload.  No host sync; the counts come back later through the ticket (sphe_slab_result).
+int sphe_slab_recv(sphe_sim* s, long long* ticket) {
+    if (!s) return fail(SPHE_ERR_ARG, "NULL handle");
+    if (!s->slab_on || !s->mbox || s->peer_seq < 1) return fail(SPHE_ERR_STATE, "sphe_slab_send has not run");
+    if (s->slab_unpacked) return fail(SPHE_ERR_STATE, "sphe_slab_recv already ran for this exchange");
+    TRY(ensure_device(s));
+    if (s->slab_seq - s->slab_done >= sphe_sim::SLAB_RING - 1) {
+        long long t = s->slab_seq - 2;
+        CU(cudaEventSynchronize(s->slab_ev[t % sphe_sim::SLAB_RING]));
+        TRY(slab_fold(s, t, nullptr));
+    }
+    const int q = s->peer_seq, par = q & 1;
+    const int ml = s->slab.has_left ? s->mbox_cap : 0, mr = s->slab.has_right ? s->mbox_cap : 0;
+    const long long t = s->slab_seq;
+    const int slot = (int)(t % sphe_sim::SLAB_RING);
+    s->slab_unpacked = true;
+    launch_slab_append(s->st, ml, mr, s->slab.has_left ? mbox_buffer(s->mbox, s->mbox_buf, 0, par) : nullptr,
+                       s->slab.has_right ? mbox_buffer(s->mbox, s->mbox_buf, 1, par) : nullptr, s->G, s->slab, s->cap, s->posA, s->velA,
+                       s->idsA, s->sedA, s->slab_counters, s->d_n,
+                       s->slab.has_left ? mbox_flag(s->mbox, s->mbox_buf, 0, par) : nullptr,
+                       s->slab.has_right ? mbox_flag(s->mbox, s->mbox_buf, 1, par) : nullptr, q, s->peer_timeout);
+    s->launches += 1;
+    CU(cudaMemcpyAsync(s->slab_host + 8 * slot, s->slab_counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaEventRecord(s->slab_ev[slot], s->st));
+    s->slab_add[slot] = ml + mr;
+    s->slab_max[slot][0] = ml; s->slab_max[slot][1] = mr;
+    s->slab_seq = t + 1;
+    s->slab_pending = (int)(s->slab_seq - s->slab_done);
+    s->n = (int)std::min<long long>((long long)s->n + ml + mr, s->cap);
+    s->binned = false; s->slot_valid = false;
+    if (ticket) *ticket = t;
+    CU(cudaGetLastError());
+    return SPHE_OK;
+}
+
+// One step of the terrain-coupled simulation in phases, for runs where several slabs share the erosion of
+// one terrain: phase 0 = binning .. forces .. contact response + erosion requests; phase 1 = grants;
+// phase 2 = apply + cull map.  Between 0 and 1 the per-vertex `want` array must hold the sum over all slabs,
+// between 1 and 2 the `delta` array (sphe_terrain_accumulators; integer sums, any order).
+int sphe_step_phase(sphe_sim* s, sphe_terrain* t, int phase) {
+    if (!s || phase < 0 || phase > 2) return fail(SPHE_ERR_ARG, "bad arguments");
+    if (phase == 0) return step_device(s, t, TERRAIN_CONTACT);
+    if (!t || s->n == 0) return SPHE_OK;
+    TRY(ensure_device(s));
+    TRY(terrain_ready(t));
+    TerrainDev T = terrain_view(t);
+    Scope k(s, SPHE_K_TERRAIN, phase == 1 ? 1 : 2);
+    // the step's sediment array is sedA after phase 0 swapped the buffers
+    launch_terrain_stage(s->st, s->surv, s->surv_count, nullptr, nullptr, nullptr, (int*)s->sedA, s->lastC, T, 1, s->req_vertex,
+                         s->req_amount, nullptr, phase == 1 ? TERRAIN_GRANT : TERRAIN_APPLY);
+    CU(cudaGetLastError());
+    return SPHE_OK;
 }
 
 void* sphe_device_ptr(sphe_sim* s, int which) {
@@ -1301,6 +1503,15 @@ int sphe_terrain_stage_host(sphe_terrain* t, int n, const float* pos_curr, float
         vel_next[3 * i] = c[i].x; vel_next[3 * i + 1] = c[i].y; vel_next[3 * i + 2] = c[i].z;
     }
     cudaFree(po); cudaFree(pn); cudaFree(vn); cudaFree(sd); cudaFree(rq); cudaFree(dh);
+    return SPHE_OK;
+}
+
+int sphe_terrain_accumulators(sphe_terrain* t, void** want, void** delta, long long* cells) {
+    if (!t) return fail(SPHE_ERR_ARG, "NULL terrain");
+    TRY(terrain_ready(t));
+    if (want) *want = t->want;
+    if (delta) *delta = t->delta;
+    if (cells) *cells = (long long)t->rows * t->cols;
     return SPHE_OK;
 }
 

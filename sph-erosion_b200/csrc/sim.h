@@ -39,7 +39,8 @@ struct TerrainDev {
 };
 void launch_terrain_stage(cudaStream_t st, const int* surv, const int* surv_count, const float4* pos_old, float4* posq, float4* velv,
                           int* sediment, const StepC& C, const TerrainDev& T, int apply_box, int* req_vertex, int* req_amount,
-                          int* hit_out);
+                          int* hit_out, int phases = 7);
+enum { TERRAIN_CONTACT = 1, TERRAIN_GRANT = 2, TERRAIN_APPLY = 4 };  // phases of the terrain stage (multi-GPU: reduce between them)
 void launch_iota(cudaStream_t st, int n, int* a, int* count);
 int terrain_stage_launches(const StepC& C, const TerrainDev& T);
 void launch_terrain_lmax(cudaStream_t st, const TerrainDev& T);
@@ -60,10 +61,13 @@ struct SlabP {
 };
 void launch_slab_classify(cudaStream_t st, int n, const int* n_dev, const float4* posq, const float4* velv, const int* ids, const float* sed,
                           const GridP& G, const SlabP& S, float4* keep_pos, float4* keep_vel, int* keep_ids, float* keep_sed,
-                          float4* send_left, float4* send_right, int cap_records, int* counters);
-void launch_slab_headers(cudaStream_t st, int* counters, float4* send_left, float4* send_right);
+                          float4* send_left, float4* send_right, int cap_records, int* counters, bool remote = false);
+// flag_* != NULL: peer-memory exchange, the buffers and flags live in the neighbour GPUs' mailboxes
+void launch_slab_headers(cudaStream_t st, int* counters, float4* send_left, float4* send_right, int* flag_left = nullptr,
+                         int* flag_right = nullptr, int seq = 0);
 void launch_slab_append(cudaStream_t st, int max_l, int max_r, const float4* rec_l, const float4* rec_r, const GridP& G,
-                        const SlabP& S, int cap_particles, float4* posq, float4* velv, int* ids, float* sed, int* counters, int* n_out);
+                        const SlabP& S, int cap_particles, float4* posq, float4* velv, int* ids, float* sed, int* counters, int* n_out,
+                        const int* flag_l = nullptr, const int* flag_r = nullptr, int seq = 0, long long timeout_cycles = 0);
 void launch_slab_gather_owned(cudaStream_t st, int n, const float4* posq, const float4* velv, const float* rho, const float* sed,
                               const int* ids, int* counter, int* out_ids, float* out_pos, float* out_vel, float* out_rho,
                               float* out_sed);

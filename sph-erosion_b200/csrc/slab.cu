@@ -60,6 +60,11 @@ __device__ __forceinline__ void block_append4(const bool flag[4], int* const cou
 }
 
 // counters: [0] kept (owned + retained ghosts), [1] to left, [2] to right, [3] owned
+// REMOTE: send_left / send_right point into the NEIGHBOUR GPU's mailbox (peer memory over NVLink, see the
+// peer-memory exchange below): the records are stored where they will be consumed, no staging copy and no
+// transport call, and every storing thread fences at system scope so the stores are performed at the peer
+// before this grid completes and k_slab_publish raises the flag.
+template <bool REMOTE>
 __global__ void __launch_bounds__(256) k_slab_classify(int n_hi, const int* __restrict__ n_dev, const float4* __restrict__ posq, const float4* __restrict__ velv,
                                                        const int* __restrict__ ids, const float* __restrict__ sed, GridP G,
                                                        SlabP S, float4* __restrict__ keep_pos, float4* __restrict__ keep_vel,
@@ -103,14 +108,34 @@ __global__ void __launch_bounds__(256) k_slab_classify(int n_hi, const int* __re
         send_right[2 * (r + 1)] = make_float4(p.x, p.y, p.z, sd);
         send_right[2 * (r + 1) + 1] = make_float4(v.x, v.y, v.z, __int_as_float(id));
     }
+    if (REMOTE && (to_l || to_r)) __threadfence_system();
+}
+
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // Record 0 of every exchange buffer is a header: int[0] = number of payload records that follow.
-__global__ void k_slab_headers(int* __restrict__ counters, float4* __restrict__ send_left, float4* __restrict__ send_right) {
+// Peer-memory exchange: the buffers are the neighbours' mailboxes; after the headers, flag_* (also in the
+// neighbour's memory) is set to the step's sequence number with release semantics at system scope.  The
+// classify grid has completed (stream order) and its threads fenced their remote stores, so a consumer
+// that acquires the flag sees the whole payload.
+__global__ void k_slab_headers(int* __restrict__ counters, float4* __restrict__ send_left, float4* __restrict__ send_right,
+                               int* flag_left, int* flag_right, int seq) {
     if (threadIdx.x == 0) {
-        send_left[0] = make_float4(__int_as_float(counters[1]), 0.f, 0.f, 0.f);
-        send_right[0] = make_float4(__int_as_float(counters[2]), 0.f, 0.f, 0.f);
+        if (send_left) send_left[0] = make_float4(__int_as_float(counters[1]), 0.f, 0.f, 0.f);
+        if (send_right) send_right[0] = make_float4(__int_as_float(counters[2]), 0.f, 0.f, 0.f);
         counters[4] = 0; counters[5] = 0; counters[6] = 0;   // the unpack counters of this step
+        if (flag_left || flag_right) {
+            __threadfence_system();
+            if (flag_left) st_release_sys(flag_left, seq);
+            if (flag_right) st_release_sys(flag_right, seq);
+        }
     }
 }
 
@@ -118,20 +143,41 @@ __global__ void k_slab_headers(int* __restrict__ counters, float4* __restrict__ 
 // device memory (the kept count from the pack counters, the payload counts from the headers), so the
 // host does not have to know them before this launch.  counters[4] += owned among the appended,
 // counters[5] = records taken from the left buffer, counters[6] = from the right buffer.
-__global__ void __launch_bounds__(256) k_slab_append(int max_l, int max_r, const float4* __restrict__ rec_l,
-                                                     const float4* __restrict__ rec_r, GridP G, SlabP S, int cap_particles,
+// PEER: rec_l / rec_r are this GPU's own mailbox, filled by the neighbours' k_slab_classify<true> over
+// NVLink.  Thread 0 of every block waits (acquire, system scope) until the mailbox flags carry this step's
+// sequence number; the payload is then read with L2-only loads (the L1 / read-only path is not coherent with
+// stores that arrive while the kernel runs).  A flag that does not arrive within `timeout` clock cycles sets
+// counters[7] (reported as an error by the host) instead of hanging the GPU.
+template <bool PEER>
+__global__ void __launch_bounds__(256) k_slab_append(int max_l, int max_r, const float4* rec_l, const float4* rec_r,
+                                                     const int* flag_l, const int* flag_r, int seq, long long timeout,
+                                                     GridP G, SlabP S, int cap_particles,
                                                      float4* __restrict__ posq, float4* __restrict__ velv,
                                                      int* __restrict__ ids, float* __restrict__ sed, int* __restrict__ counters,
                                                      int* __restrict__ n_out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (PEER) {
+        __shared__ int arrived;
+        if (threadIdx.x == 0) {
+            bool ok = true;
+            const long long t0 = clock64();
+            if (rec_l) while (ld_acquire_sys(flag_l) < seq) { if (clock64() - t0 > timeout) { ok = false; break; } __nanosleep(200); }
+            if (rec_r) while (ok && ld_acquire_sys(flag_r) < seq) { if (clock64() - t0 > timeout) { ok = false; break; } __nanosleep(200); }
+            if (!ok) atomicExch(&counters[7], 1);
+            arrived = ok;
+        }
+        __syncthreads();
+        if (!arrived) { rec_l = nullptr; rec_r = nullptr; }
+    }
     const int kept = counters[0];
-    int from_l = rec_l ? min(__float_as_int(rec_l[0].x), max_l) : 0;
-    int from_r = rec_r ? min(__float_as_int(rec_r[0].x), max_r) : 0;
+    const int head_l = rec_l ? __float_as_int(__ldcg(&rec_l[0]).x) : 0;
+    const int head_r = rec_r ? __float_as_int(__ldcg(&rec_r[0]).x) : 0;
+    int from_l = min(head_l, max_l), from_r = min(head_r, max_r);
     if (from_l < 0) from_l = 0;
     if (from_r < 0) from_r = 0;
     if (i == 0) {
-        counters[5] = rec_l ? __float_as_int(rec_l[0].x) : 0;
-        counters[6] = rec_r ? __float_as_int(rec_r[0].x) : 0;
+        counters[5] = head_l;
+        counters[6] = head_r;
         // the exact particle count of the coming step, for kernels launched before the host knows it
         *n_out = min(kept + from_l + from_r, cap_particles);
     }
@@ -141,7 +187,7 @@ __global__ void __launch_bounds__(256) k_slab_append(int max_l, int max_r, const
     if (i < from_l) { rec = rec_l; j = i; }
     else if (i < from_l + from_r) { rec = rec_r; j = i - from_l; }
     if (rec && kept + i < cap_particles) {
-        float4 a = rec[2 * (j + 1)], b = rec[2 * (j + 1) + 1];
+        float4 a = __ldcg(&rec[2 * (j + 1)]), b = __ldcg(&rec[2 * (j + 1) + 1]);
         int id = __float_as_int(b.w) & SPHE_ID_MASK;
         int cx = cell_axis(a.x, G.gx, G.cell, G.gnx);
         own = (cx >= S.x0 || !S.has_left) && (cx < S.x1 || !S.has_right);
@@ -184,19 +230,29 @@ __global__ void k_pack_state_ids(int n, const float* __restrict__ pos, const flo
 
 void launch_slab_classify(cudaStream_t st, int n, const int* n_dev, const float4* posq, const float4* velv, const int* ids, const float* sed,
                           const GridP& G, const SlabP& S, float4* keep_pos, float4* keep_vel, int* keep_ids, float* keep_sed,
-                          float4* send_left, float4* send_right, int cap_records, int* counters) {
-    if (n > 0)
-        k_slab_classify<<<(n + 255) / 256, 256, 0, st>>>(n, n_dev, posq, velv, ids, sed, G, S, keep_pos, keep_vel, keep_ids, keep_sed,
-                                                        send_left, send_right, cap_records, counters);
+                          float4* send_left, float4* send_right, int cap_records, int* counters, bool remote) {
+    if (n <= 0) return;
+    if (remote)
+        k_slab_classify<true><<<(n + 255) / 256, 256, 0, st>>>(n, n_dev, posq, velv, ids, sed, G, S, keep_pos, keep_vel, keep_ids, keep_sed,
+                                                              send_left, send_right, cap_records, counters);
+    else
+        k_slab_classify<false><<<(n + 255) / 256, 256, 0, st>>>(n, n_dev, posq, velv, ids, sed, G, S, keep_pos, keep_vel, keep_ids, keep_sed,
+                                                               send_left, send_right, cap_records, counters);
 }
-void launch_slab_headers(cudaStream_t st, int* counters, float4* send_left, float4* send_right) {
-    k_slab_headers<<<1, 32, 0, st>>>(counters, send_left, send_right);
+void launch_slab_headers(cudaStream_t st, int* counters, float4* send_left, float4* send_right, int* flag_left, int* flag_right, int seq) {
+    k_slab_headers<<<1, 32, 0, st>>>(counters, send_left, send_right, flag_left, flag_right, seq);
 }
 void launch_slab_append(cudaStream_t st, int max_l, int max_r, const float4* rec_l, const float4* rec_r, const GridP& G,
-                        const SlabP& S, int cap_particles, float4* posq, float4* velv, int* ids, float* sed, int* counters, int* n_out) {
+                        const SlabP& S, int cap_particles, float4* posq, float4* velv, int* ids, float* sed, int* counters, int* n_out,
+                        const int* flag_l, const int* flag_r, int seq, long long timeout_cycles) {
     int m = max_l + max_r;
     if (m < 1) m = 1;
-    k_slab_append<<<(m + 255) / 256, 256, 0, st>>>(max_l, max_r, rec_l, rec_r, G, S, cap_particles, posq, velv, ids, sed, counters, n_out);
+    if (flag_l || flag_r)
+        k_slab_append<true><<<(m + 255) / 256, 256, 0, st>>>(max_l, max_r, rec_l, rec_r, flag_l, flag_r, seq, timeout_cycles, G, S,
+                                                            cap_particles, posq, velv, ids, sed, counters, n_out);
+    else
+        k_slab_append<false><<<(m + 255) / 256, 256, 0, st>>>(max_l, max_r, rec_l, rec_r, nullptr, nullptr, 0, 0, G, S, cap_particles,
+                                                             posq, velv, ids, sed, counters, n_out);
 }
 void launch_slab_gather_owned(cudaStream_t st, int n, const float4* posq, const float4* velv, const float* rho, const float* sed,
                               const int* ids, int* counter, int* out_ids, float* out_pos, float* out_vel, float* out_rho,

@@ -201,7 +201,9 @@ __device__ __forceinline__ void force_epilogue(int i, float4 pi, float4 vi, floa
     // (k_terrain_contact) runs on them first and applies the box afterwards (fluid_system.h:335-347).
     bool surv = false;
     if (C.t_lmax) {
-        surv = dt != 0.0f && terrain_may_touch(C, pi.x, pi.y, pi.z, px, py, pz);
+        // ghost copies (slab mode) never enter the terrain stage: their owner rank resolves the contact and
+        // files the erosion request, the copy is dropped at the next exchange
+        surv = dt != 0.0f && terrain_may_touch(C, pi.x, pi.y, pi.z, px, py, pz) && !(__ldg(&ids[i]) & SPHE_GHOST_BIT);
         unsigned act = __activemask();
         unsigned m = __ballot_sync(act, surv);
         if (m) {

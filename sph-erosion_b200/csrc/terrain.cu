@@ -409,12 +409,17 @@ static inline int nb(int n, int b) { return (n + b - 1) / b; }
 // persistent grid: 148 SMs x 4 blocks of 128 threads stride over the survivor list
 void launch_terrain_stage(cudaStream_t st, const int* surv, const int* surv_count, const float4* pos_old, float4* posq, float4* velv,
                           int* sediment, const StepC& C, const TerrainDev& T, int apply_box, int* req_vertex, int* req_amount,
-                          int* hit_out) {
-    k_terrain_contact<<<148 * 4, 128, 0, st>>>(surv, surv_count, pos_old, posq, velv, sediment, C, T, apply_box, req_vertex, req_amount, hit_out);
+                          int* hit_out, int phases) {
+    // Multi-GPU slabs run the phases separately: per-vertex `want` is summed over the ranks between contact and
+    // grant, `delta` between grant and apply (integer sums: exact and order independent).
+    if (phases & TERRAIN_CONTACT)
+        k_terrain_contact<<<148 * 4, 128, 0, st>>>(surv, surv_count, pos_old, posq, velv, sediment, C, T, apply_box, req_vertex, req_amount, hit_out);
     if (T.erosion && C.dt != 0.0f) {
-        k_terrain_grant<<<148 * 4, 128, 0, st>>>(surv, surv_count, req_vertex, req_amount, sediment, T);
-        k_terrain_apply<<<nb(T.rows * T.cols, 256), 256, 0, st>>>(T.rows * T.cols, T);
-        k_terrain_lmax<<<nb(T.rows * T.cols, 256), 256, 0, st>>>(T, T.lmax_rw);
+        if (phases & TERRAIN_GRANT) k_terrain_grant<<<148 * 4, 128, 0, st>>>(surv, surv_count, req_vertex, req_amount, sediment, T);
+        if (phases & TERRAIN_APPLY) {
+            k_terrain_apply<<<nb(T.rows * T.cols, 256), 256, 0, st>>>(T.rows * T.cols, T);
+            k_terrain_lmax<<<nb(T.rows * T.cols, 256), 256, 0, st>>>(T, T.lmax_rw);
+        }
     }
 }
 int terrain_stage_launches(const StepC& C, const TerrainDev& T) { return (T.erosion && C.dt != 0.0f) ? 4 : 1; }

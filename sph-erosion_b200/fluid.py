@@ -174,6 +174,39 @@ class FluidSystemSPH:
         capi.check(rc)
         return dict(zip(("n_total", "n_owned", "to_left", "to_right", "from_left", "from_right"), list(out)))
 
+    # peer-memory exchange (include/sphe.h "Peer-memory exchange")
+    def slab_peer_setup(self, cap_records, reserve_particles=0):
+        capi.check(self._L.sphe_slab_peer_setup(self._h, int(cap_records), int(reserve_particles)))
+
+    def slab_peer_handle(self):
+        buf = C.create_string_buffer(64)
+        capi.check(self._L.sphe_slab_peer_handle(self._h, buf))
+        return buf.raw
+
+    def slab_peer_connect(self, left_handle, right_handle):
+        l = C.create_string_buffer(left_handle, 64) if left_handle is not None else None
+        r = C.create_string_buffer(right_handle, 64) if right_handle is not None else None
+        capi.check(self._L.sphe_slab_peer_connect(self._h, l, r))
+
+    def slab_peer_connect_local(self, left, right):
+        capi.check(self._L.sphe_slab_peer_connect_local(self._h, left._h if left is not None else None,
+                                                        right._h if right is not None else None))
+
+    def slab_peer_timeout(self, clock_cycles):
+        capi.check(self._L.sphe_slab_peer_timeout(self._h, int(clock_cycles)))
+
+    def slab_send(self):
+        capi.check(self._L.sphe_slab_send(self._h))
+
+    def slab_recv(self):
+        t = C.c_longlong(0)
+        capi.check(self._L.sphe_slab_recv(self._h, C.byref(t)))
+        return t.value
+
+    def step_phase(self, grid, phase):
+        """One phase (0, 1, 2) of a step whose terrain erosion is shared by several slabs (sphe_step_phase)."""
+        capi.check(self._L.sphe_step_phase(self._h, grid._t if grid is not None else None, int(phase)))
+
     def slab_download(self, cap=None):
         cap = self.count() if cap is None else int(cap)
         ids = np.zeros(cap, np.int32); pos = np.zeros((cap, 3), np.float32); vel = np.zeros((cap, 3), np.float32)

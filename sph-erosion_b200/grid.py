@@ -101,6 +101,13 @@ class Grid:
     def erosion(self):
         return self._L.sphe_terrain_erosion_ptr(self._t).contents
 
+    def accumulators(self):
+        """Device addresses of the per-vertex erosion accumulators (want, delta) and their length (int32 each):
+        multi-GPU runs sum them over the ranks between the phases of a step (sphe_terrain_accumulators)."""
+        w, d, n = C.c_void_p(0), C.c_void_p(0), C.c_longlong(0)
+        capi.check(self._L.sphe_terrain_accumulators(self._t, C.byref(w), C.byref(d), C.byref(n)))
+        return w.value, d.value, n.value
+
     def total_fx(self):
         v = C.c_longlong(0)
         capi.check(self._L.sphe_terrain_total_fx(self._t, C.byref(v)))

@@ -239,6 +239,120 @@ class LocalSlabGroup:
         return out
 
 
+# --------------------------------------------------------------------------- peer-memory exchange (the GPU default)
+def device_int32_view(ptr, n, device):
+    """Zero-copy torch view of an int32 device array owned by the C library (CUDA array interface)."""
+    import torch
+
+    class _Arr:
+        pass
+    a = _Arr()
+    a.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(a, device=device)
+
+
+class TerrainShare:
+    """Several ranks eroding replicas of ONE terrain: the integer accumulators are summed over the ranks
+    between the phases of a step (sphe_step_phase), so every replica stays bit-identical to a single-GPU run.
+    reduce = callable(tensor) performing the in-place sum (dist.all_reduce on GPUs)."""
+
+    def __init__(self, grid, device, reduce):
+        w, d, n = grid.accumulators()
+        self.grid = grid
+        self.want = device_int32_view(w, n, device)
+        self.delta = device_int32_view(d, n, device)
+        self.reduce = reduce
+
+    def step(self, sim):
+        if not self.grid.erosion.enabled:
+            sim.Run(self.grid)
+            return
+        sim.step_phase(self.grid, 0)
+        self.reduce(self.want)
+        sim.step_phase(self.grid, 1)
+        self.reduce(self.delta)
+        sim.step_phase(self.grid, 2)
+
+
+class PeerSlabDriver:
+    """send -> recv -> step with NO transport library and NO host sync on the data path: the pack kernel
+    stores migrants + halo straight into the neighbours' mailboxes over NVLink (peer memory mapped through
+    CUDA IPC), the append kernel waits on the device for its mailbox flags (include/sphe.h "Peer-memory
+    exchange").  torch.distributed is only used once, to hand the 64-byte mailbox handles to the
+    neighbours (and for the terrain sums when a terrain is shared)."""
+
+    def __init__(self, sim, rank, world, cap_records, reserve_particles, terrain=None):
+        self.sim, self.rank, self.world = sim, rank, world
+        self.cap = int(cap_records)
+        self.terrain = terrain
+        self.tickets = []
+        self.last = None
+        sim.slab_peer_setup(self.cap, int(reserve_particles))
+
+    def connect(self, dist):
+        """Exchange the mailbox handles (all ranks call this; it also orders every setup before any send)."""
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.sim.slab_peer_handle())
+        left = handles[self.rank - 1] if self.rank > 0 else None
+        right = handles[self.rank + 1] if self.rank < self.world - 1 else None
+        self.sim.slab_peer_connect(left, right)
+        dist.barrier()
+
+    def exchange(self):
+        self.sim.slab_send()
+        self.tickets.append(self.sim.slab_recv())
+        if len(self.tickets) > 4:
+            self.tickets.pop(0)
+
+    def step(self):
+        self.exchange()
+        if self.terrain is not None:
+            self.terrain.step(self.sim)
+        else:
+            self.sim.Run()
+
+    def drain(self):
+        """Blocks until the last exchange has finished; returns its counts (and raises on overflow/timeout)."""
+        if self.tickets:
+            self.last = self.sim.slab_result(self.tickets[-1], True)
+            self.tickets = []
+        return self.last
+
+
+class LocalPeerGroup:
+    """K slabs in ONE process on one GPU, exchanging through each other's mailboxes (connect_local): the
+    same kernels and calls as PeerSlabDriver.  grid: one terrain shared by all slabs -- every slab runs
+    phase 0, then every slab phase 1, then one phase 2, which is the K-rank sum without a collective."""
+
+    def __init__(self, sims, cap_records, reserve_particles, grid=None):
+        self.sims = list(sims)
+        self.grid = grid
+        for s in self.sims:
+            s.slab_peer_setup(cap_records, reserve_particles)
+        K = len(self.sims)
+        for r, s in enumerate(self.sims):
+            s.slab_peer_connect_local(self.sims[r - 1] if r > 0 else None, self.sims[r + 1] if r < K - 1 else None)
+        self.tickets = []
+
+    def step(self):
+        for s in self.sims:
+            s.slab_send()
+        self.tickets = [s.slab_recv() for s in self.sims]
+        g = self.grid
+        if g is not None and g.erosion.enabled:
+            for s in self.sims:
+                s.step_phase(g, 0)
+            for s in self.sims:
+                s.step_phase(g, 1)
+            self.sims[0].step_phase(g, 2)
+        else:
+            for s in self.sims:
+                s.Run(g)
+
+    def drain(self):
+        return [s.slab_result(t, True) for s, t in zip(self.sims, self.tickets)]
+
+
 # --------------------------------------------------------------------------- scenes
 def channel_block(n_axis, world, rank, jitter, spacing=0.025):
     """Rank `rank`'s share of the weak-scaling scene: the scaled dam break (bench.scaled_dam_break)
@@ -283,12 +397,12 @@ def make_gpu_slab(pkg, device, rank, world, box_half, params, bounds_x, cap_reco
 
 
 # --------------------------------------------------------------------------- bench (called by bench.py)
-def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT):
+def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT, terrain=False):
     import json
     import time
     import torch
     import torch.distributed as dist
-    from bench import ClockSampler, measured_peak, scene_gravity, ALGO_BYTES, SPACING
+    from bench import ClockSampler, measured_peak, scene_gravity, attach_terrain, emit, ALGO_BYTES, SPACING
 
     rank, world = dist.get_rank(), dist.get_world_size()
     local = torch.cuda.current_device()
@@ -302,15 +416,46 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT):
     sim, backend, cols = make_gpu_slab(pkg, local, rank, world, box, params, bounds, cap,
                                        (args.density_variant, args.force_variant))
     sim.slab_upload(pos, np.zeros_like(pos), ids)
-    drv = SlabDriver(backend, TorchComm(rank, world), lag=args.slab_lag)
+    grid, tinfo, tshare = None, {}, None
+    if terrain:
+        # every rank holds a replica of the whole terrain; the integer erosion accumulators are summed over
+        # the ranks between the phases of a step (TerrainShare), so the replicas stay bit-identical
+        grid, tinfo = attach_terrain(pkg, box[1], n_axis, nx_mult=world)
+        tshare = TerrainShare(grid, dev, lambda t: dist.all_reduce(t))
+    if args.exchange == "peer":
+        drv = PeerSlabDriver(sim, rank, world, cap, int(n_local * 1.3) + 6 * cap, tshare)
+        drv.connect(dist)
+        exchange_desc = ("peer memory: the pack kernel stores migrants + 2-layer halo straight into the x-neighbours' mailboxes over NVLink "
+                         "(CUDA IPC mapping), the append kernel waits on device flags; no transport library, no host sync, no collective")
+    else:
+        if terrain:
+            raise SystemExit("--exchange nccl has no shared-terrain support; use the default peer exchange")
+        drv = SlabDriver(backend, TorchComm(rank, world), lag=args.slab_lag)
+        exchange_desc = "NCCL P2P (one batch_isend_irecv group per step) with the x-neighbours, counts ride in the record headers, no collective"
+    if terrain:
+        exchange_desc += "; terrain replicated, per-vertex erosion accumulators summed with 2 NCCL all-reduces (int32) per step"
 
     def sync_all():
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
 
+    def sediment_all():
+        t = torch.tensor([sim.sediment_total_fx()], device=dev, dtype=torch.int64)
+        dist.all_reduce(t)
+        return int(t.item())
+
+    if grid is not None:
+        tot0 = grid.total_fx() + sediment_all()
+        for _ in range(args.settle):
+            drv.step()
+        drv.drain()
+        tinfo["settle_steps"] = args.settle
     for _ in range(args.warmup):
         drv.step()
+    if grid is not None:
+        drv.drain()
+        grid.contacts(reset=True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -325,6 +470,18 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT):
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     drv.drain()
+    if grid is not None:
+        c = torch.tensor([grid.contacts()], device=dev, dtype=torch.int64)
+        dist.all_reduce(c)
+        tinfo["terrain_contacts_per_step"] = int(c.item()) / args.steps
+        sed_now = sediment_all()
+        tinfo["sediment_in_flight_fx"] = sed_now
+        tinfo["conservation_exact"] = bool(grid.total_fx() + sed_now == tot0)
+        h = torch.from_numpy(grid.heights_fx().astype(np.int64).ravel()).to(dev)
+        hs = torch.stack([h.sum(), (h * torch.arange(1, h.numel() + 1, device=dev) % 1000003).sum()])
+        hmin, hmax = hs.clone(), hs.clone()
+        dist.all_reduce(hmin, op=dist.ReduceOp.MIN); dist.all_reduce(hmax, op=dist.ReduceOp.MAX)
+        tinfo["terrain_replicas_identical"] = bool(torch.equal(hmin, hmax))
     per_kernel, launches = sim.kernel_times()
     sim.kernel_timing(False)
     clocks = sampler.stop() if rank == 0 else None
@@ -361,7 +518,7 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT):
     if rank != 0:
         return
     peak, peak_src = measured_peak()
-    dom = max(("density", "force"), key=lambda k: per_kernel[k])
+    dom = max(("density", "force", "terrain"), key=lambda k: per_kernel[k])
     t_dom = per_kernel[dom] / args.steps * 1e-3
     n_rank0 = sim.slab_info()["n_total"]
     achieved = ALGO_BYTES[dom] * n_rank0 / t_dom / 1e9
@@ -372,10 +529,10 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT):
                        "particles": n_total, "particles_per_gpu": n_local, "h": 0.0457, "spacing": SPACING, "dt": 0.01,
                        "box_half_extents": list(box), "gravity_y": gy, "slab_columns": cols,
                        "halo_records_per_step_all_ranks": int(owned[1].item()),
-                       "exchange": "NCCL P2P (one batch_isend_irecv group per step) with the x-neighbours, counts ride in the record headers, 1 host sync per step, no collective",
-                       "exchange_resends": drv.resends, "exchange_lag": args.slab_lag,
+                       "exchange": exchange_desc, "exchange_mode": args.exchange,
+                       "exchange_resends": getattr(drv, "resends", 0), "exchange_lag": args.slab_lag if args.exchange == "nccl" else None,
                        "l2": "working set per GPU (%.0f MB of particle arrays + neighbour lists) exceeds L2" % (n_local * 400 / 1e6),
-                       "density_variant": args.density_variant, "force_variant": args.force_variant},
+                       "density_variant": args.density_variant, "force_variant": args.force_variant, **tinfo},
             "e2e": {"value": n_total / float(e2e_dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(io[0].item()),
                     "d2h_bytes_per_step": int(io[1].item()), "ms_per_step": float(e2e_dt.item()) * 1e3, "steps": e2e_steps,
                     "api": "sphe_slab_upload (pinned host) -> pack/exchange/append -> sphe_step -> sphe_slab_download (pinned host), per rank"},
@@ -385,4 +542,4 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT):
                          "algorithmic_bytes_per_particle": ALGO_BYTES[dom], "rank": 0,
                          "per_kernel_ms_per_step": {k: v / args.steps for k, v in per_kernel.items()}},
             "cpu_baseline": None}
-    print(json.dumps(line))
+    emit(line)

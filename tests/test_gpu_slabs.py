@@ -94,3 +94,138 @@ def test_anisotropic_box_matches_oracle_free_particles():
     assert abs(p[3, 0] - 0.501) < 1e-3
     v = s.download("vel")
     assert v[0, 0] < 0 and v[2, 2] < 0
+
+
+# --------------------------------------------------------------------------- peer-memory exchange
+def _single(m, box, params, variant, pos, vel):
+    one = m.FluidSystemSPH()
+    for k, v in params.items():
+        if k == "g": one.params.g[0], one.params.g[1], one.params.g[2] = v
+        else: setattr(one.params, k, v)
+    one.set_box(box); one.set_variant(*variant)
+    one.upload_state(pos, vel)
+    return one
+
+
+def _peer_group(m, slabs, K, box, params, variant, pos, vel, grid=None, cap=1 << 15):
+    import torch
+    sims = []
+    for r in range(K):
+        sim, b, cols = slabs.make_gpu_slab(m, torch.cuda.current_device(), r, K, box, params, None, cap, variant)
+        sims.append(sim)
+    order = np.argsort(pos[:, 0], kind="stable")
+    for r, part in enumerate(np.array_split(order, K)):
+        sims[r].slab_upload(pos[part], vel[part], part.astype(np.int32))
+    return sims, slabs.LocalPeerGroup(sims, cap, pos.shape[0] + 4 * cap, grid=grid)
+
+
+def _gather(sims, n):
+    got = [s.slab_download() for s in sims]
+    ids = np.concatenate([g[0] for g in got])
+    assert np.array_equal(np.sort(ids), np.arange(n)), "every particle owned exactly once"
+    o = np.argsort(ids)
+    return [np.concatenate([g[j] for g in got])[o] for j in range(1, 5)]   # pos, vel, density, sediment (float bits)
+
+
+@pytest.mark.parametrize("K", [2, 3])
+def test_peer_mailbox_slabs_equal_single_gpu(K):
+    """k_slab_classify<true> storing into the neighbours' mailboxes + k_slab_append<true> waiting on the flags
+    (the multi-GPU default, here with all slabs in one process): bit-equal to the single-handle run, with
+    the host never syncing between steps."""
+    m = product()
+    slabs = importlib.import_module("sph-erosion_b200.slabs")
+    pos, vel = scene()
+    n = pos.shape[0]
+    box = (1.2, 0.3, 0.3)
+    params = dict(len=0.3, dt=0.004, g=(0.0, -9.82, 0.0))
+    one = _single(m, box, params, (3, 3), pos, vel)
+    sims, group = _peer_group(m, slabs, K, box, params, (3, 3), pos, vel)
+    for step in range(9):
+        one.Run()
+        group.step()
+        if step % 3 != 2:
+            continue
+        info = group.drain()
+        assert all(i["from_left"] + i["from_right"] > 0 for i in info)
+        p, v, rho, _ = _gather(sims, n)
+        for a, name in ((p, "pos"), (v, "vel"), (rho, "density")):
+            b = one.download(name)
+            assert np.array_equal(a, b), "step %d %s: max |diff| %.3e" % (step, name, np.abs(a - b).max())
+
+
+def test_peer_mailbox_overflow_is_reported():
+    m = product()
+    slabs = importlib.import_module("sph-erosion_b200.slabs")
+    pos, vel = scene()
+    box = (1.2, 0.3, 0.3)
+    params = dict(len=0.3, dt=0.004, g=(0.0, -9.82, 0.0))
+    sims, group = _peer_group(m, slabs, 2, box, params, (3, 3), pos, vel, cap=64)   # far too small for the halo
+    group.step()
+    with pytest.raises(m.capi.SpheError, match="overflow"):
+        group.drain()
+
+
+def test_peer_recv_times_out_instead_of_hanging():
+    """A consumer whose neighbour never sends gives up after the timeout and reports it."""
+    import torch
+    m = product()
+    slabs = importlib.import_module("sph-erosion_b200.slabs")
+    pos, vel = scene(2000)
+    box = (1.2, 0.3, 0.3)
+    params = dict(len=0.3, dt=0.004, g=(0.0, -9.82, 0.0))
+    sims, group = _peer_group(m, slabs, 2, box, params, (3, 3), pos, vel)
+    sims[0].slab_peer_timeout(20_000_000)   # ~10 ms
+    sims[0].slab_send()                     # slab 1 never sends
+    t = sims[0].slab_recv()
+    with pytest.raises(m.capi.SpheError, match="did not arrive"):
+        sims[0].slab_result(t, True)
+
+
+def _terrain_scene(m, n=30000, seed=5):
+    """Particles raining on a rough 256 x 64 terrain strip that fills the floor of a (1.2, 0.3, 0.3) box."""
+    rng = np.random.default_rng(seed)
+    rows, cols = 256, 64
+    hts = (rng.uniform(0, 6, (rows, cols)) + 4 * np.sin(np.arange(rows) / 9.0)[:, None] + 6).astype(np.float32)
+    g = m.Grid(rows, 255, cols)
+    g.set_heights(hts)
+    cell = 2.4 / rows
+    g.set_transform((-1.2, -0.3, -0.3), cell)
+    e = g.erosion
+    e.enabled = 1; e.Kc = 2.0; e.Ke = 0.4; e.Kd = 0.3; e.hmin = 2.0; e.max_pickup = 0.5
+    pos = np.empty((n, 3), np.float32)
+    pos[:, 0] = rng.uniform(-1.15, 1.15, n); pos[:, 2] = rng.uniform(-0.28, 0.28, n)
+    ix = np.clip(((pos[:, 0] + 1.2) / cell).astype(int), 0, rows - 2); iz = np.clip(((pos[:, 2] + 0.3) / cell).astype(int), 0, cols - 2)
+    local_top = np.maximum.reduce([hts[ix, iz], hts[ix + 1, iz], hts[ix, iz + 1], hts[ix + 1, iz + 1]])
+    pos[:, 1] = -0.3 + local_top * cell + rng.uniform(0.001, 0.06, n)      # just above the local surface
+    vel = rng.normal(0, 0.6, (n, 3)).astype(np.float32); vel[:, 1] -= 1.0
+    return g, pos, vel
+
+
+@pytest.mark.parametrize("K", [2, 3])
+def test_slabs_sharing_one_eroding_terrain_equal_single_gpu(K):
+    """Erosion across slab boundaries: requests of owned particles only, per-vertex sums over all slabs
+    between the phases (sphe_step_phase).  Heights, carried sediment and particle state must be BIT-EQUAL
+    to the single-handle run, and sum(heights) + sum(sediment) exactly conserved."""
+    m = product()
+    slabs = importlib.import_module("sph-erosion_b200.slabs")
+    box = (1.2, 0.3, 0.3)
+    params = dict(len=0.3, dt=0.004, g=(0.0, -9.82, 0.0))
+    g1, pos, vel = _terrain_scene(m)
+    gk, _, _ = _terrain_scene(m)
+    n = pos.shape[0]
+    one = _single(m, box, params, (3, 3), pos, vel)
+    sims, group = _peer_group(m, slabs, K, box, params, (3, 3), pos, vel, grid=gk)
+    total0 = g1.total_fx()
+    for step in range(12):
+        one.Run(g1)
+        group.step()
+    group.drain()
+    assert g1.contacts() > 1000, "the scene must exercise terrain contacts"
+    assert g1.contacts() == gk.contacts()
+    assert np.array_equal(g1.heights_fx(), gk.heights_fx())
+    p, v, rho, sed = _gather(sims, n)
+    assert np.array_equal(p, one.download("pos")) and np.array_equal(v, one.download("vel"))
+    assert np.array_equal(rho, one.download("density"))
+    sed_k = sum(s.sediment_total_fx() for s in sims)
+    assert sed_k == one.sediment_total_fx() and sed_k > 0
+    assert gk.total_fx() + sed_k == total0, "sum(heights) + sum(carried sediment) is conserved exactly"
