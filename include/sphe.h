@@ -170,6 +170,13 @@ int sphe_debug_neighbours(sphe_sim* s, long long* nbr_start, int* nbr, long long
  * halo travel in the same buffer, the receiver classifies each record by its own cell column.
  * Particle ids are global, < 2^30 (bit 30 marks ghost copies). */
 int sphe_slab_configure(sphe_sim* s, int x0, int x1, int has_left, int has_right);
+/* Ring closure for 3 or more slabs.  The reference's box response sends a particle that sits EXACTLY on the
+ * -x wall to the +x wall (collisionS, fluid_system.h:375-382: x == -len takes the `else` branch), i.e. from
+ * the first slab to the last one in a single step.  wrap_left (first slab; configure it with has_left = 1):
+ * the left link goes to the last slab and carries those particles (cell column >= far_x0 = the last slab's
+ * x0) and nothing else.  wrap_right (last slab; has_right = 1): the right link goes to the first slab and
+ * carries no payload; it keeps the flag protocol of the mailboxes symmetric.  Wrap links carry no halo. */
+int sphe_slab_ring(sphe_sim* s, int wrap_left, int wrap_right, int far_x0);
 int sphe_slab_info(sphe_sim* s, int* gnx, int* xoff, int* n_total, int* n_owned);
 int sphe_slab_upload(sphe_sim* s, int n, const float* pos, const float* vel, const int* ids);
 /* Exchange buffers hold cap_records + 1 records; record 0 is a header whose first int is the payload

@@ -868,12 +868,25 @@ int sphe_slab_configure(sphe_sim* s, int x0, int x1, int has_left, int has_right
     TRY(ensure_device(s));
     s->slab.x0 = x0; s->slab.x1 = x1; s->slab.halo = 2;
     s->slab.has_left = has_left != 0; s->slab.has_right = has_right != 0;
+    s->slab.wrap_left = s->slab.wrap_right = 0; s->slab.far_x0 = 0x7fffffff;
     s->slab_on = true;
     s->grid_h = -1.f;  // re-window the grid
     if (!s->slab_counters) CU(cudaMalloc(&s->slab_counters, 8 * sizeof(int)));
     if (!s->d_n) CU(cudaMalloc(&s->d_n, sizeof(int)));
     if (!s->slab_host) CU(cudaMallocHost(&s->slab_host, sphe_sim::SLAB_RING * 8 * sizeof(int)));
     for (auto& e : s->slab_ev) if (!e) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return SPHE_OK;
+}
+
+int sphe_slab_ring(sphe_sim* s, int wrap_left, int wrap_right, int far_x0) {
+    if (!s) return fail(SPHE_ERR_ARG, "NULL handle");
+    if (!s->slab_on) return fail(SPHE_ERR_STATE, "call sphe_slab_configure first");
+    if (wrap_left && wrap_right) return fail(SPHE_ERR_ARG, "a ring needs at least 3 slabs: only one link of a slab can wrap");
+    if ((wrap_left && !s->slab.has_left) || (wrap_right && !s->slab.has_right))
+        return fail(SPHE_ERR_ARG, "a wrap link is a link: configure the slab with a neighbour on that side");
+    if (wrap_left && far_x0 < s->slab.x1 + s->slab.halo) return fail(SPHE_ERR_ARG, "far_x0 must lie beyond this slab's halo zone");
+    s->slab.wrap_left = wrap_left != 0; s->slab.wrap_right = wrap_right != 0;
+    s->slab.far_x0 = wrap_left ? far_x0 : 0x7fffffff;
     return SPHE_OK;
 }
 

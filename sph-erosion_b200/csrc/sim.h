@@ -58,6 +58,10 @@ struct SlabP {
     int x0, x1;      // owned global cell columns [x0, x1)
     int halo;        // cell layers mirrored from each neighbour
     int has_left, has_right;
+    // ring closure (sphe_slab_ring): the left link of the FIRST slab / the right link of the LAST slab goes to
+    // the slab at the other end of the channel.  A wrap link carries no halo, only the particles the reference's
+    // box quirk moved from the -x wall to the +x wall (cell column >= far_x0, the last slab's x0).
+    int wrap_left = 0, wrap_right = 0, far_x0 = 0x7fffffff;
 };
 void launch_slab_classify(cudaStream_t st, int n, const int* n_dev, const float4* posq, const float4* velv, const int* ids, const float* sed,
                           const GridP& G, const SlabP& S, float4* keep_pos, float4* keep_vel, int* keep_ids, float* keep_sed,

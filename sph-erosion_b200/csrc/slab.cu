@@ -83,10 +83,13 @@ __global__ void __launch_bounds__(256) k_slab_classify(int n_hi, const int* __re
             p = posq[i]; v = velv[i]; sd = sed[i];
             int cx = cell_axis(p.x, G.gx, G.cell, G.gnx);
             own = (cx >= S.x0 || !S.has_left) && (cx < S.x1 || !S.has_right);
-            to_l = S.has_left && cx < S.x0 + S.halo;
-            to_r = S.has_right && cx >= S.x1 - S.halo;
+            // a particle exactly on the -x wall is clamped to the +x wall (collisionS, fluid_system.h:375-382:
+            // x == -len takes the else branch): it leaves the first slab for the LAST one, over the wrap link
+            const bool far = S.wrap_left && cx >= S.far_x0;
+            to_l = S.has_left && (S.wrap_left ? far : cx < S.x0 + S.halo);
+            to_r = S.has_right && !S.wrap_right && !far && cx >= S.x1 - S.halo;
             // left the slab but still within the halo zone: stays here as a ghost
-            live = own || (cx >= S.x0 - S.halo && cx < S.x1 + S.halo);
+            live = own || (!far && cx >= S.x0 - S.halo && cx < S.x1 + S.halo);
         }
     }
     const bool flag[4] = {live, to_l, to_r, own};

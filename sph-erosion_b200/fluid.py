@@ -140,6 +140,9 @@ class FluidSystemSPH:
     def slab_configure(self, x0, x1, has_left, has_right):
         capi.check(self._L.sphe_slab_configure(self._h, int(x0), int(x1), int(bool(has_left)), int(bool(has_right))))
 
+    def slab_ring(self, wrap_left, wrap_right, far_x0=0):
+        capi.check(self._L.sphe_slab_ring(self._h, int(bool(wrap_left)), int(bool(wrap_right)), int(far_x0)))
+
     def slab_info(self):
         v = [C.c_int(0) for _ in range(4)]
         capi.check(self._L.sphe_slab_info(self._h, *[C.byref(x) for x in v]))

@@ -44,6 +44,17 @@ def partition_columns(gnx, world, boundaries_x=None, gmin_x=None, cell=None):
     return out
 
 
+def ring_links(rank, world):
+    """(left, right, wrap_left, wrap_right) of a slab.  3 or more slabs close into a ring: the reference's box
+    response moves a particle that sits exactly on the -x wall to the +x wall (collisionS, fluid_system.h:375-382),
+    i.e. from the first slab straight to the last one, so those two are linked as well (include/sphe.h
+    sphe_slab_ring; a wrap link carries those particles only, no halo).  With 2 slabs the last slab already is
+    the first one's neighbour."""
+    if world >= 3:
+        return (rank - 1) % world, (rank + 1) % world, rank == 0, rank == world - 1
+    return (rank - 1 if rank > 0 else None), (rank + 1 if rank < world - 1 else None), False, False
+
+
 # --------------------------------------------------------------------------- communication
 class TorchComm:
     """x-neighbour P2P over torch.distributed (backend nccl on GPUs, gloo in the CPU tests)."""
@@ -52,8 +63,7 @@ class TorchComm:
         import torch.distributed as dist
         self.dist = dist
         self.rank, self.world = rank, world
-        self.left = rank - 1 if rank > 0 else None
-        self.right = rank + 1 if rank < world - 1 else None
+        self.left, self.right, _, _ = ring_links(rank, world)
 
     def swap_records(self, send_l, out_l, send_r, out_r, recv_l, in_l, recv_r, in_r):
         """One group of sends/receives.  Buffers are float32 tensors; out_*/in_* are the payload sizes
@@ -224,8 +234,9 @@ class LocalSlabGroup:
             b.pack()
         self.last = []
         for r, b in enumerate(self.bs):
-            left = self.bs[r - 1].send_r if r > 0 else None
-            right = self.bs[r + 1].send_l if r < K - 1 else None
+            l, rt, _, _ = ring_links(r, K)
+            left = self.bs[l].send_r if l is not None else None
+            right = self.bs[rt].send_l if rt is not None else None
             if self.async_:
                 self.tickets.append((b, b.unpack_async(left, b.cap, right, b.cap)))
             else:
@@ -293,8 +304,9 @@ class PeerSlabDriver:
         """Exchange the mailbox handles (all ranks call this; it also orders every setup before any send)."""
         handles = [None] * self.world
         dist.all_gather_object(handles, self.sim.slab_peer_handle())
-        left = handles[self.rank - 1] if self.rank > 0 else None
-        right = handles[self.rank + 1] if self.rank < self.world - 1 else None
+        l, r, _, _ = ring_links(self.rank, self.world)
+        left = handles[l] if l is not None else None
+        right = handles[r] if r is not None else None
         self.sim.slab_peer_connect(left, right)
         dist.barrier()
 
@@ -331,7 +343,8 @@ class LocalPeerGroup:
             s.slab_peer_setup(cap_records, reserve_particles)
         K = len(self.sims)
         for r, s in enumerate(self.sims):
-            s.slab_peer_connect_local(self.sims[r - 1] if r > 0 else None, self.sims[r + 1] if r < K - 1 else None)
+            l, rt, _, _ = ring_links(r, K)
+            s.slab_peer_connect_local(self.sims[l] if l is not None else None, self.sims[rt] if rt is not None else None)
         self.tickets = []
 
     def step(self):
@@ -392,8 +405,11 @@ def make_gpu_slab(pkg, device, rank, world, box_half, params, bounds_x, cap_reco
     gi = sim.grid_info()
     cols = partition_columns(info["gnx"], world, bounds_x, gi.gmin[0], gi.cell)
     x0, x1 = cols[rank]
-    sim.slab_configure(x0, x1, rank > 0, rank < world - 1)
-    return sim, GpuSlabBackend(sim, device, cap_records, rank > 0, rank < world - 1), cols
+    left, right, wrap_l, wrap_r = ring_links(rank, world)
+    sim.slab_configure(x0, x1, left is not None, right is not None)
+    if wrap_l or wrap_r:
+        sim.slab_ring(wrap_l, wrap_r, cols[-1][0])
+    return sim, GpuSlabBackend(sim, device, cap_records, left is not None, right is not None), cols
 
 
 # --------------------------------------------------------------------------- bench (called by bench.py)
@@ -526,7 +542,7 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT, terrain=False):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": args.workload, "description": desc + " -- repeated %d x along x, one x-slab per GPU" % world,
-                       "particles": n_total, "particles_per_gpu": n_local, "h": 0.0457, "spacing": SPACING, "dt": 0.01,
+                       "particles": n_total, "particles_per_gpu": n_local, "particles_conserved": bool(n_total == n_local * world), "h": 0.0457, "spacing": SPACING, "dt": 0.01,
                        "box_half_extents": list(box), "gravity_y": gy, "slab_columns": cols,
                        "halo_records_per_step_all_ranks": int(owned[1].item()),
                        "exchange": exchange_desc, "exchange_mode": args.exchange,

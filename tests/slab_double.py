@@ -18,9 +18,10 @@ def cell_x(x, gmin_x, cell, gnx):
 
 
 class NumpySlabBackend:
-    def __init__(self, P, G, x0, x1, has_left, has_right, cap):
+    def __init__(self, P, G, x0, x1, has_left, has_right, cap, wrap_left=False, wrap_right=False, far_x0=1 << 30):
         self.P, self.G = P, G
         self.x0, self.x1, self.hl, self.hr = x0, x1, has_left, has_right
+        self.wl, self.wr, self.far_x0 = wrap_left, wrap_right, far_x0     # ring closure (sphe_slab_ring)
         self.cap = cap
         self.gnx = int(G.dim[0])
         self.pos = np.zeros((0, 3), np.float32); self.vel = np.zeros((0, 3), np.float32)
@@ -47,9 +48,10 @@ class NumpySlabBackend:
         self.pos, self.vel, self.ids = self.pos[real], self.vel[real], self.ids[real]
         cx = cell_x(self.pos[:, 0], self.G.gmin[0], self.G.cell, self.gnx)
         own = self._own(cx)
-        to_l = (cx < self.x0 + HALO) & self.hl
-        to_r = (cx >= self.x1 - HALO) & self.hr
-        live = own | ((cx >= self.x0 - HALO) & (cx < self.x1 + HALO))
+        far = (cx >= self.far_x0) & self.wl       # clamped from the -x wall to the +x wall: goes to the last slab
+        to_l = (far if self.wl else (cx < self.x0 + HALO)) & self.hl
+        to_r = (cx >= self.x1 - HALO) & self.hr & (not self.wr) & ~far
+        live = own | (~far & (cx >= self.x0 - HALO) & (cx < self.x1 + HALO))
         for buf, m in ((self.send_l, to_l), (self.send_r, to_r)):
             r = self._records(m)
             assert len(r) <= self.cap

@@ -20,6 +20,10 @@ def scene(n=20000, seed=11):
     pos = np.empty((n, 3), np.float32)
     pos[:, 0] = rng.uniform(-1.1, 1.1, n); pos[:, 1] = rng.uniform(-0.29, 0.0, n); pos[:, 2] = rng.uniform(-0.29, 0.29, n)
     vel = rng.normal(0, 1.5, (n, 3)).astype(np.float32)
+    # isolated particles EXACTLY on the -x wall with no x velocity: the reference's box response clamps them to the
+    # +x wall (collisionS, fluid_system.h:375-382) -- from the first slab straight to the last one (sphe_slab_ring)
+    wall = np.array([[-1.2, 0.1 + 0.06 * k, -0.2 + 0.1 * k] for k in range(4)], np.float32)
+    pos = np.concatenate([pos, wall]); vel = np.concatenate([vel, np.zeros_like(wall)])
     return pos, vel
 
 
@@ -127,7 +131,7 @@ def _gather(sims, n):
     return [np.concatenate([g[j] for g in got])[o] for j in range(1, 5)]   # pos, vel, density, sediment (float bits)
 
 
-@pytest.mark.parametrize("K", [2, 3])
+@pytest.mark.parametrize("K", [2, 3, 5])
 def test_peer_mailbox_slabs_equal_single_gpu(K):
     """k_slab_classify<true> storing into the neighbours' mailboxes + k_slab_append<true> waiting on the flags
     (the multi-GPU default, here with all slabs in one process): bit-equal to the single-handle run, with
@@ -151,6 +155,7 @@ def test_peer_mailbox_slabs_equal_single_gpu(K):
         for a, name in ((p, "pos"), (v, "vel"), (rho, "density")):
             b = one.download(name)
             assert np.array_equal(a, b), "step %d %s: max |diff| %.3e" % (step, name, np.abs(a - b).max())
+    assert (p[-4:, 0] > 1.0).all(), "the particles that started on the -x wall were clamped to the +x wall (ring closure)"
 
 
 def test_peer_mailbox_overflow_is_reported():

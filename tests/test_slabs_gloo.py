@@ -20,6 +20,10 @@ def scene(n=2000, seed=5):
     pos = np.empty((n, 3), np.float32)
     pos[:, 0] = rng.uniform(-0.55, 0.55, n); pos[:, 1] = rng.uniform(-0.14, 0.0, n); pos[:, 2] = rng.uniform(-0.14, 0.14, n)
     vel = rng.normal(0, 1.5, (n, 3)).astype(np.float32)   # fast enough to cross slab boundaries
+    # isolated particles EXACTLY on the -x wall with no x velocity: the reference's box response clamps them to the
+    # +x wall (collisionS, fluid_system.h:375-382) -- from the first slab straight to the last one (ring closure)
+    wall = np.array([[-0.6, 0.3 + 0.1 * k, -0.4 + 0.2 * k] for k in range(3)], np.float32)
+    pos = np.concatenate([pos, wall]); vel = np.concatenate([vel, np.zeros_like(wall)])
     return pos, vel
 
 
@@ -46,7 +50,9 @@ def worker(rank, world, port_no, steps, outdir, cap=4096, floor=None, lag=0):
         slabs.next_size = lambda count, cap_, floor_=floor: max(floor, count // 2)  # too small on purpose -> every step re-sends
     pos, vel = scene()
     x0, x1 = cols[rank]
-    b = NumpySlabBackend(P, G, x0, x1, rank > 0, rank < world - 1, cap=cap)
+    left, right, wrap_l, wrap_r = slabs.ring_links(rank, world)
+    b = NumpySlabBackend(P, G, x0, x1, left is not None, right is not None, cap=cap, wrap_left=wrap_l, wrap_right=wrap_r,
+                         far_x0=cols[-1][0])
     # deliberately start from a WRONG distribution: particles in the two boundary columns of their
     # owner start on the neighbour across that boundary, as if they had just migrated; the first
     # exchange must send them home and mirror them back as ghosts.
@@ -96,6 +102,7 @@ def test_slab_protocol_matches_single_domain(world, floor, lag):
         parts = [np.load(os.path.join(d, "rank%d.npz" % r)) for r in range(world)]
     ids = np.concatenate([p["ids"] for p in parts])
     assert np.array_equal(np.sort(ids), np.arange(len(pos))), "every particle owned by exactly one slab"
+    assert (S.pos[-3:, 0] > 0.5).all(), "the wall particles must have been clamped to the +x wall"
     o = np.argsort(ids)
     for name, want in (("pos", S.pos), ("vel", S.vel), ("rho", S.density)):
         got = np.concatenate([p[name] for p in parts])[o]
