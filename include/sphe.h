@@ -266,6 +266,15 @@ int sphe_terrain_stage_host(sphe_terrain* t, int n, const float* pos_curr, float
 int sphe_step_phase(sphe_sim* s, sphe_terrain* t, int phase);
 int sphe_terrain_accumulators(sphe_terrain* t, void** want, void** delta, long long* cells);
 int sphe_terrain_total_fx(sphe_terrain* t, long long* sum);     /* sum of all heights, fixed point */
+int sphe_terrain_total_fx_rows(sphe_terrain* t, int row0, int row1, long long* sum);   /* ... of the rows [row0, row1) */
+/* Slab-local terrain.  Rows map to x, so a slab's owned particles only ever touch the rows under the slab plus
+ * a margin.  set_window: this replica keeps only the rows [row0, row1) current -- apply and the cull map run over
+ * them alone, so the terrain cost of a rank does not grow with the number of slabs -- and the caller sums the
+ * accumulators with its x-neighbours over the rows both can touch instead of all-reducing whole arrays
+ * (sph-erosion_b200/slabs.py TerrainWindowShare).  row1 <= row0 restores the whole terrain.  A contact that
+ * reads or writes within 2 rows of an interior window edge is counted: window_violations must stay 0. */
+int sphe_terrain_set_window(sphe_terrain* t, int row0, int row1);
+int sphe_terrain_window_violations(sphe_terrain* t, long long* count);
 int sphe_terrain_contacts(sphe_terrain* t, long long* total, int reset); /* particle-terrain contacts since the last reset */
 int sphe_sediment_total_fx(sphe_sim* s, long long* sum);        /* sum of carried sediment (owned particles), fixed point */
 int sphe_set_sediment_fx(sphe_sim* s, const int* sediment_by_id);

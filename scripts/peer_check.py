@@ -38,7 +38,14 @@ sim.slab_upload(pos[part], vel[part], part.astype(np.int32))
 if one_gpu:
     sim.slab_peer_timeout(400_000_000_000)   # ranks time-slice one GPU: a waiting kernel can sit out whole time slices
 total0 = grid.total_fx()
-drv = slabs.PeerSlabDriver(sim, rank, world, cap, n + 4 * cap, slabs.TerrainShare(grid, dev, reduce))
+mode = os.environ.get("TERRAIN_SHARE", "window" if not one_gpu else "allreduce")
+if mode == "window":
+    cell_t = 2.4 / 256
+    share = slabs.TerrainWindowShare(grid, dev, rank, world, slabs.terrain_row_cuts(sim.grid_info(), cols, -1.2, cell_t),
+                                     slabs.terrain_margin_rows(sim.grid_info().cell, cell_t), dist=dist)
+else:
+    share = slabs.TerrainShare(grid, dev, reduce)
+drv = slabs.PeerSlabDriver(sim, rank, world, cap, n + 4 * cap, share)
 drv.connect(dist)
 for _ in range(steps):
     drv.step()
@@ -46,7 +53,9 @@ info = drv.drain()
 ids, p, v, rho, sed = sim.slab_download()
 sed_fx = sim.sediment_total_fx()
 gathered = [None] * world
-dist.all_gather_object(gathered, (ids, p, v, rho, sed_fx, grid.heights_fx(), grid.contacts(), info))
+own = share.own if mode == "window" else (0, grid.shape()[0])
+win = share.window if mode == "window" else own
+dist.all_gather_object(gathered, (ids, p, v, rho, sed_fx, grid.heights_fx(), grid.contacts(), info, own, win, grid.window_violations()))
 ok = True
 if rank == 0:
     one = T._single(pkg, box, params, (3, 3), pos, vel)
@@ -61,18 +70,20 @@ if rank == 0:
         same = np.array_equal(a, b)
         ok &= same
         print("%-8s bit-equal: %s" % (name, same))
+    h1 = g1.heights_fx()
     for r, g in enumerate(gathered):
-        same = np.array_equal(g[5], g1.heights_fx())
+        w0, w1 = g[9]
+        same = np.array_equal(g[5][w0:w1], h1[w0:w1]) and g[10] == 0
         ok &= same
-        print("terrain replica of rank %d bit-equal to the single-GPU terrain: %s" % (r, same))
+        print("terrain rows [%d,%d) kept by rank %d bit-equal to the single-GPU terrain, no window violations: %s" % (w0, w1, r, same))
     sed_k = sum(g[4] for g in gathered)
-    cons = gathered[0][5].astype(np.int64).sum() + sed_k == total0
+    cons = sum(int(g[5][g[8][0]:g[8][1]].astype(np.int64).sum()) for g in gathered) + sed_k == total0
     ok &= bool(cons) and sed_k == one.sediment_total_fx() and sed_k > 0
     print("sediment in flight %d (single GPU %d), conservation exact: %s" % (sed_k, one.sediment_total_fx(), cons))
     contacts = sum(g[6] for g in gathered)
     ok &= contacts == g1.contacts() and contacts > 1000
     print("contacts %d (single GPU %d); exchange counts per rank: %s" % (contacts, g1.contacts(), [g[7] for g in gathered]))
-    print("PEER_CHECK %s world=%d one_gpu=%s" % ("OK" if ok else "FAILED", world, one_gpu))
+    print("PEER_CHECK %s world=%d one_gpu=%s terrain_share=%s" % ("OK" if ok else "FAILED", world, one_gpu, mode))
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

@@ -93,6 +93,9 @@ SYMBOLS = {
     "sphe_terrain_stage_host": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _f, _f, _vp]),
     "sphe_terrain_total_fx": (_i, [_vp, C.POINTER(_ll)]),
     "sphe_terrain_contacts": (_i, [_vp, C.POINTER(_ll), _i]),
+    "sphe_terrain_total_fx_rows": (_i, [_vp, _i, _i, C.POINTER(_ll)]),
+    "sphe_terrain_set_window": (_i, [_vp, _i, _i]),
+    "sphe_terrain_window_violations": (_i, [_vp, C.POINTER(_ll)]),
     "sphe_sediment_total_fx": (_i, [_vp, C.POINTER(_ll)]),
     "sphe_set_sediment_fx": (_i, [_vp, _vp]),
     "sphe_kernel_timing": (_i, [_vp, _i]),

@@ -53,7 +53,8 @@ struct sphe_terrain {
     float* d_surface = nullptr;
     unsigned* d_indices = nullptr;
     long long surface_floats = 0, index_count = 0;
-    long long* d_sum = nullptr;   // [0] scratch sum, [1] cumulative contact count
+    long long* d_sum = nullptr;   // [0] scratch sum, [1] cumulative contact count, [2] contacts outside the maintained rows
+    int win0 = 0, win1 = 0;       // rows kept current on this rank (sphe_terrain_set_window); win1 <= win0: all rows
     sphe_terrain() { E.enabled = 0; E.Kc = 0.05f; E.Ke = 0.3f; E.Kd = 0.3f; E.hmin = 0.0f; E.max_pickup = 0.25f; }
 };
 
@@ -1295,8 +1296,8 @@ static int terrain_ready(sphe_terrain* t) {
     if (t->device < 0) CU(cudaGetDevice(&t->device));
     CU(cudaSetDevice(t->device));
     CU(cudaMalloc(&t->hmax, sizeof(int)));
-    CU(cudaMalloc(&t->d_sum, 2 * sizeof(long long)));
-    CU(cudaMemset(t->d_sum, 0, 2 * sizeof(long long)));
+    CU(cudaMalloc(&t->d_sum, 3 * sizeof(long long)));
+    CU(cudaMemset(t->d_sum, 0, 3 * sizeof(long long)));
     TRY(terrain_alloc(t, t->rows, t->cols));  // Grid(): 512 x 512 heightfield, zeroed (grid.h:78-81)
     t->ready = true;
     return SPHE_OK;
@@ -1311,6 +1312,10 @@ static TerrainDev terrain_view(const sphe_terrain* t) {
     T.hmin_fx = (int)lrint((double)t->E.hmin * 4096.0); T.max_pickup_fx = (int)lrint((double)t->E.max_pickup * 4096.0);
     T.erosion = t->E.enabled ? 1 : 0;
     T.contacts = (unsigned long long*)(t->d_sum + 1);
+    T.violations = (unsigned long long*)(t->d_sum + 2);
+    const bool windowed = t->win1 > t->win0;
+    T.win0 = windowed ? std::max(t->win0, 0) : 0;
+    T.win1 = windowed ? std::min(t->win1, t->rows) : t->rows;
     return T;
 }
 
@@ -1528,13 +1533,36 @@ int sphe_terrain_accumulators(sphe_terrain* t, void** want, void** delta, long l
     return SPHE_OK;
 }
 
-int sphe_terrain_total_fx(sphe_terrain* t, long long* sum) {
+int sphe_terrain_total_fx_rows(sphe_terrain* t, int row0, int row1, long long* sum) {
     if (!t || !sum) return fail(SPHE_ERR_ARG, "bad arguments");
     TRY(terrain_ready(t));
+    row0 = std::max(row0, 0); row1 = std::min(row1, t->rows);
+    *sum = 0;
+    if (row1 <= row0) return SPHE_OK;
     CU(cudaDeviceSynchronize());
     CU(cudaMemset(t->d_sum, 0, sizeof(long long)));
-    launch_sum_i32(0, t->rows * t->cols, t->hfx, nullptr, t->d_sum);
+    launch_sum_i32(0, (row1 - row0) * t->cols, t->hfx + (size_t)row0 * t->cols, nullptr, t->d_sum);
     CU(cudaMemcpy(sum, t->d_sum, sizeof(long long), cudaMemcpyDeviceToHost));
+    return SPHE_OK;
+}
+
+int sphe_terrain_total_fx(sphe_terrain* t, long long* sum) {
+    if (!t) return fail(SPHE_ERR_ARG, "bad arguments");
+    return sphe_terrain_total_fx_rows(t, 0, t->rows, sum);
+}
+
+int sphe_terrain_set_window(sphe_terrain* t, int row0, int row1) {
+    if (!t) return fail(SPHE_ERR_ARG, "NULL terrain");
+    if (row1 > row0 && row1 - row0 < 8) return fail(SPHE_ERR_ARG, "terrain window [%d,%d) is narrower than 8 rows", row0, row1);
+    t->win0 = row0; t->win1 = row1;
+    return SPHE_OK;
+}
+
+int sphe_terrain_window_violations(sphe_terrain* t, long long* count) {
+    if (!t || !count) return fail(SPHE_ERR_ARG, "bad arguments");
+    TRY(terrain_ready(t));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(count, t->d_sum + 2, sizeof(long long), cudaMemcpyDeviceToHost));
     return SPHE_OK;
 }
 

@@ -32,6 +32,10 @@ struct TerrainDev {
     const int* lmax;         // per cell: max height of the 4x4 vertex neighbourhood (exact contact culling)
     int* lmax_rw;
     unsigned long long* contacts;  // cumulative number of particle-terrain contacts
+    // slab-local maintenance (sphe_terrain_set_window): only the rows [win0, win1) are kept current on this rank
+    // (apply + cull map run over them only); a contact that reaches outside them is counted in *violations
+    int win0, win1;
+    unsigned long long* violations;
     float ox, oy, oz, scale, inv_scale;   // world = origin + scale * terrain coordinates
     float Kc, Ke, Kd;
     int hmin_fx, max_pickup_fx;

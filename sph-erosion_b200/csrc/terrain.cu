@@ -231,6 +231,10 @@ __global__ void __launch_bounds__(128) k_terrain_contact(const int* __restrict__
             V3 pn = mk((p4.x - T.ox) * T.inv_scale, (p4.y - T.oy) * T.inv_scale, (p4.z - T.oz) * T.inv_scale);
             V3 vn = mk(v4.x * T.inv_scale, v4.y * T.inv_scale, v4.z * T.inv_scale);
             hit = C.dt != 0.0f && collide(T, pc, pn, vn, cp, nn);
+            // slab-local terrain: everything this contact read or will write must lie inside the maintained rows
+            const float lo = fminf(pc.x, pn.x), hi = fmaxf(pc.x, pn.x);
+            if (hit && ((T.win0 > 0 && lo < (float)(T.win0 + 2)) || (T.win1 < T.rows && hi > (float)(T.win1 - 3))))
+                atomicAdd(T.violations, 1ull);
         }
         int dep_vertex = 0, dep_amount = 0, want_vertex = 0, want_amount = 0;
         bool dep = false, want = false;
@@ -300,9 +304,10 @@ __global__ void __launch_bounds__(128) k_terrain_grant(const int* __restrict__ s
     }
 }
 
-__global__ void __launch_bounds__(256) k_terrain_apply(int cells, TerrainDev T) {
+__global__ void __launch_bounds__(256) k_terrain_apply(int first, int cells, TerrainDev T) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cells) return;
+    c += first;
     int d = T.delta[c];
     if (d) { T.hfx_rw[c] += d; T.delta[c] = 0; }
     if (T.want[c]) T.want[c] = 0;
@@ -318,7 +323,8 @@ __global__ void k_iota(int n, int* __restrict__ a, int* __restrict__ count) {
 // lmax[x, z] = max height over the vertices [x-1, x+2] x [z-1, z+2]: everything collide() can touch from cell (x, z)
 __global__ void __launch_bounds__(256) k_terrain_lmax(TerrainDev T, int* __restrict__ lmax) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= T.rows * T.cols) return;
+    if (c >= (T.win1 - T.win0) * T.cols) return;
+    c += T.win0 * T.cols;
     int x = c / T.cols, z = c - x * T.cols;
     int m = -0x7fffffff;
 #pragma unroll
@@ -417,8 +423,9 @@ void launch_terrain_stage(cudaStream_t st, const int* surv, const int* surv_coun
     if (T.erosion && C.dt != 0.0f) {
         if (phases & TERRAIN_GRANT) k_terrain_grant<<<148 * 4, 128, 0, st>>>(surv, surv_count, req_vertex, req_amount, sediment, T);
         if (phases & TERRAIN_APPLY) {
-            k_terrain_apply<<<nb(T.rows * T.cols, 256), 256, 0, st>>>(T.rows * T.cols, T);
-            k_terrain_lmax<<<nb(T.rows * T.cols, 256), 256, 0, st>>>(T, T.lmax_rw);
+            const int cells = (T.win1 - T.win0) * T.cols;
+            k_terrain_apply<<<nb(cells, 256), 256, 0, st>>>(T.win0 * T.cols, cells, T);
+            k_terrain_lmax<<<nb(cells, 256), 256, 0, st>>>(T, T.lmax_rw);
         }
     }
 }
@@ -427,7 +434,7 @@ void launch_iota(cudaStream_t st, int n, int* a, int* count) {
     if (n > 0) k_iota<<<nb(n, 256), 256, 0, st>>>(n, a, count);
 }
 void launch_terrain_lmax(cudaStream_t st, const TerrainDev& T) {
-    k_terrain_lmax<<<nb(T.rows * T.cols, 256), 256, 0, st>>>(T, T.lmax_rw);
+    k_terrain_lmax<<<nb((T.win1 - T.win0) * T.cols, 256), 256, 0, st>>>(T, T.lmax_rw);
 }
 
 void launch_terrain_surface(cudaStream_t st, const TerrainDev& T, float* out) {

@@ -108,9 +108,22 @@ class Grid:
         capi.check(self._L.sphe_terrain_accumulators(self._t, C.byref(w), C.byref(d), C.byref(n)))
         return w.value, d.value, n.value
 
-    def total_fx(self):
+    def total_fx(self, rows=None):
+        """Sum of the fixed-point heights (of the rows [rows[0], rows[1]) when given)."""
         v = C.c_longlong(0)
-        capi.check(self._L.sphe_terrain_total_fx(self._t, C.byref(v)))
+        if rows is None:
+            capi.check(self._L.sphe_terrain_total_fx(self._t, C.byref(v)))
+        else:
+            capi.check(self._L.sphe_terrain_total_fx_rows(self._t, int(rows[0]), int(rows[1]), C.byref(v)))
+        return v.value
+
+    def set_window(self, row0, row1):
+        """Slab-local terrain: keep only the rows [row0, row1) current on this replica (sphe_terrain_set_window)."""
+        capi.check(self._L.sphe_terrain_set_window(self._t, int(row0), int(row1)))
+
+    def window_violations(self):
+        v = C.c_longlong(0)
+        capi.check(self._L.sphe_terrain_window_violations(self._t, C.byref(v)))
         return v.value
 
     def contacts(self, reset=False):

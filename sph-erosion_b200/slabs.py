@@ -285,6 +285,78 @@ class TerrainShare:
         sim.step_phase(self.grid, 2)
 
 
+def terrain_row_cuts(grid_info, cols, origin_x, scale):
+    """Terrain rows at the slab boundaries: rows map to x (H(x, z), grid.h:104-107), slab r owns the neighbour-grid
+    columns cols[r] = [x0, x1), i.e. x in [gmin_x + x0*cell, gmin_x + x1*cell).  Returns the world-1 cut rows."""
+    return [int(round((grid_info.gmin[0] + c[0] * grid_info.cell - origin_x) / scale)) for c in cols[1:]]
+
+
+def terrain_margin_rows(cell, scale):
+    """Rows an owned particle can touch beyond its slab's own rows within one step: HALO + 1 neighbour-grid columns of
+    travel (a particle moving further than the halo per step breaks the slab exchange long before) + the 4 x 4 vertex
+    neighbourhood of the contact search.  Checked at run time: sphe_terrain_window_violations must stay 0."""
+    return int(np.ceil((HALO + 1) * cell / scale)) + 4
+
+
+class TerrainWindowShare:
+    """Slab-local terrain (the multi-GPU default).  Every rank holds the whole heightfield array but keeps only the
+    rows under its slab + a margin of W rows current (sphe_terrain_set_window): the terrain kernels of a rank touch
+    that window only, and instead of all-reducing the whole accumulator arrays (33 MB each at 8 x 1024 rows) the
+    rank sums the 2W rows around each slab boundary with the ONE neighbour that can also touch them -- two small
+    NCCL P2P groups per step.  Integer sums, so the result is bit-identical to the single-GPU run on every row a
+    rank owns.  swap = callable(array, zone_left, zone_right) adding the neighbours' rows in place."""
+
+    def __init__(self, grid, device, rank, world, cuts, margin, swap=None, dist=None):
+        w, d, n = grid.accumulators()
+        rows, cols = grid.shape()
+        self.grid, self.rank, self.world = grid, rank, world
+        self.want = device_int32_view(w, n, device)
+        self.delta = device_int32_view(d, n, device)
+        self.own = (0 if rank == 0 else cuts[rank - 1], rows if rank == world - 1 else cuts[rank])
+        W = int(margin)
+        if world > 1 and min(b - a for a, b in zip([0] + list(cuts), list(cuts) + [rows])) < 2 * W:
+            raise ValueError("a slab covers fewer than %d terrain rows: the boundary zones of its two neighbours would overlap" % (2 * W))
+        self.window = (max(self.own[0] - W, 0), min(self.own[1] + W, rows))
+        grid.set_window(*self.window)
+        # the rows both this rank and a neighbour can touch: [cut - W, cut + W) around each interior boundary
+        self.zone_l = slice((self.own[0] - W) * cols, (self.own[0] + W) * cols) if rank > 0 else None
+        self.zone_r = slice((self.own[1] - W) * cols, (self.own[1] + W) * cols) if rank < world - 1 else None
+        self.zone_bytes = 2 * W * cols * 4
+        self.swap = swap      # False: the caller sums the zones itself (LocalPeerGroup)
+        if swap is None:
+            import torch
+            self.dist = dist
+            self.buf_l = torch.empty(2 * W * cols, dtype=torch.int32, device=device) if rank > 0 else None
+            self.buf_r = torch.empty(2 * W * cols, dtype=torch.int32, device=device) if rank < world - 1 else None
+            self.swap = self._swap_p2p
+
+    def _swap_p2p(self, arr, zl, zr):
+        d, P = self.dist, self.dist.P2POp
+        ops = []
+        if zl is not None:
+            ops += [P(d.isend, arr[zl], self.rank - 1), P(d.irecv, self.buf_l, self.rank - 1)]
+        if zr is not None:
+            ops += [P(d.isend, arr[zr], self.rank + 1), P(d.irecv, self.buf_r, self.rank + 1)]
+        if ops:
+            for w in d.batch_isend_irecv(ops):
+                w.wait()
+        if zl is not None: arr[zl] += self.buf_l
+        if zr is not None: arr[zr] += self.buf_r
+
+    def step(self, sim):
+        if not self.grid.erosion.enabled:
+            sim.Run(self.grid)
+            return
+        sim.step_phase(self.grid, 0)
+        self.swap(self.want, self.zone_l, self.zone_r)
+        sim.step_phase(self.grid, 1)
+        self.swap(self.delta, self.zone_l, self.zone_r)
+        sim.step_phase(self.grid, 2)
+
+    def own_total_fx(self):
+        return self.grid.total_fx(self.own)
+
+
 class PeerSlabDriver:
     """send -> recv -> step with NO transport library and NO host sync on the data path: the pack kernel
     stores migrants + halo straight into the neighbours' mailboxes over NVLink (peer memory mapped through
@@ -336,9 +408,12 @@ class LocalPeerGroup:
     same kernels and calls as PeerSlabDriver.  grid: one terrain shared by all slabs -- every slab runs
     phase 0, then every slab phase 1, then one phase 2, which is the K-rank sum without a collective."""
 
-    def __init__(self, sims, cap_records, reserve_particles, grid=None):
+    def __init__(self, sims, cap_records, reserve_particles, grid=None, shares=None):
+        """shares: one TerrainWindowShare per slab (each slab its own terrain replica, slab-local windows); their
+        boundary-zone sums are done here with plain tensor adds between the replicas."""
         self.sims = list(sims)
         self.grid = grid
+        self.shares = shares
         for s in self.sims:
             s.slab_peer_setup(cap_records, reserve_particles)
         K = len(self.sims)
@@ -352,7 +427,18 @@ class LocalPeerGroup:
             s.slab_send()
         self.tickets = [s.slab_recv() for s in self.sims]
         g = self.grid
-        if g is not None and g.erosion.enabled:
+        if self.shares is not None:
+            sh = self.shares
+            for name, phase in (("want", 0), ("delta", 1)):
+                for s, t in zip(self.sims, sh):
+                    s.step_phase(t.grid, phase)
+                for a, b in zip(sh[:-1], sh[1:]):     # the zone right of a == the zone left of b (same rows)
+                    x, y = getattr(a, name)[a.zone_r], getattr(b, name)[b.zone_l]
+                    tot = x + y
+                    x.copy_(tot); y.copy_(tot)
+            for s, t in zip(self.sims, sh):
+                s.step_phase(t.grid, 2)
+        elif g is not None and g.erosion.enabled:
             for s in self.sims:
                 s.step_phase(g, 0)
             for s in self.sims:
@@ -437,7 +523,11 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT, terrain=False):
         # every rank holds a replica of the whole terrain; the integer erosion accumulators are summed over
         # the ranks between the phases of a step (TerrainShare), so the replicas stay bit-identical
         grid, tinfo = attach_terrain(pkg, box[1], n_axis, nx_mult=world)
-        tshare = TerrainShare(grid, dev, lambda t: dist.all_reduce(t))
+        if args.terrain_share == "window":
+            cuts = terrain_row_cuts(sim.grid_info(), cols, tinfo["terrain_origin"][0], tinfo["terrain_cell"])
+            tshare = TerrainWindowShare(grid, dev, rank, world, cuts, terrain_margin_rows(sim.grid_info().cell, tinfo["terrain_cell"]), dist=dist)
+        else:
+            tshare = TerrainShare(grid, dev, lambda t: dist.all_reduce(t))
     if args.exchange == "peer":
         drv = PeerSlabDriver(sim, rank, world, cap, int(n_local * 1.3) + 6 * cap, tshare)
         drv.connect(dist)
@@ -448,8 +538,21 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT, terrain=False):
             raise SystemExit("--exchange nccl has no shared-terrain support; use the default peer exchange")
         drv = SlabDriver(backend, TorchComm(rank, world), lag=args.slab_lag)
         exchange_desc = "NCCL P2P (one batch_isend_irecv group per step) with the x-neighbours, counts ride in the record headers, no collective"
-    if terrain:
+    windowed = terrain and args.terrain_share == "window"
+    if windowed:
+        exchange_desc += ("; terrain slab-local: each rank keeps the rows under its slab + %d margin rows current and sums the erosion accumulators "
+                          "of the %d rows around each slab boundary with that x-neighbour (2 NCCL P2P groups of %d KB per step, int32, no collective)"
+                          % (tshare.window[1] - tshare.own[1] if rank < world - 1 else tshare.own[0] - tshare.window[0],
+                             2 * (tshare.own[0] - tshare.window[0] if rank else tshare.window[1] - tshare.own[1]), tshare.zone_bytes // 1024))
+    elif terrain:
         exchange_desc += "; terrain replicated, per-vertex erosion accumulators summed with 2 NCCL all-reduces (int32) per step"
+
+    def terrain_total():
+        if not windowed:
+            return grid.total_fx()
+        t = torch.tensor([tshare.own_total_fx()], device=dev, dtype=torch.int64)
+        dist.all_reduce(t)
+        return int(t.item())
 
     def sync_all():
         torch.cuda.synchronize()
@@ -462,7 +565,7 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT, terrain=False):
         return int(t.item())
 
     if grid is not None:
-        tot0 = grid.total_fx() + sediment_all()
+        tot0 = terrain_total() + sediment_all()
         for _ in range(args.settle):
             drv.step()
         drv.drain()
@@ -492,14 +595,30 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT, terrain=False):
         tinfo["terrain_contacts_per_step"] = int(c.item()) / args.steps
         sed_now = sediment_all()
         tinfo["sediment_in_flight_fx"] = sed_now
-        tinfo["conservation_exact"] = bool(grid.total_fx() + sed_now == tot0)
-        h = torch.from_numpy(grid.heights_fx().astype(np.int64).ravel()).to(dev)
-        hs = torch.stack([h.sum(), (h * torch.arange(1, h.numel() + 1, device=dev) % 1000003).sum()])
-        hmin, hmax = hs.clone(), hs.clone()
-        dist.all_reduce(hmin, op=dist.ReduceOp.MIN); dist.all_reduce(hmax, op=dist.ReduceOp.MAX)
-        tinfo["terrain_replicas_identical"] = bool(torch.equal(hmin, hmax))
+        tinfo["conservation_exact"] = bool(terrain_total() + sed_now == tot0)
+        hfx = grid.heights_fx()
+        if windowed:
+            # every row a rank keeps current must agree with the neighbour that keeps it current too
+            W = tshare.own[0] - tshare.window[0] if rank else tshare.window[1] - tshare.own[1]
+            zones = [None] * world
+            dist.all_gather_object(zones, (hfx[tshare.own[0] - W:tshare.own[0] + W] if rank else None,
+                                           hfx[tshare.own[1] - W:tshare.own[1] + W] if rank < world - 1 else None))
+            tinfo["terrain_boundary_rows_identical"] = bool(all(np.array_equal(zones[r][1], zones[r + 1][0]) for r in range(world - 1)))
+            v = torch.tensor([grid.window_violations()], device=dev, dtype=torch.int64)
+            dist.all_reduce(v)
+            tinfo["terrain_window_violations"] = int(v.item())
+            tinfo["terrain_window_rows"] = list(tshare.window)
+        else:
+            h = torch.from_numpy(hfx.astype(np.int64).ravel()).to(dev)
+            hs = torch.stack([h.sum(), (h * torch.arange(1, h.numel() + 1, device=dev) % 1000003).sum()])
+            hmin, hmax = hs.clone(), hs.clone()
+            dist.all_reduce(hmin, op=dist.ReduceOp.MIN); dist.all_reduce(hmax, op=dist.ReduceOp.MAX)
+            tinfo["terrain_replicas_identical"] = bool(torch.equal(hmin, hmax))
     per_kernel, launches = sim.kernel_times()
     sim.kernel_timing(False)
+    per_rank = [None] * world
+    dist.all_gather_object(per_rank, {"particles": sim.slab_info()["n_total"], "owned": sim.slab_info()["n_owned"],
+                                      **{k: round(v / args.steps, 4) for k, v in per_kernel.items()}})
     clocks = sampler.stop() if rank == 0 else None
     owned = torch.tensor([sim.slab_info()["n_owned"], drv.last["to_left"] + drv.last["to_right"]], device=dev, dtype=torch.int64)
     dist.all_reduce(owned, op=dist.ReduceOp.SUM)
@@ -556,6 +675,7 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT, terrain=False):
             "roofline": {"bound": "hbm", "kernel": "k_%s" % dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_particle": ALGO_BYTES[dom], "rank": 0,
-                         "per_kernel_ms_per_step": {k: v / args.steps for k, v in per_kernel.items()}},
+                         "per_kernel_ms_per_step": {k: v / args.steps for k, v in per_kernel.items()},
+                         "per_rank": per_rank},
             "cpu_baseline": None}
     emit(line)

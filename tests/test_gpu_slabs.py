@@ -234,3 +234,56 @@ def test_slabs_sharing_one_eroding_terrain_equal_single_gpu(K):
     sed_k = sum(s.sediment_total_fx() for s in sims)
     assert sed_k == one.sediment_total_fx() and sed_k > 0
     assert gk.total_fx() + sed_k == total0, "sum(heights) + sum(carried sediment) is conserved exactly"
+
+
+@pytest.mark.parametrize("K", [2, 3])
+def test_slab_local_terrain_windows_equal_single_gpu(K):
+    """The multi-GPU default for the terrain (slabs.TerrainWindowShare): every slab has its OWN terrain replica and
+    keeps only the rows under the slab + a margin current (sphe_terrain_set_window); the erosion accumulators are
+    summed with the x-neighbour over the rows around the common boundary only.  Every row a slab owns, the
+    carried sediment and the particle state must be BIT-EQUAL to the single-handle run; no contact may reach
+    outside a window; sum(owned rows) + sum(sediment) is conserved exactly."""
+    import torch
+    m = product()
+    slabs = importlib.import_module("sph-erosion_b200.slabs")
+    box = (1.2, 0.3, 0.3)
+    params = dict(len=0.3, dt=0.004, g=(0.0, -9.82, 0.0))
+    g1, pos, vel = _terrain_scene(m)
+    n = pos.shape[0]
+    one = _single(m, box, params, (3, 3), pos, vel)
+    total0 = g1.total_fx()
+    cap = 1 << 15
+    sims, replicas = [], []
+    for r in range(K):
+        sim, b, cols = slabs.make_gpu_slab(m, torch.cuda.current_device(), r, K, box, params, None, cap, (3, 3))
+        sims.append(sim); replicas.append(_terrain_scene(m)[0])
+    order = np.argsort(pos[:, 0], kind="stable")
+    for r, part in enumerate(np.array_split(order, K)):
+        sims[r].slab_upload(pos[part], vel[part], part.astype(np.int32))
+    gi = sims[0].grid_info()
+    cell_t = 2.4 / 256
+    cuts = slabs.terrain_row_cuts(gi, cols, -1.2, cell_t)
+    W = slabs.terrain_margin_rows(gi.cell, cell_t)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    shares = [slabs.TerrainWindowShare(replicas[r], dev, r, K, cuts, W, swap=False) for r in range(K)]
+    assert all(s.window[1] - s.window[0] < 256 for s in shares), "the windows must be real restrictions"
+    group = slabs.LocalPeerGroup(sims, cap, n + 4 * cap, shares=shares)
+    for step in range(12):
+        one.Run(g1)
+        group.step()
+    group.drain()
+    assert g1.contacts() > 1000
+    assert sum(g.contacts() for g in replicas) == g1.contacts()
+    assert all(g.window_violations() == 0 for g in replicas)
+    want = g1.heights_fx()
+    assert not np.array_equal(want, _terrain_scene(m)[0].heights_fx()), "the terrain must have eroded"
+    for r, (g, sh) in enumerate(zip(replicas, shares)):
+        got = g.heights_fx()
+        assert np.array_equal(got[sh.own[0]:sh.own[1]], want[sh.own[0]:sh.own[1]]), "slab %d: owned terrain rows" % r
+        assert np.array_equal(got[sh.window[0]:sh.window[1]], want[sh.window[0]:sh.window[1]]), "slab %d: window rows" % r
+    p, v, rho, sed = _gather(sims, n)
+    assert np.array_equal(p, one.download("pos")) and np.array_equal(v, one.download("vel"))
+    assert np.array_equal(rho, one.download("density"))
+    sed_k = sum(s.sediment_total_fx() for s in sims)
+    assert sed_k == one.sediment_total_fx() and sed_k > 0
+    assert sum(sh.own_total_fx() for sh in shares) + sed_k == total0, "sum(owned rows) + sum(carried sediment) is conserved exactly"
