@@ -179,6 +179,12 @@ int sphe_slab_configure(sphe_sim* s, int x0, int x1, int has_left, int has_right
 int sphe_slab_ring(sphe_sim* s, int wrap_left, int wrap_right, int far_x0);
 int sphe_slab_info(sphe_sim* s, int* gnx, int* xoff, int* n_total, int* n_owned);
 int sphe_slab_upload(sphe_sim* s, int n, const float* pos, const float* vel, const int* ids);
+/* A particle that crosses MORE than one slab in a step (the reference's contact response can eject particles at
+ * hundreds of box units per second) is received by a slab that is not its owner: that slab hands the record on
+ * in the same direction at the next exchange, so the particle reaches its owner one step per extra slab later
+ * instead of being lost.  out[3] = {records waiting to go left, waiting to go right, forwarded so far};
+ * owned + in-transit particles over all slabs is conserved. */
+int sphe_slab_transit(sphe_sim* s, int out[3]);
 /* Exchange buffers hold cap_records + 1 records; record 0 is a header whose first int is the payload
  * count, so a buffer can be sent with a size both sides agree on beforehand and no count has to reach
  * the host before the transfer is posted.

@@ -103,6 +103,7 @@ SYMBOLS = {
     "sphe_slab_configure": (_i, [_vp, _i, _i, _i, _i]),
     "sphe_slab_ring": (_i, [_vp, _i, _i, _i]),
     "sphe_slab_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "sphe_slab_transit": (_i, [_vp, _vp]),
     "sphe_slab_upload": (_i, [_vp, _i, _vp, _vp, _vp]),
     "sphe_slab_pack": (_i, [_vp, _vp, _vp, _i, _i]),
     "sphe_slab_unpack": (_i, [_vp, _vp, _i, _vp, _i, _vp]),

@@ -97,6 +97,8 @@ struct sphe_sim {
     int n_owned = 0;
     int* slab_counters = nullptr;  // device int[8]
     int* slab_host = nullptr;      // pinned ring of counter snapshots, SLAB_RING x 8 ints
+    float4* transit[2] = {nullptr, nullptr};   // records heading further left / right than the neighbour (slab.cu k_slab_forward)
+    int* transit_n = nullptr;      // device int[4]: in transit left, right, -, forwarded so far
     int slab_cap_sent = 0;
     bool slab_unpacked = false;    // unpack already ran since the last pack (a repeat must clear its counters)
     int* d_n = nullptr;            // device word: exact particle count after the last unpack
@@ -447,6 +449,7 @@ void sphe_destroy(sphe_sim* s) {
         for (int k = 0; k < 2; k++) if (s->peer_mbox[k] && s->peer_ipc[k]) cudaIpcCloseMemHandle(s->peer_mbox[k]);
         if (s->mbox) cudaFree(s->mbox);
         if (s->slab_host) cudaFreeHost(s->slab_host);
+        cudaFree(s->transit[0]); cudaFree(s->transit[1]); cudaFree(s->transit_n);
         if (s->d_n) cudaFree(s->d_n);
         for (auto& e : s->slab_ev) if (e) cudaEventDestroy(e);
         if (s->own_stream && s->st) cudaStreamDestroy(s->st);
@@ -875,6 +878,8 @@ int sphe_slab_configure(sphe_sim* s, int x0, int x1, int has_left, int has_right
     if (!s->slab_counters) CU(cudaMalloc(&s->slab_counters, 8 * sizeof(int)));
     if (!s->d_n) CU(cudaMalloc(&s->d_n, sizeof(int)));
     if (!s->slab_host) CU(cudaMallocHost(&s->slab_host, sphe_sim::SLAB_RING * 8 * sizeof(int)));
+    for (int k = 0; k < 2; k++) if (!s->transit[k]) CU(cudaMalloc(&s->transit[k], 2 * SPHE_TRANSIT_CAP * sizeof(float4)));
+    if (!s->transit_n) { CU(cudaMalloc(&s->transit_n, 4 * sizeof(int))); CU(cudaMemset(s->transit_n, 0, 4 * sizeof(int))); }
     for (auto& e : s->slab_ev) if (!e) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     return SPHE_OK;
 }
@@ -903,6 +908,17 @@ int sphe_slab_info(sphe_sim* s, int* gnx, int* xoff, int* n_total, int* n_owned)
     return SPHE_OK;
 }
 
+int sphe_slab_transit(sphe_sim* s, int out[3]) {
+    if (!s || !out) return fail(SPHE_ERR_ARG, "bad arguments");
+    if (!s->slab_on) return fail(SPHE_ERR_STATE, "call sphe_slab_configure first");
+    TRY(ensure_device(s));
+    int h[4];
+    CU(cudaMemcpyAsync(h, s->transit_n, sizeof h, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    out[0] = h[0]; out[1] = h[1]; out[2] = h[3];
+    return SPHE_OK;
+}
+
 int sphe_slab_upload(sphe_sim* s, int n, const float* pos, const float* vel, const int* ids) {
     if (!s || n < 0 || (n > 0 && (!pos || !vel || !ids))) return fail(SPHE_ERR_ARG, "bad arguments");
     if (!s->slab_on) return fail(SPHE_ERR_STATE, "call sphe_slab_configure first");
@@ -917,6 +933,7 @@ int sphe_slab_upload(sphe_sim* s, int n, const float* pos, const float* vel, con
     CU(cudaMemcpyAsync(dids, ids, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s->st));
     launch_pack_state_ids(s->st, n, dpos, dvel, dids, s->posA, s->velA, s->idsA, s->sedA);
     CU(cudaStreamSynchronize(s->st));
+    CU(cudaMemset(s->transit_n, 0, 4 * sizeof(int)));
     s->n = n; s->n_owned = n;
     s->slab_done = s->slab_seq; s->slab_pending = 0;
     s->num = n; s->init_num = n; s->next_label = n;
@@ -935,8 +952,10 @@ int sphe_slab_pack(sphe_sim* s, void* dev_send_left, void* dev_send_right, int c
     CU(cudaMemsetAsync(s->slab_counters, 0, 8 * sizeof(int), s->st));
     launch_slab_classify(s->st, s->n, s->slab_pending ? s->d_n : nullptr, s->posA, s->velA, s->idsA, s->sedA, s->G, s->slab, s->posB, s->velB, s->idsB, s->sedB,
                          (float4*)dev_send_left, (float4*)dev_send_right, cap_records, s->slab_counters);
+    launch_slab_forward(s->st, s->transit[0], s->transit[1], s->transit_n, s->slab.has_left ? (float4*)dev_send_left : nullptr,
+                        s->slab.has_right ? (float4*)dev_send_right : nullptr, cap_records, s->slab_counters, false);
     launch_slab_headers(s->st, s->slab_counters, (float4*)dev_send_left, (float4*)dev_send_right);
-    s->launches += 2;
+    s->launches += 3;
     std::swap(s->posA, s->posB); std::swap(s->velA, s->velB); std::swap(s->idsA, s->idsB); std::swap(s->sedA, s->sedB);
     s->binned = false; s->slot_valid = false;
     s->slab_cap_sent = cap_records;
@@ -949,6 +968,7 @@ int sphe_slab_pack(sphe_sim* s, void* dev_send_left, void* dev_send_right, int c
 static int slab_fold(sphe_sim* s, long long t, int out[6]) {
     const int slot = (int)(t % sphe_sim::SLAB_RING);
     const int* c = s->slab_host + 8 * slot;  // kept, to_left, to_right, owned(kept), owned(appended), from_left, from_right, error
+    if (c[7] == 2) return fail(SPHE_ERR_NOMEM, "more than %d records in transit to a slab beyond the neighbour", SPHE_TRANSIT_CAP);
     if (c[7]) return fail(SPHE_ERR_STATE, "peer exchange: a neighbour's records did not arrive within %lld clock cycles", s->peer_timeout);
     if (c[1] > s->slab_cap_sent || c[2] > s->slab_cap_sent)
         return fail(SPHE_ERR_NOMEM, "slab send overflow: %d left / %d right records > buffer capacity %d", c[1], c[2], s->slab_cap_sent);
@@ -991,10 +1011,13 @@ int sphe_slab_unpack_async(sphe_sim* s, const void* dev_recv_left, int max_left,
     }
     const long long t = s->slab_seq;
     const int slot = (int)(t % sphe_sim::SLAB_RING);
-    if (s->slab_unpacked) CU(cudaMemsetAsync(s->slab_counters + 4, 0, 3 * sizeof(int), s->st));  // repeated after a re-send
+    if (s->slab_unpacked) {  // repeated after a re-send
+        CU(cudaMemsetAsync(s->slab_counters + 4, 0, 3 * sizeof(int), s->st));
+        CU(cudaMemsetAsync(s->transit_n, 0, 2 * sizeof(int), s->st));
+    }
     s->slab_unpacked = true;
     launch_slab_append(s->st, max_left, max_right, (const float4*)dev_recv_left, (const float4*)dev_recv_right, s->G, s->slab,
-                       s->cap, s->posA, s->velA, s->idsA, s->sedA, s->slab_counters, s->d_n);
+                       s->cap, s->posA, s->velA, s->idsA, s->sedA, s->slab_counters, s->d_n, s->transit[0], s->transit[1], s->transit_n);
     s->launches += 1;
     CU(cudaMemcpyAsync(s->slab_host + 8 * slot, s->slab_counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, s->st));
     CU(cudaEventRecord(s->slab_ev[slot], s->st));
@@ -1186,8 +1209,9 @@ int sphe_slab_send(sphe_sim* s) {
     CU(cudaMemsetAsync(s->slab_counters, 0, 8 * sizeof(int), s->st));
     launch_slab_classify(s->st, s->n, s->slab_pending ? s->d_n : nullptr, s->posA, s->velA, s->idsA, s->sedA, s->G, s->slab, s->posB, s->velB,
                          s->idsB, s->sedB, dl, dr, s->mbox_cap, s->slab_counters, true);
+    launch_slab_forward(s->st, s->transit[0], s->transit[1], s->transit_n, dl, dr, s->mbox_cap, s->slab_counters, true);
     launch_slab_headers(s->st, s->slab_counters, dl, dr, fl, fr, q);
-    s->launches += 2;
+    s->launches += 3;
     std::swap(s->posA, s->posB); std::swap(s->velA, s->velB); std::swap(s->idsA, s->idsB); std::swap(s->sedA, s->sedB);
     s->binned = false; s->slot_valid = false;
     s->slab_cap_sent = s->mbox_cap;
@@ -1215,7 +1239,7 @@ int sphe_slab_recv(sphe_sim* s, long long* ticket) {
     s->slab_unpacked = true;
     launch_slab_append(s->st, ml, mr, s->slab.has_left ? mbox_buffer(s->mbox, s->mbox_buf, 0, par) : nullptr,
                        s->slab.has_right ? mbox_buffer(s->mbox, s->mbox_buf, 1, par) : nullptr, s->G, s->slab, s->cap, s->posA, s->velA,
-                       s->idsA, s->sedA, s->slab_counters, s->d_n,
+                       s->idsA, s->sedA, s->slab_counters, s->d_n, s->transit[0], s->transit[1], s->transit_n,
                        s->slab.has_left ? mbox_flag(s->mbox, s->mbox_buf, 0, par) : nullptr,
                        s->slab.has_right ? mbox_flag(s->mbox, s->mbox_buf, 1, par) : nullptr, q, s->peer_timeout);
     s->launches += 1;

@@ -73,8 +73,13 @@ void launch_slab_classify(cudaStream_t st, int n, const int* n_dev, const float4
 // flag_* != NULL: peer-memory exchange, the buffers and flags live in the neighbour GPUs' mailboxes
 void launch_slab_headers(cudaStream_t st, int* counters, float4* send_left, float4* send_right, int* flag_left = nullptr,
                          int* flag_right = nullptr, int seq = 0);
+// records in transit: received from one side, owned further along (k_slab_append -> k_slab_forward at the next pack)
+#define SPHE_TRANSIT_CAP 8192
+void launch_slab_forward(cudaStream_t st, const float4* transit_l, const float4* transit_r, int* transit_n, float4* send_left,
+                         float4* send_right, int cap_records, int* counters, bool remote);
 void launch_slab_append(cudaStream_t st, int max_l, int max_r, const float4* rec_l, const float4* rec_r, const GridP& G,
                         const SlabP& S, int cap_particles, float4* posq, float4* velv, int* ids, float* sed, int* counters, int* n_out,
+                        float4* transit_l, float4* transit_r, int* transit_n,
                         const int* flag_l = nullptr, const int* flag_r = nullptr, int seq = 0, long long timeout_cycles = 0);
 void launch_slab_gather_owned(cudaStream_t st, int n, const float4* posq, const float4* velv, const float* rho, const float* sed,
                               const int* ids, int* counter, int* out_ids, float* out_pos, float* out_vel, float* out_rho,

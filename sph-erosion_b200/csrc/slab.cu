@@ -157,7 +157,8 @@ __global__ void __launch_bounds__(256) k_slab_append(int max_l, int max_r, const
                                                      GridP G, SlabP S, int cap_particles,
                                                      float4* __restrict__ posq, float4* __restrict__ velv,
                                                      int* __restrict__ ids, float* __restrict__ sed, int* __restrict__ counters,
-                                                     int* __restrict__ n_out) {
+                                                     int* __restrict__ n_out, float4* __restrict__ transit_l,
+                                                     float4* __restrict__ transit_r, int* __restrict__ transit_n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (PEER) {
         __shared__ int arrived;
@@ -198,8 +199,44 @@ __global__ void __launch_bounds__(256) k_slab_append(int max_l, int max_r, const
         velv[kept + i] = make_float4(b.x, b.y, b.z, 0.f);
         sed[kept + i] = a.w;
         ids[kept + i] = own ? id : (id | SPHE_GHOST_BIT);
+        // A record whose owner lies FURTHER along its direction of travel (a particle that crossed more than
+        // one slab in a step -- the contact response of the reference can eject particles at hundreds of
+        // box units per second) is handed on at the next exchange; here it stays a ghost for one step (binned
+        // at the window edge, too far from everything to be anybody's neighbour).
+        const bool from_left = i < from_l;
+        const bool onward = !own && (from_left ? (cx >= S.x1 && S.has_right && !S.wrap_right) : (cx < S.x0 && S.has_left && !S.wrap_left));
+        if (onward) {
+            const int k = atomicAdd(&transit_n[from_left ? 1 : 0], 1);
+            if (k < SPHE_TRANSIT_CAP) {
+                float4* t = from_left ? transit_r : transit_l;
+                t[2 * k] = a; t[2 * k + 1] = make_float4(b.x, b.y, b.z, __int_as_float(id));
+            } else atomicExch(&counters[7], 2);
+        }
     }
     warp_append(own, &counters[4]);
+}
+
+// Records in transit (see k_slab_append) join the send buffer of their direction; runs between k_slab_classify
+// and k_slab_headers, one block.  transit_n: [0] heading left, [1] heading right, [3] total forwarded so far.
+template <bool REMOTE>
+__global__ void __launch_bounds__(256) k_slab_forward(const float4* __restrict__ transit_l, const float4* __restrict__ transit_r,
+                                                      int* __restrict__ transit_n, float4* __restrict__ send_left,
+                                                      float4* __restrict__ send_right, int cap_records, int* __restrict__ counters) {
+    int moved = 0;
+    for (int dir = 0; dir < 2; dir++) {
+        const int n = min(transit_n[dir], SPHE_TRANSIT_CAP);
+        const float4* t = dir ? transit_r : transit_l;
+        float4* send = dir ? send_right : send_left;
+        if (!send) continue;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int slot = atomicAdd(&counters[1 + dir], 1);
+            if (slot < cap_records) { send[2 * (slot + 1)] = t[2 * i]; send[2 * (slot + 1) + 1] = t[2 * i + 1]; }
+            if (REMOTE) __threadfence_system();
+        }
+        moved += n;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { transit_n[3] += moved; transit_n[0] = 0; transit_n[1] = 0; }
 }
 
 // owned particles only, storage order, packed xyz (tests, checkpoints, rendering hand-off)
@@ -242,20 +279,26 @@ void launch_slab_classify(cudaStream_t st, int n, const int* n_dev, const float4
         k_slab_classify<false><<<(n + 255) / 256, 256, 0, st>>>(n, n_dev, posq, velv, ids, sed, G, S, keep_pos, keep_vel, keep_ids, keep_sed,
                                                                send_left, send_right, cap_records, counters);
 }
+void launch_slab_forward(cudaStream_t st, const float4* transit_l, const float4* transit_r, int* transit_n, float4* send_left,
+                         float4* send_right, int cap_records, int* counters, bool remote) {
+    if (remote) k_slab_forward<true><<<1, 256, 0, st>>>(transit_l, transit_r, transit_n, send_left, send_right, cap_records, counters);
+    else k_slab_forward<false><<<1, 256, 0, st>>>(transit_l, transit_r, transit_n, send_left, send_right, cap_records, counters);
+}
 void launch_slab_headers(cudaStream_t st, int* counters, float4* send_left, float4* send_right, int* flag_left, int* flag_right, int seq) {
     k_slab_headers<<<1, 32, 0, st>>>(counters, send_left, send_right, flag_left, flag_right, seq);
 }
 void launch_slab_append(cudaStream_t st, int max_l, int max_r, const float4* rec_l, const float4* rec_r, const GridP& G,
                         const SlabP& S, int cap_particles, float4* posq, float4* velv, int* ids, float* sed, int* counters, int* n_out,
+                        float4* transit_l, float4* transit_r, int* transit_n,
                         const int* flag_l, const int* flag_r, int seq, long long timeout_cycles) {
     int m = max_l + max_r;
     if (m < 1) m = 1;
     if (flag_l || flag_r)
         k_slab_append<true><<<(m + 255) / 256, 256, 0, st>>>(max_l, max_r, rec_l, rec_r, flag_l, flag_r, seq, timeout_cycles, G, S,
-                                                            cap_particles, posq, velv, ids, sed, counters, n_out);
+                                                            cap_particles, posq, velv, ids, sed, counters, n_out, transit_l, transit_r, transit_n);
     else
         k_slab_append<false><<<(m + 255) / 256, 256, 0, st>>>(max_l, max_r, rec_l, rec_r, nullptr, nullptr, 0, 0, G, S, cap_particles,
-                                                             posq, velv, ids, sed, counters, n_out);
+                                                             posq, velv, ids, sed, counters, n_out, transit_l, transit_r, transit_n);
 }
 void launch_slab_gather_owned(cudaStream_t st, int n, const float4* posq, const float4* velv, const float* rho, const float* sed,
                               const int* ids, int* counter, int* out_ids, float* out_pos, float* out_vel, float* out_rho,

@@ -148,6 +148,11 @@ class FluidSystemSPH:
         capi.check(self._L.sphe_slab_info(self._h, *[C.byref(x) for x in v]))
         return dict(zip(("gnx", "xoff", "n_total", "n_owned"), [x.value for x in v]))
 
+    def slab_transit(self):
+        out = (C.c_int * 3)()
+        capi.check(self._L.sphe_slab_transit(self._h, out))
+        return dict(zip(("to_left", "to_right", "forwarded"), list(out)))
+
     def slab_upload(self, pos, vel, ids):
         pos = np.ascontiguousarray(pos, np.float32); vel = np.ascontiguousarray(vel, np.float32)
         ids = np.ascontiguousarray(ids, np.int32)

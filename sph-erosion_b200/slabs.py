@@ -620,7 +620,9 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT, terrain=False):
     dist.all_gather_object(per_rank, {"particles": sim.slab_info()["n_total"], "owned": sim.slab_info()["n_owned"],
                                       **{k: round(v / args.steps, 4) for k, v in per_kernel.items()}})
     clocks = sampler.stop() if rank == 0 else None
-    owned = torch.tensor([sim.slab_info()["n_owned"], drv.last["to_left"] + drv.last["to_right"]], device=dev, dtype=torch.int64)
+    tr = sim.slab_transit()
+    owned = torch.tensor([sim.slab_info()["n_owned"], drv.last["to_left"] + drv.last["to_right"], tr["to_left"] + tr["to_right"], tr["forwarded"]],
+                         device=dev, dtype=torch.int64)
     dist.all_reduce(owned, op=dist.ReduceOp.SUM)
     n_total = int(owned[0].item())
     ms_step = float(ms.item()) / args.steps
@@ -661,7 +663,8 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT, terrain=False):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": args.workload, "description": desc + " -- repeated %d x along x, one x-slab per GPU" % world,
-                       "particles": n_total, "particles_per_gpu": n_local, "particles_conserved": bool(n_total == n_local * world), "h": 0.0457, "spacing": SPACING, "dt": 0.01,
+                       "particles": n_total, "particles_per_gpu": n_local, "particles_conserved": bool(n_total + int(owned[2].item()) == n_local * world),
+                       "records_forwarded_beyond_the_neighbour": int(owned[3].item()), "h": 0.0457, "spacing": SPACING, "dt": 0.01,
                        "box_half_extents": list(box), "gravity_y": gy, "slab_columns": cols,
                        "halo_records_per_step_all_ranks": int(owned[1].item()),
                        "exchange": exchange_desc, "exchange_mode": args.exchange,

@@ -29,6 +29,8 @@ class NumpySlabBackend:
         self.send_l = torch.zeros((cap + 1) * F); self.send_r = torch.zeros((cap + 1) * F)
         self.recv_l = torch.zeros((cap + 1) * F); self.recv_r = torch.zeros((cap + 1) * F)
         self.n_owned = 0
+        self.transit = [np.zeros((0, F), np.float32), np.zeros((0, F), np.float32)]   # records heading further left / right
+        self.forwarded = 0
 
     def upload(self, pos, vel, ids):
         self.pos = np.ascontiguousarray(pos, np.float32); self.vel = np.ascontiguousarray(vel, np.float32)
@@ -52,12 +54,15 @@ class NumpySlabBackend:
         to_l = (far if self.wl else (cx < self.x0 + HALO)) & self.hl
         to_r = (cx >= self.x1 - HALO) & self.hr & (not self.wr) & ~far
         live = own | (~far & (cx >= self.x0 - HALO) & (cx < self.x1 + HALO))
-        for buf, m in ((self.send_l, to_l), (self.send_r, to_r)):
+        for d, (buf, m, has) in enumerate(((self.send_l, to_l, self.hl), (self.send_r, to_r, self.hr))):
             r = self._records(m)
+            if has and len(self.transit[d]):      # k_slab_forward: records in transit join the buffer of their direction
+                r = np.concatenate([r, self.transit[d]]); self.forwarded += len(self.transit[d])
+            self.transit[d] = np.zeros((0, F), np.float32)
             assert len(r) <= self.cap
             buf[0] = float(np.array([len(r)], np.int32).view(np.float32)[0])   # header: payload count
             buf[F:F + r.size] = torch.from_numpy(r.reshape(-1))
-        self.sent = (int(to_l.sum()), int(to_r.sum()))
+        self.sent = (int(self.send_l[0:1].numpy().view(np.int32)[0]), int(self.send_r[0:1].numpy().view(np.int32)[0]))
         ids = np.where(own, self.ids, self.ids | GHOST)
         self.pos, self.vel, self.ids = self.pos[live], self.vel[live], ids[live]
         self.kept = (self.pos.copy(), self.vel.copy(), self.ids.copy(), int(own.sum()))
@@ -65,7 +70,8 @@ class NumpySlabBackend:
     def unpack(self, buf_l, max_l, buf_r, max_r):
         self.pos, self.vel, self.ids, self.n_owned = self.kept[0], self.kept[1], self.kept[2], self.kept[3]
         got = []
-        for buf, mx, has in ((buf_l, max_l, self.hl), (buf_r, max_r, self.hr)):
+        self.transit = [np.zeros((0, F), np.float32), np.zeros((0, F), np.float32)]
+        for side, (buf, mx, has) in enumerate(((buf_l, max_l, self.hl), (buf_r, max_r, self.hr))):
             if not has or buf is None:
                 got.append(0); continue
             cnt = int(buf[0:1].numpy().view(np.int32)[0])
@@ -76,6 +82,11 @@ class NumpySlabBackend:
                 ids = r[:, 7].copy().view(np.int32).astype(np.int64) & (GHOST - 1)
                 cx = cell_x(r[:, 0], self.G.gmin[0], self.G.cell, self.gnx)
                 own = self._own(cx)
+                # owner further along the direction of travel: hand the record on at the next exchange (k_slab_append)
+                onward = ~own & ((cx >= self.x1) & self.hr & (not self.wr) if side == 0 else (cx < self.x0) & self.hl & (not self.wl))
+                if onward.any():
+                    t = r[onward].copy(); t[:, 7] = ids[onward].astype(np.int32).view(np.float32)
+                    self.transit[1 - side] = np.concatenate([self.transit[1 - side], t])
                 self.pos = np.concatenate([self.pos, r[:, 0:3]]); self.vel = np.concatenate([self.vel, r[:, 4:7]])
                 self.ids = np.concatenate([self.ids, np.where(own, ids, ids | GHOST)])
                 self.n_owned += int(own.sum())

@@ -287,3 +287,37 @@ def test_slab_local_terrain_windows_equal_single_gpu(K):
     sed_k = sum(s.sediment_total_fx() for s in sims)
     assert sed_k == one.sediment_total_fx() and sed_k > 0
     assert sum(sh.own_total_fx() for sh in shares) + sed_k == total0, "sum(owned rows) + sum(carried sediment) is conserved exactly"
+
+
+def test_particles_crossing_more_than_one_slab_are_forwarded_not_lost():
+    """A particle that lands beyond its neighbour slab (the reference's contact response can eject particles that
+    fast) is handed on by the slab that received it, one exchange per extra slab (sphe_slab_transit): nothing is
+    lost, nothing is duplicated, and every other particle stays bit-equal to the single-handle run."""
+    m = product()
+    slabs = importlib.import_module("sph-erosion_b200.slabs")
+    pos, vel = scene()
+    box = (1.2, 0.3, 0.3)
+    params = dict(len=0.3, dt=0.004, g=(0.0, -9.82, 0.0))
+    # isolated, far above the fluid: +x at 150 units/s = 13 columns per step (a slab of K = 5 is 11 columns wide), and -x
+    fast = np.array([[-1.0, 0.15, 0.0], [-0.9, 0.2, 0.1], [1.0, 0.25, -0.1]], np.float32)
+    fvel = np.array([[150.0, 0, 0], [230.0, 0, 0], [-260.0, 0, 0]], np.float32)
+    pos = np.concatenate([pos, fast]); vel = np.concatenate([vel, fvel])
+    n = pos.shape[0]
+    one = _single(m, box, params, (3, 3), pos, vel)
+    sims, group = _peer_group(m, slabs, 5, box, params, (3, 3), pos, vel)
+    seen_transit = 0
+    for step in range(8):
+        one.Run()
+        group.step()
+        group.drain()
+        got = [s.slab_download() for s in sims]
+        ids = np.concatenate([g[0] for g in got])
+        in_transit = sum(t["to_left"] + t["to_right"] for t in (s.slab_transit() for s in sims))
+        seen_transit += in_transit
+        assert len(np.unique(ids)) == len(ids), "step %d: a particle is owned twice" % step
+        assert len(ids) + in_transit == n, "step %d: %d owned + %d in transit != %d" % (step, len(ids), in_transit, n)
+    assert seen_transit > 0 and sum(s.slab_transit()["forwarded"] for s in sims) > 0, "the scene must exercise forwarding"
+    assert np.array_equal(np.sort(ids), np.arange(n)), "after the fast particles hit the walls everybody is owned again"
+    o = np.argsort(ids)
+    p = np.concatenate([g[1] for g in got])[o]
+    assert np.array_equal(p[:n - 3], one.download("pos")[:n - 3]), "the rest of the scene is unaffected"
