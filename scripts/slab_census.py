@@ -40,7 +40,7 @@ if not multi:
     K = int(os.environ.get("K", "8"))
     sims = []; n_tot = 0; allpos = []; shares = None
     for r in range(K):
-        pos, ids, box, bounds = slabs.channel_block(n_axis, K, r, jitter)
+        pos, ids, box, bounds = slabs.channel_block(n_axis, K, r, jitter, layout=os.environ.get('LAYOUT', 'contiguous'))
         sim, b, cols = slabs.make_gpu_slab(pkg, 0, r, K, box, dict(len=box[1], dt=0.01, g=(0.0, gy, 0.0)), bounds, cap)
         sim.slab_upload(pos, np.zeros_like(pos), ids); sims.append(sim); n_tot += len(ids); allpos.append(pos)
         print("rank", r, "cols", cols[r])
@@ -71,14 +71,14 @@ else:
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local); dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    pos, ids, box, bounds = slabs.channel_block(n_axis, world, rank, False)
+    pos, ids, box, bounds = slabs.channel_block(n_axis, world, rank, False, layout=os.environ.get('LAYOUT', 'contiguous'))
     sim, b, cols = slabs.make_gpu_slab(pkg, local, rank, world, box, dict(len=box[1], dt=0.01, g=(0.0, gy, 0.0)), bounds, cap)
     sim.slab_upload(pos, np.zeros_like(pos), ids)
     drv = slabs.PeerSlabDriver(sim, rank, world, cap, int(n_axis ** 3 * 1.3) + 6 * cap)
     drv.connect(dist)
     prev = None
     if rank == 0:
-        allpos = np.concatenate([slabs.channel_block(n_axis, world, r, False)[0] for r in range(world)])
+        allpos = np.concatenate([slabs.channel_block(n_axis, world, r, False, layout=os.environ.get('LAYOUT', 'contiguous'))[0] for r in range(world)])
         prev = {"n": world * n_axis ** 3, "owner": np.repeat(np.arange(world), n_axis ** 3), "pos": allpos}
     bad = 0
     for s in range(1, steps + 1):

@@ -453,15 +453,24 @@ class LocalPeerGroup:
 
 
 # --------------------------------------------------------------------------- scenes
-def channel_block(n_axis, world, rank, jitter, spacing=0.025):
-    """Rank `rank`'s share of the weak-scaling scene: the scaled dam break (bench.scaled_dam_break)
-    repeated `world` times along x inside a box of half-extents (world*L, L, L), L = 0.02*n_axis.
+def channel_block(n_axis, world, rank, jitter, spacing=0.025, layout="tiled"):
+    """Rank `rank`'s share of the weak-scaling scene: `world` copies of the single-GPU scene (bench.scaled_dam_break:
+    a block of n_axis^3 particles at the left end of a box of half-extent L = 0.02*n_axis) side by side in a channel
+    of half-extents (world*L, L, L) without the walls in between, each block centred in its compartment, so every
+    rank sees the same collapse (the blocks spread into the gaps between them) and the per-GPU work really is
+    constant -- the compartment boundaries are symmetry planes, a slab neither gains nor loses particles on average.
+    layout = "contiguous": see below.
     Returns (pos, ids, box_half, boundaries_x) with global ids = lattice index."""
     L = 0.02 * n_axis
     Lx = L * world
-    ix = np.arange(rank * n_axis, (rank + 1) * n_axis)
     i = np.arange(n_axis)
-    x = (-Lx + ix * spacing).astype(np.float32)
+    # block r sits in the MIDDLE of the r-th box-sized compartment: the compartment boundaries (and the two end walls)
+    # are mirror planes of the initial state, so no compartment gains particles at the expense of another
+    x = (-Lx + rank * 2 * L + (L - 0.5 * (n_axis - 1) * spacing) + i * spacing).astype(np.float32)
+    if layout == "contiguous":
+        # ONE block `world` times as long at the left end of the channel (the single-GPU scene stretched along x): fluid
+        # on both sides of every slab boundary from the first step on, i.e. a full halo exchange every step
+        x = (-Lx + (rank * n_axis + i) * spacing).astype(np.float32)
     y = (-L / 4 + i * spacing).astype(np.float32)
     z = (-0.75 * L + i * spacing).astype(np.float32)
     pos = np.empty((x.size, y.size, z.size, 3), np.float32)
@@ -472,7 +481,9 @@ def channel_block(n_axis, world, rank, jitter, spacing=0.025):
         pos += rng.uniform(-0.2 * spacing, 0.2 * spacing, pos.shape).astype(np.float32)
     per = n_axis ** 3
     ids = (rank * per + np.arange(per)).astype(np.int32)
-    bounds = [-Lx + (r * n_axis - 0.5) * spacing for r in range(1, world)]
+    bounds = [-Lx + r * 2 * L - 0.5 * spacing for r in range(1, world)]
+    if layout == "contiguous":
+        bounds = [-Lx + (r * n_axis - 0.5) * spacing for r in range(1, world)]
     return pos, ids, (Lx, L, L), bounds
 
 
@@ -509,7 +520,11 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT, terrain=False):
     rank, world = dist.get_rank(), dist.get_world_size()
     local = torch.cuda.current_device()
     dev = torch.device("cuda", local)
-    pos, ids, box, bounds = channel_block(n_axis, world, rank, jitter)
+    # no settle phase (c2): one long block, so the timed steps carry a full halo from step one.  With a settle phase (c3)
+    # a long block compresses far beyond the single-GPU scene; tiled compartments keep the per-GPU work constant and
+    # the settle phase brings the fluid across every slab boundary before the timed steps.
+    layout = args.layout if args.layout != "auto" else ("tiled" if terrain else "contiguous")
+    pos, ids, box, bounds = channel_block(n_axis, world, rank, jitter, layout=layout)
     gy = scene_gravity(n_axis, args.gravity_unscaled)
     n_local = pos.shape[0]
     layer = int(n_axis * n_axis * (0.0457 * 1.001 / SPACING + 1))      # particles per cell layer
@@ -663,6 +678,8 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT, terrain=False):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": args.workload, "description": desc + " -- repeated %d x along x, one x-slab per GPU" % world,
+                       "layout": layout + (": one block %d x as long at the left end of a channel %d x as long" % (world, world) if layout == "contiguous"
+                                           else ": %d blocks, each centred in its own box-sized compartment of the channel" % world),
                        "particles": n_total, "particles_per_gpu": n_local, "particles_conserved": bool(n_total + int(owned[2].item()) == n_local * world),
                        "records_forwarded_beyond_the_neighbour": int(owned[3].item()), "h": 0.0457, "spacing": SPACING, "dt": 0.01,
                        "box_half_extents": list(box), "gravity_y": gy, "slab_columns": cols,
