@@ -601,6 +601,168 @@ __global__ void __launch_bounds__(NLIST_THREADS) k_density_list(int n_hi, const 
     }
 }
 
+// ------------------------------------------------------------------ variant 7: FOUR targets per thread
+// ncu on k_density_list (profiles/r01_ncu_density_list_c2.txt): the L1 data pipe is the binding resource (lsu
+// wavefronts 80 % of peak, issue active 55 %): every candidate costs one divergent LDG.128 (~8 distinct lines per
+// warp request) that serves only two targets.  Here one candidate load serves FOUR consecutive particles (two
+// packed pairs): the union z-range of 4 neighbours in the sorted order is almost always the same 3-4 cells as for
+// 2, so the gathers per target halve while the packed math per target stays the same.  Each thread keeps TWO
+// pair lists (the format k_force_list reads), 64 threads per CTA = the same 33 KB of shared memory per CTA.
+constexpr int QUAD_THREADS = 64;
+
+template <bool PF>
+__global__ void __launch_bounds__(QUAD_THREADS) k_density_quad(int n_hi, const int* __restrict__ n_dev, int npairs_pad, const float4* __restrict__ posq,
+                                                               float4* __restrict__ posq_q, float4* __restrict__ velv,
+                                                               const uint32_t* __restrict__ cell_sorted,
+                                                               const int* __restrict__ cell_start, GridP G, StepC C,
+                                                               float* __restrict__ rho, int* __restrict__ nlist,
+                                                               int2* __restrict__ ncount) {
+    const int n = n_dev ? __ldg(n_dev) : n_hi;
+    __shared__ int list[2 * (NLIST_CAP + 1) * QUAD_THREADS];   // [pair of the quad][entry][thread], +1: trash slot
+    const int tid = threadIdx.x;
+    const int q = blockIdx.x * blockDim.x + tid;
+    const float FAR = 1.0e18f;
+    // targets: pair 0 = (i[0], i[1]), pair 1 = (i[2], i[3]); a missing partner repeats its pair's first target
+    int i[4];
+    const bool live0 = 4 * q < n, live1 = 4 * q + 2 < n;
+    i[0] = live0 ? 4 * q : 0;
+    i[1] = (i[0] + 1 < n) ? i[0] + 1 : i[0];
+    i[2] = live1 ? 4 * q + 2 : i[0];
+    i[3] = (live1 && 4 * q + 3 < n) ? 4 * q + 3 : i[2];
+    float4 p[4];
+    uint32_t col[4];
+    int cz[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        p[j] = posq[i[j]];
+        const uint32_t c = cell_sorted[i[j]];
+        col[j] = c / (uint32_t)G.nz;
+        cz[j] = (int)(c - col[j] * (uint32_t)G.nz);
+    }
+    // the sorted order makes cz non-decreasing inside a column
+    const bool quad = live1 && col[0] == col[3] && col[0] == col[1] && col[0] == col[2] && (cz[3] - cz[0] <= 3);
+    const bool m0 = (i[1] != i[0]) && col[0] == col[1] && (cz[1] - cz[0] <= 3);
+    const bool m1 = (i[3] != i[2]) && col[2] == col[3] && (cz[3] - cz[2] <= 3);
+    const int np0 = !live0 ? 0 : ((m0 || i[1] == i[0]) ? 1 : 2);
+    const int np1 = !live1 ? 0 : ((m1 || i[3] == i[2]) ? 1 : 2);
+    const int nwalk = quad ? 1 : np0 + np1;
+
+    float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+    int* const l0 = list + tid;
+    int* const l1 = list + (NLIST_CAP + 1) * QUAD_THREADS + tid;
+    int off0 = 0, off1 = 0;      // slot * QUAD_THREADS
+    int seg0 = -1, seg1 = -1;    // start of the second segment of a split pair
+#pragma unroll 1
+    for (int w = 0; w < nwalk; w++) {
+        // which targets take part in this walk
+        bool u[4];
+        int lo, hi;              // targets whose cells bound the z-range
+        if (quad) { u[0] = u[1] = u[2] = u[3] = true; lo = 0; hi = 3; }
+        else if (w < np0) {
+            u[0] = m0 || w == 0; u[1] = m0 || w == 1; u[2] = u[3] = false;
+            lo = (w == 0) ? 0 : 1; hi = m0 ? 1 : lo;
+            if (w == 1) seg0 = off0;
+        } else {
+            const int v = w - np0;
+            u[0] = u[1] = false; u[2] = m1 || v == 0; u[3] = m1 || v == 1;
+            lo = (v == 0) ? 2 : 3; hi = m1 ? 3 : lo;
+            if (v == 1) seg1 = off1;
+        }
+        const float2 X0 = make_float2(u[0] ? p[0].x : FAR, u[1] ? p[1].x : FAR), X1 = make_float2(u[2] ? p[2].x : FAR, u[3] ? p[3].x : FAR);
+        const float2 Y0 = make_float2(u[0] ? p[0].y : FAR, u[1] ? p[1].y : FAR), Y1 = make_float2(u[2] ? p[2].y : FAR, u[3] ? p[3].y : FAR);
+        const float2 Z0 = make_float2(u[0] ? p[0].z : FAR, u[1] ? p[1].z : FAR), Z1 = make_float2(u[2] ? p[2].z : FAR, u[3] ? p[3].z : FAR);
+        const uint32_t cc = lo == 0 ? col[0] : (lo == 1 ? col[1] : (lo == 2 ? col[2] : col[3]));
+        const int czlo = lo == 0 ? cz[0] : (lo == 1 ? cz[1] : (lo == 2 ? cz[2] : cz[3]));
+        const int czhi = hi == 0 ? cz[0] : (hi == 1 ? cz[1] : (hi == 2 ? cz[2] : cz[3]));
+        const int cy = (int)(cc % (uint32_t)G.ny), cx = (int)(cc / (uint32_t)G.ny);
+        const int z0 = czlo > 0 ? czlo - 1 : 0, z1 = czhi < G.nz - 1 ? czhi + 1 : czhi;
+        auto test = [&](const int k, const float4 pj) {
+            const float2 nx = make_float2(-pj.x, -pj.x), ny = make_float2(-pj.y, -pj.y), nz = make_float2(-pj.z, -pj.z);
+            float2 dx = __fadd2_rn(X0, nx), dy = __fadd2_rn(Y0, ny), dz = __fadd2_rn(Z0, nz);
+            float2 ex = __fadd2_rn(X1, nx), ey = __fadd2_rn(Y1, ny), ez = __fadd2_rn(Z1, nz);
+            float2 d2 = __fmul2_rn(dx, dx), e2 = __fmul2_rn(ex, ex);
+            d2 = __ffma2_rn(dy, dy, d2); e2 = __ffma2_rn(ey, ey, e2);
+            d2 = __ffma2_rn(dz, dz, d2); e2 = __ffma2_rn(ez, ez, e2);
+            float2 wa = __fadd2_rn(make_float2(C.hh, C.hh), make_float2(-d2.x, -d2.y));
+            float2 wb = __fadd2_rn(make_float2(C.hh, C.hh), make_float2(-e2.x, -e2.y));
+            // branch-free append to both pair lists: store at the current slot, advance only on a pass
+            l0[min(off0, NLIST_CAP * QUAD_THREADS)] = k;
+            l1[min(off1, NLIST_CAP * QUAD_THREADS)] = k;
+            off0 += (fmaxf(wa.x, wa.y) >= 0.f) ? QUAD_THREADS : 0;
+            off1 += (fmaxf(wb.x, wb.y) >= 0.f) ? QUAD_THREADS : 0;
+            wa.x = fmaxf(wa.x, 0.f); wa.y = fmaxf(wa.y, 0.f);
+            wb.x = fmaxf(wb.x, 0.f); wb.y = fmaxf(wb.y, 0.f);
+            acc0 = __ffma2_rn(__fmul2_rn(wa, wa), wa, acc0);
+            acc1 = __ffma2_rn(__fmul2_rn(wb, wb), wb, acc1);
+        };
+        auto bounds = [&](const int r, int& s, int& e) {
+            int x = cx + r / 3 - 1, y = cy + r % 3 - 1;
+            bool ok = r < 9 && x >= 0 && x < G.nx && y >= 0 && y < G.ny;
+            int base = ok ? (x * G.ny + y) * G.nz : 0;
+            s = __ldg(&cell_start[base + z0]);
+            e = ok ? __ldg(&cell_start[base + z1 + 1]) : s;
+        };
+        if (!PF) {
+#pragma unroll 1
+            for (int r = 0; r < 9; r++) {
+                int s, e;
+                bounds(r, s, e);
+#pragma unroll 4
+                for (int k = s; k < e; k++) test(k, __ldg(&posq[k]));
+            }
+        } else {
+            int s, e, sn, en;
+            bounds(0, s, e);
+#pragma unroll 1
+            for (int r = 0; r < 9; r++) {
+                bounds(r + 1, sn, en);
+                int k = s;
+                if (k + 4 <= e) {
+                    float4 q0 = __ldg(&posq[k]), q1 = __ldg(&posq[k + 1]), q2 = __ldg(&posq[k + 2]), q3 = __ldg(&posq[k + 3]);
+#pragma unroll 1
+                    for (; k + 8 <= e; k += 4) {
+                        const float4 n0 = __ldg(&posq[k + 4]), n1 = __ldg(&posq[k + 5]), n2 = __ldg(&posq[k + 6]), n3 = __ldg(&posq[k + 7]);
+                        test(k, q0); test(k + 1, q1); test(k + 2, q2); test(k + 3, q3);
+                        q0 = n0; q1 = n1; q2 = n2; q3 = n3;
+                    }
+                    test(k, q0); test(k + 1, q1); test(k + 2, q2); test(k + 3, q3);
+                    k += 4;
+                }
+#pragma unroll 1
+                for (; k < e; k++) test(k, __ldg(&posq[k]));
+                s = sn; e = en;
+            }
+        }
+    }
+    // lists: pair 2q and 2q+1 sit next to each other in every entry row -> one 8-byte store per entry per thread
+    const int cnt0 = off0 / QUAD_THREADS, cnt1 = off1 / QUAD_THREADS;
+    const bool fit0 = cnt0 <= NLIST_CAP, fit1 = cnt1 <= NLIST_CAP;
+    if (seg0 < 0) seg0 = off0;
+    if (seg1 < 0) seg1 = off1;
+    const int2 c0 = fit0 ? make_int2(seg0 / QUAD_THREADS, cnt0) : make_int2(-1, -1);
+    const int2 c1 = fit1 ? make_int2(seg1 / QUAD_THREADS, cnt1) : make_int2(-1, -1);
+    if (live0) ncount[2 * q] = c0;
+    if (live1) ncount[2 * q + 1] = c1;
+    {
+        const int rows = max(fit0 ? cnt0 : 0, fit1 ? cnt1 : 0);
+        int2* dst = reinterpret_cast<int2*>(nlist + 2 * q);
+        const size_t stride = (size_t)npairs_pad / 2;   // in int2
+#pragma unroll 4
+        for (int e = 0; e < rows; e++) dst[e * stride] = make_int2(l0[min(e, NLIST_CAP) * QUAD_THREADS], l1[min(e, NLIST_CAP) * QUAD_THREADS]);
+    }
+    const float racc[4] = {acc0.x, acc0.y, acc1.x, acc1.y};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const bool first = (j == 0 && live0) || (j == 1 && live0 && i[1] != i[0]) || (j == 2 && live1) || (j == 3 && live1 && i[3] != i[2]);
+        if (!first) continue;
+        const float r = racc[j] * C.densK;
+        const float P = C.k * (r - C.p0);
+        rho[i[j]] = r;
+        posq_q[i[j]] = make_float4(p[j].x, p[j].y, p[j].z, P / (r * r));
+        velv[i[j]].w = C.mass / r;
+    }
+}
+
 // one 256-bit read-only gather of an interleaved particle record
 __device__ __forceinline__ void ldg_rec(const float4* __restrict__ rec, int k, float4& p, float4& v) {
     asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -1134,6 +1296,12 @@ void launch_density(cudaStream_t st, int variant, int n, const int* n_dev, const
     if (variant == 52) return launch_density_s<2>(st, n, n_dev, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount);
     if (variant == 54) return launch_density_s<4>(st, n, n_dev, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount);
     if (variant == 58) return launch_density_s<8>(st, n, n_dev, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount);
+    if (variant == 7 || variant == 9) {
+        int pp = nlist_pairs_pad(n);
+        if (variant == 9) k_density_quad<true><<<pp / 2 / QUAD_THREADS, QUAD_THREADS, 0, st>>>(n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount);
+        else k_density_quad<false><<<pp / 2 / QUAD_THREADS, QUAD_THREADS, 0, st>>>(n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount);
+        return;
+    }
     if (variant == 3 || variant == 4 || variant == 6) {
         int pp = nlist_pairs_pad(n);
         if (variant == 4) k_density_list<true, false><<<pp / NLIST_THREADS, NLIST_THREADS, 0, st>>>(n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount);
@@ -1156,6 +1324,7 @@ void launch_force(cudaStream_t st, int variant, int n, const int* n_dev, const f
     if (variant == 52) return launch_force_s<2>(st, n, n_dev, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, posq_out, velv_out, diag, nlist, ncount);
     if (variant == 54) return launch_force_s<4>(st, n, n_dev, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, posq_out, velv_out, diag, nlist, ncount);
     if (variant == 58) return launch_force_s<8>(st, n, n_dev, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, posq_out, velv_out, diag, nlist, ncount);
+    if (variant == 7 || variant == 9) variant = 3;   // the quad density pass writes the same pair lists
     if (variant == 3 || variant == 4 || variant == 6) {
         int pp = nlist_pairs_pad(n);
         dim3 g(pp / NLIST_THREADS), b(NLIST_THREADS);

@@ -31,8 +31,8 @@ def close(got, want, what, rtol=RTOL):
 VARIANT = {"density": 0, "force": 0}
 
 
-@pytest.fixture(autouse=True, params=[(0, 0), (1, 1), (3, 3), (4, 4), (6, 6), (54, 54)],
-                ids=["tpp", "pair", "list", "list256", "listpf", "slist4"])
+@pytest.fixture(autouse=True, params=[(0, 0), (1, 1), (3, 3), (4, 4), (6, 6), (54, 54), (7, 7), (9, 9)],
+                ids=["tpp", "pair", "list", "list256", "listpf", "slist4", "quad", "quadpf"])
 def kernel_variant(request):
     """Every test runs against both kernel families: thread-per-particle and packed-pair."""
     VARIANT["density"], VARIANT["force"] = request.param
