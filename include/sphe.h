@@ -292,6 +292,15 @@ int sphe_set_stream(sphe_sim* s, void* cuda_stream); /* run on a caller-provided
 /* Kernel-variant selector for the two neighbour passes (tuning / ncu A-B runs).  3 = neighbour lists
  * (default, must be set for both passes), 1 = packed pair, 0 = thread per particle. */
 int sphe_set_variant(sphe_sim* s, int density_variant, int force_variant);
+/* Entries per neighbour list of the default (list) kernels.  64 covers the reference's regime (~25 neighbours; a
+ * pair whose list overflows is handled by a direct walk in the force pass, still exact).  128 / 256 keep denser
+ * scenes (60-120 neighbours) on the list path at the price of shared memory, i.e. occupancy, in the density pass:
+ * measured on B200 that pays only when most pairs overflow (62 neighbours: 1.25 -> 0.89 ms per 1M-particle step
+ * with 128 entries; 114 neighbours: 1.91 -> 1.59 ms with 256; 28 neighbours: 64 is fastest).  So the default is
+ * to START at 64 and double when more than half of the pairs overflowed in a recent step (entries = 0 selects
+ * this policy again after a fixed capacity was set). */
+int sphe_nlist_capacity(sphe_sim* s);
+int sphe_set_nlist_capacity(sphe_sim* s, int entries);
 
 #ifdef __cplusplus
 }

@@ -22,6 +22,7 @@ for n_axis in axes:
             sim = pkg.FluidSystemSPH()
             sim.params.len = L; sim.params.h = h; sim.params.g[1] = bench.scene_gravity(n_axis); sim.SetDeltaTime(0.0)  # dt = 0: static scene, every step identical
             sim.set_variant(dv, fv)
+            if "CAP" in os.environ: sim.set_nlist_capacity(int(os.environ["CAP"]))
             sim.upload_state(pos, np.zeros_like(pos))
             sim.set_l2_flush(256 << 20)
             sim.timed_steps(3, per_kernel=False)
@@ -31,7 +32,7 @@ for n_axis in axes:
             cells = gi.dim[0] * gi.dim[1] * gi.dim[2]
             cand = 27.0 * n / max(cells * (L * 2) ** 3 / ((gi.dim[0] * gi.cell) * (gi.dim[1] * gi.cell) * (gi.dim[2] * gi.cell)), 1)  # ~ candidates per particle per pass in the filled region
             t = {k: v / steps for k, v in pk.items()}
-            line = {"particles": n, "h": h, "mean_neighbours": nb, "variant": [dv, fv], "ms_per_step": ms / steps,
+            line = {"particles": n, "h": h, "mean_neighbours": nb, "variant": [dv, fv], "list_capacity": sim.nlist_capacity(), "ms_per_step": ms / steps,
                     "particle_updates_per_s": n / (ms / steps * 1e-3), "per_kernel_ms": t,
                     "hbm_GBps_algorithmic": {k: bench.ALGO_BYTES[k] * n / (t[k] * 1e-3) / 1e9 for k in ("hash", "scatter", "reorder", "density", "force") if t[k] > 0},
                     "hbm_frac_step": 234 * n / (ms / steps * 1e-3) / 1e9 / peak}

@@ -100,6 +100,8 @@ SYMBOLS = {
     "sphe_set_sediment_fx": (_i, [_vp, _vp]),
     "sphe_kernel_timing": (_i, [_vp, _i]),
     "sphe_kernel_times": (_i, [_vp, C.POINTER(_f), C.POINTER(_i)]),
+    "sphe_nlist_capacity": (_i, [_vp]),
+    "sphe_set_nlist_capacity": (_i, [_vp, _i]),
     "sphe_slab_configure": (_i, [_vp, _i, _i, _i, _i]),
     "sphe_slab_ring": (_i, [_vp, _i, _i, _i]),
     "sphe_slab_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),

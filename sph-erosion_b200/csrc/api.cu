@@ -84,6 +84,12 @@ struct sphe_sim {
     int* nlist = nullptr;   // variant 3: [nlist_cap][pairs_pad] neighbour indices
     int2* ncount = nullptr;
     size_t nlist_pairs = 0;
+    int nlist_capacity = 64;       // entries per pair list: 64 -> 128 -> 256 as the overflow counter demands
+    int nlist_alloc_cap = 0;
+    int overflow_cooldown = 0;
+    bool nlist_auto = true;        // grow the lists when more than half of the pairs overflow (measured: pays only then)
+    int* d_overflow = nullptr;     // pairs whose list overflowed in the current step
+    int* h_overflow = nullptr;     // pinned: [0] the count of a recent step (copied without a sync), [1] pairs of that step
 
     long long ncells = 0, ncells_cap = 0;
     int *count = nullptr, *cell_start = nullptr, *cursor = nullptr, *tile_sum = nullptr;
@@ -348,16 +354,34 @@ static int step_device(sphe_sim* s, sphe_terrain* t, int terrain_phases = 7) {
     if (s->variant_density >= 3 || s->variant_force >= 3) {
         if (s->variant_density != s->variant_force) return fail(SPHE_ERR_ARG, "variants 3/4 (neighbour lists) must be selected for both passes");
         // capacity for every list variant: S sub-lists of slist_entries(S) entries per pair, S <= 8 -> <= 96 ints per pair
+        if (!s->d_overflow) {
+            CU(cudaMalloc(&s->d_overflow, sizeof(int))); CU(cudaMemsetAsync(s->d_overflow, 0, sizeof(int), s->st));
+            CU(cudaMallocHost(&s->h_overflow, 2 * sizeof(int))); s->h_overflow[0] = 0; s->h_overflow[1] = 1;
+        }
+        // a recent step's overflow count (copied back asynchronously, so possibly a step or two old): more than 1 % of the
+        // pairs fell back to the direct walk -> longer lists from now on
+        if (s->overflow_cooldown > 0) s->overflow_cooldown--;
+        else if (s->nlist_auto && s->variant_density == 3 && s->nlist_capacity < 256 && s->h_overflow[0] * 2LL > s->h_overflow[1]) {
+            s->nlist_capacity *= 2;
+            s->overflow_cooldown = 4;   // counts still in flight belong to the old capacity
+        }
         size_t pp = (size_t)nlist_pairs_pad(s->cap) + 128;
-        if (pp > s->nlist_pairs) {
-            TRY(grow(&s->nlist, 0, pp * 96, s->st, false));
+        const int entries = std::max(96, s->nlist_capacity);
+        if (pp > s->nlist_pairs || entries > s->nlist_alloc_cap) {
+            pp = std::max(pp, s->nlist_pairs);
+            TRY(grow(&s->nlist, 0, pp * (size_t)entries, s->st, false));
             TRY(grow(&s->ncount, 0, pp * 8, s->st, false));
-            s->nlist_pairs = pp;
+            s->nlist_pairs = pp; s->nlist_alloc_cap = entries;
         }
     }
     { Scope k(s, SPHE_K_DENSITY);
       launch_density(s->st, s->variant_density, n, nd, s->posB, s->posC, s->velB, s->cell_sorted, s->cell_start, s->G, C, s->rho,
-                     s->nlist, s->ncount); }
+                     s->nlist, s->ncount, s->nlist_capacity, s->d_overflow);
+      if (s->variant_density == 3 && s->d_overflow) {
+          s->h_overflow[1] = std::max((n + 1) / 2, 1);
+          CU(cudaMemcpyAsync(s->h_overflow, s->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, s->st));
+          CU(cudaMemsetAsync(s->d_overflow, 0, sizeof(int), s->st));
+      } }
     { Scope k(s, SPHE_K_FORCE);
       launch_force(s->st, s->variant_force, n, nd, s->posC, s->velB, s->rho, s->idsB, s->cell_sorted, s->cell_start, s->G, C,
                    s->posA, s->velA, s->diag ? &s->D : nullptr, s->nlist, s->ncount); }
@@ -450,6 +474,7 @@ void sphe_destroy(sphe_sim* s) {
         if (s->mbox) cudaFree(s->mbox);
         if (s->slab_host) cudaFreeHost(s->slab_host);
         cudaFree(s->transit[0]); cudaFree(s->transit[1]); cudaFree(s->transit_n);
+        cudaFree(s->d_overflow); if (s->h_overflow) cudaFreeHost(s->h_overflow);
         if (s->d_n) cudaFree(s->d_n);
         for (auto& e : s->slab_ev) if (e) cudaEventDestroy(e);
         if (s->own_stream && s->st) cudaStreamDestroy(s->st);
@@ -675,6 +700,16 @@ int sphe_set_diagnostics(sphe_sim* s, int on) {
     if (!s) return fail(SPHE_ERR_ARG, "NULL handle");
     s->diag = on != 0;
     if (s->diag && s->ready) TRY(reserve_diag(s));
+    return SPHE_OK;
+}
+
+int sphe_nlist_capacity(sphe_sim* s) { return s ? s->nlist_capacity : 0; }
+
+int sphe_set_nlist_capacity(sphe_sim* s, int entries) {
+    if (!s) return fail(SPHE_ERR_ARG, "NULL handle");
+    if (entries == 0) { s->nlist_auto = true; return SPHE_OK; }     // grow on demand: when more than half of the pairs overflow
+    if (entries != 64 && entries != 128 && entries != 256) return fail(SPHE_ERR_ARG, "list capacity must be 64, 128, 256 or 0 (grow on demand)");
+    s->nlist_auto = false; s->nlist_capacity = entries;
     return SPHE_OK;
 }
 

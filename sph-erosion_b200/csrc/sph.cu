@@ -474,15 +474,26 @@ constexpr int NLIST_THREADS = 128;
 // stall samples sit on the first use of the gathered positions and 9 % on the run bounds (cell_start) -- the
 // kernel waits on its own loads.  Here the next group of four candidates and the next run's bounds are
 // already in flight while the current group is processed.
-template <bool REC, bool PF>
-__global__ void __launch_bounds__(NLIST_THREADS) k_density_list(int n_hi, const int* __restrict__ n_dev, int npairs_pad, const float4* __restrict__ posq,
-                                                                float4* __restrict__ posq_q, float4* __restrict__ velv,
-                                                                const uint32_t* __restrict__ cell_sorted,
-                                                                const int* __restrict__ cell_start, GridP G, StepC C,
-                                                                float* __restrict__ rho, int* __restrict__ nlist,
-                                                                int2* __restrict__ ncount) {
+// CAP / THREADS: list capacity per pair and CTA size.  64 entries are plenty at the reference's ~25 neighbours; scenes with
+// 60-120 neighbours per particle (BASELINE configs[4]) overflow them and fall back to the direct walk in the force
+// pass, which costs 2-4x.  The host raises CAP to 128 / 256 when the overflow counter says so (api.cu step_device).
+// The list lives in dynamic shared memory: (CAP + 1) * THREADS ints = 33 / 66 / 66 KB.
+template <bool REC, bool PF, int CAP, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_density_list(int n_hi, const int* __restrict__ n_dev, int npairs_pad, const float4* __restrict__ posq,
+                                                          float4* __restrict__ posq_q, float4* __restrict__ velv,
+                                                          const uint32_t* __restrict__ cell_sorted,
+                                                          const int* __restrict__ cell_start, GridP G, StepC C,
+                                                          float* __restrict__ rho, int* __restrict__ nlist,
+                                                          int2* __restrict__ ncount, int* __restrict__ overflow) {
+    constexpr int NLIST_CAP = CAP, NLIST_THREADS = THREADS;   // shadow the file-scope defaults
     const int n = n_dev ? __ldg(n_dev) : n_hi;  // exact count from the device in slab mode, else the launch bound
-    __shared__ int list[(NLIST_CAP + 1) * NLIST_THREADS];  // +1: trash slot for saturated appends
+    // (CAP + 1) * THREADS ints, +1: trash slot for saturated appends.  Static when it fits the 48 KB static limit:
+    // with a dynamic array ptxas does not know the CTAs/SM bound and settles for 48 registers (serialised gathers,
+    // measured 0.23 ms instead of 0.15 ms at 1M particles)
+    constexpr bool STATIC_LIST = (CAP + 1) * THREADS * sizeof(int) <= 48 * 1024;
+    __shared__ int list_static[STATIC_LIST ? (CAP + 1) * THREADS : 1];
+    extern __shared__ int list_dynamic[];
+    int* const list = STATIC_LIST ? list_static : list_dynamic;
     const int tid = threadIdx.x;
     const int t = blockIdx.x * blockDim.x + tid;
     int a = 2 * t;
@@ -570,6 +581,7 @@ __global__ void __launch_bounds__(NLIST_THREADS) k_density_list(int n_hi, const 
     const int cnt = off / NLIST_THREADS;
     const bool fits = cnt <= NLIST_CAP;
     if (live) ncount[t] = fits ? make_int2(off0 / NLIST_THREADS, cnt) : make_int2(-1, -1);
+    if (live && !fits) atomicAdd(overflow, 1);
     if (fits) {
         int* dst = nlist + t;
 #pragma unroll 4
@@ -1288,9 +1300,21 @@ static inline int nblk(int n, int b) { return (n + b - 1) / b; }
 int nlist_cap() { return NLIST_CAP; }
 int nlist_pairs_pad(int n) { return (((n + 1) / 2) + 127) & ~127; }
 
+template <bool REC, bool PF, int CAP, int THREADS>
+static void launch_density_list(cudaStream_t st, int n, const int* n_dev, int pp, const float4* posq, float4* posq_q, float4* velv,
+                                const uint32_t* cell_sorted, const int* cell_start, const GridP& G, const StepC& C, float* rho,
+                                int* nlist, int2* ncount, int* overflow) {
+    int smem = (CAP + 1) * THREADS * (int)sizeof(int);
+    if (smem <= 48 * 1024) smem = 0;   // static in the kernel
+    auto kern = k_density_list<REC, PF, CAP, THREADS>;
+    static bool configured = false;   // per instantiation
+    if (!configured && smem > 48 * 1024) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); configured = true; }
+    kern<<<pp / THREADS, THREADS, smem, st>>>(n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount, overflow);
+}
+
 void launch_density(cudaStream_t st, int variant, int n, const int* n_dev, const float4* posq, float4* posq_q, float4* velv,
                     const uint32_t* cell_sorted, const int* cell_start, const GridP& G, const StepC& C, float* rho,
-                    int* nlist, int2* ncount) {
+                    int* nlist, int2* ncount, int cap, int* overflow) {
     if (n <= 0) return;
     int pairs = (n + 1) / 2;
     if (variant == 52) return launch_density_s<2>(st, n, n_dev, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount);
@@ -1304,9 +1328,13 @@ void launch_density(cudaStream_t st, int variant, int n, const int* n_dev, const
     }
     if (variant == 3 || variant == 4 || variant == 6) {
         int pp = nlist_pairs_pad(n);
-        if (variant == 4) k_density_list<true, false><<<pp / NLIST_THREADS, NLIST_THREADS, 0, st>>>(n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount);
-        else if (variant == 6) k_density_list<false, true><<<pp / NLIST_THREADS, NLIST_THREADS, 0, st>>>(n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount);
-        else k_density_list<false, false><<<pp / NLIST_THREADS, NLIST_THREADS, 0, st>>>(n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount);
+#define SPHE_DL(RC, PFv, CP, TH) launch_density_list<RC, PFv, CP, TH>(st, n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount, overflow)
+        if (variant == 4) SPHE_DL(true, false, 64, 128);
+        else if (variant == 6) SPHE_DL(false, true, 64, 128);
+        else if (cap > 128) SPHE_DL(false, true, 256, 64);    // explicit prefetch: ptxas serialises the gathers of the
+        else if (cap > 64) SPHE_DL(false, true, 128, 128);    // dynamic-shared-memory instantiations otherwise (48 registers)
+        else SPHE_DL(false, false, 64, 128);
+#undef SPHE_DL
         return;
     }
     if (variant == 1) k_density_pair<1><<<nblk(pairs, 128), 128, 0, st>>>(n, n_dev, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho);

@@ -137,6 +137,12 @@ class FluidSystemSPH:
         return dict(zip(capi.K_NAMES, [float(x) for x in mk])), nl.value
 
     # ---- multi-GPU x-slabs (include/sphe.h "multi-GPU x-slabs")
+    def nlist_capacity(self):
+        return int(self._L.sphe_nlist_capacity(self._h))
+
+    def set_nlist_capacity(self, entries):
+        capi.check(self._L.sphe_set_nlist_capacity(self._h, int(entries)))
+
     def slab_configure(self, x0, x1, has_left, has_right):
         capi.check(self._L.sphe_slab_configure(self._h, int(x0), int(x1), int(bool(has_left)), int(bool(has_right))))
 

@@ -252,3 +252,31 @@ def test_million_particle_properties():
     s.Run()
     c2, o2, cs2 = port.bin_particles(G, before)
     assert np.array_equal(s.debug_sorted_order(), o2)
+
+
+def test_dense_neighbourhoods_grow_the_lists():
+    """BASELINE configs[4]: smoothing radius 0.0765 on the 0.025 lattice = ~115 neighbours per particle.  The 64-entry
+    neighbour lists overflow; results are correct anyway (the force pass falls back to the direct walk), and the list
+    variant doubles its capacity on its own (sphe_nlist_capacity) so the later steps run from lists again.  Every step
+    starts from the oracle's state: each comparison is a one-step comparison."""
+    n, length = 16 ** 3, 0.45
+    P = port.default_params(dt=0.002, len=length, h=0.0765)
+    S = port.State(port.lattice(n))
+    s = make_sim(P)
+    G = None
+    caps = []
+    for step in range(14):
+        s.upload_state(S.pos, S.vel)
+        before = S.pos.copy()
+        s.Run()
+        caps.append(s.nlist_capacity())
+        if G is None:
+            G = oracle_grid_like(s, P)
+        port.step_grid(P, G, S)
+        check_fields(s, S, "step %d " % step)
+        if step in (0, 13):
+            check_binning(s, P, before)
+    if VARIANT["density"] == 3:
+        assert caps[0] == 64 and caps[-1] == 256, caps
+    else:
+        assert set(caps) == {64}
