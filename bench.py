@@ -382,7 +382,9 @@ def run_gpu_arm(args):
                        "dt": 0.01, "box_half_extent": L, "gravity_y": gy,
                        "gravity_note": "g scaled by 10/n_axis: dynamic similarity with the reference default scene (see bench.scene_gravity)" if not args.gravity_unscaled else "unscaled g",
                        "mean_neighbours_after_run": (ns_total / n) if ns_total else None, "l2": "flushed between timed steps (%d MiB memset, outside the event brackets)" % (flush_bytes >> 20),
-                       "density_variant": args.density_variant, "force_variant": args.force_variant, **tinfo},
+                       "density_variant": args.density_variant, "force_variant": args.force_variant,
+                       "neighbour_list_rows": sim.nlist_capacity(), "neighbour_list_smem_entries": sim.nlist_smem_entries(),
+                       "list_overflow_pairs_last_step": sim.nlist_overflowed(), **tinfo},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cb}
     emit(line)
 
@@ -410,11 +412,11 @@ def main():
     quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=100, help="timed steps (SURVEY.md 8d C2: 100 steps after 10 warm-up)")
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--density-variant", type=int, default=3)
+    ap.add_argument("--density-variant", type=int, default=6, help="6 = neighbour lists with a software-prefetched candidate stream (default); 3 = plain lists; 10 = 16-bit entries; 1 = packed pair; 0 = thread per particle")
     ap.add_argument("--force-variant", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],

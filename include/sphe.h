@@ -292,15 +292,17 @@ int sphe_set_stream(sphe_sim* s, void* cuda_stream); /* run on a caller-provided
 /* Kernel-variant selector for the two neighbour passes (tuning / ncu A-B runs).  3 = neighbour lists
  * (default, must be set for both passes), 1 = packed pair, 0 = thread per particle. */
 int sphe_set_variant(sphe_sim* s, int density_variant, int force_variant);
-/* Entries per neighbour list of the default (list) kernels.  64 covers the reference's regime (~25 neighbours; a
- * pair whose list overflows is handled by a direct walk in the force pass, still exact).  128 / 256 keep denser
- * scenes (60-120 neighbours) on the list path at the price of shared memory, i.e. occupancy, in the density pass:
- * measured on B200 that pays only when most pairs overflow (62 neighbours: 1.25 -> 0.89 ms per 1M-particle step
- * with 128 entries; 114 neighbours: 1.91 -> 1.59 ms with 256; 28 neighbours: 64 is fastest).  So the default is
- * to START at 64 and double when more than half of the pairs overflowed in a recent step (entries = 0 selects
- * this policy again after a fixed capacity was set). */
+/* Sizing of the neighbour lists of the default (list) kernels; all of it is automatic, these are for tests/tuning.
+ * A list has `sphe_nlist_capacity` rows per particle pair in HBM (128, doubled up to 512 as soon as 0.1 % of the
+ * pairs need more: a pair beyond its rows is handled by a direct walk in the force pass -- still exact, but ~10x
+ * slower and it stalls its warp).  The density pass stages the first `sphe_nlist_smem_entries` entries in shared
+ * memory (64: 6 CTAs/SM) and writes longer lists straight to their rows (a saturated run is walked twice);
+ * when most pairs spill (60-120 neighbours) it switches to 128 / 256 staged entries, and back.
+ * sphe_set_nlist_capacity(64|128|256) pins the staged entries, 0 returns to the automatic choice. */
 int sphe_nlist_capacity(sphe_sim* s);
+int sphe_nlist_smem_entries(sphe_sim* s);
 int sphe_set_nlist_capacity(sphe_sim* s, int entries);
+int sphe_nlist_overflowed(sphe_sim* s);   /* particle pairs whose list overflowed in a recent step (read back without a sync) */
 
 #ifdef __cplusplus
 }

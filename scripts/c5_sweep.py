@@ -32,7 +32,7 @@ for n_axis in axes:
             cells = gi.dim[0] * gi.dim[1] * gi.dim[2]
             cand = 27.0 * n / max(cells * (L * 2) ** 3 / ((gi.dim[0] * gi.cell) * (gi.dim[1] * gi.cell) * (gi.dim[2] * gi.cell)), 1)  # ~ candidates per particle per pass in the filled region
             t = {k: v / steps for k, v in pk.items()}
-            line = {"particles": n, "h": h, "mean_neighbours": nb, "variant": [dv, fv], "list_capacity": sim.nlist_capacity(), "ms_per_step": ms / steps,
+            line = {"particles": n, "h": h, "mean_neighbours": nb, "variant": [dv, fv], "list_capacity": "%d/%d" % (sim.nlist_capacity(), sim.nlist_smem_entries()), "ms_per_step": ms / steps,
                     "particle_updates_per_s": n / (ms / steps * 1e-3), "per_kernel_ms": t,
                     "hbm_GBps_algorithmic": {k: bench.ALGO_BYTES[k] * n / (t[k] * 1e-3) / 1e9 for k in ("hash", "scatter", "reorder", "density", "force") if t[k] > 0},
                     "hbm_frac_step": 234 * n / (ms / steps * 1e-3) / 1e9 / peak}

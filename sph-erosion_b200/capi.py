@@ -101,6 +101,8 @@ SYMBOLS = {
     "sphe_kernel_timing": (_i, [_vp, _i]),
     "sphe_kernel_times": (_i, [_vp, C.POINTER(_f), C.POINTER(_i)]),
     "sphe_nlist_capacity": (_i, [_vp]),
+    "sphe_nlist_overflowed": (_i, [_vp]),
+    "sphe_nlist_smem_entries": (_i, [_vp]),
     "sphe_set_nlist_capacity": (_i, [_vp, _i]),
     "sphe_slab_configure": (_i, [_vp, _i, _i, _i, _i]),
     "sphe_slab_ring": (_i, [_vp, _i, _i, _i]),

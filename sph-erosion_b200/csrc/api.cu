@@ -84,10 +84,11 @@ struct sphe_sim {
     int* nlist = nullptr;   // variant 3: [nlist_cap][pairs_pad] neighbour indices
     int2* ncount = nullptr;
     size_t nlist_pairs = 0;
-    int nlist_capacity = 64;       // entries per pair list: 64 -> 128 -> 256 as the overflow counter demands
+    int nlist_capacity = 128;      // rows allocated per pair list in HBM: doubled (up to 512) when pairs need more
+    int nlist_smem = 64;           // entries of a list staged in shared memory by the density pass: 64 / 128 / 256
     int nlist_alloc_cap = 0;
-    int overflow_cooldown = 0;
-    bool nlist_auto = true;        // grow the lists when more than half of the pairs overflow (measured: pays only then)
+    int overflow_cooldown = 0, smem_cooldown = 0;
+    bool nlist_auto = true;        // choose the shared-memory entries from the spill statistics
     int* d_overflow = nullptr;     // pairs whose list overflowed in the current step
     int* h_overflow = nullptr;     // pinned: [0] the count of a recent step (copied without a sync), [1] pairs of that step
 
@@ -132,7 +133,7 @@ struct sphe_sim {
 
     bool binned = false;  // debug hooks valid
     StepC lastC{};
-    int variant_density = 3, variant_force = 3;  // 0 tpp, 1 packed pair, 3 neighbour lists (default)
+    int variant_density = 6, variant_force = 3;  // 0 tpp, 1 packed pair, 3 neighbour lists, 6 = 3 + software prefetch (default), 10 = 6 with 16-bit entries
 
     bool timing = false;
     void* flush_buf = nullptr;
@@ -352,21 +353,41 @@ static int step_device(sphe_sim* s, sphe_terrain* t, int terrain_phases = 7) {
       launch_rank_reorder(s->st, n, nd, s->tmp, s->cell, s->cell_start, s->posA, s->velA, s->sedA, s->posB, s->velB, s->sedB,
                           s->idsB, s->cell_sorted); }
     if (s->variant_density >= 3 || s->variant_force >= 3) {
-        if (s->variant_density != s->variant_force) return fail(SPHE_ERR_ARG, "variants 3/4 (neighbour lists) must be selected for both passes");
+        // the plain pair-list format is shared by 3 (plain), 6 (software-prefetched), 7/9 (quad density) and 31-33 (unroll A/B):
+        // any of those may be combined; the record (4) and sub-list (52/54/58) formats need the same variant in both passes
+        auto plain = [](int v) { return v == 3 || v == 6 || v == 7 || v == 9 || v == 10 || v == 11 || (v >= 31 && v <= 33); };
+        if (s->variant_density != s->variant_force && !(plain(s->variant_density) && plain(s->variant_force)))
+            return fail(SPHE_ERR_ARG, "neighbour-list variants with different list formats cannot be combined");
         // capacity for every list variant: S sub-lists of slist_entries(S) entries per pair, S <= 8 -> <= 96 ints per pair
         if (!s->d_overflow) {
-            CU(cudaMalloc(&s->d_overflow, sizeof(int))); CU(cudaMemsetAsync(s->d_overflow, 0, sizeof(int), s->st));
-            CU(cudaMallocHost(&s->h_overflow, 2 * sizeof(int))); s->h_overflow[0] = 0; s->h_overflow[1] = 1;
+            CU(cudaMalloc(&s->d_overflow, 4 * sizeof(int))); CU(cudaMemsetAsync(s->d_overflow, 0, 4 * sizeof(int), s->st));
+            CU(cudaMallocHost(&s->h_overflow, 4 * sizeof(int))); s->h_overflow[0] = s->h_overflow[1] = s->h_overflow[2] = 0; s->h_overflow[3] = 1;
         }
-        // a recent step's overflow count (copied back asynchronously, so possibly a step or two old): more than 1 % of the
-        // pairs fell back to the direct walk -> longer lists from now on
+        // List sizing from the counters of a recent step (copied back without a sync, so a step or two old):
+        // h_overflow = {pairs beyond the allocated rows, pairs that spilled out of shared memory, pairs that would
+        // spill at half the shared-memory capacity, pairs of that step}.
+        //  * rows (HBM, per pair): a pair beyond them falls back to the direct walk in the force pass, ~10x the cost
+        //    of a list walk and it stalls its whole warp -> double the rows as soon as 0.1 % of the pairs need it.
+        //  * shared-memory entries: 64 keeps the density pass at 6 CTAs/SM; spilling re-walks the saturated runs, so
+        //    when MOST pairs spill (dense scenes, 60-120 neighbours) the 128 / 256-entry instantiations win.
+        const int dv = s->variant_density;
+        const bool sized = dv == 3 || dv == 6 || dv == 10 || dv == 11 || (dv >= 31 && dv <= 33);
+        const long long pairs = s->h_overflow[3];
         if (s->overflow_cooldown > 0) s->overflow_cooldown--;
-        else if (s->nlist_auto && s->variant_density == 3 && s->nlist_capacity < 256 && s->h_overflow[0] * 2LL > s->h_overflow[1]) {
-            s->nlist_capacity *= 2;
-            s->overflow_cooldown = 4;   // counts still in flight belong to the old capacity
+        else if (sized && s->nlist_capacity < 512 && s->h_overflow[0] * 1000LL > pairs) { s->nlist_capacity *= 2; s->overflow_cooldown = 4; }
+        // staged entries: 64 (32-bit entries) -> 128 (16-bit entries, same shared memory, ~10 % more instructions) once 10 %
+        // of the pairs spill (a spill stalls its warp) -> 256 (32-bit, 66 KB per 64-thread CTA) once 60 % spill even then
+        if (s->smem_cooldown > 0) s->smem_cooldown--;
+        else if (s->nlist_auto && (dv == 3 || dv == 6)) {
+            const long long spilled = s->h_overflow[1], half = s->h_overflow[2];
+            const int m = s->nlist_smem;
+            if (m == 64 && spilled * 10 > pairs) { s->nlist_smem = 128; s->smem_cooldown = 4; }
+            else if (m == 128 && spilled * 10 > pairs * 6) { s->nlist_smem = 256; s->smem_cooldown = 4; }
+            else if (m == 128 && half * 20 < pairs) { s->nlist_smem = 64; s->smem_cooldown = 4; }
+            else if (m == 256 && half * 10 < pairs * 3) { s->nlist_smem = 128; s->smem_cooldown = 4; }
         }
         size_t pp = (size_t)nlist_pairs_pad(s->cap) + 128;
-        const int entries = std::max(96, s->nlist_capacity);
+        const int entries = std::max(std::max(96, s->nlist_capacity), s->nlist_smem);
         if (pp > s->nlist_pairs || entries > s->nlist_alloc_cap) {
             pp = std::max(pp, s->nlist_pairs);
             TRY(grow(&s->nlist, 0, pp * (size_t)entries, s->st, false));
@@ -376,11 +397,11 @@ static int step_device(sphe_sim* s, sphe_terrain* t, int terrain_phases = 7) {
     }
     { Scope k(s, SPHE_K_DENSITY);
       launch_density(s->st, s->variant_density, n, nd, s->posB, s->posC, s->velB, s->cell_sorted, s->cell_start, s->G, C, s->rho,
-                     s->nlist, s->ncount, s->nlist_capacity, s->d_overflow);
-      if (s->variant_density == 3 && s->d_overflow) {
-          s->h_overflow[1] = std::max((n + 1) / 2, 1);
-          CU(cudaMemcpyAsync(s->h_overflow, s->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, s->st));
-          CU(cudaMemsetAsync(s->d_overflow, 0, sizeof(int), s->st));
+                     s->nlist, s->ncount, s->nlist_capacity, s->d_overflow, s->nlist_smem);
+      if (s->d_overflow) {
+          s->h_overflow[3] = std::max((n + 1) / 2, 1);
+          CU(cudaMemcpyAsync(s->h_overflow, s->d_overflow, 3 * sizeof(int), cudaMemcpyDeviceToHost, s->st));
+          CU(cudaMemsetAsync(s->d_overflow, 0, 3 * sizeof(int), s->st));
       } }
     { Scope k(s, SPHE_K_FORCE);
       launch_force(s->st, s->variant_force, n, nd, s->posC, s->velB, s->rho, s->idsB, s->cell_sorted, s->cell_start, s->G, C,
@@ -704,12 +725,16 @@ int sphe_set_diagnostics(sphe_sim* s, int on) {
 }
 
 int sphe_nlist_capacity(sphe_sim* s) { return s ? s->nlist_capacity : 0; }
+int sphe_nlist_overflowed(sphe_sim* s) { return (s && s->h_overflow) ? s->h_overflow[0] : 0; }
+
+int sphe_nlist_smem_entries(sphe_sim* s) { return s ? s->nlist_smem : 0; }
 
 int sphe_set_nlist_capacity(sphe_sim* s, int entries) {
     if (!s) return fail(SPHE_ERR_ARG, "NULL handle");
-    if (entries == 0) { s->nlist_auto = true; return SPHE_OK; }     // grow on demand: when more than half of the pairs overflow
-    if (entries != 64 && entries != 128 && entries != 256) return fail(SPHE_ERR_ARG, "list capacity must be 64, 128, 256 or 0 (grow on demand)");
-    s->nlist_auto = false; s->nlist_capacity = entries;
+    if (entries == 0) { s->nlist_auto = true; return SPHE_OK; }
+    if (entries != 64 && entries != 128 && entries != 256) return fail(SPHE_ERR_ARG, "shared-memory list entries must be 64, 128, 256 or 0 (chosen from the spill statistics)");
+    s->nlist_auto = false; s->nlist_smem = entries;
+    s->nlist_capacity = std::max(s->nlist_capacity, entries);
     return SPHE_OK;
 }
 

@@ -103,7 +103,7 @@ struct DiagOut {
 
 void launch_density(cudaStream_t st, int variant, int n, const int* n_dev, const float4* posq, float4* posq_q, float4* velv,
                     const uint32_t* cell_sorted, const int* cell_start, const GridP& G, const StepC& C, float* rho,
-                    int* nlist, int2* ncount, int cap = 64, int* overflow = nullptr);
+                    int* nlist, int2* ncount, int cap = 64, int* overflow = nullptr, int smem_cap = 64);
 int nlist_cap();
 int nlist_pairs_pad(int n);
 void launch_force(cudaStream_t st, int variant, int n, const int* n_dev, const float4* posq, const float4* velv, const float* rho,

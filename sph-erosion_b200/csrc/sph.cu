@@ -478,13 +478,13 @@ constexpr int NLIST_THREADS = 128;
 // 60-120 neighbours per particle (BASELINE configs[4]) overflow them and fall back to the direct walk in the force
 // pass, which costs 2-4x.  The host raises CAP to 128 / 256 when the overflow counter says so (api.cu step_device).
 // The list lives in dynamic shared memory: (CAP + 1) * THREADS ints = 33 / 66 / 66 KB.
-template <bool REC, bool PF, int CAP, int THREADS>
+template <bool REC, bool PF, int CAP, int THREADS, int UNROLL = 4>
 __global__ void __launch_bounds__(THREADS) k_density_list(int n_hi, const int* __restrict__ n_dev, int npairs_pad, const float4* __restrict__ posq,
                                                           float4* __restrict__ posq_q, float4* __restrict__ velv,
                                                           const uint32_t* __restrict__ cell_sorted,
                                                           const int* __restrict__ cell_start, GridP G, StepC C,
                                                           float* __restrict__ rho, int* __restrict__ nlist,
-                                                          int2* __restrict__ ncount, int* __restrict__ overflow) {
+                                                          int2* __restrict__ ncount, int* __restrict__ overflow, int rows) {
     constexpr int NLIST_CAP = CAP, NLIST_THREADS = THREADS;   // shadow the file-scope defaults
     const int n = n_dev ? __ldg(n_dev) : n_hi;  // exact count from the device in slab mode, else the launch bound
     // (CAP + 1) * THREADS ints, +1: trash slot for saturated appends.  Static when it fits the 48 KB static limit:
@@ -537,6 +537,27 @@ __global__ void __launch_bounds__(THREADS) k_density_list(int n_hi, const int* _
             w.y = fmaxf(w.y, 0.f);
             acc = __ffma2_rn(__fmul2_rn(w, w), w, acc);
         };
+        // SPILL: the shared-memory list holds CAP entries; when a run saturates it, that run is walked again (rare,
+        // outside the hot loop) and the entries with index >= CAP go straight to their rows in HBM, up to the `rows`
+        // the host allocated.  Same candidates, same order, same predicate: the list the force pass reads is exactly
+        // the one an unbounded list would have held, so results do not depend on the capacity.
+        auto spill = [&](const int s, const int e, int idx) {
+#pragma unroll 4
+            for (int k = s; k < e; k++) {
+                const float4 pj = __ldg(&posq[k]);
+                float2 dx = __fadd2_rn(X, make_float2(-pj.x, -pj.x));
+                float2 dy = __fadd2_rn(Y, make_float2(-pj.y, -pj.y));
+                float2 dz = __fadd2_rn(Z, make_float2(-pj.z, -pj.z));
+                float2 d2 = __fmul2_rn(dx, dx);
+                d2 = __ffma2_rn(dy, dy, d2);
+                d2 = __ffma2_rn(dz, dz, d2);
+                float2 w = __fadd2_rn(make_float2(C.hh, C.hh), make_float2(-d2.x, -d2.y));
+                if (fmaxf(w.x, w.y) >= 0.f) {
+                    if (idx >= NLIST_CAP && idx < rows) nlist[(size_t)idx * npairs_pad + t] = k;
+                    idx++;
+                }
+            }
+        };
         auto bounds = [&](const int r, int& s, int& e) {
             int x = cx + r / 3 - 1, y = cy + r % 3 - 1;
             bool ok = r < 9 && x >= 0 && x < G.nx && y >= 0 && y < G.ny;
@@ -549,8 +570,10 @@ __global__ void __launch_bounds__(THREADS) k_density_list(int n_hi, const int* _
             for (int r = 0; r < 9; r++) {
                 int s, e;
                 bounds(r, s, e);
-#pragma unroll 4
+                const int off_run = off;
+#pragma unroll UNROLL
                 for (int k = s; k < e; k++) test(k, __ldg(&posq[k]));
+                if (off > NLIST_CAP * NLIST_THREADS) spill(s, e, off_run / NLIST_THREADS);
             }
         } else {
             int s, e, sn, en;
@@ -558,6 +581,7 @@ __global__ void __launch_bounds__(THREADS) k_density_list(int n_hi, const int* _
 #pragma unroll 1
             for (int r = 0; r < 9; r++) {
                 bounds(r + 1, sn, en);   // next run's bounds in flight (r + 1 == 9 yields an empty range)
+                const int off_run = off;
                 int k = s;
                 if (k + 4 <= e) {
                     float4 q0 = __ldg(&posq[k]), q1 = __ldg(&posq[k + 1]), q2 = __ldg(&posq[k + 2]), q3 = __ldg(&posq[k + 3]);
@@ -572,6 +596,7 @@ __global__ void __launch_bounds__(THREADS) k_density_list(int n_hi, const int* _
                 }
 #pragma unroll 1
                 for (; k < e; k++) test(k, __ldg(&posq[k]));
+                if (off > NLIST_CAP * NLIST_THREADS) spill(s, e, off_run / NLIST_THREADS);
                 s = sn; e = en;
             }
         }
@@ -579,13 +604,16 @@ __global__ void __launch_bounds__(THREADS) k_density_list(int n_hi, const int* _
     if (npass == 1) off0 = off;
     // coalesced flush of the lists: entry e of all threads of the block is one contiguous row
     const int cnt = off / NLIST_THREADS;
-    const bool fits = cnt <= NLIST_CAP;
+    const bool fits = cnt <= rows;
     if (live) ncount[t] = fits ? make_int2(off0 / NLIST_THREADS, cnt) : make_int2(-1, -1);
-    if (live && !fits) atomicAdd(overflow, 1);
+    if (live && !fits) atomicAdd(overflow, 1);                          // beyond the allocated rows: direct walk in the force pass
+    if (live && cnt > NLIST_CAP) atomicAdd(overflow + 1, 1);            // spilled (statistics for the host's choice of CAP)
+    if (live && cnt > NLIST_CAP / 2) atomicAdd(overflow + 2, 1);        // would spill at the next smaller CAP
     if (fits) {
         int* dst = nlist + t;
+        const int stop = min(off, NLIST_CAP * NLIST_THREADS);           // the rest is already in place
 #pragma unroll 4
-        for (int o = 0, e = 0; o < off; o += NLIST_THREADS, e++) dst[(size_t)e * npairs_pad] = lbase[o];
+        for (int o = 0, e = 0; o < stop; o += NLIST_THREADS, e++) dst[(size_t)e * npairs_pad] = lbase[o];
     }
     if (!live) return;
     float ra = acc.x * C.densK, rb = acc.y * C.densK;
@@ -772,6 +800,173 @@ __global__ void __launch_bounds__(QUAD_THREADS) k_density_quad(int n_hi, const i
         rho[i[j]] = r;
         posq_q[i[j]] = make_float4(p[j].x, p[j].y, p[j].z, P / (r * r));
         velv[i[j]].w = C.mass / r;
+    }
+}
+
+// ------------------------------------------------------------------ variant 10: 16-bit list entries, 128 per pair
+// Along the dam-break transient the fluid compresses to ~2x rest density (the reference's equation of state is soft,
+// k = 3): a third of the pairs then overflow 64-entry lists and the direct-walk fallback of the force pass costs
+// 6x (scripts/transient.py).  Doubling the capacity with 32-bit entries doubles the shared memory and halves the
+// occupancy of this pass (+30 %).  Here an entry is 16 bits -- run index (4 bits) | offset inside the run (12 bits) --
+// so 128 entries per pair fit the SAME 33 KB per CTA; the flush expands them to particle indices with the run starts
+// kept in shared memory (9 ints per thread).  A run longer than 4095 particles marks the pair as overflowed.
+constexpr int L16_CAP = 128, L16_THREADS = 128;
+
+template <bool PF>
+__global__ void __launch_bounds__(L16_THREADS) k_density_list16(int n_hi, const int* __restrict__ n_dev, int npairs_pad, const float4* __restrict__ posq,
+                                                                float4* __restrict__ posq_q, float4* __restrict__ velv,
+                                                                const uint32_t* __restrict__ cell_sorted,
+                                                                const int* __restrict__ cell_start, GridP G, StepC C,
+                                                                float* __restrict__ rho, int* __restrict__ nlist,
+                                                                int2* __restrict__ ncount, int* __restrict__ overflow, int rows) {
+    constexpr int T = L16_THREADS;
+    const int n = n_dev ? __ldg(n_dev) : n_hi;
+    __shared__ unsigned short list16[(L16_CAP + 1) * T];   // +1: trash slot for saturated appends
+    __shared__ int sbase[9 * T];                           // run starts of pass 0
+    const int tid = threadIdx.x;
+    const int t = blockIdx.x * blockDim.x + tid;
+    int a = 2 * t;
+    const bool live = a < n;
+    if (!live) a = 0;
+    const int b = (a + 1 < n) ? a + 1 : a;
+    const float4 pa = posq[a], pb = posq[b];
+    const uint32_t ca = cell_sorted[a], cb = cell_sorted[b];
+    const uint32_t cola = ca / (uint32_t)G.nz, colb = cb / (uint32_t)G.nz;
+    const int cza = (int)(ca - cola * (uint32_t)G.nz), czb = (int)(cb - colb * (uint32_t)G.nz);
+    const bool merged = (b != a) && (cola == colb) && (czb - cza <= 3);
+    const float FAR = 1.0e18f;
+    const int npass = !live ? 0 : ((merged || b == a) ? 1 : 2);
+
+    float2 acc = make_float2(0.f, 0.f);
+    unsigned short* const lbase = list16 + tid;
+    int* const sb = sbase + tid;
+    int off = 0, off0 = 0;  // slot * T
+    bool too_long = false;
+#pragma unroll 1
+    for (int p = 0; p < npass; p++) {
+        const bool useA = merged || p == 0, useB = merged || p == 1;
+        const float2 X = make_float2(useA ? pa.x : FAR, useB ? pb.x : FAR);
+        const float2 Y = make_float2(useA ? pa.y : FAR, useB ? pb.y : FAR);
+        const float2 Z = make_float2(useA ? pa.z : FAR, useB ? pb.z : FAR);
+        const uint32_t col = p ? colb : cola;
+        const int czlo = p ? czb : cza, czhi = merged ? czb : czlo;
+        const int cy = (int)(col % (uint32_t)G.ny), cx = (int)(col / (uint32_t)G.ny);
+        const int z0 = czlo > 0 ? czlo - 1 : 0, z1 = czhi < G.nz - 1 ? czhi + 1 : czhi;
+        if (p == 1) off0 = off;
+        auto test = [&](const unsigned code, const float4 pj) {
+            float2 dx = __fadd2_rn(X, make_float2(-pj.x, -pj.x));
+            float2 dy = __fadd2_rn(Y, make_float2(-pj.y, -pj.y));
+            float2 dz = __fadd2_rn(Z, make_float2(-pj.z, -pj.z));
+            float2 d2 = __fmul2_rn(dx, dx);
+            d2 = __ffma2_rn(dy, dy, d2);
+            d2 = __ffma2_rn(dz, dz, d2);
+            float2 w = __fadd2_rn(make_float2(C.hh, C.hh), make_float2(-d2.x, -d2.y));
+            lbase[min(off, L16_CAP * T)] = (unsigned short)code;   // branch-free append
+            off += (fmaxf(w.x, w.y) >= 0.f) ? T : 0;
+            w.x = fmaxf(w.x, 0.f);
+            w.y = fmaxf(w.y, 0.f);
+            acc = __ffma2_rn(__fmul2_rn(w, w), w, acc);
+        };
+        // entries beyond the shared-memory capacity go straight to their rows in HBM (see k_density_list)
+        auto spill = [&](const int s, const int e, int idx) {
+#pragma unroll 4
+            for (int k = s; k < e; k++) {
+                const float4 pj = __ldg(&posq[k]);
+                float2 dx = __fadd2_rn(X, make_float2(-pj.x, -pj.x));
+                float2 dy = __fadd2_rn(Y, make_float2(-pj.y, -pj.y));
+                float2 dz = __fadd2_rn(Z, make_float2(-pj.z, -pj.z));
+                float2 d2 = __fmul2_rn(dx, dx);
+                d2 = __ffma2_rn(dy, dy, d2);
+                d2 = __ffma2_rn(dz, dz, d2);
+                float2 w = __fadd2_rn(make_float2(C.hh, C.hh), make_float2(-d2.x, -d2.y));
+                if (fmaxf(w.x, w.y) >= 0.f) {
+                    if (idx >= L16_CAP && idx < rows) nlist[(size_t)idx * npairs_pad + t] = k;
+                    idx++;
+                }
+            }
+        };
+        auto bounds = [&](const int r, int& s, int& e) {
+            int x = cx + r / 3 - 1, y = cy + r % 3 - 1;
+            bool ok = r < 9 && x >= 0 && x < G.nx && y >= 0 && y < G.ny;
+            int base = ok ? (x * G.ny + y) * G.nz : 0;
+            s = __ldg(&cell_start[base + z0]);
+            e = ok ? __ldg(&cell_start[base + z1 + 1]) : s;
+        };
+        if (!PF) {
+#pragma unroll 1
+            for (int r = 0; r < 9; r++) {
+                int s, e;
+                bounds(r, s, e);
+                if (p == 0) sb[r * T] = s;
+                too_long |= (e - s) > 4095;
+                const unsigned rb = (unsigned)r << 12;
+                const int off_run = off;
+#pragma unroll 4
+                for (int k = s; k < e; k++) test(rb + (unsigned)(k - s), __ldg(&posq[k]));
+                if (off > L16_CAP * T) spill(s, e, off_run / T);
+            }
+        } else {
+            int s, e, sn, en;
+            bounds(0, s, e);
+#pragma unroll 1
+            for (int r = 0; r < 9; r++) {
+                bounds(r + 1, sn, en);   // next run's bounds in flight (r + 1 == 9 yields an empty range)
+                if (p == 0) sb[r * T] = s;
+                too_long |= (e - s) > 4095;
+                unsigned code = (unsigned)r << 12;
+                const int off_run = off;
+                int k = s;
+                if (k + 4 <= e) {
+                    float4 q0 = __ldg(&posq[k]), q1 = __ldg(&posq[k + 1]), q2 = __ldg(&posq[k + 2]), q3 = __ldg(&posq[k + 3]);
+#pragma unroll 1
+                    for (; k + 8 <= e; k += 4, code += 4) {
+                        const float4 n0 = __ldg(&posq[k + 4]), n1 = __ldg(&posq[k + 5]), n2 = __ldg(&posq[k + 6]), n3 = __ldg(&posq[k + 7]);
+                        test(code, q0); test(code + 1, q1); test(code + 2, q2); test(code + 3, q3);
+                        q0 = n0; q1 = n1; q2 = n2; q3 = n3;
+                    }
+                    test(code, q0); test(code + 1, q1); test(code + 2, q2); test(code + 3, q3);
+                    k += 4; code += 4;
+                }
+#pragma unroll 1
+                for (; k < e; k++, code++) test(code, __ldg(&posq[k]));
+                if (off > L16_CAP * T) spill(s, e, off_run / T);
+                s = sn; e = en;
+            }
+        }
+    }
+    if (npass == 1) off0 = off;
+    const int cnt = off / T;
+    const bool fits = cnt <= max(rows, L16_CAP) && !too_long;
+    if (live) ncount[t] = fits ? make_int2(off0 / T, cnt) : make_int2(-1, -1);
+    if (live && !fits) atomicAdd(overflow, 1);
+    if (live && cnt > L16_CAP) atomicAdd(overflow + 1, 1);
+    if (live && cnt > L16_CAP / 2) atomicAdd(overflow + 2, 1);
+    if (fits) {
+        // coalesced flush: entry e of all threads of the block is one contiguous row; decode run | offset -> particle index
+        int* dst = nlist + t;
+        const int seg = (npass == 2) ? off0 : off;          // entries from pass 0 use the stored run starts
+        const int cyb = (int)(colb % (uint32_t)G.ny), cxb = (int)(colb / (uint32_t)G.ny), z0b = czb > 0 ? czb - 1 : 0;
+#pragma unroll 2
+        const int stop = min(off, L16_CAP * T);             // longer lists: the rest is already in place
+        for (int o = 0, e = 0; o < stop; o += T, e++) {
+            const unsigned v = lbase[o];
+            const int r = (int)(v >> 12);
+            int base;
+            if (o < seg) base = sb[r * T];
+            else base = __ldg(&cell_start[((cxb + r / 3 - 1) * G.ny + (cyb + r % 3 - 1)) * G.nz + z0b]);   // split pair, second pass (rare)
+            dst[(size_t)e * npairs_pad] = base + (int)(v & 4095u);
+        }
+    }
+    if (!live) return;
+    float ra = acc.x * C.densK, rb = acc.y * C.densK;
+    float Pa = C.k * (ra - C.p0), Pb = C.k * (rb - C.p0);
+    rho[a] = ra;
+    posq_q[a] = make_float4(pa.x, pa.y, pa.z, Pa / (ra * ra));
+    velv[a].w = C.mass / ra;
+    if (b != a) {
+        rho[b] = rb;
+        posq_q[b] = make_float4(pb.x, pb.y, pb.z, Pb / (rb * rb));
+        velv[b].w = C.mass / rb;
     }
 }
 
@@ -1300,21 +1495,21 @@ static inline int nblk(int n, int b) { return (n + b - 1) / b; }
 int nlist_cap() { return NLIST_CAP; }
 int nlist_pairs_pad(int n) { return (((n + 1) / 2) + 127) & ~127; }
 
-template <bool REC, bool PF, int CAP, int THREADS>
+template <bool REC, bool PF, int CAP, int THREADS, int UNROLL = 4>
 static void launch_density_list(cudaStream_t st, int n, const int* n_dev, int pp, const float4* posq, float4* posq_q, float4* velv,
                                 const uint32_t* cell_sorted, const int* cell_start, const GridP& G, const StepC& C, float* rho,
-                                int* nlist, int2* ncount, int* overflow) {
+                                int* nlist, int2* ncount, int* overflow, int rows) {
     int smem = (CAP + 1) * THREADS * (int)sizeof(int);
     if (smem <= 48 * 1024) smem = 0;   // static in the kernel
-    auto kern = k_density_list<REC, PF, CAP, THREADS>;
+    auto kern = k_density_list<REC, PF, CAP, THREADS, UNROLL>;
     static bool configured = false;   // per instantiation
     if (!configured && smem > 48 * 1024) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); configured = true; }
-    kern<<<pp / THREADS, THREADS, smem, st>>>(n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount, overflow);
+    kern<<<pp / THREADS, THREADS, smem, st>>>(n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount, overflow, rows < CAP ? CAP : rows);
 }
 
 void launch_density(cudaStream_t st, int variant, int n, const int* n_dev, const float4* posq, float4* posq_q, float4* velv,
                     const uint32_t* cell_sorted, const int* cell_start, const GridP& G, const StepC& C, float* rho,
-                    int* nlist, int2* ncount, int cap, int* overflow) {
+                    int* nlist, int2* ncount, int cap, int* overflow, int smem_cap) {
     if (n <= 0) return;
     int pairs = (n + 1) / 2;
     if (variant == 52) return launch_density_s<2>(st, n, n_dev, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount);
@@ -1326,13 +1521,32 @@ void launch_density(cudaStream_t st, int variant, int n, const int* n_dev, const
         else k_density_quad<false><<<pp / 2 / QUAD_THREADS, QUAD_THREADS, 0, st>>>(n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount);
         return;
     }
+    if (variant == 10 || variant == 11) {
+        int pp = nlist_pairs_pad(n);
+        if (variant == 10) k_density_list16<true><<<pp / L16_THREADS, L16_THREADS, 0, st>>>(n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount, overflow, cap);
+        else k_density_list16<false><<<pp / L16_THREADS, L16_THREADS, 0, st>>>(n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount, overflow, cap);
+        return;
+    }
+    if (variant == 31 || variant == 32 || variant == 33) {   // A/B: unroll depth of the candidate loop (gathers in flight)
+        int pp = nlist_pairs_pad(n);
+        if (variant == 31) launch_density_list<false, false, 64, 128, 8>(st, n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount, overflow, cap);
+        else if (variant == 32) launch_density_list<false, false, 64, 128, 6>(st, n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount, overflow, cap);
+        else launch_density_list<false, false, 64, 128, 2>(st, n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount, overflow, cap);
+        return;
+    }
     if (variant == 3 || variant == 4 || variant == 6) {
         int pp = nlist_pairs_pad(n);
-#define SPHE_DL(RC, PFv, CP, TH) launch_density_list<RC, PFv, CP, TH>(st, n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount, overflow)
+#define SPHE_DL(RC, PFv, CP, TH) launch_density_list<RC, PFv, CP, TH>(st, n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount, overflow, cap)
+        // cap = rows allocated per pair.  The shared-memory part stays at 64 entries (occupancy), longer lists spill; only
+        // when MOST pairs spill (smem_cap, chosen by the host from the spill statistics) the wide-shared-memory
+        // instantiations take over (explicit prefetch: ptxas serialises the gathers of those otherwise, 48 registers)
         if (variant == 4) SPHE_DL(true, false, 64, 128);
+        else if (smem_cap > 128) SPHE_DL(false, true, 256, 64);
+        else if (smem_cap > 64) {   // 128 staged entries: the 16-bit kernel holds them in the same 33 KB (6 CTAs/SM)
+            if (variant == 6) k_density_list16<true><<<pp / L16_THREADS, L16_THREADS, 0, st>>>(n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount, overflow, cap);
+            else k_density_list16<false><<<pp / L16_THREADS, L16_THREADS, 0, st>>>(n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount, overflow, cap);
+        }
         else if (variant == 6) SPHE_DL(false, true, 64, 128);
-        else if (cap > 128) SPHE_DL(false, true, 256, 64);    // explicit prefetch: ptxas serialises the gathers of the
-        else if (cap > 64) SPHE_DL(false, true, 128, 128);    // dynamic-shared-memory instantiations otherwise (48 registers)
         else SPHE_DL(false, false, 64, 128);
 #undef SPHE_DL
         return;
@@ -1352,7 +1566,7 @@ void launch_force(cudaStream_t st, int variant, int n, const int* n_dev, const f
     if (variant == 52) return launch_force_s<2>(st, n, n_dev, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, posq_out, velv_out, diag, nlist, ncount);
     if (variant == 54) return launch_force_s<4>(st, n, n_dev, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, posq_out, velv_out, diag, nlist, ncount);
     if (variant == 58) return launch_force_s<8>(st, n, n_dev, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, posq_out, velv_out, diag, nlist, ncount);
-    if (variant == 7 || variant == 9) variant = 3;   // the quad density pass writes the same pair lists
+    if (variant == 7 || variant == 9 || variant == 10 || variant == 11 || (variant >= 31 && variant <= 33)) variant = 3;   // the quad density pass writes the same pair lists
     if (variant == 3 || variant == 4 || variant == 6) {
         int pp = nlist_pairs_pad(n);
         dim3 g(pp / NLIST_THREADS), b(NLIST_THREADS);

@@ -140,6 +140,12 @@ class FluidSystemSPH:
     def nlist_capacity(self):
         return int(self._L.sphe_nlist_capacity(self._h))
 
+    def nlist_smem_entries(self):
+        return int(self._L.sphe_nlist_smem_entries(self._h))
+
+    def nlist_overflowed(self):
+        return int(self._L.sphe_nlist_overflowed(self._h))
+
     def set_nlist_capacity(self, entries):
         capi.check(self._L.sphe_set_nlist_capacity(self._h, int(entries)))
 

@@ -487,7 +487,7 @@ def channel_block(n_axis, world, rank, jitter, spacing=0.025, layout="tiled"):
     return pos, ids, (Lx, L, L), bounds
 
 
-def make_gpu_slab(pkg, device, rank, world, box_half, params, bounds_x, cap_records, variant=(3, 3)):
+def make_gpu_slab(pkg, device, rank, world, box_half, params, bounds_x, cap_records, variant=(6, 3)):
     """Configured FluidSystemSPH handle + backend for rank `rank` of `world` x-slabs."""
     sim = pkg.FluidSystemSPH(device=device)
     p = sim.params
