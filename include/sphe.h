@@ -285,6 +285,13 @@ int sphe_terrain_contacts(sphe_terrain* t, long long* total, int reset); /* part
 int sphe_sediment_total_fx(sphe_sim* s, long long* sum);        /* sum of carried sediment (owned particles), fixed point */
 int sphe_set_sediment_fx(sphe_sim* s, const int* sediment_by_id);
 
+/* ---- on-disk state (the reference has no format).  One little-endian file with everything a bit-exact resume
+ * needs: parameters and bookkeeping, positions / velocities in id order, carried sediment (fixed point) and, when
+ * `t` is given, the terrain's fixed-point heights, transform and erosion parameters.  A run resumed from a file
+ * continues bit for bit (results do not depend on the storage order of the particles). */
+int sphe_save_state(sphe_sim* s, sphe_terrain* t /* or NULL */, const char* path);
+int sphe_load_state(sphe_sim* s, sphe_terrain* t /* required when the file holds a terrain */, const char* path);
+
 /* ---- raw device access for multi-GPU plumbing (halo exchange lives above this ABI) ---- */
 enum { SPHE_D_POSQ = 0, SPHE_D_VELV = 1, SPHE_D_IDS = 2, SPHE_D_RHO = 3 };
 void* sphe_device_ptr(sphe_sim* s, int which);

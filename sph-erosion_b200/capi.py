@@ -122,6 +122,8 @@ SYMBOLS = {
     "sphe_slab_send": (_i, [_vp]),
     "sphe_slab_recv": (_i, [_vp, C.POINTER(_ll)]),
     "sphe_step_phase": (_i, [_vp, _vp, _i]),
+    "sphe_save_state": (_i, [_vp, _vp, C.c_char_p]),
+    "sphe_load_state": (_i, [_vp, _vp, C.c_char_p]),
     "sphe_terrain_accumulators": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_ll)]),
 }
 

@@ -1689,4 +1689,112 @@ int sphe_set_sediment_fx(sphe_sim* s, const int* sediment_by_id) {
     return SPHE_OK;
 }
 
+
+// ---- on-disk state (the reference has no format).  Little-endian, everything a bit-exact resume
+// needs: parameters, bookkeeping, positions/velocities (id order), carried sediment (fixed point), and -- when a
+// terrain is given -- its fixed-point heights, transform and erosion parameters.  Results do not depend on the
+// storage order of the particles (the binning makes the order canonical), so a resumed run continues bit for bit.
+namespace {
+struct StateHeader {
+    char magic[8];          // "SPHESTA1"
+    int n, has_terrain, n_labels, box_user;
+    sphe_params P;
+    float origin[3], box[3];
+    int num, init_num, next_label, reserved;
+};
+struct TerrainHeader {
+    int rows, cols, dims[3];
+    float origin[3], scale;
+    sphe_erosion E;
+};
+struct File {
+    FILE* f = nullptr;
+    ~File() { if (f) fclose(f); }
+};
+}  // namespace
+
+int sphe_save_state(sphe_sim* s, sphe_terrain* t, const char* path) {
+    if (!s || !path) return fail(SPHE_ERR_ARG, "bad arguments");
+    if (s->slab_on) return fail(SPHE_ERR_STATE, "not available in slab mode (use sphe_slab_download per rank)");
+    TRY(ensure_device(s));
+    const int n = s->n;
+    StateHeader H{};
+    memcpy(H.magic, "SPHESTA1", 8);
+    H.n = n; H.has_terrain = t ? 1 : 0; H.n_labels = (int)s->labels.size(); H.box_user = s->box_user ? 1 : 0;
+    H.P = s->P;
+    for (int a = 0; a < 3; a++) { H.origin[a] = s->origin[a]; H.box[a] = s->box[a]; }
+    H.num = s->num; H.init_num = s->init_num; H.next_label = s->next_label;
+    std::vector<float> pos(3 * (size_t)n), vel(3 * (size_t)n);
+    std::vector<int> sed((size_t)n);
+    if (n > 0) {
+        TRY(sphe_download(s, SPHE_F_POS, pos.data()));
+        TRY(sphe_download(s, SPHE_F_VEL, vel.data()));
+        launch_unsort_f1(s->st, n, s->sedA, s->idsA, s->stage);    // raw fixed-point words, id order
+        CU(cudaMemcpyAsync(sed.data(), s->stage, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s->st));
+        CU(cudaStreamSynchronize(s->st));
+    }
+    File F; F.f = fopen(path, "wb");
+    if (!F.f) return fail(SPHE_ERR_ARG, "cannot write %s", path);
+    bool ok = fwrite(&H, sizeof H, 1, F.f) == 1;
+    ok = ok && (s->labels.empty() || fwrite(s->labels.data(), sizeof(int), s->labels.size(), F.f) == s->labels.size());
+    ok = ok && (n == 0 || (fwrite(pos.data(), sizeof(float), pos.size(), F.f) == pos.size() &&
+                           fwrite(vel.data(), sizeof(float), vel.size(), F.f) == vel.size() &&
+                           fwrite(sed.data(), sizeof(int), sed.size(), F.f) == sed.size()));
+    if (ok && t) {
+        TRY(terrain_ready(t));
+        TerrainHeader T{};
+        T.rows = t->rows; T.cols = t->cols; T.dims[0] = t->dimx; T.dims[1] = t->dimy; T.dims[2] = t->dimz;
+        for (int a = 0; a < 3; a++) T.origin[a] = t->origin[a];
+        T.scale = t->scale; T.E = t->E;
+        std::vector<int> hfx((size_t)t->rows * t->cols);
+        TRY(sphe_terrain_get_heights_fx(t, hfx.data()));
+        ok = fwrite(&T, sizeof T, 1, F.f) == 1 && fwrite(hfx.data(), sizeof(int), hfx.size(), F.f) == hfx.size();
+    }
+    if (!ok) return fail(SPHE_ERR_ARG, "short write to %s", path);
+    return SPHE_OK;
+}
+
+int sphe_load_state(sphe_sim* s, sphe_terrain* t, const char* path) {
+    if (!s || !path) return fail(SPHE_ERR_ARG, "bad arguments");
+    if (s->slab_on) return fail(SPHE_ERR_STATE, "not available in slab mode");
+    File F; F.f = fopen(path, "rb");
+    if (!F.f) return fail(SPHE_ERR_ARG, "cannot read %s", path);
+    StateHeader H;
+    if (fread(&H, sizeof H, 1, F.f) != 1 || memcmp(H.magic, "SPHESTA1", 8) != 0) return fail(SPHE_ERR_ARG, "%s is not a sphe state file", path);
+    if (H.n < 0 || H.n_labels < 0 || (H.n_labels != 0 && H.n_labels != H.n)) return fail(SPHE_ERR_ARG, "%s: corrupt header", path);
+    if (H.has_terrain && !t) return fail(SPHE_ERR_ARG, "%s holds a terrain: pass a terrain handle to receive it", path);
+    const size_t n = (size_t)H.n;
+    std::vector<int> labels((size_t)H.n_labels), sed(n);
+    std::vector<float> pos(3 * n), vel(3 * n);
+    bool ok = labels.empty() || fread(labels.data(), sizeof(int), labels.size(), F.f) == labels.size();
+    ok = ok && (n == 0 || (fread(pos.data(), sizeof(float), pos.size(), F.f) == pos.size() &&
+                           fread(vel.data(), sizeof(float), vel.size(), F.f) == vel.size() &&
+                           fread(sed.data(), sizeof(int), sed.size(), F.f) == sed.size()));
+    if (!ok) return fail(SPHE_ERR_ARG, "%s: truncated particle data", path);
+    s->P = H.P;
+    for (int a = 0; a < 3; a++) { s->origin[a] = H.origin[a]; s->box[a] = H.box[a]; }
+    s->box_user = H.box_user != 0;
+    s->grid_h = -1.f;   // re-derive the neighbour grid from the loaded parameters
+    TRY(sphe_upload_state(s, H.n, pos.data(), vel.data()));
+    s->num = H.num; s->init_num = H.init_num; s->next_label = H.next_label;
+    s->labels = labels; s->labels_identity = labels.empty();
+    if (n > 0) TRY(sphe_set_sediment_fx(s, sed.data()));
+    if (H.has_terrain) {
+        TerrainHeader T;
+        if (fread(&T, sizeof T, 1, F.f) != 1 || T.rows < 2 || T.cols < 2) return fail(SPHE_ERR_ARG, "%s: truncated terrain header", path);
+        std::vector<int> hfx((size_t)T.rows * T.cols);
+        if (fread(hfx.data(), sizeof(int), hfx.size(), F.f) != hfx.size()) return fail(SPHE_ERR_ARG, "%s: truncated terrain heights", path);
+        std::vector<float> h(hfx.size());
+        for (size_t i = 0; i < hfx.size(); i++) {
+            if (hfx[i] > (1 << 24) || hfx[i] < -(1 << 24)) return fail(SPHE_ERR_ARG, "%s: height out of the exactly representable range", path);
+            h[i] = (float)hfx[i] * (1.0f / 4096.0f);     // exact: |hfx| < 2^24, and set_heights rounds h * 4096 back to hfx
+        }
+        t->dimx = T.dims[0]; t->dimy = T.dims[1]; t->dimz = T.dims[2];
+        TRY(sphe_terrain_set_heights(t, h.data(), T.rows, T.cols));
+        TRY(sphe_terrain_set_transform(t, T.origin, T.scale));
+        t->E = T.E;
+    }
+    return SPHE_OK;
+}
+
 }  // extern "C"

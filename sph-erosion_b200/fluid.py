@@ -140,6 +140,13 @@ class FluidSystemSPH:
     def nlist_capacity(self):
         return int(self._L.sphe_nlist_capacity(self._h))
 
+    def save_state(self, path, grid=None):
+        """Checkpoint: particles (+ the terrain when given) to one file (sphe_save_state)."""
+        capi.check(self._L.sphe_save_state(self._h, getattr(grid, "_t", None), str(path).encode()))
+
+    def load_state(self, path, grid=None):
+        capi.check(self._L.sphe_load_state(self._h, getattr(grid, "_t", None), str(path).encode()))
+
     def nlist_smem_entries(self):
         return int(self._L.sphe_nlist_smem_entries(self._h))
 

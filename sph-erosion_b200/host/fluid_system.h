@@ -102,6 +102,10 @@ public:
     void UseTerrain(bool on) { m_UseTerrain = on; }
     sphe_sim* handle() const { return m_S; }
     int Count() const { return sphe_count(m_S); }
+    // Checkpoint / resume (the reference has no on-disk format): particles + parameters, and the terrain with its
+    // eroded heights when `grid` is given.  A resumed run continues bit for bit.
+    bool Save(const char* path, Grid* grid = nullptr) { int rc = sphe_save_state(m_S, grid ? grid->handle() : nullptr, path); check(rc, "Save"); return rc == SPHE_OK; }
+    bool Load(const char* path, Grid* grid = nullptr) { int rc = sphe_load_state(m_S, grid ? grid->handle() : nullptr, path); check(rc, "Load"); return rc == SPHE_OK; }
 
 private:
     static glm::vec3 v(const float* a) { return glm::vec3(a[0], a[1], a[2]); }

@@ -5,6 +5,7 @@
 // pointers (:278-290) and the particle inspector (:292-305) driven from the command line.
 //
 //   headless [--steps N] [--particles N] [--terrain raw512.bin] [--erosion] [--add-at STEP] [--dump file]
+//            [--save file] [--load file]      checkpoint after the run / resume from a checkpoint instead of Initialize
 //
 // --dump writes the final state as raw little-endian float32: count (int32), then pos[3n], vel[3n], density[n].
 #include <cstdio>
@@ -21,7 +22,7 @@ FluidSystemSPH fluidsph;   // constructed before main(), like main.cpp:50
 int main(int argc, char** argv) {
     int steps = 100, particles = 1000, add_at = -1;
     bool erosion = false;
-    std::string terrain_file, dump_file;
+    std::string terrain_file, dump_file, save_file, load_file;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&](const char* what) -> const char* { if (i + 1 >= argc) { std::fprintf(stderr, "missing value for %s\n", what); std::exit(2); } return argv[++i]; };
@@ -31,6 +32,8 @@ int main(int argc, char** argv) {
         else if (a == "--erosion") erosion = true;
         else if (a == "--add-at") add_at = std::atoi(next("--add-at"));
         else if (a == "--dump") dump_file = next("--dump");
+        else if (a == "--save") save_file = next("--save");
+        else if (a == "--load") load_file = next("--load");
         else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
     }
 
@@ -53,11 +56,15 @@ int main(int argc, char** argv) {
     }
 
     fluidsph.SetOrigin(glm::vec3(0.0f));
-    fluidsph.Initialize(particles);
-    if (sphe_count(fluidsph.handle()) == 0) { std::fprintf(stderr, "no particles: %s\n", sphe_last_error()); return 1; }
-    fluidsph.Run(grid);                       // paused frame: deltaT = 0 recomputes forces, moves nothing
-    if (fluidsph.GetDeltaTime() == 0) fluidsph.SetDeltaTime(0.01f);   // the F key
-    *fluidsph.GetVisc() = 3.5f;               // ImGui-style write through the parameter pointers
+    if (!load_file.empty()) {
+        if (!fluidsph.Load(load_file.c_str(), terrain_file.empty() ? nullptr : &grid)) return 1;
+    } else {
+        fluidsph.Initialize(particles);
+        if (sphe_count(fluidsph.handle()) == 0) { std::fprintf(stderr, "no particles: %s\n", sphe_last_error()); return 1; }
+        fluidsph.Run(grid);                       // paused frame: deltaT = 0 recomputes forces, moves nothing
+        if (fluidsph.GetDeltaTime() == 0) fluidsph.SetDeltaTime(0.01f);   // the F key
+        *fluidsph.GetVisc() = 3.5f;               // ImGui-style write through the parameter pointers
+    }
     for (int s = 0; s < steps; s++) {
         if (s == add_at) fluidsph.AddParticles(125);
         fluidsph.Run(grid);
@@ -65,6 +72,7 @@ int main(int argc, char** argv) {
     FluidParticle p = fluidsph.GetParticle(0);
     std::printf("particles %d  particle 0: pos %.9g %.9g %.9g  density %.9g  pressure %.9g\n", fluidsph.Count(),
                 p.Position.x, p.Position.y, p.Position.z, p.Density, p.Pressure);
+    if (!save_file.empty() && !fluidsph.Save(save_file.c_str(), terrain_file.empty() ? nullptr : &grid)) return 1;
     if (!dump_file.empty()) {
         int n = fluidsph.Count();
         std::vector<float> pos(3 * (size_t)n), vel(3 * (size_t)n), rho((size_t)n);

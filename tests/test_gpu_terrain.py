@@ -229,3 +229,40 @@ def test_no_terrain_and_flat_far_terrain_agree():
         a.Run(); b.Run(g)
     assert np.array_equal(bits(a.download("pos")), bits(b.download("pos")))
     assert np.array_equal(bits(a.download("vel")), bits(b.download("vel")))
+
+
+def test_checkpoint_resume_continues_bit_for_bit(tmp_path):
+    """sphe_save_state / sphe_load_state: particles (+ carried sediment, fixed point) and the eroded terrain go to one
+    file; a fresh handle + a fresh terrain loaded from it continue EXACTLY like the uninterrupted run -- positions,
+    velocities, densities, sediment, heights, contact for contact.  Also: a file with a terrain refuses to load
+    without a terrain handle, and a non-state file is rejected."""
+    import importlib
+    m = product()
+    T = importlib.import_module("test_gpu_slabs")
+    box = (1.2, 0.3, 0.3)
+    params = dict(len=0.3, dt=0.004, g=(0.0, -9.82, 0.0))
+    g1, pos, vel = T._terrain_scene(m)
+    one = T._single(m, box, params, (6, 3), pos, vel)
+    for _ in range(6):
+        one.Run(g1)
+    ck = str(tmp_path / "state.sphe")
+    one.save_state(ck, g1)
+    for _ in range(6):
+        one.Run(g1)
+
+    two = m.FluidSystemSPH()
+    g2 = m.Grid(4, 255, 4)                      # wrong size on purpose: the file brings its own
+    with pytest.raises(m.capi.SpheError, match="terrain"):
+        two.load_state(ck)
+    two.load_state(ck, g2)
+    assert g2.shape() == g1.shape() and two.count() == one.count()
+    for _ in range(6):
+        two.Run(g2)
+    for f in ("pos", "vel", "density", "sediment"):
+        assert np.array_equal(one.download(f), two.download(f)), f
+    assert np.array_equal(g1.heights_fx(), g2.heights_fx())
+    assert one.sediment_total_fx() == two.sediment_total_fx() > 0
+
+    bad = tmp_path / "bad.sphe"; bad.write_bytes(b"not a state file at all" * 10)
+    with pytest.raises(m.capi.SpheError, match="not a sphe state file"):
+        two.load_state(str(bad))

@@ -71,3 +71,23 @@ def test_headless_terrain_and_erosion(tmp_path):
     assert "terrain: 15000 surface floats, 14406 indices, H(5,7) = %d" % int(gold["hf64"][5, 7]) in r.stdout
     pos, vel, rho = read_dump(str(tmp_path / "e.bin"))
     assert np.isfinite(pos).all()
+
+
+@pytest.mark.gpu
+def test_headless_checkpoint_resume_is_bit_exact(tmp_path):
+    """--save / --load (FluidSystemSPH::Save / Load -> sphe_save_state / sphe_load_state): 30 steps, checkpoint, 30 more
+    steps in a second process == 60 steps in one process, bit for bit, terrain erosion included."""
+    build()
+    gold = np.load(os.path.join(GOLDEN, "terrain.npz"))
+    img = np.zeros((512, 512), np.uint8); img[:64, :64] = gold["hf64"]
+    raw = str(tmp_path / "hf.bin"); img.tofile(raw)
+    common = ["--terrain", raw, "--erosion"]
+    full, part, ck = str(tmp_path / "full.bin"), str(tmp_path / "part.bin"), str(tmp_path / "ck.sphe")
+    r = subprocess.run([EXE, "--steps", "60", "--dump", full] + common, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([EXE, "--steps", "30", "--save", ck] + common, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([EXE, "--steps", "30", "--load", ck, "--dump", part] + common, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    a, b = np.fromfile(full, np.uint8), np.fromfile(part, np.uint8)
+    assert a.size == b.size and np.array_equal(a, b), "resumed run differs from the uninterrupted one"
