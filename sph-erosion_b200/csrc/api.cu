@@ -69,6 +69,11 @@ struct sphe_sim {
     bool ready = false;
     cudaStream_t st = nullptr;
     bool own_stream = false, user_stream = false;
+    // end-to-end path (sphe_step_host): a second stream carries the velocity upload and the density download while
+    // the main stream computes
+    cudaStream_t st_io = nullptr;
+    cudaEvent_t ev_vel = nullptr, ev_density = nullptr, ev_io_done = nullptr;
+    struct HostIO { bool wait_vel = false; float* density_out = nullptr; } io;
 
     int n = 0, cap = 0;
     float4 *posA = nullptr, *posB = nullptr, *posC = nullptr, *velA = nullptr, *velB = nullptr;
@@ -349,6 +354,7 @@ static int step_device(sphe_sim* s, sphe_terrain* t, int terrain_phases = 7) {
     { Scope k(s, SPHE_K_HASH); launch_hash(s->st, n, nd, s->posA, s->G, s->cell, s->count); }
     { Scope k(s, SPHE_K_SCAN, 3); launch_scan(s->st, s->ncells, n, nd, s->count, s->tile_sum, s->cell_start, s->cursor); }
     { Scope k(s, SPHE_K_SCATTER); launch_scatter(s->st, n, nd, s->cell, s->idsA, s->cursor, s->tmp); }
+    if (s->io.wait_vel) CU(cudaStreamWaitEvent(s->st, s->ev_vel, 0));   // velocities arrive on the io stream (sphe_step_host)
     { Scope k(s, SPHE_K_REORDER);
       launch_rank_reorder(s->st, n, nd, s->tmp, s->cell, s->cell_start, s->posA, s->velA, s->sedA, s->posB, s->velB, s->sedB,
                           s->idsB, s->cell_sorted); }
@@ -403,6 +409,14 @@ static int step_device(sphe_sim* s, sphe_terrain* t, int terrain_phases = 7) {
           CU(cudaMemcpyAsync(s->h_overflow, s->d_overflow, 3 * sizeof(int), cudaMemcpyDeviceToHost, s->st));
           CU(cudaMemsetAsync(s->d_overflow, 0, 3 * sizeof(int), s->st));
       } }
+    if (s->io.density_out) {
+        // the densities leave for the host while the force pass runs (idsB = this step's sorted ids)
+        CU(cudaEventRecord(s->ev_density, s->st));
+        CU(cudaStreamWaitEvent(s->st_io, s->ev_density, 0));
+        float* drho = s->stage + 6 * (size_t)s->cap;
+        launch_unsort_f1(s->st_io, n, s->rho, s->idsB, drho);
+        CU(cudaMemcpyAsync(s->io.density_out, drho, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->st_io));
+    }
     { Scope k(s, SPHE_K_FORCE);
       launch_force(s->st, s->variant_force, n, nd, s->posC, s->velB, s->rho, s->idsB, s->cell_sorted, s->cell_start, s->G, C,
                    s->posA, s->velA, s->diag ? &s->D : nullptr, s->nlist, s->ncount); }
@@ -496,6 +510,7 @@ void sphe_destroy(sphe_sim* s) {
         if (s->slab_host) cudaFreeHost(s->slab_host);
         cudaFree(s->transit[0]); cudaFree(s->transit[1]); cudaFree(s->transit_n);
         cudaFree(s->d_overflow); if (s->h_overflow) cudaFreeHost(s->h_overflow);
+        if (s->st_io) { cudaStreamDestroy(s->st_io); cudaEventDestroy(s->ev_vel); cudaEventDestroy(s->ev_density); cudaEventDestroy(s->ev_io_done); }
         if (s->d_n) cudaFree(s->d_n);
         for (auto& e : s->slab_ev) if (e) cudaEventDestroy(e);
         if (s->own_stream && s->st) cudaStreamDestroy(s->st);
@@ -623,20 +638,44 @@ int sphe_sync(sphe_sim* s) {
 int sphe_step_host(sphe_sim* s, sphe_terrain* t, int n, const float* pos_in, const float* vel_in, float* pos_out,
                    float* vel_out, float* density_out) {
     if (!s || n <= 0 || !pos_in || !vel_in || !pos_out || !vel_out) return fail(SPHE_ERR_ARG, "bad arguments");
-    TRY(upload_from_host(s, n, pos_in, vel_in));
-    TRY(step_device(s, t));
+    if (s->slab_on) return fail(SPHE_ERR_STATE, "not available in slab mode (sphe_slab_upload / sphe_slab_download)");
+    TRY(ensure_device(s));
+    if (!s->st_io) {
+        CU(cudaStreamCreateWithFlags(&s->st_io, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&s->ev_vel, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s->ev_density, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s->ev_io_done, cudaEventDisableTiming));
+    }
+    // PCIe is the bottleneck of this path (52 B/particle/step against a 0.37 us/particle... step): keep both DMA
+    // directions busy while the kernels run.  Positions first (the binning needs only them); the velocities
+    // follow on the io stream and are awaited right before the reorder gathers them; the densities go back while
+    // the force pass runs.
+    s->n = 0;
+    TRY(reserve(s, n));
     float* dpos = s->stage;
     float* dvel = s->stage + 3 * (size_t)s->cap;
-    float* drho = s->stage + 6 * (size_t)s->cap;
+    CU(cudaStreamSynchronize(s->st));          // the staging area may still be read by an earlier download
+    CU(cudaMemcpyAsync(dpos, pos_in, 3 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s->st));
+    CU(cudaEventRecord(s->ev_io_done, s->st));
+    launch_pack_state(s->st, n, dpos, nullptr, s->posA, s->velA, s->idsA, s->sedA);
+    // the velocity copy starts when the position copy has finished (two concurrent copies would only share the
+    // link and delay the positions the binning is waiting for)
+    CU(cudaStreamWaitEvent(s->st_io, s->ev_io_done, 0));
+    CU(cudaMemcpyAsync(dvel, vel_in, 3 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s->st_io));
+    launch_pack_state(s->st_io, n, nullptr, dvel, s->posA, s->velA, s->idsA, nullptr);
+    CU(cudaEventRecord(s->ev_vel, s->st_io));
+    s->n = n;
+    s->binned = false; s->slot_valid = false;
+    s->io.wait_vel = true; s->io.density_out = density_out;
+    int rc = step_device(s, t);
+    s->io.wait_vel = false; s->io.density_out = nullptr;
+    if (rc != SPHE_OK) { cudaStreamSynchronize(s->st_io); return rc; }
     launch_unsort_f4(s->st, n, s->posA, s->idsA, dpos);
-    launch_unsort_f4(s->st, n, s->velA, s->idsA, dvel);
     CU(cudaMemcpyAsync(pos_out, dpos, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->st));
+    launch_unsort_f4(s->st, n, s->velA, s->idsA, dvel);
     CU(cudaMemcpyAsync(vel_out, dvel, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->st));
-    if (density_out) {
-        launch_unsort_f1(s->st, n, s->rho, s->idsA, drho);
-        CU(cudaMemcpyAsync(density_out, drho, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->st));
-    }
     CU(cudaStreamSynchronize(s->st));
+    CU(cudaStreamSynchronize(s->st_io));
     return SPHE_OK;
 }
 

@@ -946,8 +946,8 @@ __global__ void __launch_bounds__(L16_THREADS) k_density_list16(int n_hi, const 
         int* dst = nlist + t;
         const int seg = (npass == 2) ? off0 : off;          // entries from pass 0 use the stored run starts
         const int cyb = (int)(colb % (uint32_t)G.ny), cxb = (int)(colb / (uint32_t)G.ny), z0b = czb > 0 ? czb - 1 : 0;
-#pragma unroll 2
         const int stop = min(off, L16_CAP * T);             // longer lists: the rest is already in place
+#pragma unroll 2
         for (int o = 0, e = 0; o < stop; o += T, e++) {
             const unsigned v = lbase[o];
             const int r = (int)(v >> 12);
@@ -1475,14 +1475,18 @@ __global__ void k_unsort_u32(int n, const uint32_t* __restrict__ src, const int*
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[ids[i]] = (int)src[i];
 }
+// pos / vel may be NULL: the end-to-end path packs the two halves on different streams (velocities are still on the
+// PCIe bus while the positions are already being binned)
 __global__ void k_pack_state(int n, const float* __restrict__ pos, const float* __restrict__ vel, float4* __restrict__ posq,
                              float4* __restrict__ velv, int* __restrict__ ids, float* __restrict__ sed) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    posq[i] = make_float4(pos[3 * (size_t)i], pos[3 * (size_t)i + 1], pos[3 * (size_t)i + 2], 0.f);
-    velv[i] = make_float4(vel[3 * (size_t)i], vel[3 * (size_t)i + 1], vel[3 * (size_t)i + 2], 0.f);
-    ids[i] = i;
-    if (sed) sed[i] = 0.f;
+    if (pos) {
+        posq[i] = make_float4(pos[3 * (size_t)i], pos[3 * (size_t)i + 1], pos[3 * (size_t)i + 2], 0.f);
+        ids[i] = i;
+        if (sed) sed[i] = 0.f;
+    }
+    if (vel) velv[i] = make_float4(vel[3 * (size_t)i], vel[3 * (size_t)i + 1], vel[3 * (size_t)i + 2], 0.f);
 }
 __global__ void k_slot_of_id(int n, const int* __restrict__ ids, int* __restrict__ slot) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
