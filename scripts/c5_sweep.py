@@ -25,7 +25,8 @@ for n_axis in axes:
             if "CAP" in os.environ: sim.set_nlist_capacity(int(os.environ["CAP"]))
             sim.upload_state(pos, np.zeros_like(pos))
             sim.set_l2_flush(256 << 20)
-            sim.timed_steps(3, per_kernel=False)
+            for _ in range(16):      # the list sizing adapts from counters the host reads between calls
+                sim.timed_steps(1, per_kernel=False)
             ms, pk, _ = sim.timed_steps(steps)
             nb = sim.debug_neighbours_total() / n if n <= 33_000_000 else None
             gi = sim.grid_info()

@@ -366,8 +366,8 @@ static int step_device(sphe_sim* s, sphe_terrain* t, int terrain_phases = 7) {
             return fail(SPHE_ERR_ARG, "neighbour-list variants with different list formats cannot be combined");
         // capacity for every list variant: S sub-lists of slist_entries(S) entries per pair, S <= 8 -> <= 96 ints per pair
         if (!s->d_overflow) {
-            CU(cudaMalloc(&s->d_overflow, 4 * sizeof(int))); CU(cudaMemsetAsync(s->d_overflow, 0, 4 * sizeof(int), s->st));
-            CU(cudaMallocHost(&s->h_overflow, 4 * sizeof(int))); s->h_overflow[0] = s->h_overflow[1] = s->h_overflow[2] = 0; s->h_overflow[3] = 1;
+            CU(cudaMalloc(&s->d_overflow, 8 * sizeof(int))); CU(cudaMemsetAsync(s->d_overflow, 0, 8 * sizeof(int), s->st));
+            CU(cudaMallocHost(&s->h_overflow, 8 * sizeof(int))); memset(s->h_overflow, 0, 8 * sizeof(int));
         }
         // List sizing from the counters of a recent step (copied back without a sync, so a step or two old):
         // h_overflow = {pairs beyond the allocated rows, pairs that spilled out of shared memory, pairs that would
@@ -378,19 +378,21 @@ static int step_device(sphe_sim* s, sphe_terrain* t, int terrain_phases = 7) {
         //    when MOST pairs spill (dense scenes, 60-120 neighbours) the 128 / 256-entry instantiations win.
         const int dv = s->variant_density;
         const bool sized = dv == 3 || dv == 6 || dv == 10 || dv == 11 || (dv >= 31 && dv <= 33);
-        const long long pairs = s->h_overflow[3];
-        if (s->overflow_cooldown > 0) s->overflow_cooldown--;
-        else if (sized && s->nlist_capacity < 512 && s->h_overflow[0] * 1000LL > pairs) { s->nlist_capacity *= 2; s->overflow_cooldown = 4; }
+        // The host may be many steps ahead of the GPU, so the counts can be old: every block of counts carries the
+        // sizing it was produced with ([3] staged entries, [4] rows) and is ignored unless that is still the current one.
+        const long long pairs = std::max((s->n + 1) / 2, 1);
+        const bool rows_current = s->h_overflow[4] == s->nlist_capacity;
+        const bool smem_current = s->h_overflow[3] == s->nlist_smem;
+        if (sized && rows_current && s->nlist_capacity < 512 && s->h_overflow[0] * 1000LL > pairs) s->nlist_capacity *= 2;
         // staged entries: 64 (32-bit entries) -> 128 (16-bit entries, same shared memory, ~10 % more instructions) once 10 %
         // of the pairs spill (a spill stalls its warp) -> 256 (32-bit, 66 KB per 64-thread CTA) once 60 % spill even then
-        if (s->smem_cooldown > 0) s->smem_cooldown--;
-        else if (s->nlist_auto && (dv == 3 || dv == 6)) {
+        if (s->nlist_auto && (dv == 3 || dv == 6) && smem_current) {
             const long long spilled = s->h_overflow[1], half = s->h_overflow[2];
             const int m = s->nlist_smem;
-            if (m == 64 && spilled * 10 > pairs) { s->nlist_smem = 128; s->smem_cooldown = 4; }
-            else if (m == 128 && spilled * 10 > pairs * 6) { s->nlist_smem = 256; s->smem_cooldown = 4; }
-            else if (m == 128 && half * 20 < pairs) { s->nlist_smem = 64; s->smem_cooldown = 4; }
-            else if (m == 256 && half * 10 < pairs * 3) { s->nlist_smem = 128; s->smem_cooldown = 4; }
+            if (m == 64 && spilled * 10 > pairs) s->nlist_smem = 128;
+            else if (m == 128 && spilled * 10 > pairs * 6) s->nlist_smem = 256;
+            else if (m == 128 && half * 20 < pairs) s->nlist_smem = 64;
+            else if (m == 256 && half * 10 < pairs * 3) s->nlist_smem = 128;
         }
         size_t pp = (size_t)nlist_pairs_pad(s->cap) + 128;
         const int entries = std::max(std::max(96, s->nlist_capacity), s->nlist_smem);
@@ -405,8 +407,7 @@ static int step_device(sphe_sim* s, sphe_terrain* t, int terrain_phases = 7) {
       launch_density(s->st, s->variant_density, n, nd, s->posB, s->posC, s->velB, s->cell_sorted, s->cell_start, s->G, C, s->rho,
                      s->nlist, s->ncount, s->nlist_capacity, s->d_overflow, s->nlist_smem);
       if (s->d_overflow) {
-          s->h_overflow[3] = std::max((n + 1) / 2, 1);
-          CU(cudaMemcpyAsync(s->h_overflow, s->d_overflow, 3 * sizeof(int), cudaMemcpyDeviceToHost, s->st));
+          CU(cudaMemcpyAsync(s->h_overflow, s->d_overflow, 5 * sizeof(int), cudaMemcpyDeviceToHost, s->st));
           CU(cudaMemsetAsync(s->d_overflow, 0, 3 * sizeof(int), s->st));
       } }
     if (s->io.density_out) {

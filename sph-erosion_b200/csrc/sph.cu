@@ -618,6 +618,7 @@ __global__ void __launch_bounds__(THREADS) k_density_list(int n_hi, const int* _
     if (live && !fits) atomicAdd(overflow, 1);                          // beyond the allocated rows: direct walk in the force pass
     if (live && cnt > NLIST_CAP) atomicAdd(overflow + 1, 1);            // spilled (statistics for the host's choice of CAP)
     if (live && cnt > NLIST_CAP / 2) atomicAdd(overflow + 2, 1);        // would spill at the next smaller CAP
+    if (t == 0) { overflow[3] = NLIST_CAP; overflow[4] = rows; }        // which sizing these counts belong to (the host reads them late)
     if (fits) {
         int* dst = nlist + t;
         const int stop = min(off, NLIST_CAP * NLIST_THREADS);           // the rest is already in place
@@ -950,6 +951,7 @@ __global__ void __launch_bounds__(L16_THREADS) k_density_list16(int n_hi, const 
     if (live && !fits) atomicAdd(overflow, 1);
     if (live && cnt > L16_CAP) atomicAdd(overflow + 1, 1);
     if (live && cnt > L16_CAP / 2) atomicAdd(overflow + 2, 1);
+    if (t == 0) { overflow[3] = L16_CAP; overflow[4] = max(rows, L16_CAP); }
     if (fits) {
         // coalesced flush: entry e of all threads of the block is one contiguous row; decode run | offset -> particle index
         int* dst = nlist + t;
