@@ -55,8 +55,8 @@ info = drv.drain()
 ids, p, v, rho, sed = sim.slab_download()
 sed_fx = sim.sediment_total_fx()
 gathered = [None] * world
-own = share.own if mode == "window" else (0, grid.shape()[0])
-win = share.window if mode == "window" else own
+own = share.own if mode == "window" else ((0, grid.shape()[0]) if rank == 0 else (0, 0))   # replicas: count the terrain once
+win = share.window if mode == "window" else (0, grid.shape()[0])
 dist.all_gather_object(gathered, (ids, p, v, rho, sed_fx, grid.heights_fx(), grid.contacts(), info, own, win, grid.window_violations()))
 ok = True
 if rank == 0:
