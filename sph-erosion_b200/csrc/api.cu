@@ -352,7 +352,7 @@ static int step_device(sphe_sim* s, sphe_terrain* t, int terrain_phases = 7) {
     int n = s->n;
     const int* nd = s->slab_pending ? s->d_n : nullptr;  // exact count on the device while unpack results are in flight
     { Scope k(s, SPHE_K_HASH); launch_hash(s->st, n, nd, s->posA, s->G, s->cell, s->count); }
-    { Scope k(s, SPHE_K_SCAN, 3); launch_scan(s->st, s->ncells, n, nd, s->count, s->tile_sum, s->cell_start, s->cursor); }
+    { Scope k(s, SPHE_K_SCAN, 2); launch_scan(s->st, s->ncells, n, nd, s->count, s->tile_sum, s->cell_start, s->cursor); }
     { Scope k(s, SPHE_K_SCATTER); launch_scatter(s->st, n, nd, s->cell, s->idsA, s->cursor, s->tmp); }
     if (s->io.wait_vel) CU(cudaStreamWaitEvent(s->st, s->ev_vel, 0));   // velocities arrive on the io stream (sphe_step_host)
     { Scope k(s, SPHE_K_REORDER);

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) k_hash(int n_hi, const int* __restrict__ 
 }
 
 // ---------------------------------------------------------------- exclusive scan over cells
-// Reduce-then-scan in three launches: per-tile sums, scan of tile sums (one CTA), per-tile scan.
+// Reduce-then-scan in two launches: per-tile sums, then per-tile scan (each block sums the tile sums before it).
 // The final pass also primes the scatter cursor and clears the counts for the next step.
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 16;
@@ -132,9 +132,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(long long ncells, i
     }
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) s += v[k];
+    // offset of this tile = sum of the raw tile sums before it, computed by every block for itself (a few KB from L2):
+    // no separate single-CTA launch for the scan of the tile sums
+    int pre = 0;
+    for (int i = threadIdx.x; i < (int)blockIdx.x; i += SCAN_THREADS) pre += tile_off[i];
+    int tile_base;
+    block_incl_scan(pre, &tile_base);
     int total;
     int inc = block_incl_scan(s, &total);
-    int run = tile_off[blockIdx.x] + inc - s;
+    int run = tile_base + inc - s;
     if (e0 + SCAN_ITEMS <= ncells) {
         int o[SCAN_ITEMS];
 #pragma unroll
@@ -221,7 +227,6 @@ int scan_tiles_for(long long ncells) { return (int)((ncells + SCAN_TILE - 1) / S
 void launch_scan(cudaStream_t st, long long ncells, int n_total, const int* n_dev, int* count, int* tile_sum, int* cell_start, int* cursor) {
     int ntiles = scan_tiles_for(ncells);
     k_scan_reduce<<<ntiles, SCAN_THREADS, 0, st>>>(ncells, count, tile_sum);
-    k_scan_tiles<<<1, 1024, 0, st>>>(ntiles, tile_sum);
     k_scan_final<<<ntiles, SCAN_THREADS, 0, st>>>(ncells, n_total, n_dev, count, tile_sum, cell_start, cursor);
 }
 
