@@ -290,6 +290,7 @@ def run_reference_arm(args):
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic"}
     if not ref.available(omp=True):
+        os.environ["OMP_NUM_THREADS"] = os.environ.get("SPHE_REF_THREADS", str(os.cpu_count() or 1))
         # the oracle always exists: fall back to the C port of the same algorithm
         pos, L = scaled_dam_break(n_axis, jitter)
         cb = cpu_port_baseline(pos, L, scene_gravity(n_axis, args.gravity_unscaled))
@@ -298,7 +299,9 @@ def run_reference_arm(args):
                      "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         emit(line)
         return
-    os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
+    # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank); the OpenMP runtime reads the
+    # variable when the reference library is loaded, which happens below
+    os.environ["OMP_NUM_THREADS"] = os.environ.get("SPHE_REF_THREADS", str(os.cpu_count() or 1))
     sample_axis = 22
     pos, L = scaled_dam_break(sample_axis, jitter)
     gy_ref = scene_gravity(sample_axis, args.gravity_unscaled)
@@ -385,7 +388,7 @@ def run_gpu_arm(args):
     rows_end, smem_end, ovf_end = sim.nlist_capacity(), sim.nlist_smem_entries(), sim.nlist_overflowed()
     # second pass, instrumented
     sim.load_state(ck, grid)
-    os.remove(ck)
+    os.remove(ck); os.rmdir(os.path.dirname(ck))
     sim.timed_steps(args.warmup, grid=grid, per_kernel=False)
     ms_instrumented, per_kernel, _ = sim.timed_steps(args.steps, grid=grid, per_kernel=True)
     if grid is not None:
