@@ -36,7 +36,7 @@ def setup(world):
     return port, slabs, P, G, cols
 
 
-def worker(rank, world, port_no, steps, outdir, cap=4096, floor=None, lag=0):
+def worker(rank, world, port_no, steps, outdir, cap=4096, floor=None, lag=0, extra=None):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
     import torch.distributed as dist
@@ -49,6 +49,8 @@ def worker(rank, world, port_no, steps, outdir, cap=4096, floor=None, lag=0):
         _ns = slabs.next_size
         slabs.next_size = lambda count, cap_, floor_=floor: max(floor, count // 2)  # too small on purpose -> every step re-sends
     pos, vel = scene()
+    if extra is not None:
+        pos = np.concatenate([pos, extra[0]]); vel = np.concatenate([vel, extra[1]])
     x0, x1 = cols[rank]
     left, right, wrap_l, wrap_r = slabs.ring_links(rank, world)
     b = NumpySlabBackend(P, G, x0, x1, left is not None, right is not None, cap=cap, wrap_left=wrap_l, wrap_right=wrap_r,
@@ -74,7 +76,8 @@ def worker(rank, world, port_no, steps, outdir, cap=4096, floor=None, lag=0):
         log.append([info[k] for k in ("n_total", "n_owned", "to_left", "to_right", "from_left", "from_right")] + [drv.resends])
     drv.drain()
     i, p, v, r = b.owned()
-    np.savez(os.path.join(outdir, "rank%d.npz" % rank), ids=i, pos=p, vel=v, rho=r, log=np.array(log))
+    np.savez(os.path.join(outdir, "rank%d.npz" % rank), ids=i, pos=p, vel=v, rho=r, log=np.array(log),
+             transit=np.array([len(b.transit[0]) + len(b.transit[1]), b.forwarded]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -124,3 +127,35 @@ def test_partition_columns():
     assert cols == [(0, 30), (30, 54), (54, 100)] or cols == [(0, 29), (29, 53), (53, 100)] or cols[0][0] == 0 and cols[-1][1] == 100
     with pytest.raises(ValueError):
         slabs.partition_columns(10, 4)
+
+
+def test_far_migrant_is_forwarded_hop_by_hop():
+    """A particle that crosses MORE than one slab in a step (slab 1 -> slab 3 of 4) is received by slab 2, which is not
+    its owner, and handed on at the next exchange (slab.cu k_slab_append / k_slab_forward, restated in slab_double.py):
+    owned + in transit is conserved every step, it ends up owned by slab 3, and every other particle stays bit-equal
+    to the single-domain run."""
+    world, steps = 4, 3
+    port, slabs, P, G, cols = setup(world)
+    pos, vel = scene()
+    fast_p = np.array([[-0.2, 0.4, 0.0]], np.float32)       # isolated, in slab 1
+    fast_v = np.array([[160.0, 0.0, 0.0]], np.float32)      # 0.64 box units per step: lands in slab 3
+    n = len(pos) + 1
+    S = port.State(np.concatenate([pos, fast_p]), np.concatenate([vel, fast_v]))
+    port.step_grid(P, G, S, steps)
+    with tempfile.TemporaryDirectory() as d:
+        ctx = mp.get_context("spawn")
+        pn = free_port()
+        procs = [ctx.Process(target=worker, args=(r, world, pn, steps, d, 4096, None, 0, (fast_p, fast_v))) for r in range(world)]
+        for p in procs: p.start()
+        for p in procs: p.join(300)
+        assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+        parts = [np.load(os.path.join(d, "rank%d.npz" % r)) for r in range(world)]
+    ids = np.concatenate([p["ids"] for p in parts])
+    in_transit = sum(int(p["transit"][0]) for p in parts)
+    assert len(np.unique(ids)) == len(ids) and len(ids) + in_transit == n
+    assert sum(int(p["transit"][1]) for p in parts) >= 1, "the scene must exercise forwarding"
+    assert np.array_equal(np.sort(ids), np.arange(n)), "after 3 exchanges the fast particle is owned again"
+    assert (n - 1) in parts[3]["ids"], "... by the slab its position belongs to"
+    o = np.argsort(ids)
+    got = np.concatenate([p["pos"] for p in parts])[o]
+    assert np.array_equal(got[:n - 1], S.pos[:n - 1]), "everybody else is unaffected"
