@@ -93,6 +93,7 @@ int sphe_abi_version(void);
 int sphe_create(sphe_sim** out);
 void sphe_destroy(sphe_sim* s);
 int sphe_set_device(sphe_sim* s, int device); /* before first use; default = current device */
+int sphe_device_count(void);                  /* visible CUDA devices (0 when there is none) */
 
 /* ---- scene ---- */
 int sphe_initialize(sphe_sim* s, int n_parts);   /* Initialize(int)   fluid_system.h:74-102  */
@@ -215,7 +216,9 @@ int sphe_slab_result(sphe_sim* s, long long ticket, int wait, int out[6]);
  *            reserves particle storage (so the arrays never grow mid-run);
  *   handle:  64-byte cudaIpcMemHandle of the mailbox, to be handed to the two neighbour processes;
  *   connect: maps the neighbours' mailboxes (NULL = no neighbour on that side);
- *   connect_local: the same for slabs that live in ONE process on one GPU (tests). */
+ *   connect_local: the same for slabs that live in ONE process -- on one GPU (tests) or on several GPUs of the
+ *            node (direct peer access is enabled; host/headless_slabs.cpp drives N GPUs from one C++ thread,
+ *            every call only enqueues). */
 int sphe_slab_peer_setup(sphe_sim* s, int cap_records, int reserve_particles);
 int sphe_slab_peer_handle(sphe_sim* s, void* handle64);
 int sphe_slab_peer_connect(sphe_sim* s, const void* left_handle64, const void* right_handle64);

@@ -100,6 +100,7 @@ SYMBOLS = {
     "sphe_set_sediment_fx": (_i, [_vp, _vp]),
     "sphe_kernel_timing": (_i, [_vp, _i]),
     "sphe_kernel_times": (_i, [_vp, C.POINTER(_f), C.POINTER(_i)]),
+    "sphe_device_count": (_i, []),
     "sphe_nlist_capacity": (_i, [_vp]),
     "sphe_nlist_overflowed": (_i, [_vp]),
     "sphe_nlist_smem_entries": (_i, [_vp]),

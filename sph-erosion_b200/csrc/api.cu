@@ -764,6 +764,12 @@ int sphe_set_diagnostics(sphe_sim* s, int on) {
     return SPHE_OK;
 }
 
+int sphe_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
 int sphe_nlist_capacity(sphe_sim* s) { return s ? s->nlist_capacity : 0; }
 int sphe_nlist_overflowed(sphe_sim* s) { return (s && s->h_overflow) ? s->h_overflow[0] : 0; }
 
@@ -979,7 +985,8 @@ int sphe_slab_configure(sphe_sim* s, int x0, int x1, int has_left, int has_right
     if (!s->d_n) CU(cudaMalloc(&s->d_n, sizeof(int)));
     if (!s->slab_host) CU(cudaMallocHost(&s->slab_host, sphe_sim::SLAB_RING * 8 * sizeof(int)));
     for (int k = 0; k < 2; k++) if (!s->transit[k]) CU(cudaMalloc(&s->transit[k], 2 * SPHE_TRANSIT_CAP * sizeof(float4)));
-    if (!s->transit_n) { CU(cudaMalloc(&s->transit_n, 4 * sizeof(int))); CU(cudaMemset(s->transit_n, 0, 4 * sizeof(int))); }
+    // (the handle's stream is non-blocking: a memset on the legacy stream is NOT ordered before kernels on it -- synchronise)
+    if (!s->transit_n) { CU(cudaMalloc(&s->transit_n, 4 * sizeof(int))); CU(cudaMemset(s->transit_n, 0, 4 * sizeof(int))); CU(cudaDeviceSynchronize()); }
     for (auto& e : s->slab_ev) if (!e) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     return SPHE_OK;
 }
@@ -1033,7 +1040,8 @@ int sphe_slab_upload(sphe_sim* s, int n, const float* pos, const float* vel, con
     CU(cudaMemcpyAsync(dids, ids, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s->st));
     launch_pack_state_ids(s->st, n, dpos, dvel, dids, s->posA, s->velA, s->idsA, s->sedA);
     CU(cudaStreamSynchronize(s->st));
-    CU(cudaMemset(s->transit_n, 0, 4 * sizeof(int)));
+    CU(cudaMemsetAsync(s->transit_n, 0, 4 * sizeof(int), s->st));
+    CU(cudaStreamSynchronize(s->st));
     s->n = n; s->n_owned = n;
     s->slab_done = s->slab_seq; s->slab_pending = 0;
     s->num = n; s->init_num = n; s->next_label = n;
@@ -1214,6 +1222,7 @@ int sphe_slab_peer_setup(sphe_sim* s, int cap_records, int reserve_particles) {
     cudaError_t e = cudaMalloc(&s->mbox, bytes);
     if (e != cudaSuccess) return fail(SPHE_ERR_NOMEM, "mailbox of %zu bytes: %s", bytes, cudaGetErrorString(e));
     CU(cudaMemset(s->mbox, 0, bytes));
+    CU(cudaDeviceSynchronize());   // flags and headers must be zero before ANY stream (ours or a neighbour's) touches the mailbox
     s->peer_seq = 0;
     if (reserve_particles > 0) TRY(reserve(s, reserve_particles));
     return SPHE_OK;
@@ -1264,7 +1273,16 @@ int sphe_slab_peer_connect_local(sphe_sim* s, sphe_sim* left, sphe_sim* right) {
         s->peer_mbox[k] = nullptr; s->peer_ipc[k] = false;
         if (!ns[k]) continue;
         if (!ns[k]->mbox || ns[k]->mbox_cap != s->mbox_cap) return fail(SPHE_ERR_STATE, "neighbour mailbox missing or of a different capacity");
-        if (ns[k]->device != s->device) return fail(SPHE_ERR_ARG, "sphe_slab_peer_connect_local needs both slabs on one device");
+        if (ns[k]->device != s->device) {
+            // another GPU of the same process: direct peer access over NVLink instead of an IPC mapping
+            TRY(ensure_device(s));
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, s->device, ns[k]->device));
+            if (!can) return fail(SPHE_ERR_CUDA, "device %d cannot access device %d as a peer", s->device, ns[k]->device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(ns[k]->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) return fail(SPHE_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", ns[k]->device, cudaGetErrorString(e));
+        }
         s->peer_mbox[k] = ns[k]->mbox;
     }
     return SPHE_OK;
@@ -1296,6 +1314,7 @@ int sphe_slab_send(sphe_sim* s) {
     if ((s->slab.has_left && !s->peer_mbox[0]) || (s->slab.has_right && !s->peer_mbox[1]))
         return fail(SPHE_ERR_STATE, "neighbour mailbox not connected");
     TRY(ensure_device(s));
+    TRY(setup_grid(s));            // the classification needs the global grid (a host that never asked for slab_info has none yet)
     TRY(slab_fold_ready(s));
     const int incoming = 2 * s->mbox_cap;
     if ((long long)s->n + incoming > s->cap) TRY(slab_settle(s));   // exact count before deciding to grow
