@@ -126,3 +126,29 @@ def test_grid_definition_invariants():
         want = np.nonzero(dist[i] <= np.float32(P.h))[0]
         got = np.sort(nb[ns[s]:ns[s + 1]])
         assert np.array_equal(got, want)
+
+
+def test_grid_step_is_bit_identical_to_all_pairs_property():
+    """Property (hypothesis): for random clouds, smoothing radii, box sizes and time steps the oracle's cell-grid step
+    -- the one that stands in for the reference at 1M+ particles -- gives the SAME BITS as its all-pairs step, which is
+    bit-identical to the compiled reference (test_oracle_vs_ref.py).  Several particles per cell, particles outside the
+    grid (clamped cells) and on the walls included."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=25, deadline=None, derandomize=True)
+    @given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(1, 350), h=st.floats(0.02, 0.09), length=st.floats(0.08, 0.4),
+           dt=st.sampled_from([0.0, 0.002, 0.01]), spread=st.floats(0.3, 1.3))
+    def check(seed, n, h, length, dt, spread):
+        rng = np.random.default_rng(seed)
+        P = port.default_params(dt=dt, len=length, h=h)
+        pos = rng.uniform(-spread * length, spread * length, (n, 3)).astype(np.float32)
+        pos[: n // 7, 0] = -np.float32(length)            # some exactly on the -x wall (the +len clamp of collisionS)
+        vel = rng.normal(0, 0.4, (n, 3)).astype(np.float32)
+        A = port.State(pos, vel); B = port.State(pos, vel)
+        port.step_allpairs(P, A)
+        port.step_grid(P, port.grid_for_box(P, [-length] * 3, [length] * 3), B)
+        for f in FLOAT_FIELDS:
+            a, b = getattr(A, f), getattr(B, f)
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) or (np.isnan(a) == np.isnan(b)).all() and np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)]), f
+
+    check()
