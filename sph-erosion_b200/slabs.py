@@ -44,6 +44,56 @@ def partition_columns(gnx, world, boundaries_x=None, gmin_x=None, cell=None):
     return out
 
 
+def balanced_cuts(hist, world, old_cuts=None, max_shift=None):
+    """Column cuts that give every slab about the same number of particles ("slab boundaries by
+    particle-count quantiles of cell-x, re-cut every K steps").  hist[c] = particles in global cell column c (summed
+    over the ranks); returns world-1 ascending cut columns.  Every slab keeps at least 2*HALO columns; with old_cuts
+    every cut stays HALO columns inside the span of its two old neighbours (one exchange moves data one slab over, halo
+    included; a large imbalance converges over a few re-cuts) and, if given, moves by at
+    most max_shift columns."""
+    hist = np.asarray(hist, np.int64)
+    gnx = hist.shape[0]
+    if gnx < world * 2 * HALO:
+        raise ValueError("%d columns cannot hold %d slabs of at least %d columns" % (gnx, world, 2 * HALO))
+    cum = np.concatenate([[0], np.cumsum(hist)])
+    total = int(cum[-1])
+    cuts = []
+    for r in range(1, world):
+        c = int(np.searchsorted(cum, total * r / world, side="left"))
+        cuts.append(c)
+    if old_cuts is not None:
+        # Everything a slab needs right after the re-cut -- its new columns AND its halo -- must already be held by
+        # itself or by an x-neighbour, because one exchange only moves data one slab over: every cut stays at least
+        # HALO columns inside the span of its two old neighbours.
+        edges = [0] + list(old_cuts) + [gnx]
+        cuts = [int(min(max(c, edges[i] + HALO), edges[i + 2] - HALO)) for i, c in enumerate(cuts)]
+        if max_shift is not None:
+            cuts = [int(min(max(c, o - int(max_shift)), o + int(max_shift))) for c, o in zip(cuts, old_cuts)]
+    # minimum widths, left to right then right to left
+    lo = 0
+    for i in range(world - 1):
+        cuts[i] = max(cuts[i], lo + 2 * HALO); lo = cuts[i]
+    hi = gnx
+    for i in range(world - 2, -1, -1):
+        cuts[i] = min(cuts[i], hi - 2 * HALO); hi = cuts[i]
+    return cuts
+
+
+def rebalance(backend, dist_reduce, rank, world, cols, max_shift=None):
+    """Re-cuts the slabs by particle count.  backend: column_histogram(gnx) + reconfigure(x0, x1, far_x0);
+    dist_reduce(array) sums an int64 numpy array over the ranks in place.  Call it BETWEEN steps with nothing in
+    flight (after drain()); the next exchange migrates the particles that changed owner.  Returns the new column
+    ranges.  Not for runs that share a terrain (the row windows would have to move with the cuts)."""
+    gnx = cols[-1][1]
+    hist = np.asarray(backend.column_histogram(gnx), np.int64)
+    dist_reduce(hist)
+    cuts = balanced_cuts(hist, world, [c[0] for c in cols[1:]], max_shift)
+    edges = [0] + cuts + [gnx]
+    new_cols = [(edges[r], edges[r + 1]) for r in range(world)]
+    backend.reconfigure(new_cols[rank][0], new_cols[rank][1], new_cols[-1][0])
+    return new_cols
+
+
 def ring_links(rank, world):
     """(left, right, wrap_left, wrap_right) of a slab.  3 or more slabs close into a ring: the reference's box
     response moves a particle that sits exactly on the -x wall to the +x wall (collisionS, fluid_system.h:375-382),
@@ -93,6 +143,7 @@ class GpuSlabBackend:
         self.sim = sim
         self.cap = int(cap_records)
         self.has_left, self.has_right = has_left, has_right
+        self.wrap = (False, False)     # set by make_gpu_slab for the first / last slab of a ring
         f32 = dict(dtype=torch.float32, device=device)
         n = (self.cap + 1) * RECORD_FLOATS
         self.send_l = torch.zeros(n, **f32); self.send_r = torch.zeros(n, **f32)
@@ -116,6 +167,20 @@ class GpuSlabBackend:
 
     def step(self):
         self.sim.Run()
+
+    # ---- load balancing (slabs.rebalance): only calls the driver already makes elsewhere
+    def column_histogram(self, gnx):
+        """Owned particles per global cell column (a download: meant for every ~100 steps, not every step)."""
+        gi = self.sim.grid_info()
+        ids, pos, vel, rho, sed = self.sim.slab_download()
+        cx = np.floor((pos[:, 0].astype(np.float32) - np.float32(gi.gmin[0])) / np.float32(gi.cell))
+        return np.bincount(np.clip(cx, 0, gnx - 1).astype(np.int64), minlength=gnx)
+
+    def reconfigure(self, x0, x1, far_x0):
+        s = self.sim
+        s.slab_configure(x0, x1, self.has_left, self.has_right)
+        if self.wrap[0] or self.wrap[1]:
+            s.slab_ring(self.wrap[0], self.wrap[1], far_x0)
 
 
 # --------------------------------------------------------------------------- the per-step protocol
@@ -506,7 +571,9 @@ def make_gpu_slab(pkg, device, rank, world, box_half, params, bounds_x, cap_reco
     sim.slab_configure(x0, x1, left is not None, right is not None)
     if wrap_l or wrap_r:
         sim.slab_ring(wrap_l, wrap_r, cols[-1][0])
-    return sim, GpuSlabBackend(sim, device, cap_records, left is not None, right is not None), cols
+    backend = GpuSlabBackend(sim, device, cap_records, left is not None, right is not None)
+    backend.wrap = (wrap_l, wrap_r)
+    return sim, backend, cols
 
 
 # --------------------------------------------------------------------------- bench (called by bench.py)

@@ -102,6 +102,15 @@ class NumpySlabBackend:
     def result(self, ticket, wait=True):
         return self._results[ticket]
 
+    def column_histogram(self, gnx):
+        m = (self.ids & GHOST) == 0
+        return np.bincount(cell_x(self.pos[m, 0], self.G.gmin[0], self.G.cell, self.gnx), minlength=gnx)
+
+    def reconfigure(self, x0, x1, far_x0):
+        self.x0, self.x1 = x0, x1
+        if self.wl:
+            self.far_x0 = far_x0
+
     def step(self):
         # the oracle sums neighbours in ascending array order: present the particles in global-id order
         o = np.argsort(self.ids & (GHOST - 1), kind="stable")

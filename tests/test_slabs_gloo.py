@@ -27,6 +27,13 @@ def scene(n=2000, seed=5):
     return pos, vel
 
 
+def squeeze_scene(pos, factor):
+    """Most of the particles into the left part of the box: an unbalanced load for equal-width slabs."""
+    p = pos.copy()
+    p[:, 0] = (-0.55 + (p[:, 0] + 0.55) * np.float32(factor)).astype(np.float32)
+    return p
+
+
 def setup(world):
     from oracle import port
     slabs = __import__("importlib").import_module("sph-erosion_b200.slabs")
@@ -36,7 +43,7 @@ def setup(world):
     return port, slabs, P, G, cols
 
 
-def worker(rank, world, port_no, steps, outdir, cap=4096, floor=None, lag=0, extra=None):
+def worker(rank, world, port_no, steps, outdir, cap=4096, floor=None, lag=0, extra=None, rebalance_at=None, squeeze=None):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
     import torch.distributed as dist
@@ -51,6 +58,8 @@ def worker(rank, world, port_no, steps, outdir, cap=4096, floor=None, lag=0, ext
     pos, vel = scene()
     if extra is not None:
         pos = np.concatenate([pos, extra[0]]); vel = np.concatenate([vel, extra[1]])
+    if squeeze is not None:
+        pos = squeeze_scene(pos, squeeze)
     x0, x1 = cols[rank]
     left, right, wrap_l, wrap_r = slabs.ring_links(rank, world)
     b = NumpySlabBackend(P, G, x0, x1, left is not None, right is not None, cap=cap, wrap_left=wrap_l, wrap_right=wrap_r,
@@ -70,13 +79,23 @@ def worker(rank, world, port_no, steps, outdir, cap=4096, floor=None, lag=0, ext
     b.upload(pos[mine], vel[mine], ids[mine])
     drv = slabs.SlabDriver(b, slabs.TorchComm(rank, world), lag=lag, sync_steps=1)
     log = []
-    for _ in range(steps):
+    counts = []
+    for k in range(steps):
+        if rebalance_at is not None and k in rebalance_at:
+            drv.drain()
+
+            def reduce(a):
+                t = torch.from_numpy(a); dist.all_reduce(t)
+
+            counts.append(b.n_owned)
+            cols = slabs.rebalance(b, reduce, rank, world, cols)
         drv.step()
         info = b.last_info
         log.append([info[k] for k in ("n_total", "n_owned", "to_left", "to_right", "from_left", "from_right")] + [drv.resends])
     drv.drain()
     i, p, v, r = b.owned()
-    np.savez(os.path.join(outdir, "rank%d.npz" % rank), ids=i, pos=p, vel=v, rho=r, log=np.array(log),
+    counts.append(b.n_owned)
+    np.savez(os.path.join(outdir, "rank%d.npz" % rank), ids=i, pos=p, vel=v, rho=r, log=np.array(log), counts=np.array(counts), cols=np.array(cols),
              transit=np.array([len(b.transit[0]) + len(b.transit[1]), b.forwarded]))
     dist.barrier()
     dist.destroy_process_group()
@@ -159,3 +178,33 @@ def test_far_migrant_is_forwarded_hop_by_hop():
     o = np.argsort(ids)
     got = np.concatenate([p["pos"] for p in parts])[o]
     assert np.array_equal(got[:n - 1], S.pos[:n - 1]), "everybody else is unaffected"
+
+
+def test_rebalance_by_particle_count_keeps_results_bit_equal():
+    """slabs.rebalance (SURVEY.md 8e "re-cut by particle-count quantiles"): an unbalanced scene (all particles in the left
+    40 % of the box) on 3 equal-width slabs, re-cut before steps 1-4 (a cut may only move between its old neighbours, so a large imbalance converges over a
+    few re-cuts).  The cuts move, the owned counts even out, every exchange migrates who changed owner, and the run stays BIT-EQUAL to the single-domain oracle."""
+    world, steps = 3, 6
+    port, slabs, P, G, cols = setup(world)
+    pos, vel = scene()
+    pos = squeeze_scene(pos, 0.4)
+    S = port.State(pos, vel)
+    port.step_grid(P, G, S, steps)
+    with tempfile.TemporaryDirectory() as d:
+        ctx = mp.get_context("spawn")
+        pn = free_port()
+        procs = [ctx.Process(target=worker, args=(r, world, pn, steps, d, 4096, None, 0, None, (1, 2, 3, 4), 0.4)) for r in range(world)]
+        for p in procs: p.start()
+        for p in procs: p.join(300)
+        assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+        parts = [np.load(os.path.join(d, "rank%d.npz" % r)) for r in range(world)]
+    ids = np.concatenate([p["ids"] for p in parts])
+    assert np.array_equal(np.sort(ids), np.arange(len(pos)))
+    o = np.argsort(ids)
+    for name, want in (("pos", S.pos), ("vel", S.vel), ("rho", S.density)):
+        assert np.array_equal(np.concatenate([p[name] for p in parts])[o], want), name
+    before = [int(p["counts"][0]) for p in parts]; after = [int(p["counts"][-1]) for p in parts]
+    assert max(before) > 0.65 * len(pos) and min(before) == 0, "the equal-width cut must be badly unbalanced: %r" % before
+    assert max(after) < 0.5 * len(pos) and min(after) > 0.15 * len(pos), "the re-cuts even the load out: %r -> %r" % (before, after)
+    new_cols = parts[0]["cols"].tolist()
+    assert new_cols != [list(c) for c in cols] and all(np.array_equal(p["cols"], parts[0]["cols"]) for p in parts)
