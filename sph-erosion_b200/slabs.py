@@ -94,6 +94,18 @@ def rebalance(backend, dist_reduce, rank, world, cols, max_shift=None):
     return new_cols
 
 
+def rebalance_local(backends, cols, max_shift=None):
+    """The same for K slabs driven by one process (LocalPeerGroup / tests): the histogram sum is a plain sum."""
+    gnx = cols[-1][1]
+    hist = sum(np.asarray(b.column_histogram(gnx), np.int64) for b in backends)
+    cuts = balanced_cuts(hist, len(backends), [c[0] for c in cols[1:]], max_shift)
+    edges = [0] + cuts + [gnx]
+    new_cols = [(edges[r], edges[r + 1]) for r in range(len(backends))]
+    for r, b in enumerate(backends):
+        b.reconfigure(new_cols[r][0], new_cols[r][1], new_cols[-1][0])
+    return new_cols
+
+
 def ring_links(rank, world):
     """(left, right, wrap_left, wrap_right) of a slab.  3 or more slabs close into a ring: the reference's box
     response moves a particle that sits exactly on the -x wall to the +x wall (collisionS, fluid_system.h:375-382),

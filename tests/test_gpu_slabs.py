@@ -321,3 +321,44 @@ def test_particles_crossing_more_than_one_slab_are_forwarded_not_lost():
     o = np.argsort(ids)
     p = np.concatenate([g[1] for g in got])[o]
     assert np.array_equal(p[:n - 3], one.download("pos")[:n - 3]), "the rest of the scene is unaffected"
+
+
+@pytest.mark.xfail(reason="round 1: the only GPU run of a mid-run re-cut (last GPU minute of the round) was NOT bit-equal to the "
+                          "single-handle run (positions off by ~4e-5) although the same protocol is bit-equal under gloo with the "
+                          "numpy double (tests/test_slabs_gloo.py); open item, DESIGN.md section 4", strict=False)
+def test_rebalance_on_the_gpu_keeps_results_bit_equal():
+    """slabs.rebalance_local on real slab handles: an unbalanced cloud on 3 equal-width slabs, re-cut by particle count
+    before steps 2-5 (slab_download histogram, slab_configure, slab_ring -- mid-run); the exchange migrates whoever
+    changed owner and the run stays BIT-EQUAL to the single-handle run while the owned counts even out."""
+    import torch
+    m = product()
+    slabs = importlib.import_module("sph-erosion_b200.slabs")
+    pos, vel = scene()
+    pos = pos.copy(); pos[:-4, 0] = (-1.1 + (pos[:-4, 0] + 1.1) * np.float32(0.4)).astype(np.float32)   # everybody into the left 40 %
+    n = pos.shape[0]
+    box = (1.2, 0.3, 0.3)
+    params = dict(len=0.3, dt=0.004, g=(0.0, -9.82, 0.0))
+    one = _single(m, box, params, (6, 3), pos, vel)
+    K, cap = 3, 1 << 15
+    sims, backs = [], []
+    for r in range(K):
+        sim, b, cols = slabs.make_gpu_slab(m, torch.cuda.current_device(), r, K, box, params, None, cap, (6, 3))
+        sims.append(sim); backs.append(b)
+    order = np.argsort(pos[:, 0], kind="stable")
+    for r, part in enumerate(np.array_split(order, K)):
+        sims[r].slab_upload(pos[part], vel[part], part.astype(np.int32))
+    group = slabs.LocalPeerGroup(sims, cap, n + 4 * cap)
+    counts = []
+    for step in range(8):
+        if step in (2, 3, 4, 5):
+            group.drain()
+            counts.append([s.slab_info()["n_owned"] for s in sims])
+            cols = slabs.rebalance_local(backs, cols)
+        one.Run()
+        group.step()
+    group.drain()
+    counts.append([s.slab_info()["n_owned"] for s in sims])
+    p, v, rho, _ = _gather(sims, n)
+    for a, name in ((p, "pos"), (v, "vel"), (rho, "density")):
+        assert np.array_equal(a, one.download(name)), name
+    assert max(counts[0]) > 0.6 * n and max(counts[-1]) < 0.5 * n and min(counts[-1]) > 0.15 * n, counts
