@@ -323,9 +323,6 @@ def test_particles_crossing_more_than_one_slab_are_forwarded_not_lost():
     assert np.array_equal(p[:n - 3], one.download("pos")[:n - 3]), "the rest of the scene is unaffected"
 
 
-@pytest.mark.xfail(reason="round 1: the only GPU run of a mid-run re-cut (last GPU minute of the round) was NOT bit-equal to the "
-                          "single-handle run (positions off by ~4e-5) although the same protocol is bit-equal under gloo with the "
-                          "numpy double (tests/test_slabs_gloo.py); open item, DESIGN.md section 4", strict=False)
 def test_rebalance_on_the_gpu_keeps_results_bit_equal():
     """slabs.rebalance_local on real slab handles: an unbalanced cloud on 3 equal-width slabs, re-cut by particle count
     before steps 2-5 (slab_download histogram, slab_configure, slab_ring -- mid-run); the exchange migrates whoever
@@ -344,8 +341,13 @@ def test_rebalance_on_the_gpu_keeps_results_bit_equal():
     for r in range(K):
         sim, b, cols = slabs.make_gpu_slab(m, torch.cuda.current_device(), r, K, box, params, None, cap, (6, 3))
         sims.append(sim); backs.append(b)
-    order = np.argsort(pos[:, 0], kind="stable")
-    for r, part in enumerate(np.array_split(order, K)):
+    # initial distribution by OWNER (cell column): with x-quantile thirds the right third of this squeezed cloud would
+    # start two slabs away from its owner and be forwarded, i.e. arrive a step late
+    gi = sims[0].grid_info()
+    cx = np.clip(np.floor((pos[:, 0] - np.float32(gi.gmin[0])) / np.float32(gi.cell)), 0, cols[-1][1] - 1).astype(np.int64)
+    owner = np.searchsorted([c[1] for c in cols], cx, side="right")
+    for r in range(K):
+        part = np.nonzero(owner == r)[0]
         sims[r].slab_upload(pos[part], vel[part], part.astype(np.int32))
     group = slabs.LocalPeerGroup(sims, cap, n + 4 * cap)
     counts = []
