@@ -479,6 +479,21 @@ class PeerSlabDriver:
             self.tickets = []
         return self.last
 
+    def rebalance(self, dist, cols, backend, max_shift=None):
+        """Re-cut the slabs by particle count (slabs.rebalance) between two steps; every rank calls it.  backend: the
+        GpuSlabBackend make_gpu_slab returned for this sim.  Returns the new column ranges."""
+        import torch
+        if self.terrain is not None:
+            raise RuntimeError("re-cutting is not available for runs that share a terrain (the row windows would have to move)")
+        self.drain()
+
+        def reduce(hist):
+            t = torch.from_numpy(hist).to(torch.device("cuda", torch.cuda.current_device())) if dist.get_backend() == "nccl" else torch.from_numpy(hist)
+            dist.all_reduce(t)
+            hist[:] = t.cpu().numpy()
+
+        return rebalance(backend, reduce, self.rank, self.world, cols, max_shift)
+
 
 class LocalPeerGroup:
     """K slabs in ONE process on one GPU, exchanging through each other's mailboxes (connect_local): the
@@ -664,6 +679,7 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT, terrain=False):
             drv.step()
         drv.drain()
         tinfo["settle_steps"] = args.settle
+    recut = getattr(args, "rebalance_every", 0) if args.exchange == "peer" and not terrain else 0
     for _ in range(args.warmup):
         drv.step()
     if grid is not None:
@@ -675,7 +691,9 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT, terrain=False):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     e0.record()
-    for _ in range(args.steps):
+    for k in range(args.steps):
+        if recut and k and k % recut == 0:
+            cols = drv.rebalance(dist, cols, backend)      # inside the timed region: its cost is part of the step budget
         drv.step()
     e1.record()
     sync_all()
