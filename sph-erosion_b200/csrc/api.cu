@@ -651,14 +651,21 @@ int sphe_step_host(sphe_sim* s, sphe_terrain* t, int n, const float* pos_in, con
     // directions busy while the kernels run.  Positions first (the binning needs only them); the velocities
     // follow on the io stream and are awaited right before the reorder gathers them; the densities go back while
     // the force pass runs.
+    // The signature carries no sediment: what the particles picked up in earlier calls stays on the device, indexed by id
+    // (the terrain keeps its eroded heights, so dropping the load would break  sum(heights) + sum(carried) = const).
+    // A call with a different particle count is a new system and starts with empty loads.
+    const bool keep_sed = t && t->E.enabled && s->n == n && s->cap >= n;
     s->n = 0;
     TRY(reserve(s, n));
     float* dpos = s->stage;
     float* dvel = s->stage + 3 * (size_t)s->cap;
+    float* dsed = s->stage + 7 * (size_t)s->cap;
     CU(cudaStreamSynchronize(s->st));          // the staging area may still be read by an earlier download
+    if (keep_sed) launch_unsort_f1(s->st, n, s->sedA, s->idsA, dsed);   // sorted slots -> id order, before the ids are reset
     CU(cudaMemcpyAsync(dpos, pos_in, 3 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s->st));
     CU(cudaEventRecord(s->ev_io_done, s->st));
-    launch_pack_state(s->st, n, dpos, nullptr, s->posA, s->velA, s->idsA, s->sedA);
+    launch_pack_state(s->st, n, dpos, nullptr, s->posA, s->velA, s->idsA, keep_sed ? nullptr : s->sedA);
+    if (keep_sed) CU(cudaMemcpyAsync(s->sedA, dsed, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, s->st));
     // the velocity copy starts when the position copy has finished (two concurrent copies would only share the
     // link and delay the positions the binning is waiting for)
     CU(cudaStreamWaitEvent(s->st_io, s->ev_io_done, 0));
@@ -799,8 +806,16 @@ static int copy_f4_by_id(sphe_sim* s, const float4* by_id, float* host_xyz) {
     return SPHE_OK;
 }
 
+// Slab handles keep GLOBAL ids (ghost copies carry SPHE_GHOST_BIT) and, while exchange results are in flight, only an upper
+// bound of the particle count: the id-indexed accessors below would write outside their staging area.
+static int not_in_slab_mode(sphe_sim* s, const char* what) {
+    if (s->slab_on) return fail(SPHE_ERR_STATE, "%s is indexed by local particle id and is not available in slab mode (use sphe_slab_download)", what);
+    return SPHE_OK;
+}
+
 int sphe_download(sphe_sim* s, int field, void* out) {
     if (!s || !out) return fail(SPHE_ERR_ARG, "NULL argument");
+    TRY(not_in_slab_mode(s, "sphe_download"));
     if (s->n == 0) return SPHE_OK;
     TRY(ensure_device(s));
     int n = s->n;
@@ -861,6 +876,7 @@ int sphe_download_positions(sphe_sim* s, float* host_xyz) { return sphe_download
 
 int sphe_get_particle(sphe_sim* s, int id, sphe_particle* out) {
     if (!s || !out) return fail(SPHE_ERR_ARG, "NULL argument");
+    TRY(not_in_slab_mode(s, "sphe_get_particle"));
     // the reference indexes unchecked (fluid_system.h:286-289); we report instead of reading out of bounds
     if (id < 0 || id >= s->n) return fail(SPHE_ERR_ARG, "particle id %d out of range [0,%d)", id, s->n);
     TRY(ensure_device(s));
@@ -907,6 +923,7 @@ static int need_binned(sphe_sim* s) {
 
 int sphe_debug_cells(sphe_sim* s, int* cell_of_id) {
     TRY(need_binned(s));
+    TRY(not_in_slab_mode(s, "sphe_debug_cells"));
     int* d = (int*)s->stage;
     launch_unsort_u32(s->st, s->n, s->cell_sorted, s->idsA, d);
     CU(cudaMemcpyAsync(cell_of_id, d, (size_t)s->n * sizeof(int), cudaMemcpyDeviceToHost, s->st));
@@ -930,6 +947,7 @@ int sphe_debug_cell_start(sphe_sim* s, int* cell_start) {
 
 int sphe_debug_neighbours(sphe_sim* s, long long* nbr_start, int* nbr, long long cap, long long* total) {
     TRY(need_binned(s));
+    TRY(not_in_slab_mode(s, "sphe_debug_neighbours"));
     int n = s->n;
     int* dcount = nullptr;
     CU(cudaMalloc(&dcount, (size_t)n * sizeof(int)));

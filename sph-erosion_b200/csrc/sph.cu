@@ -1517,8 +1517,8 @@ static void launch_density_list(cudaStream_t st, int n, const int* n_dev, int pp
     int smem = (CAP + 1) * THREADS * (int)sizeof(int);
     if (smem <= 48 * 1024) smem = 0;   // static in the kernel
     auto kern = k_density_list<REC, PF, CAP, THREADS, UNROLL>;
-    static bool configured = false;   // per instantiation
-    if (!configured && smem > 48 * 1024) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); configured = true; }
+    // the opt-in is per DEVICE (one process may drive several GPUs): set it before every launch that needs it, it is cheap
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     kern<<<pp / THREADS, THREADS, smem, st>>>(n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount, overflow, rows < CAP ? CAP : rows);
 }
 
