@@ -501,7 +501,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--density-variant", type=int, default=6, help="6 = neighbour lists with a software-prefetched candidate stream (default); 3 = plain lists; 10 = 16-bit entries; 1 = packed pair; 0 = thread per particle")
+    ap.add_argument("--density-variant", type=int, default=6, help="6 = pair index lists, software-prefetched candidate stream (default); 3 = plain lists; 20 = TMA-staged candidates in shared memory + bit-mask lists; 0 = thread per particle")
     ap.add_argument("--force-variant", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],

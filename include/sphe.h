@@ -162,6 +162,12 @@ int sphe_debug_cell_start(sphe_sim* s, int* cell_start);     /* [ncells+1]      
 /* CSR neighbour lists by sorted slot, ids in grid-walk order, self included.  Call with nbr=NULL to
  * get the total in *total. */
 int sphe_debug_neighbours(sphe_sim* s, long long* nbr_start, int* nbr, long long cap, long long* total);
+/* The PRODUCTION neighbour lists of the last step (the pair index lists, or the bit masks of the staged variant, that
+ * the force pass walked), decoded: for the particle in sorted slot i, entries[i*cap .. i*cap+counts[i]) are the sorted
+ * slots of the candidates recorded for it (a pair of targets shares one list, so this is a superset of its neighbours;
+ * extra entries have zero weight); counts[i] = -1: the force pass walked the cells directly for this particle (list
+ * beyond its rows / cell neighbourhood larger than the stage). */
+int sphe_debug_pair_lists(sphe_sim* s, int cap, int* counts, int* entries);
 
 /* ---- multi-GPU x-slabs (no reference counterpart) ----
  * One handle per GPU owns the global cell columns [x0, x1) of the neighbour grid and bins into the

@@ -31,7 +31,7 @@ params = dict(len=0.3, dt=0.004, g=(0.0, -9.82, 0.0))
 grid, pos, vel = T._terrain_scene(pkg)
 n = pos.shape[0]
 cap = 1 << 15
-sim, backend, cols = slabs.make_gpu_slab(pkg, devno, rank, world, box, params, None, cap, (3, 3))
+sim, backend, cols = slabs.make_gpu_slab(pkg, devno, rank, world, box, params, None, cap, (6, 3))
 order = np.argsort(pos[:, 0], kind="stable")
 part = np.array_split(order, world)[rank]
 sim.slab_upload(pos[part], vel[part], part.astype(np.int32))
@@ -60,7 +60,7 @@ win = share.window if mode == "window" else (0, grid.shape()[0])
 dist.all_gather_object(gathered, (ids, p, v, rho, sed_fx, grid.heights_fx(), grid.contacts(), info, own, win, grid.window_violations()))
 ok = True
 if rank == 0:
-    one = T._single(pkg, box, params, (3, 3), pos, vel)
+    one = T._single(pkg, box, params, (6, 3), pos, vel)
     g1, _, _ = T._terrain_scene(pkg)
     for _ in range(steps):
         one.Run(g1)

@@ -86,6 +86,10 @@ struct sphe_sim {
     int *req_vertex = nullptr, *req_amount = nullptr;  // terrain stage: pending pick-up requests per survivor
     int *surv = nullptr, *surv_count = nullptr;        // terrain stage: survivors of the contact cull
     bool slot_valid = false;
+    unsigned* nmask = nullptr;     // variant 20 (default): neighbour bit masks, [warp][row][lane] (stage.cu)
+    size_t nmask_words = 0;
+    bool masks_valid = false;      // the masks belong to the last step (sphe_debug_pair_lists)
+    bool lists_valid = false;      // the pair index lists belong to the last step
     int* nlist = nullptr;   // variant 3: [nlist_cap][pairs_pad] neighbour indices
     int2* ncount = nullptr;
     size_t nlist_pairs = 0;
@@ -138,7 +142,9 @@ struct sphe_sim {
 
     bool binned = false;  // debug hooks valid
     StepC lastC{};
-    int variant_density = 6, variant_force = 3;  // 0 tpp, 1 packed pair, 3 neighbour lists, 6 = 3 + software prefetch (default), 10 = 6 with 16-bit entries
+    // 6 / 3 = pair index lists, density pass software-prefetched (default); 20 = TMA-staged candidates in shared memory +
+    // bit-mask lists (stage.cu; measured slower); 0 = thread per particle (readable baseline)
+    int variant_density = 6, variant_force = 3;
 
     bool timing = false;
     void* flush_buf = nullptr;
@@ -358,11 +364,18 @@ static int step_device(sphe_sim* s, sphe_terrain* t, int terrain_phases = 7) {
     { Scope k(s, SPHE_K_REORDER);
       launch_rank_reorder(s->st, n, nd, s->tmp, s->cell, s->cell_start, s->posA, s->velA, s->sedA, s->posB, s->velB, s->sedB,
                           s->idsB, s->cell_sorted); }
-    if (s->variant_density >= 3 || s->variant_force >= 3) {
+    const int vd = s->variant_density, vf = s->variant_force;
+    if (vf == 20 && vd != 20) return fail(SPHE_ERR_ARG, "force variant 20 reads the masks of density variant 20");
+    s->masks_valid = false; s->lists_valid = false;
+    if (vd == 20) {
+        size_t need = stage_mask_words(s->cap);
+        if (need > s->nmask_words) { TRY(grow(&s->nmask, 0, need, s->st, false)); s->nmask_words = need; }
+    }
+    if ((vd >= 3 && vd != 20) || (vf >= 3 && vf != 20)) {
         // the plain pair-list format is shared by 3 (plain), 6 (software-prefetched), 7/9 (quad density) and 31-33 (unroll A/B):
         // any of those may be combined; the record (4) and sub-list (52/54/58) formats need the same variant in both passes
         auto plain = [](int v) { return v == 3 || v == 6 || v == 7 || v == 9 || v == 10 || v == 11 || (v >= 31 && v <= 33); };
-        if (s->variant_density != s->variant_force && !(plain(s->variant_density) && plain(s->variant_force)))
+        if (vd != vf && !(plain(vd) && plain(vf)) && !(vf < 3 && plain(vd)) && !(vd == 20 && vf < 3))
             return fail(SPHE_ERR_ARG, "neighbour-list variants with different list formats cannot be combined");
         // capacity for every list variant: S sub-lists of slist_entries(S) entries per pair, S <= 8 -> <= 96 ints per pair
         if (!s->d_overflow) {
@@ -403,9 +416,16 @@ static int step_device(sphe_sim* s, sphe_terrain* t, int terrain_phases = 7) {
             s->nlist_pairs = pp; s->nlist_alloc_cap = entries;
         }
     }
-    { Scope k(s, SPHE_K_DENSITY);
+    if (vd == 20) {
+        Scope k(s, SPHE_K_DENSITY);
+        launch_density_stage(s->st, n, nd, s->posB, s->posC, s->velB, s->cell_sorted, s->cell_start, s->G, C, s->rho, s->nmask);
+        s->masks_valid = true;
+    } else {
+      Scope k(s, SPHE_K_DENSITY);
       launch_density(s->st, s->variant_density, n, nd, s->posB, s->posC, s->velB, s->cell_sorted, s->cell_start, s->G, C, s->rho,
                      s->nlist, s->ncount, s->nlist_capacity, s->d_overflow, s->nlist_smem);
+      { auto plain = [](int v) { return v == 3 || v == 4 || v == 6 || v == 7 || v == 9 || v == 10 || v == 11 || (v >= 31 && v <= 33); };
+        s->lists_valid = plain(vd) && vf >= 3; }
       if (s->d_overflow) {
           CU(cudaMemcpyAsync(s->h_overflow, s->d_overflow, 5 * sizeof(int), cudaMemcpyDeviceToHost, s->st));
           CU(cudaMemsetAsync(s->d_overflow, 0, 3 * sizeof(int), s->st));
@@ -418,8 +438,13 @@ static int step_device(sphe_sim* s, sphe_terrain* t, int terrain_phases = 7) {
         launch_unsort_f1(s->st_io, n, s->rho, s->idsB, drho);
         CU(cudaMemcpyAsync(s->io.density_out, drho, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->st_io));
     }
-    { Scope k(s, SPHE_K_FORCE);
-      launch_force(s->st, s->variant_force, n, nd, s->posC, s->velB, s->rho, s->idsB, s->cell_sorted, s->cell_start, s->G, C,
+    if (vf == 20) {
+        Scope k(s, SPHE_K_FORCE);
+        launch_force_stage(s->st, n, nd, s->posC, s->velB, s->rho, s->idsB, s->cell_sorted, s->cell_start, s->G, C, s->nmask, s->posA, s->velA,
+                           s->diag ? &s->D : nullptr);
+    } else {
+      Scope k(s, SPHE_K_FORCE);
+      launch_force(s->st, vf, n, nd, s->posC, s->velB, s->rho, s->idsB, s->cell_sorted, s->cell_start, s->G, C,
                    s->posA, s->velA, s->diag ? &s->D : nullptr, s->nlist, s->ncount); }
     if (t) {
         TerrainDev T = terrain_view(t);
@@ -973,6 +998,26 @@ int sphe_debug_neighbours(sphe_sim* s, long long* nbr_start, int* nbr, long long
     CU(cudaMemcpyAsync(nbr, dn, (size_t)starts[n] * sizeof(int), cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));
     CU(cudaFree(dstart)); CU(cudaFree(dn));
+    return SPHE_OK;
+}
+
+int sphe_debug_pair_lists(sphe_sim* s, int cap, int* counts, int* entries) {
+    TRY(need_binned(s));
+    TRY(not_in_slab_mode(s, "sphe_debug_pair_lists"));
+    if (!counts || !entries || cap <= 0) return fail(SPHE_ERR_ARG, "bad arguments");
+    if (!s->masks_valid && !s->lists_valid) return fail(SPHE_ERR_STATE, "the last step left no pair lists or masks (thread-per-particle kernels?)");
+    int n = s->n;
+    int *dc = nullptr, *de = nullptr;
+    CU(cudaMalloc(&dc, (size_t)n * sizeof(int)));
+    CU(cudaMalloc(&de, (size_t)n * cap * sizeof(int)));
+    // posB / cell_sorted / cell_start still hold the sorted pre-integration state the masks were recorded against
+    if (s->masks_valid) launch_stage_decode(s->st, n, s->posB, s->cell_sorted, s->cell_start, s->G, s->nmask, cap, dc, de);
+    else launch_list_decode(s->st, n, s->nlist, s->ncount, cap, dc, de);
+    CU(cudaMemcpyAsync(counts, dc, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(entries, de, (size_t)n * cap * sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    CU(cudaFree(dc)); CU(cudaFree(de));
+    CU(cudaGetLastError());
     return SPHE_OK;
 }
 

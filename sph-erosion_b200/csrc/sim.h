@@ -109,6 +109,19 @@ int nlist_pairs_pad(int n);
 void launch_force(cudaStream_t st, int variant, int n, const int* n_dev, const float4* posq, const float4* velv, const float* rho,
                   const int* ids, const uint32_t* cell_sorted, const int* cell_start, const GridP& G, const StepC& C,
                   float4* posq_out, float4* velv_out, const DiagOut* diag, const int* nlist, const int2* ncount);
+// ---- stage.cu: cell-cooperative passes with shared-memory-staged candidates and bit-mask neighbour lists (variant 20)
+int stage_pairs_pad(int n);
+size_t stage_mask_words(int n);
+void launch_density_stage(cudaStream_t st, int n, const int* n_dev, const float4* posq, float4* posq_q, float4* velv,
+                          const uint32_t* cell_sorted, const int* cell_start, const GridP& G, const StepC& C, float* rho, unsigned* nmask);
+void launch_force_stage(cudaStream_t st, int n, const int* n_dev, const float4* posq_q, const float4* velv, const float* rho,
+                        const int* ids, const uint32_t* cell_sorted, const int* cell_start, const GridP& G, const StepC& C,
+                        const unsigned* nmask, float4* posq_out, float4* velv_out, const DiagOut* diag);
+void launch_list_decode(cudaStream_t st, int n, const int* nlist, const int2* ncount, int cap, int* counts, int* out);
+void launch_neighb_id(cudaStream_t st, int n, const int* n_dev, const float4* posq, const int* ids, const uint32_t* cell_sorted,
+                      const int* cell_start, const GridP& G, const StepC& C, int* neighb_by_id);
+void launch_stage_decode(cudaStream_t st, int n, const float4* posq, const uint32_t* cell_sorted, const int* cell_start,
+                         const GridP& G, const unsigned* nmask, int cap, int* counts, int* out);
 void launch_neighbour_count(cudaStream_t st, int n, const float4* posq, const uint32_t* cell_sorted, const int* cell_start,
                             const GridP& G, const StepC& C, int* counts);
 void launch_neighbour_fill(cudaStream_t st, int n, const float4* posq, const int* ids, const uint32_t* cell_sorted,

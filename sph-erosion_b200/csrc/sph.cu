@@ -14,6 +14,7 @@
 // are continuous in the predicate).
 #include "common.cuh"
 #include "sim.h"
+#include "sph_device.cuh"
 
 namespace sphe {
 
@@ -174,60 +175,6 @@ __global__ void __launch_bounds__(128) k_density_pair(int n_hi, const int* __res
     }
 }
 
-// ------------------------------------------------------------------ force -> integrate -> collide (per particle)
-// PressureForce = -(fPress*rho_i), fPress = -mass*c45*A (fluid_system.h:145,151); ViscosityForce = c45*visc*F
-// (:146,153); SurfaceNormal = -c945*N (:147,154); colorFieldLapl = -c945*cf, SurfaceForce = -surf_tens*cfl*n
-// (:171,177); GravityForce = rho_i*g (:163); then advance() (:318-350) with collisionS (:342-347).
-template <bool DIAG>
-__device__ __forceinline__ void force_epilogue(int i, float4 pi, float4 vi, float rho_i, float ax, float ay, float az,
-                                               float fx, float fy, float fz, float nx, float ny, float nz, float cf, int maxid,
-                                               const StepC& C, const int* __restrict__ ids, float4* __restrict__ posq_out,
-                                               float4* __restrict__ velv_out, const DiagOut& D) {
-    float kp = rho_i * C.mass * C.c45;
-    float Fpx = kp * ax, Fpy = kp * ay, Fpz = kp * az;
-    float kv = C.visc * C.c45;
-    float Fvx = kv * fx, Fvy = kv * fy, Fvz = kv * fz;
-    float Nx = -C.c945 * nx, Ny = -C.c945 * ny, Nz = -C.c945 * nz;
-    float cfl = -C.c945 * cf;
-    float ks = -C.surf * cfl;
-    float Fsx = ks * Nx, Fsy = ks * Ny, Fsz = ks * Nz;
-    float Fgx = rho_i * C.gx, Fgy = rho_i * C.gy, Fgz = rho_i * C.gz;
-    float Fx = (Fpx + Fvx) + (Fgx + Fsx), Fy = (Fpy + Fvy) + (Fgy + Fsy), Fz = (Fpz + Fvz) + (Fgz + Fsz);
-    float acx = Fx / rho_i, acy = Fy / rho_i, acz = Fz / rho_i;
-    float dt = C.dt;
-    float vx = fmaf(acx, dt, vi.x), vy = fmaf(acy, dt, vi.y), vz = fmaf(acz, dt, vi.z);
-    float px = fmaf(vx, dt, pi.x), py = fmaf(vy, dt, pi.y), pz = fmaf(vz, dt, pi.z);
-    // With a terrain, particles that may touch it keep their un-boxed state: the contact search
-    // (k_terrain_contact) runs on them first and applies the box afterwards (fluid_system.h:335-347).
-    bool surv = false;
-    if (C.t_lmax) {
-        // ghost copies (slab mode) never enter the terrain stage: their owner rank resolves the contact and
-        // files the erosion request, the copy is dropped at the next exchange
-        surv = dt != 0.0f && terrain_may_touch(C, pi.x, pi.y, pi.z, px, py, pz) && !(__ldg(&ids[i]) & SPHE_GHOST_BIT);
-        unsigned act = __activemask();
-        unsigned m = __ballot_sync(act, surv);
-        if (m) {
-            int lane = threadIdx.x & 31, leader = __ffs(m) - 1, base = 0;
-            if (lane == leader) base = atomicAdd(C.t_count, __popc(m));
-            base = __shfl_sync(act, base, leader);
-            if (surv) C.t_surv[base + __popc(m & ((1u << lane) - 1u))] = i;
-        }
-    }
-    if (C.box && !surv) box_collide(C, px, py, pz, vx, vy, vz);
-    posq_out[i] = make_float4(px, py, pz, 0.0f);
-    velv_out[i] = make_float4(vx, vy, vz, 0.0f);
-    if (DIAG) {
-        int id = ids[i];
-        D.acc[id] = make_float4(acx, acy, acz, 0.f);
-        D.fpress[id] = make_float4(Fpx, Fpy, Fpz, 0.f);
-        D.fvisc[id] = make_float4(Fvx, Fvy, Fvz, 0.f);
-        D.fgrav[id] = make_float4(Fgx, Fgy, Fgz, 0.f);
-        D.fsurf[id] = make_float4(Fsx, Fsy, Fsz, 0.f);
-        D.normal[id] = make_float4(Nx, Ny, Nz, 0.f);
-        if (maxid >= 0) D.neighb[id] = maxid;  // last neighbour in ascending-id order (:144)
-    }
-}
-
 // ------------------------------------------------------------------ passes 2+3 + integrate + collide
 template <bool DIAG>
 __global__ void __launch_bounds__(128) k_force_tpp(int n_hi, const int* __restrict__ n_dev, const float4* __restrict__ posq_q, const float4* __restrict__ velv,
@@ -277,12 +224,6 @@ __global__ void __launch_bounds__(128) k_force_tpp(int n_hi, const int* __restri
     });
 
     force_epilogue<DIAG>(i, pi, vi, rho_i, ax, ay, az, fx, fy, fz, nx, ny, nz, cf, maxid, C, ids, posq_out, velv_out, D);
-}
-
-__device__ __forceinline__ float rsqrt_ftz(float x) {
-    float y;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
 }
 
 // ------------------------------------------------------------------ passes 2+3, variant 1: pair + compaction
@@ -465,6 +406,11 @@ __global__ void __launch_bounds__(FORCE_THREADS) k_force_pair(int n_hi, const in
 //   k_force_list   : passes 2+3 + integrate, walking the stored list only (no candidate test at all).
 // Cost: one extra 4-byte write + read per stored neighbour (about 40 per pair).
 constexpr int NLIST_CAP = 64;       // entries per pair (both split passes together)
+// A candidate enters a pair list when hh - d2 >= -2^-20 hh with the FMA-contracted d2.  The reference predicate is
+// sqrt(d2_exact) <= h  <=>  d2_exact <= T with T within 1 ulp of hh, and the contracted d2 is within 3 ulp of the exact one,
+// so the lists are a SUPERSET of the exact neighbour sets; the extra entries have clamped weights of 0 or a few ulp
+// (tests/test_gpu_parity.py::test_pair_masks_cover_the_exact_neighbour_sets reads the production lists back).
+constexpr float LIST_NEG_EPS = -9.5367431640625e-07f;
 constexpr int NLIST_THREADS = 128;
 
 // REC = true (variant 4): instead of (posC, vel.w) the pass writes ONE interleaved 32-byte record per particle,
@@ -539,7 +485,7 @@ __global__ void __launch_bounds__(THREADS) k_density_list(int n_hi, const int* _
             float2 w = __fadd2_rn(make_float2(C.hh, C.hh), make_float2(-d2.x, -d2.y));
             // branch-free append: store at the current slot (the trash slot once saturated), advance only on a pass
             asm volatile("st.shared.u32 [%0], %1;" ::"r"(min(wp, cap_sa)), "r"(k) : "memory");
-            asm("{ .reg .pred q; setp.ge.f32 q, %1, 0f00000000; @q add.u32 %0, %0, %2; }" : "+r"(wp) : "f"(fmaxf(w.x, w.y)), "n"(4 * NLIST_THREADS));
+            asm("{ .reg .pred q; setp.ge.f32 q, %1, %3; @q add.u32 %0, %0, %2; }" : "+r"(wp) : "f"(fmaxf(w.x, w.y)), "n"(4 * NLIST_THREADS), "f"(LIST_NEG_EPS * C.hh));
             w.x = fmaxf(w.x, 0.f);
             w.y = fmaxf(w.y, 0.f);
             acc = __ffma2_rn(__fmul2_rn(w, w), w, acc);
@@ -559,7 +505,7 @@ __global__ void __launch_bounds__(THREADS) k_density_list(int n_hi, const int* _
                 d2 = __ffma2_rn(dy, dy, d2);
                 d2 = __ffma2_rn(dz, dz, d2);
                 float2 w = __fadd2_rn(make_float2(C.hh, C.hh), make_float2(-d2.x, -d2.y));
-                if (fmaxf(w.x, w.y) >= 0.f) {
+                if (fmaxf(w.x, w.y) >= LIST_NEG_EPS * C.hh) {
                     if (idx >= NLIST_CAP && idx < rows) nlist[(size_t)idx * npairs_pad + t] = k;
                     idx++;
                 }
@@ -872,7 +818,7 @@ __global__ void __launch_bounds__(L16_THREADS) k_density_list16(int n_hi, const 
             d2 = __ffma2_rn(dz, dz, d2);
             float2 w = __fadd2_rn(make_float2(C.hh, C.hh), make_float2(-d2.x, -d2.y));
             lbase[min(off, L16_CAP * T)] = (unsigned short)code;   // branch-free append
-            off += (fmaxf(w.x, w.y) >= 0.f) ? T : 0;
+            off += (fmaxf(w.x, w.y) >= LIST_NEG_EPS * C.hh) ? T : 0;
             w.x = fmaxf(w.x, 0.f);
             w.y = fmaxf(w.y, 0.f);
             acc = __ffma2_rn(__fmul2_rn(w, w), w, acc);
@@ -889,7 +835,7 @@ __global__ void __launch_bounds__(L16_THREADS) k_density_list16(int n_hi, const 
                 d2 = __ffma2_rn(dy, dy, d2);
                 d2 = __ffma2_rn(dz, dz, d2);
                 float2 w = __fadd2_rn(make_float2(C.hh, C.hh), make_float2(-d2.x, -d2.y));
-                if (fmaxf(w.x, w.y) >= 0.f) {
+                if (fmaxf(w.x, w.y) >= LIST_NEG_EPS * C.hh) {
                     if (idx >= L16_CAP && idx < rows) nlist[(size_t)idx * npairs_pad + t] = k;
                     idx++;
                 }
@@ -1470,6 +1416,47 @@ __global__ void __launch_bounds__(128) k_nbr_fill(int n, const float4* __restric
     });
 }
 
+// Test hook: the PRODUCTION pair lists of the index-list kernels (what k_force_list walks), per target:
+// out[target * cap + i] = sorted slot of the i-th recorded candidate, counts[target] (-1: the pair's list overflowed its
+// rows and the force pass walked the cells directly).  Segment 0 of a pair list serves (a, b) when the pair was merged,
+// else a; segment 1 serves b.
+__global__ void k_list_decode(int n, int npairs_pad, const int* __restrict__ nlist, const int2* __restrict__ ncount, int cap,
+                              int* __restrict__ counts, int* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int a = 2 * t;
+    if (a >= n) return;
+    const bool hasb = a + 1 < n;
+    const int2 cn = ncount[t];
+    if (cn.y < 0) { counts[a] = -1; if (hasb) counts[a + 1] = -1; return; }
+    const bool merged = cn.x == cn.y;
+    int na = 0, nb = 0;
+    for (int e = 0; e < cn.y; e++) {
+        const int k = nlist[(size_t)e * npairs_pad + t];
+        const bool forA = e < cn.x, forB = hasb && (merged || e >= cn.x);
+        if (forA) { if (na < cap) out[(size_t)a * cap + na] = k; na++; }
+        if (forB) { if (nb < cap) out[(size_t)(a + 1) * cap + nb] = k; nb++; }
+    }
+    counts[a] = na;
+    if (hasb) counts[a + 1] = nb;
+}
+
+// NeighbId (fluid_system.h:144, debug only): the last neighbour in ascending-id order = the largest id among the exact
+// neighbours j != i.  The staged force kernel has no ids at hand, so the diagnostics get them from this walk.
+__global__ void __launch_bounds__(128) k_neighb_id(int n_hi, const int* __restrict__ n_dev, const float4* __restrict__ posq, const int* __restrict__ ids,
+                                                   const uint32_t* __restrict__ cell_sorted, const int* __restrict__ cell_start,
+                                                   GridP G, StepC C, int* __restrict__ neighb) {
+    const int n = n_dev ? __ldg(n_dev) : n_hi;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 pi = posq[i];
+    int maxid = -1;
+    walk27(G, cell_start, cell_sorted[i], [&](int k) {
+        float4 pj = __ldg(&posq[k]);
+        if (k != i && dist2_exact(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z) <= C.T) maxid = max(maxid, __ldg(&ids[k]));
+    });
+    if (maxid >= 0) neighb[ids[i]] = maxid;
+}
+
 // ------------------------------------------------------------------ id-order gathers / packing
 __global__ void k_unsort_f4(int n, const float4* __restrict__ src, const int* __restrict__ ids, float* __restrict__ dst) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1602,6 +1589,13 @@ void launch_force(cudaStream_t st, int variant, int n, const int* n_dev, const f
     else k_force_tpp<false><<<nblk(n, 128), 128, 0, st>>>(n, n_dev, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, posq_out, velv_out, DiagOut{});
 }
 
+void launch_list_decode(cudaStream_t st, int n, const int* nlist, const int2* ncount, int cap, int* counts, int* out) {
+    if (n > 0) k_list_decode<<<nblk((n + 1) / 2, 128), 128, 0, st>>>(n, nlist_pairs_pad(n), nlist, ncount, cap, counts, out);
+}
+void launch_neighb_id(cudaStream_t st, int n, const int* n_dev, const float4* posq, const int* ids, const uint32_t* cell_sorted,
+                      const int* cell_start, const GridP& G, const StepC& C, int* neighb_by_id) {
+    if (n > 0) k_neighb_id<<<nblk(n, 128), 128, 0, st>>>(n, n_dev, posq, ids, cell_sorted, cell_start, G, C, neighb_by_id);
+}
 void launch_neighbour_count(cudaStream_t st, int n, const float4* posq, const uint32_t* cell_sorted, const int* cell_start,
                             const GridP& G, const StepC& C, int* counts) {
     if (n > 0) k_nbr_count<<<nblk(n, 128), 128, 0, st>>>(n, posq, cell_sorted, cell_start, G, C, counts);

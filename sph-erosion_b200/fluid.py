@@ -65,7 +65,7 @@ class FluidSystemSPH:
     def count(self): return self._L.sphe_count(self._h)
     def sync(self): capi.check(self._L.sphe_sync(self._h))
     def set_diagnostics(self, on=True): capi.check(self._L.sphe_set_diagnostics(self._h, int(on)))
-    def set_variant(self, density=3, force=3): capi.check(self._L.sphe_set_variant(self._h, density, force))
+    def set_variant(self, density=6, force=3): capi.check(self._L.sphe_set_variant(self._h, density, force))
 
     def set_grid_bounds(self, lo, hi):
         lo = np.asarray(lo, np.float32); hi = np.asarray(hi, np.float32)
@@ -269,6 +269,13 @@ class FluidSystemSPH:
         tot = C.c_longlong(0)
         capi.check(self._L.sphe_debug_neighbours(self._h, None, None, 0, C.byref(tot)))
         return tot.value
+
+    def debug_pair_lists(self, cap=512):
+        """Decoded production neighbour masks of the last step: (counts[n], entries[n, cap]) by sorted slot."""
+        n = self.count()
+        counts = np.zeros(n, np.int32); entries = np.zeros((n, cap), np.int32)
+        capi.check(self._L.sphe_debug_pair_lists(self._h, cap, _p(counts), _p(entries)))
+        return counts, entries
 
     def debug_neighbours(self):
         n = self.count()

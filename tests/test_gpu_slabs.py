@@ -28,7 +28,7 @@ def scene(n=20000, seed=11):
 
 
 @pytest.mark.parametrize("async_", [False, True], ids=["sync", "async"])
-@pytest.mark.parametrize("variant", [(0, 0), (3, 3)], ids=["tpp", "list"])
+@pytest.mark.parametrize("variant", [(6, 3), (0, 0), (20, 20)], ids=["default", "tpp", "staged"])
 @pytest.mark.parametrize("K", [2, 3])
 def test_k_slabs_equal_single_gpu(K, variant, async_):
     import torch
@@ -142,8 +142,8 @@ def test_peer_mailbox_slabs_equal_single_gpu(K):
     n = pos.shape[0]
     box = (1.2, 0.3, 0.3)
     params = dict(len=0.3, dt=0.004, g=(0.0, -9.82, 0.0))
-    one = _single(m, box, params, (3, 3), pos, vel)
-    sims, group = _peer_group(m, slabs, K, box, params, (3, 3), pos, vel)
+    one = _single(m, box, params, (6, 3), pos, vel)
+    sims, group = _peer_group(m, slabs, K, box, params, (6, 3), pos, vel)
     for step in range(9):
         one.Run()
         group.step()
@@ -164,7 +164,7 @@ def test_peer_mailbox_overflow_is_reported():
     pos, vel = scene()
     box = (1.2, 0.3, 0.3)
     params = dict(len=0.3, dt=0.004, g=(0.0, -9.82, 0.0))
-    sims, group = _peer_group(m, slabs, 2, box, params, (3, 3), pos, vel, cap=64)   # far too small for the halo
+    sims, group = _peer_group(m, slabs, 2, box, params, (6, 3), pos, vel, cap=64)   # far too small for the halo
     group.step()
     with pytest.raises(m.capi.SpheError, match="overflow"):
         group.drain()
@@ -178,7 +178,7 @@ def test_peer_recv_times_out_instead_of_hanging():
     pos, vel = scene(2000)
     box = (1.2, 0.3, 0.3)
     params = dict(len=0.3, dt=0.004, g=(0.0, -9.82, 0.0))
-    sims, group = _peer_group(m, slabs, 2, box, params, (3, 3), pos, vel)
+    sims, group = _peer_group(m, slabs, 2, box, params, (6, 3), pos, vel)
     sims[0].slab_peer_timeout(20_000_000)   # ~10 ms
     sims[0].slab_send()                     # slab 1 never sends
     t = sims[0].slab_recv()
@@ -218,8 +218,8 @@ def test_slabs_sharing_one_eroding_terrain_equal_single_gpu(K):
     g1, pos, vel = _terrain_scene(m)
     gk, _, _ = _terrain_scene(m)
     n = pos.shape[0]
-    one = _single(m, box, params, (3, 3), pos, vel)
-    sims, group = _peer_group(m, slabs, K, box, params, (3, 3), pos, vel, grid=gk)
+    one = _single(m, box, params, (6, 3), pos, vel)
+    sims, group = _peer_group(m, slabs, K, box, params, (6, 3), pos, vel, grid=gk)
     total0 = g1.total_fx()
     for step in range(12):
         one.Run(g1)
@@ -250,12 +250,12 @@ def test_slab_local_terrain_windows_equal_single_gpu(K):
     params = dict(len=0.3, dt=0.004, g=(0.0, -9.82, 0.0))
     g1, pos, vel = _terrain_scene(m)
     n = pos.shape[0]
-    one = _single(m, box, params, (3, 3), pos, vel)
+    one = _single(m, box, params, (6, 3), pos, vel)
     total0 = g1.total_fx()
     cap = 1 << 15
     sims, replicas = [], []
     for r in range(K):
-        sim, b, cols = slabs.make_gpu_slab(m, torch.cuda.current_device(), r, K, box, params, None, cap, (3, 3))
+        sim, b, cols = slabs.make_gpu_slab(m, torch.cuda.current_device(), r, K, box, params, None, cap, (6, 3))
         sims.append(sim); replicas.append(_terrain_scene(m)[0])
     order = np.argsort(pos[:, 0], kind="stable")
     for r, part in enumerate(np.array_split(order, K)):
@@ -303,8 +303,8 @@ def test_particles_crossing_more_than_one_slab_are_forwarded_not_lost():
     fvel = np.array([[150.0, 0, 0], [230.0, 0, 0], [-260.0, 0, 0]], np.float32)
     pos = np.concatenate([pos, fast]); vel = np.concatenate([vel, fvel])
     n = pos.shape[0]
-    one = _single(m, box, params, (3, 3), pos, vel)
-    sims, group = _peer_group(m, slabs, 5, box, params, (3, 3), pos, vel)
+    one = _single(m, box, params, (6, 3), pos, vel)
+    sims, group = _peer_group(m, slabs, 5, box, params, (6, 3), pos, vel)
     seen_transit = 0
     for step in range(8):
         one.Run()

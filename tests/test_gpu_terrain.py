@@ -156,7 +156,7 @@ def _attach(gold, erosion):
     return g, T, E
 
 
-@pytest.mark.parametrize("variant", [(0, 0), (3, 3)], ids=["tpp", "list"])
+@pytest.mark.parametrize("variant", [(6, 3), (0, 0), (20, 20)], ids=["default", "tpp", "staged"])
 def test_step_with_terrain_lockstep_vs_oracle(gold, variant):
     m = product()
     pos, vel = _scene()
