@@ -24,8 +24,15 @@ sys.path.insert(0, ROOT)
 METRIC = "sph_particle_updates_per_sec"
 UNIT = "particle-updates/s"
 SPACING = 0.025
-# algorithmic HBM bytes per particle per launch (SURVEY.md section 8d / DESIGN.md "kernels")
-ALGO_BYTES = {"hash": 20, "scatter": 16, "reorder": 92, "density": 44, "force": 72, "terrain": 92}
+# Algorithmic HBM bytes per particle per launch: SURVEY.md section 8(d)'s table, the official figure behind roofline.achieved
+# (hash 24; sort 52 + cell-start 6 -> here the counting sort's scan + scatter; reorder 68; density 20; force+integrate 64;
+# whole step ~234).  The terrain stage is not in that table (no reference erosion): builder's figure.
+ALGO_BYTES = {"hash": 24, "scan": 6, "scatter": 52, "reorder": 68, "density": 20, "force": 64, "terrain": 92}
+STEP_BYTES = 234
+# What THIS implementation's arrays make compulsory per launch, reported beside it as "layout":
+# density also writes posC + m/rho and reads the cell ids, force also reads rho + the list segment counts, reorder also
+# moves ids / sediment / cell ids.  Neighbour-list traffic (written by one pass, read by the other) is NOT in either figure.
+LAYOUT_BYTES = {"hash": 20, "scan": 0, "scatter": 16, "reorder": 92, "density": 44, "force": 72, "terrain": 92}
 
 
 # ----------------------------------------------------------------------------- scenes
@@ -89,12 +96,25 @@ def synthetic_heightmap(size=1024, seed=0x7E44A1):
     return np.clip(np.rint(34 + h * (246 - 34)), 0, 255).astype(np.uint8)
 
 
+def heightmap_1024():
+    """the reference's Erosion/lena_gray.png mirrored 2 x 2 to 1024 x 1024, exact bytes (fixture written
+    by tests/golden/make_heightmap.py from the reference asset); the synthetic map only if the fixture is missing."""
+    p = os.path.join(ROOT, "tests", "golden", "lena_gray_512.npz")
+    if os.path.exists(p):
+        a = np.load(p)["heights_u8"]
+        top = np.concatenate([a, a[:, ::-1]], axis=1)
+        return np.ascontiguousarray(np.concatenate([top, top[::-1, :]], axis=0)), \
+            "Erosion/lena_gray.png (512 x 512, 8-bit) mirrored 2 x 2 to 1024 x 1024, exact bytes (tests/golden/lena_gray_512.npz)"
+    return synthetic_heightmap(), "synthetic 1024x1024 8-bit value noise (lena_gray statistics), seed 0x7E44A1 -- lena fixture missing"
+
+
 def attach_terrain(pkg, L, n_axis, nx_mult=1):
     """1024 x 1024 terrain under the whole box floor: cell = 2L/1024 world units (uniform scale), heights
     0..255 levels scaled to 0..0.25*block height so the relief is a fraction of the fluid depth, terrain
     top just under the block so the fluid lands on it during the settle phase.  nx_mult > 1 (multi-GPU weak
     scaling): the heightmap is repeated nx_mult times along x under the (nx_mult*L, L, L) channel."""
-    img = np.tile(synthetic_heightmap(), (nx_mult, 1))
+    base, what = heightmap_1024()
+    img = np.tile(base, (nx_mult, 1))
     cell = 2.0 * L / 1024.0
     relief = 0.1 * L                                    # world units between the lowest and highest vertex
     heights = img.astype(np.float32) * np.float32(relief / 255.0 / cell)   # in cells
@@ -105,7 +125,7 @@ def attach_terrain(pkg, L, n_axis, nx_mult=1):
     g.set_transform(origin, cell)
     e = g.erosion
     e.enabled = 1; e.Kc = 2.0; e.Ke = 0.3; e.Kd = 0.3; e.hmin = 0.0; e.max_pickup = 0.25
-    return g, {"heightmap": "synthetic 1024x1024 8-bit value noise (lena_gray statistics), seed 0x7E44A1" + (", repeated %d x along x" % nx_mult if nx_mult > 1 else ""),
+    return g, {"heightmap": what + (", repeated %d x along x" % nx_mult if nx_mult > 1 else ""),
                "terrain_cell": cell, "terrain_relief": relief, "terrain_origin": list(origin),
                "erosion": {"Kc": 2.0, "Ke": 0.3, "Kd": 0.3, "hmin": 0.0, "max_pickup": 0.25}}
 
@@ -302,34 +322,124 @@ def run_reference_arm(args):
     # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank); the OpenMP runtime reads the
     # variable when the reference library is loaded, which happens below
     os.environ["OMP_NUM_THREADS"] = os.environ.get("SPHE_REF_THREADS", str(os.cpu_count() or 1))
+    # same parameters as the GPU arm, g included (scene_gravity of the WORKLOAD's n_axis); only the particle count is bounded
+    gy_ref = scene_gravity(n_axis, args.gravity_unscaled)
+
+    def make(sample_axis):
+        pos, L = scaled_dam_break(sample_axis, jitter)
+        sim = ref.RefSim(omp=True)
+        sim.set_len(L); sim.set_dt(0.01); sim.set_params(0.02, 3.5, 0.0728, 998.29, [0.0, gy_ref, 0.0])
+        sim.set_state(pos, np.zeros_like(pos))
+        return sim, pos
+
     sample_axis = 22
-    pos, L = scaled_dam_break(sample_axis, jitter)
-    gy_ref = scene_gravity(sample_axis, args.gravity_unscaled)
-    sim = ref.RefSim(omp=True)
-    sim.set_len(L); sim.set_dt(0.01); sim.set_params(0.02, 3.5, 0.0728, 998.29, [0.0, gy_ref, 0.0])
-    sim.set_state(pos, np.zeros_like(pos))
+    sim, pos = make(sample_axis)
     t = time.perf_counter(); sim.run(1); t1 = time.perf_counter() - t
     if t1 * (args.steps + args.warmup) > 150.0:
         sample_axis = 16
-        pos, L = scaled_dam_break(sample_axis, jitter)
-        sim = ref.RefSim(omp=True); sim.set_len(L); sim.set_dt(0.01)
-        sim.set_params(0.02, 3.5, 0.0728, 998.29, [0.0, scene_gravity(sample_axis, args.gravity_unscaled), 0.0])
-        sim.set_state(pos, np.zeros_like(pos))
+        sim, pos = make(sample_axis)
     sim.run(args.warmup)
     t = time.perf_counter(); sim.run(args.steps); dt = (time.perf_counter() - t) / max(args.steps, 1)
     n = pos.shape[0]
     full_n = n_axis ** 3
     cores = ref._load(True).ref_omp_max_threads()
+    extrap = (n / dt) * n / full_n
     cb = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "reference",
-          "sample": "%d^3 = %d-particle block of the same scaled dam break; reference is all-pairs O(N^2), "
-                    "so at the full %d particles it extrapolates to %.3g updates/s" % (sample_axis, n, full_n, (n / dt) * n / full_n)}
+          "sample": "%d^3 = %d-particle block of the same scaled dam break (same h, dt, g = %.3f as the GPU arm; the reference has no terrain "
+                    "stage: Grid::collision is commented out at its only call site, fluid_system.h:335-340); the reference is all-pairs O(N^2), "
+                    "so at the workload's %d particles it extrapolates to %.3g updates/s" % (sample_axis, n, gy_ref, full_n, extrap)}
     line.update({"value": n / dt, "ms_per_step": dt * 1e3, "cpu_baseline": cb,
-                 "config": {"workload": args.workload, "description": desc, "reference_sample_particles": n},
+                 "same_config": False,
+                 "extrapolated_full_n_value": extrap,
+                 "extrapolation": "value x sample_particles / workload_particles: one reference step costs 3 all-pairs passes, time ~ N^2 (SURVEY.md section 6)",
+                 "config": {"workload": args.workload, "description": desc, "particles": full_n, "reference_sample_particles": n, "gravity_y": gy_ref},
                  "e2e": {"value": n / dt, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     emit(line)
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def oracle_like(sim, port):
+    gi = sim.grid_info()
+    G = port.Grid(); G.gmin[:] = list(gi.gmin); G.cell = gi.cell; G.dim[:] = list(gi.dim)
+    return G
+
+
+def parity_gate(sim, grid, L, gy, tinfo):
+    """In-bench parity at FULL size: one more step from the state the timed region left, the same step by the oracle
+    (oracle/sph_oracle.c + terrain_oracle.c: the checker, never the thing measured) on the same input, all particles.
+    Bars as in tests/: binning bit-exact; density, positions, velocities within RTOL = 1e-5 of the field's scale (20x
+    that with a terrain: the contact response amplifies 1e-5 velocity differences, tests/test_gpu_terrain.py); terrain
+    heights within 8 fixed-point units (1/4096 height unit) on every vertex, carried sediment total within the same."""
+    from oracle import port
+    t0 = time.perf_counter()
+    pos = sim.download("pos"); vel = sim.download("vel")
+    sed = np.rint(sim.download("sediment").astype(np.float64) * 4096.0).astype(np.int32) if grid is not None else None
+    h0 = grid.heights() if grid is not None else None
+    sim.Run(grid)
+    P = port.default_params(dt=0.01, len=L, g=(0.0, gy, 0.0))
+    G = oracle_like(sim, port)
+    cell_of, order, cell_start = port.bin_particles(G, pos)
+    out = {"particles": int(pos.shape[0]), "oracle": "so_forces_grid + so_terrain_stage + so_box, all particles" if grid is not None else "so_step_grid, all particles"}
+    out["binning_bit_exact"] = bool(np.array_equal(sim.debug_sorted_order(), order) and np.array_equal(sim.debug_cell_start(), cell_start))
+    S = port.State(pos, vel)
+    if grid is not None:
+        T = port.Terrain(h0, (h0.shape[0], 255, h0.shape[1]))
+        E = port.erosion_params(enabled=True, origin=tinfo["terrain_origin"], scale=tinfo["terrain_cell"], **tinfo["erosion"])
+        hit = port.step_grid_terrain(P, G, S, T, E, sed)
+        out["oracle_contacts"] = int(hit.sum())
+        dh = np.abs(grid.heights_fx().astype(np.int64) - T.hfx.astype(np.int64))
+        out["height_max_diff_fx"] = int(dh.max()); out["height_vertices_differing"] = int((dh > 0).sum())
+        out["sediment_total_diff_fx"] = int(abs(int(sim.sediment_total_fx()) - int(sed.astype(np.int64).sum())))
+    else:
+        port.step_grid(P, G, S)
+    tol = 20e-5 if grid is not None else 1e-5
+    ok = out["binning_bit_exact"]
+    for name, want, t in (("density", S.density, 1e-5), ("pos", S.pos, tol), ("vel", S.vel, tol)):
+        got = sim.download(name).astype(np.float64); want = want.astype(np.float64)
+        err = float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-30))
+        out[name + "_max_err_over_scale"] = err
+        ok = ok and err <= t
+    rel = np.abs(sim.download("density").astype(np.float64) - S.density) / np.maximum(S.density, 1e-30)
+    out["density_worst_particle_rel_err"] = float(rel.max())
+    if grid is not None:
+        ok = ok and out["height_max_diff_fx"] <= 8
+    out["tolerance"] = {"density": 1e-5, "pos_vel": tol, "heights_fx": 8 if grid is not None else None}
+    out["seconds"] = round(time.perf_counter() - t0, 2)
+    return bool(ok), out
+
+
+def reference_gravity_run(args, pkg, local, pos, L, n_axis, terrain, budget_s=30.0):
+    """The same scene with the reference's default g = -9.82 (fluid_system.h:460) instead of the scaled one: a second,
+    labelled value.  Bounded: at most min(steps, 20) timed steps, and the settle phase stops when the budget is spent."""
+    import torch
+    sim = pkg.FluidSystemSPH(device=local)
+    sim.params.len = L; sim.params.g[1] = -9.82; sim.SetDeltaTime(0.01)
+    sim.set_variant(args.density_variant, args.force_variant)
+    sim.set_stream(torch.cuda.current_stream().cuda_stream)
+    sim.upload_state(pos, np.zeros_like(pos))
+    grid = attach_terrain(pkg, L, n_axis)[0] if terrain else None
+    t = time.perf_counter(); settled = 0
+    while grid is not None and settled < args.settle and time.perf_counter() - t < budget_s:
+        for _ in range(10):
+            sim.Run(grid)
+        settled += 10; torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        sim.Run(grid)
+    k = max(3, min(args.steps, 20))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(k):
+        sim.Run(grid)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / k
+    n = pos.shape[0]
+    nb = int(sim.debug_neighbours_total()) / n if n <= 4200000 else None
+    return {"gravity_y": -9.82, "value": n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": k, "settle_steps": settled,
+            "mean_neighbours_after_run": nb, "neighbour_list_rows": sim.nlist_capacity(),
+            "note": "reference default g on a scene %d x the reference's: the soft equation of state (k = 3) lets the column compress far beyond the "
+                    "reference's regime (bench.scene_gravity); reported for completeness, the headline uses the dynamically similar g" % (n_axis // 10)}
+
+
 def run_gpu_arm(args):
     import torch
     rank, world, local = dist_env()
@@ -355,13 +465,17 @@ def run_gpu_arm(args):
     sim.params.g[1] = gy
     sim.SetDeltaTime(0.01)
     sim.set_variant(args.density_variant, args.force_variant)
+    # ONE timing method for N = 1 and N > 1 (slabs.bench_multi): the step runs on torch's current stream and ONE pair of CUDA
+    # events brackets all K steps; no flush between steps -- the working set of every workload exceeds the 126 MB L2
+    sim.set_stream(torch.cuda.current_stream().cuda_stream)
     sim.upload_state(pos, np.zeros_like(pos))
-    flush_bytes = 256 << 20
-    sim.set_l2_flush(flush_bytes)
+    if args.l2_flush_mib > 0:
+        sim.set_l2_flush(args.l2_flush_mib << 20)
     grid, tinfo = (attach_terrain(pkg, L, n_axis) if terrain else (None, {}))
     if grid is not None:
         # untimed settle phase: let the block land on the terrain so the timed steps exercise contacts
-        sim.timed_steps(args.settle, grid=grid, per_kernel=False)
+        for _ in range(args.settle):
+            sim.Run(grid)
         tinfo["settle_steps"] = args.settle
         tot0 = grid.total_fx() + sim.sediment_total_fx()
 
@@ -371,14 +485,22 @@ def run_gpu_arm(args):
     import tempfile
     ck = os.path.join(tempfile.mkdtemp(prefix="sphe_bench_"), "window.sphe")
     sim.save_state(ck, grid)
-    sim.timed_steps(args.warmup, grid=grid, per_kernel=False)
+    for _ in range(args.warmup):
+        sim.Run(grid)
     if grid is not None:
         grid.contacts(reset=True)
     sampler = ClockSampler(local)
     sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sim.kernel_timing(False)   # also zeroes the launch counter
     torch.cuda.synchronize()
-    ms, _, launches = sim.timed_steps(args.steps, grid=grid, per_kernel=False)
+    e0.record()
+    for _ in range(args.steps):
+        sim.Run(grid)
+    e1.record()
     torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    _, launches = sim.kernel_times()
     clocks = sampler.stop()
     contacts = grid.contacts() if grid is not None else 0
     sed_end = sim.sediment_total_fx() if grid is not None else 0
@@ -386,6 +508,7 @@ def run_gpu_arm(args):
     state_end = (sim.download("pos"), sim.download("vel"), grid.heights() if grid is not None else None)
     nbr_end = int(sim.debug_neighbours_total()) if n <= 4200000 else None
     rows_end, smem_end, ovf_end = sim.nlist_capacity(), sim.nlist_smem_entries(), sim.nlist_overflowed()
+    gate_ok, gate = (None, None) if args.no_parity_gate else parity_gate(sim, grid, L, gy, tinfo)
     # second pass, instrumented
     sim.load_state(ck, grid)
     os.remove(ck); os.rmdir(os.path.dirname(ck))
@@ -426,17 +549,24 @@ def run_gpu_arm(args):
     dom = max(("density", "force", "terrain"), key=lambda k: per_kernel[k])
     t_dom = per_kernel[dom] / args.steps * 1e-3
     achieved = ALGO_BYTES[dom] * n / t_dom / 1e9
+    frac_of = lambda table: {k: (table[k] * n / (per_kernel[k] / args.steps * 1e-3) / 1e9 / peak)
+                             for k in table if per_kernel.get(k, 0) > 0 and table[k] > 0}
     roofline = {"bound": "hbm", "kernel": "k_%s" % dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic(dom, args.workload), "peak_source": peak_src,
                 "algorithmic_bytes_per_particle": ALGO_BYTES[dom],
+                "algorithmic_bytes_source": "SURVEY.md section 8(d) table (terrain: builder's figure, the table has none)",
+                "whole_step": {"bytes_per_particle": STEP_BYTES + (ALGO_BYTES["terrain"] if grid is not None else 0),
+                               "GB/s": (STEP_BYTES + (ALGO_BYTES["terrain"] if grid is not None else 0)) * n / (ms_step * 1e-3) / 1e9,
+                               "frac": (STEP_BYTES + (ALGO_BYTES["terrain"] if grid is not None else 0)) * n / (ms_step * 1e-3) / 1e9 / peak},
                 "note": "neighbour passes are fp32-issue/LSU bound, not HBM bound (DESIGN.md); "
                         "frac is reported against HBM as the contract asks",
                 "per_kernel_timing": "second pass over the same %d-step window (replayed from a checkpoint) with a CUDA-event pair around every "
                                      "launch; that instrumentation makes the step %.1f %% slower than the headline loop, which has none"
                                      % (args.steps, 100.0 * (ms_instrumented / ms - 1.0)),
                 "per_kernel_ms_per_step": {k: v / args.steps for k, v in per_kernel.items()},
-                "per_kernel_hbm_frac": {k: (ALGO_BYTES[k] * n / (per_kernel[k] / args.steps * 1e-3) / 1e9 / peak)
-                                        for k in ALGO_BYTES if per_kernel.get(k, 0) > 0}}
+                "per_kernel_hbm_frac": frac_of(ALGO_BYTES),
+                "layout": {"what": "the same with the bytes this implementation's arrays make compulsory (DESIGN.md section 3), labelled, not the official figure",
+                           "bytes_per_particle": LAYOUT_BYTES, "per_kernel_hbm_frac": frac_of(LAYOUT_BYTES)}}
     # secondary figure: the bytes the neighbour passes GATHER -- candidates x 16 B per pass -- served by
     # L1/L2, never to be read as DRAM traffic.  Candidates of a particle = population of its 27 cells, from the cell table.
     if n <= 4200000:
@@ -459,18 +589,28 @@ def run_gpu_arm(args):
                                    vel=sim.download("vel"))
         else:
             cb = cpu_port_baseline(pos, L, gy)
+    refg = None
+    if not args.gravity_unscaled and not args.no_reference_gravity:
+        del sim2
+        refg = reference_gravity_run(args, pkg, local, pos, L, n_axis, terrain)
     ns_total = nbr_end
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": args.workload, "description": desc, "particles": n, "h": 0.0457, "spacing": SPACING,
                        "dt": 0.01, "box_half_extent": L, "gravity_y": gy,
-                       "gravity_note": "g scaled by 10/n_axis: dynamic similarity with the reference default scene (see bench.scene_gravity)" if not args.gravity_unscaled else "unscaled g",
-                       "mean_neighbours_after_run": (ns_total / n) if ns_total else None, "l2": "flushed between timed steps (%d MiB memset, outside the event brackets)" % (flush_bytes >> 20),
+                       "gravity_note": "g scaled by 10/n_axis: dynamic similarity with the reference default scene (bench.scene_gravity); the run with the "
+                                       "reference's g = -9.82 is under reference_gravity" if not args.gravity_unscaled else "unscaled g (the reference default)",
+                       "mean_neighbours_after_run": (ns_total / n) if ns_total else None,
+                       "l2": ("flushed between timed steps (%d MiB memset)" % args.l2_flush_mib) if args.l2_flush_mib else
+                             "not flushed: the working set (%.0f MB of particle arrays + neighbour lists) exceeds the 126 MB L2" % (n * 400 / 1e6),
+                       "timing": "one CUDA-event pair around all %d steps on the launching stream (same method at every N)" % args.steps,
                        "density_variant": args.density_variant, "force_variant": args.force_variant,
                        "neighbour_list_rows": rows_end, "neighbour_list_smem_entries": smem_end,
                        "list_overflow_pairs_last_step": ovf_end, **tinfo},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cb}
+            "parity_sampled": gate_ok, "parity_gate": gate,
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cb,
+            "reference_gravity": refg}
     emit(line)
 
 
@@ -497,9 +637,10 @@ def main():
     quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100, help="timed steps (SURVEY.md 8d C2: 100 steps after 10 warm-up)")
+    ap.add_argument("--steps", type=int, default=50, help="timed steps")
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS),
+                    help="c3 (default) = BASELINE configs[2], the largest single-GPU configuration; under torchrun the same default is 4.096M particles per GPU = configs[3] at N = 8")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--density-variant", type=int, default=6, help="6 = pair index lists, software-prefetched candidate stream (default); 3 = plain lists; 20 = TMA-staged candidates in shared memory + bit-mask lists; 0 = thread per particle")
     ap.add_argument("--force-variant", type=int, default=3)
@@ -513,6 +654,9 @@ def main():
     ap.add_argument("--slab-lag", type=int, default=2, help="multi-GPU: steps the host may run ahead (0 = one host sync per step)")
     ap.add_argument("--settle", type=int, default=150, help="untimed steps before warm-up when the workload has a terrain")
     ap.add_argument("--gravity-unscaled", action="store_true")
+    ap.add_argument("--no-parity-gate", action="store_true", help="skip the full-size one-step comparison with the oracle after the timed region")
+    ap.add_argument("--no-reference-gravity", action="store_true", help="skip the second, labelled run with the reference's g = -9.82")
+    ap.add_argument("--l2-flush-mib", type=int, default=0, help="flush L2 with a memset of this size between the steps of the instrumented pass (small workloads only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
