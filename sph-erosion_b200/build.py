@@ -21,7 +21,7 @@ def sources():
 
 
 def _deps():
-    return sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + \
+    return sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "experiments", "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + \
         glob.glob(os.path.join(HERE, "..", "include", "*.h"))
 
 
@@ -34,6 +34,10 @@ def needs_build():
 
 # per-file extra flags: the terrain contact search must round every multiply/add separately (terrain.cu)
 EXTRA = {"terrain.cu": ["-fmad=false"]}
+
+
+if os.environ.get("SPHE_WITH_EXPERIMENTS") == "1":
+    NVCC_FLAGS.append("-DSPHE_WITH_EXPERIMENTS")   # also compile csrc/experiments/ (rejected round-1 kernel variants)
 
 
 def build_library(force=False, verbose=False):

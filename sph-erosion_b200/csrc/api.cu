@@ -818,6 +818,9 @@ int sphe_set_nlist_capacity(sphe_sim* s, int entries) {
 
 int sphe_set_variant(sphe_sim* s, int density_variant, int force_variant) {
     if (!s) return fail(SPHE_ERR_ARG, "NULL handle");
+    if (!variant_supported(density_variant, force_variant))
+        return fail(SPHE_ERR_ARG, "kernel variant (%d, %d) is not in this build (0 tpp, 3 / 6 / 10 index lists, 20 staged; the round-1 experiments need "
+                                  "SPHE_WITH_EXPERIMENTS=1 python sph-erosion_b200/build.py)", density_variant, force_variant);
     s->variant_density = density_variant; s->variant_force = force_variant;
     return SPHE_OK;
 }

@@ -105,6 +105,7 @@ void launch_density(cudaStream_t st, int variant, int n, const int* n_dev, const
                     const uint32_t* cell_sorted, const int* cell_start, const GridP& G, const StepC& C, float* rho,
                     int* nlist, int2* ncount, int cap = 64, int* overflow = nullptr, int smem_cap = 64);
 int nlist_cap();
+bool variant_supported(int density, int force);
 int nlist_pairs_pad(int n);
 void launch_force(cudaStream_t st, int variant, int n, const int* n_dev, const float4* posq, const float4* velv, const float* rho,
                   const int* ids, const uint32_t* cell_sorted, const int* cell_start, const GridP& G, const StepC& C,
