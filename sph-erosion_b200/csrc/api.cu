@@ -210,10 +210,11 @@ static int reserve(sphe_sim* s, int need) {
     TRY(grow(&s->tmp, 0, nc, s->st, false));
     TRY(grow(&s->stage, 0, nc * 10, s->st, false));
     TRY(grow(&s->slot_of_id, 0, nc, s->st, false));
-    TRY(grow(&s->req_vertex, 0, nc, s->st, false));
-    TRY(grow(&s->req_amount, 0, nc, s->st, false));
-    TRY(grow(&s->surv, 0, nc, s->st, false));
-    if (!s->surv_count) CU(cudaMalloc(&s->surv_count, sizeof(int)));
+    // terrain stage: survivors per contact-path class (SPHE_SURV_CLASSES lists of nc entries), requests by padded survivor index
+    TRY(grow(&s->req_vertex, 0, nc + 32 * SPHE_SURV_CLASSES, s->st, false));
+    TRY(grow(&s->req_amount, 0, nc + 32 * SPHE_SURV_CLASSES, s->st, false));
+    TRY(grow(&s->surv, 0, nc * SPHE_SURV_CLASSES, s->st, false));
+    if (!s->surv_count) CU(cudaMalloc(&s->surv_count, 4 * sizeof(int)));
     s->cap = (int)nc;
     s->binned = false;
     s->slot_valid = false;
@@ -349,10 +350,10 @@ static int step_device(sphe_sim* s, sphe_terrain* t, int terrain_phases = 7) {
     C.t_lmax = nullptr;
     if (t) {
         // exact contact cull in the force epilogue; survivors skip the box there and get it after the contact search
-        C.t_lmax = t->lmax; C.t_surv = s->surv; C.t_count = s->surv_count;
+        C.t_lmax = t->lmax; C.t_surv = s->surv; C.t_count = s->surv_count; C.t_cap = s->cap;
         C.t_rows = t->rows; C.t_cols = t->cols; C.t_dimx = t->dimx; C.t_dimz = t->dimz;
         C.t_ox = t->origin[0]; C.t_oy = t->origin[1]; C.t_oz = t->origin[2]; C.t_inv = 1.0f / t->scale;
-        CU(cudaMemsetAsync(s->surv_count, 0, sizeof(int), s->st));
+        CU(cudaMemsetAsync(s->surv_count, 0, 4 * sizeof(int), s->st));
     }
     s->lastC = C;
     int n = s->n;
@@ -449,7 +450,7 @@ static int step_device(sphe_sim* s, sphe_terrain* t, int terrain_phases = 7) {
     if (t) {
         TerrainDev T = terrain_view(t);
         Scope k(s, SPHE_K_TERRAIN, terrain_stage_launches(C, T));
-        launch_terrain_stage(s->st, s->surv, s->surv_count, s->posB, s->posA, s->velA, (int*)s->sedB, C, T, 1, s->req_vertex, s->req_amount, nullptr,
+        launch_terrain_stage(s->st, s->surv, s->surv_count, s->cap, s->posB, s->posA, s->velA, (int*)s->sedB, C, T, 1, s->req_vertex, s->req_amount, nullptr,
                              terrain_phases);
     }
     std::swap(s->idsA, s->idsB);
@@ -1454,7 +1455,7 @@ int sphe_step_phase(sphe_sim* s, sphe_terrain* t, int phase) {
     TerrainDev T = terrain_view(t);
     Scope k(s, SPHE_K_TERRAIN, phase == 1 ? 1 : 2);
     // the step's sediment array is sedA after phase 0 swapped the buffers
-    launch_terrain_stage(s->st, s->surv, s->surv_count, nullptr, nullptr, nullptr, (int*)s->sedA, s->lastC, T, 1, s->req_vertex,
+    launch_terrain_stage(s->st, s->surv, s->surv_count, s->cap, nullptr, nullptr, nullptr, (int*)s->sedA, s->lastC, T, 1, s->req_vertex,
                          s->req_amount, nullptr, phase == 1 ? TERRAIN_GRANT : TERRAIN_APPLY);
     CU(cudaGetLastError());
     return SPHE_OK;
@@ -1704,7 +1705,7 @@ int sphe_terrain_stage_host(sphe_terrain* t, int n, const float* pos_curr, float
     int *sd = nullptr, *rq = nullptr, *dh = nullptr;
     CU(cudaMalloc(&po, (size_t)n * sizeof(float4))); CU(cudaMalloc(&pn, (size_t)n * sizeof(float4)));
     CU(cudaMalloc(&vn, (size_t)n * sizeof(float4))); CU(cudaMalloc(&sd, (size_t)n * sizeof(int)));
-    CU(cudaMalloc(&rq, (3 * (size_t)n + 1) * sizeof(int))); CU(cudaMalloc(&dh, (size_t)n * sizeof(int)));
+    CU(cudaMalloc(&rq, (3 * (size_t)n + 4 + 64 * SPHE_SURV_CLASSES) * sizeof(int))); CU(cudaMalloc(&dh, (size_t)n * sizeof(int)));
     CU(cudaMemset(dh, 0, (size_t)n * sizeof(int)));
     std::vector<float4> a((size_t)n), b((size_t)n), c((size_t)n);
     for (int i = 0; i < n; i++) {
@@ -1718,8 +1719,10 @@ int sphe_terrain_stage_host(sphe_terrain* t, int n, const float* pos_curr, float
     CU(cudaMemcpy(sd, sediment, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
     StepC C{};
     C.dt = dt; C.cR = cR; C.box = 0; C.cube = 1; C.lenx = C.leny = C.lenz = C.len = 3.0e38f;
-    launch_iota(0, n, rq + 2 * (size_t)n, rq + 3 * (size_t)n);   // no cull in front of the hook: everyone is a survivor
-    launch_terrain_stage(0, rq + 2 * (size_t)n, rq + 3 * (size_t)n, po, pn, vn, sd, C, terrain_view(t), 0, rq, rq + n, dh);
+    // layout of rq: request vertices [n + 32 K], request amounts [n + 32 K], survivor list [n] (class 0 only), counts [4]
+    const size_t rn = (size_t)n + 32 * SPHE_SURV_CLASSES;
+    launch_iota(0, n, rq + 2 * rn, rq + 2 * rn + n);   // no cull in front of the hook: everyone is a survivor
+    launch_terrain_stage(0, rq + 2 * rn, rq + 2 * rn + n, n, po, pn, vn, sd, C, terrain_view(t), 0, rq, rq + rn, dh);
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(b.data(), pn, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(c.data(), vn, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost));

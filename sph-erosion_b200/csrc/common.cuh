@@ -40,8 +40,9 @@ struct StepC {
     // Terrain attached: the force kernels' epilogue runs the exact contact cull (terrain.cu) on the state
     // it has in registers and appends the survivors to t_surv; only those go through the contact search.
     const int* t_lmax;        // NULL: no terrain
-    int* t_surv;              // survivor slots
-    int* t_count;             // number of survivors
+    int* t_surv;              // survivor slots: SPHE_SURV_CLASSES lists of t_cap entries each, one per contact-path class
+    int* t_count;             // survivors per class
+    int t_cap;
     int t_rows, t_cols, t_dimx, t_dimz;
     float t_ox, t_oy, t_oz, t_inv;
 };
@@ -49,15 +50,20 @@ struct StepC {
 // Exact contact culling (see k_terrain_contact): nothing above the local maxima of the cells of posCurr and
 // posNext can touch the heightfield.  Same arithmetic in sph.cu (FMA contraction allowed) and terrain.cu
 // (not allowed): (p - o) * inv has nothing to contract.
-__device__ __forceinline__ bool terrain_may_touch(const StepC& C, float ox_, float oy_, float oz_, float px, float py, float pz) {
+// Returns -1 (cannot touch) or the CLASS of the path Grid::collision will take (grid.h:476, :623, :640): 0 = posCurr and
+// posNext in the same terrain cell, 1 = cells differ along one axis, 2 = along both (straight to the corner fans).
+// Survivors are listed per class so a warp of the contact kernel runs ONE of the three branches instead of all of them.
+#define SPHE_SURV_CLASSES 3
+__device__ __forceinline__ int terrain_may_touch(const StepC& C, float ox_, float oy_, float oz_, float px, float py, float pz) {
     float cx = floorf((ox_ - C.t_ox) * C.t_inv), cz = floorf((oz_ - C.t_oz) * C.t_inv);
     float nx = floorf((px - C.t_ox) * C.t_inv), nz = floorf((pz - C.t_oz) * C.t_inv);
     float mx = (float)(C.t_dimx - 1), mz = (float)(C.t_dimz - 1);
-    if (cx < 0.0f || cx >= mx || cz < 0.0f || cz >= mz || nx < 0.0f || nx >= mx || nz < 0.0f || nz >= mz) return false;
+    if (cx < 0.0f || cx >= mx || cz < 0.0f || cz >= mz || nx < 0.0f || nx >= mx || nz < 0.0f || nz >= mz) return -1;
     int ia = min((int)cx, C.t_rows - 1) * C.t_cols + min((int)cz, C.t_cols - 1);
     int ib = min((int)nx, C.t_rows - 1) * C.t_cols + min((int)nz, C.t_cols - 1);
     int top = max(__ldg(&C.t_lmax[ia]), __ldg(&C.t_lmax[ib]));
-    return (py - C.t_oy) * C.t_inv <= (float)top * (1.0f / 4096.0f) + 0.01f;
+    if (!((py - C.t_oy) * C.t_inv <= (float)top * (1.0f / 4096.0f) + 0.01f)) return -1;
+    return (cx != nx ? 1 : 0) + (cz != nz ? 1 : 0);
 }
 
 __device__ __forceinline__ int cell_axis(float p, float gmin, float cell, int dim) {

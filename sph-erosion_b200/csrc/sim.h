@@ -41,7 +41,7 @@ struct TerrainDev {
     int hmin_fx, max_pickup_fx;
     int erosion;
 };
-void launch_terrain_stage(cudaStream_t st, const int* surv, const int* surv_count, const float4* pos_old, float4* posq, float4* velv,
+void launch_terrain_stage(cudaStream_t st, const int* surv, const int* surv_count, int surv_cap, const float4* pos_old, float4* posq, float4* velv,
                           int* sediment, const StepC& C, const TerrainDev& T, int apply_box, int* req_vertex, int* req_amount,
                           int* hit_out, int phases = 7);
 enum { TERRAIN_CONTACT = 1, TERRAIN_GRANT = 2, TERRAIN_APPLY = 4 };  // phases of the terrain stage (multi-GPU: reduce between them)

@@ -35,14 +35,16 @@ __device__ __forceinline__ void force_epilogue(int i, float4 pi, float4 vi, floa
     if (C.t_lmax) {
         // ghost copies (slab mode) never enter the terrain stage: their owner rank resolves the contact and
         // files the erosion request, the copy is dropped at the next exchange
-        surv = dt != 0.0f && terrain_may_touch(C, pi.x, pi.y, pi.z, px, py, pz) && !(__ldg(&ids[i]) & SPHE_GHOST_BIT);
+        const int cls = (dt != 0.0f && !(__ldg(&ids[i]) & SPHE_GHOST_BIT)) ? terrain_may_touch(C, pi.x, pi.y, pi.z, px, py, pz) : -1;
+        surv = cls >= 0;
+        // one atomic per class per warp: lanes of the same class take consecutive slots of that class's list
         unsigned act = __activemask();
-        unsigned m = __ballot_sync(act, surv);
-        if (m) {
-            int lane = threadIdx.x & 31, leader = __ffs(m) - 1, base = 0;
-            if (lane == leader) base = atomicAdd(C.t_count, __popc(m));
-            base = __shfl_sync(act, base, leader);
-            if (surv) C.t_surv[base + __popc(m & ((1u << lane) - 1u))] = i;
+        unsigned peers = __match_any_sync(act, cls);
+        if (surv) {
+            int lane = threadIdx.x & 31, leader = __ffs(peers) - 1, base = 0;
+            if (lane == leader) base = atomicAdd(C.t_count + cls, __popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            C.t_surv[(size_t)cls * C.t_cap + base + __popc(peers & ((1u << lane) - 1u))] = i;
         }
     }
     if (C.box && !surv) box_collide(C, px, py, pz, vx, vy, vz);

@@ -201,6 +201,26 @@ __device__ __forceinline__ void vertex_add(unsigned participants, bool active, i
     if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&table[vertex], total);
 }
 
+// Survivors come in SPHE_SURV_CLASSES lists (surv + c * cap, counts[c]).  The stage kernels walk ONE index space in which
+// every class starts at a multiple of 32, so a warp only ever holds survivors of one class: j -> (slot i, live).
+struct SurvMap {
+    int start[SPHE_SURV_CLASSES + 1];
+    __device__ __forceinline__ SurvMap(const int* __restrict__ counts) {
+        start[0] = 0;
+#pragma unroll
+        for (int c = 0; c < SPHE_SURV_CLASSES; c++) start[c + 1] = ((start[c] + __ldg(&counts[c]) + 31) & ~31);
+        // start[c + 1] - start[c] is the padded size of class c; the live part is counts[c]
+    }
+    __device__ __forceinline__ int total() const { return start[SPHE_SURV_CLASSES]; }
+    __device__ __forceinline__ int slot(const int* __restrict__ surv, const int* __restrict__ counts, int cap, int j) const {
+        int c = 0;
+#pragma unroll
+        for (int k = 1; k < SPHE_SURV_CLASSES; k++) c += (j >= start[k]) ? 1 : 0;
+        const int local = j - start[c];
+        return (local < __ldg(&counts[c])) ? __ldg(&surv[(size_t)c * cap + local]) : -1;
+    }
+};
+
 }  // namespace
 
 // ------------------------------------------------------------------ contact response + erosion requests
@@ -209,23 +229,23 @@ __device__ __forceinline__ void vertex_add(unsigned participants, bool active, i
 // persistent one and every warp strides over the list).  pos_old: positions before the step (.xyz);
 // posq / velv: the integrated, un-boxed state the force kernel wrote for survivors; updated in place,
 // then the box collision.  req_vertex[j] = vertex of survivor j's pending pick-up request (or -1).
-__global__ void __launch_bounds__(128) k_terrain_contact(const int* __restrict__ surv, const int* __restrict__ surv_count,
+__global__ void __launch_bounds__(128) k_terrain_contact(const int* __restrict__ surv, const int* __restrict__ surv_count, int surv_cap,
                                                          const float4* __restrict__ pos_old, float4* __restrict__ posq,
                                                          float4* __restrict__ velv, int* __restrict__ sediment, StepC C,
                                                          TerrainDev T, int apply_box, int* __restrict__ req_vertex,
                                                          int* __restrict__ req_amount, int* __restrict__ hit_out) {
-    const int count = __ldg(surv_count);
+    const SurvMap M(surv_count);
+    const int count = M.total();
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int base = warp * 32; base < count; base += nwarps * 32) {
         const int j = base + lane;
-        const bool live = j < count;
-        int i = 0;
+        int i = M.slot(surv, surv_count, surv_cap, j);
+        const bool live = i >= 0;
         float4 po = make_float4(0, 0, 0, 0), p4 = po, v4 = po;
         bool hit = false;
         V3 cp = mk(0, 0, 0), nn = mk(0, 0, 0);
         if (live) {
-            i = surv[j];
             po = pos_old[i]; p4 = posq[i]; v4 = velv[i];
             V3 pc = mk((po.x - T.ox) * T.inv_scale, (po.y - T.oy) * T.inv_scale, (po.z - T.oz) * T.inv_scale);
             V3 pn = mk((p4.x - T.ox) * T.inv_scale, (p4.y - T.oy) * T.inv_scale, (p4.z - T.oz) * T.inv_scale);
@@ -280,15 +300,17 @@ __global__ void __launch_bounds__(128) k_terrain_contact(const int* __restrict__
 }
 
 // ------------------------------------------------------------------ share what is above bedrock
-__global__ void __launch_bounds__(128) k_terrain_grant(const int* __restrict__ surv, const int* __restrict__ surv_count,
+__global__ void __launch_bounds__(128) k_terrain_grant(const int* __restrict__ surv, const int* __restrict__ surv_count, int surv_cap,
                                                        const int* __restrict__ req_vertex, const int* __restrict__ req_amount,
                                                        int* __restrict__ sediment, TerrainDev T) {
-    const int count = __ldg(surv_count);
+    const SurvMap M(surv_count);
+    const int count = M.total();
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int base = warp * 32; base < count; base += nwarps * 32) {
         const int j = base + lane;
-        int c = (j < count) ? req_vertex[j] : -1;
+        const int i = M.slot(surv, surv_count, surv_cap, j);
+        int c = (i >= 0) ? req_vertex[j] : -1;
         bool act = c >= 0;
         int g = 0;
         if (act) {
@@ -297,7 +319,7 @@ __global__ void __launch_bounds__(128) k_terrain_grant(const int* __restrict__ s
             long long w = T.want[c];
             int q = req_amount[j];
             g = (w <= avail) ? q : (int)(((long long)q * avail) / w);
-            sediment[surv[j]] += g;
+            sediment[i] += g;
         }
         unsigned m = __ballot_sync(SPHE_FULL, act);
         vertex_add(m, act, T.delta, c, -g);
@@ -313,11 +335,11 @@ __global__ void __launch_bounds__(256) k_terrain_apply(int first, int cells, Ter
     if (T.want[c]) T.want[c] = 0;
 }
 
-// every slot is a survivor (the test hook sphe_terrain_stage_host has no force kernel in front of it)
+// every slot is a survivor, all in class 0 (the test hook sphe_terrain_stage_host has no force kernel in front of it)
 __global__ void k_iota(int n, int* __restrict__ a, int* __restrict__ count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) a[i] = i;
-    if (i == 0) *count = n;
+    if (i == 0) { count[0] = n; for (int c = 1; c < SPHE_SURV_CLASSES; c++) count[c] = 0; }
 }
 
 // lmax[x, z] = max height over the vertices [x-1, x+2] x [z-1, z+2]: everything collide() can touch from cell (x, z)
@@ -412,16 +434,27 @@ __global__ void __launch_bounds__(256) k_sum_i32(int n, const int* __restrict__ 
 // ------------------------------------------------------------------ launch wrappers
 static inline int nb(int n, int b) { return (n + b - 1) / b; }
 
-// persistent grid: 148 SMs x 4 blocks of 128 threads stride over the survivor list
-void launch_terrain_stage(cudaStream_t st, const int* surv, const int* surv_count, const float4* pos_old, float4* posq, float4* velv,
+// persistent grid: (SMs of the current device) x 4 blocks of 128 threads stride over the survivor lists
+static int stage_grid() {
+    static int sms[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!sms[dev]) {
+        cudaDeviceProp p;
+        sms[dev] = (cudaGetDeviceProperties(&p, dev) == cudaSuccess && p.multiProcessorCount > 0) ? p.multiProcessorCount : 148;
+    }
+    return sms[dev] * 4;
+}
+void launch_terrain_stage(cudaStream_t st, const int* surv, const int* surv_count, int surv_cap, const float4* pos_old, float4* posq, float4* velv,
                           int* sediment, const StepC& C, const TerrainDev& T, int apply_box, int* req_vertex, int* req_amount,
                           int* hit_out, int phases) {
     // Multi-GPU slabs run the phases separately: per-vertex `want` is summed over the ranks between contact and
     // grant, `delta` between grant and apply (integer sums: exact and order independent).
     if (phases & TERRAIN_CONTACT)
-        k_terrain_contact<<<148 * 4, 128, 0, st>>>(surv, surv_count, pos_old, posq, velv, sediment, C, T, apply_box, req_vertex, req_amount, hit_out);
+        k_terrain_contact<<<stage_grid(), 128, 0, st>>>(surv, surv_count, surv_cap, pos_old, posq, velv, sediment, C, T, apply_box, req_vertex, req_amount, hit_out);
     if (T.erosion && C.dt != 0.0f) {
-        if (phases & TERRAIN_GRANT) k_terrain_grant<<<148 * 4, 128, 0, st>>>(surv, surv_count, req_vertex, req_amount, sediment, T);
+        if (phases & TERRAIN_GRANT) k_terrain_grant<<<stage_grid(), 128, 0, st>>>(surv, surv_count, surv_cap, req_vertex, req_amount, sediment, T);
         if (phases & TERRAIN_APPLY) {
             const int cells = (T.win1 - T.win0) * T.cols;
             k_terrain_apply<<<nb(cells, 256), 256, 0, st>>>(T.win0 * T.cols, cells, T);
