@@ -117,7 +117,13 @@ struct sphe_sim {
     int* transit_n = nullptr;      // device int[4]: in transit left, right, -, forwarded so far
     int slab_cap_sent = 0;
     bool slab_unpacked = false;    // unpack already ran since the last pack (a repeat must clear its counters)
-    int* d_n = nullptr;            // device word: exact particle count after the last unpack
+    int* d_n = nullptr;            // device word: exact EXTENT of the storage arrays after the last unpack (dead entries included)
+    // In-place exchange (slab.cu k_slab_classify): between an unpack and the next step the storage arrays hold dead
+    // entries and the appended records: `extent` (host upper bound) / d_n (exact) entries.  The step's binning compacts
+    // them; from then on the LIVE count is on the device at cell_start[ncells] (live_dev) and s->n bounds it.
+    bool extent_pending = false;
+    int extent = 0, extent_base = 0;
+    bool live_dev = false;
     // asynchronous unpack: results of the last SLAB_RING steps, read back without stalling the stream
     static const int SLAB_RING = 8;
     cudaEvent_t slab_ev[SLAB_RING] = {};
@@ -277,6 +283,13 @@ static int setup_grid(sphe_sim* s) {
     if (!(P.h > 0.0f) || !isfinite(P.h)) return fail(SPHE_ERR_ARG, "smoothing radius h must be positive");
     bool same = (s->grid_h == P.h) && (s->grid_user || s->box_user || s->grid_len == P.len) && s->ncells > 0;
     if (same) return SPHE_OK;
+    // slab mode keeps the live particle count of the compacted arrays at cell_start[ncells]: move it to d_n before the
+    // table is rebuilt (re-windowing after a re-cut, new h) and treat the arrays as a pending extent
+    if (s->slab_on && s->live_dev && !s->extent_pending && s->cell_start && s->d_n) {
+        CU(cudaMemcpyAsync(s->d_n, s->cell_start + s->ncells, sizeof(int), cudaMemcpyDeviceToDevice, s->st));
+        s->extent = s->n; s->extent_pending = true;
+    }
+    s->live_dev = false;
     float cell = P.h * 1.0009765625f;  // h * (1 + 2^-10), see oracle so_grid_for_box
     float lo[3], hi[3];
     for (int a = 0; a < 3; a++) {
@@ -333,6 +346,12 @@ struct Scope {
 // ------------------------------------------------------------------ the step
 static int terrain_ready(sphe_terrain* t);
 extern "C" { static int slab_settle(sphe_sim* s); }
+// Extent of the storage arrays in slab mode: host upper bound and the device word holding the exact value (NULL: the
+// bound is exact).  After a step the arrays are compact: s->n bounds the live count the scan left at cell_start[ncells].
+static int slab_extent_bound(const sphe_sim* s) { return s->extent_pending ? s->extent : s->n; }
+static const int* slab_extent_dev(const sphe_sim* s) {
+    return s->extent_pending ? s->d_n : (s->live_dev ? s->cell_start + s->ncells : nullptr);
+}
 static TerrainDev terrain_view(const sphe_terrain* t);
 
 static int step_device(sphe_sim* s, sphe_terrain* t, int terrain_phases = 7) {
@@ -357,10 +376,14 @@ static int step_device(sphe_sim* s, sphe_terrain* t, int terrain_phases = 7) {
     }
     s->lastC = C;
     int n = s->n;
-    const int* nd = s->slab_pending ? s->d_n : nullptr;  // exact count on the device while unpack results are in flight
-    { Scope k(s, SPHE_K_HASH); launch_hash(s->st, n, nd, s->posA, s->G, s->cell, s->count); }
-    { Scope k(s, SPHE_K_SCAN, 2); launch_scan(s->st, s->ncells, n, nd, s->count, s->tile_sum, s->cell_start, s->cursor); }
-    { Scope k(s, SPHE_K_SCATTER); launch_scatter(s->st, n, nd, s->cell, s->idsA, s->cursor, s->tmp); }
+    // Slab mode: the storage arrays may hold dead entries + appended records (extent_pending): hash and scatter walk that
+    // extent (exact count on the device), every later kernel works on the live count the scan leaves at cell_start[ncells].
+    const int n_in = (s->slab_on && s->extent_pending) ? s->extent : n;
+    const int* nd_in = !s->slab_on ? nullptr : (s->extent_pending ? s->d_n : (s->live_dev ? s->cell_start + s->ncells : nullptr));
+    const int* nd = s->slab_on ? s->cell_start + s->ncells : nullptr;
+    { Scope k(s, SPHE_K_HASH); launch_hash(s->st, n_in, nd_in, s->posA, s->slab_on ? s->idsA : nullptr, s->G, s->cell, s->count); }
+    { Scope k(s, SPHE_K_SCAN, 2); launch_scan(s->st, s->ncells, s->count, s->tile_sum, s->cell_start, s->cursor); }
+    { Scope k(s, SPHE_K_SCATTER); launch_scatter(s->st, n_in, nd_in, s->cell, s->idsA, s->cursor, s->tmp); }
     if (s->io.wait_vel) CU(cudaStreamWaitEvent(s->st, s->ev_vel, 0));   // velocities arrive on the io stream (sphe_step_host)
     { Scope k(s, SPHE_K_REORDER);
       launch_rank_reorder(s->st, n, nd, s->tmp, s->cell, s->cell_start, s->posA, s->velA, s->sedA, s->posB, s->velB, s->sedB,
@@ -457,6 +480,7 @@ static int step_device(sphe_sim* s, sphe_terrain* t, int terrain_phases = 7) {
     std::swap(s->sedA, s->sedB);
     s->binned = true;
     s->slot_valid = false;
+    if (s->slab_on) { s->extent_pending = false; s->live_dev = true; }
     CU(cudaGetLastError());
     return SPHE_OK;
 }
@@ -1048,7 +1072,7 @@ int sphe_slab_configure(sphe_sim* s, int x0, int x1, int has_left, int has_right
     s->slab.wrap_left = s->slab.wrap_right = 0; s->slab.far_x0 = 0x7fffffff;
     s->slab_on = true;
     s->grid_h = -1.f;  // re-window the grid
-    if (!s->slab_counters) CU(cudaMalloc(&s->slab_counters, 8 * sizeof(int)));
+    if (!s->slab_counters) CU(cudaMalloc(&s->slab_counters, 16 * sizeof(int)));
     if (!s->d_n) CU(cudaMalloc(&s->d_n, sizeof(int)));
     if (!s->slab_host) CU(cudaMallocHost(&s->slab_host, sphe_sim::SLAB_RING * 8 * sizeof(int)));
     for (int k = 0; k < 2; k++) if (!s->transit[k]) CU(cudaMalloc(&s->transit[k], 2 * SPHE_TRANSIT_CAP * sizeof(float4)));
@@ -1110,6 +1134,7 @@ int sphe_slab_upload(sphe_sim* s, int n, const float* pos, const float* vel, con
     CU(cudaMemsetAsync(s->transit_n, 0, 4 * sizeof(int), s->st));
     CU(cudaStreamSynchronize(s->st));
     s->n = n; s->n_owned = n;
+    s->extent_pending = false; s->live_dev = false;
     s->slab_done = s->slab_seq; s->slab_pending = 0;
     s->num = n; s->init_num = n; s->next_label = n;
     s->labels.clear(); s->labels_identity = true;
@@ -1123,15 +1148,15 @@ int sphe_slab_pack(sphe_sim* s, void* dev_send_left, void* dev_send_right, int c
     TRY(ensure_device(s));
     TRY(setup_grid(s));
     // room for everything that can arrive, so nothing has to grow between pack and unpack
-    TRY(reserve(s, std::max(s->n + reserve_incoming, 1)));
-    CU(cudaMemsetAsync(s->slab_counters, 0, 8 * sizeof(int), s->st));
-    launch_slab_classify(s->st, s->n, s->slab_pending ? s->d_n : nullptr, s->posA, s->velA, s->idsA, s->sedA, s->G, s->slab, s->posB, s->velB, s->idsB, s->sedB,
+    TRY(reserve(s, std::max(slab_extent_bound(s) + reserve_incoming, 1)));
+    CU(cudaMemsetAsync(s->slab_counters, 0, 16 * sizeof(int), s->st));
+    launch_slab_classify(s->st, slab_extent_bound(s), slab_extent_dev(s), s->posA, s->velA, s->idsA, s->sedA, s->G, s->slab,
                          (float4*)dev_send_left, (float4*)dev_send_right, cap_records, s->slab_counters);
     launch_slab_forward(s->st, s->transit[0], s->transit[1], s->transit_n, s->slab.has_left ? (float4*)dev_send_left : nullptr,
                         s->slab.has_right ? (float4*)dev_send_right : nullptr, cap_records, s->slab_counters, false);
     launch_slab_headers(s->st, s->slab_counters, (float4*)dev_send_left, (float4*)dev_send_right);
     s->launches += 3;
-    std::swap(s->posA, s->posB); std::swap(s->velA, s->velB); std::swap(s->idsA, s->idsB); std::swap(s->sedA, s->sedB);
+    s->extent_base = slab_extent_bound(s);   // the appended records go behind it (sphe_slab_unpack*)
     s->binned = false; s->slot_valid = false;
     s->slab_cap_sent = cap_records;
     s->slab_unpacked = false;
@@ -1200,8 +1225,10 @@ int sphe_slab_unpack_async(sphe_sim* s, const void* dev_recv_left, int max_left,
     s->slab_max[slot][0] = max_left; s->slab_max[slot][1] = max_right;
     s->slab_seq = t + 1;
     s->slab_pending = (int)(s->slab_seq - s->slab_done);
-    // until the result is folded, n is an upper bound (pack made room for it) and kernels read d_n
+    // until the result is folded, n is an upper bound (pack made room for it) and kernels read the device counts
     s->n = (int)std::min<long long>((long long)s->n + max_left + max_right, s->cap);
+    s->extent = (int)std::min<long long>((long long)s->extent_base + max_left + max_right, s->cap);
+    s->extent_pending = true;
     s->binned = false; s->slot_valid = false;
     if (ticket) *ticket = t;
     CU(cudaGetLastError());
@@ -1232,16 +1259,16 @@ int sphe_slab_download(sphe_sim* s, int cap, int* ids, float* pos, float* vel, f
     if (!s || !ids || !pos || !vel || !n_out) return fail(SPHE_ERR_ARG, "bad arguments");
     TRY(ensure_device(s));
     TRY(slab_settle(s));
-    int n = s->n;
+    int n = slab_extent_bound(s);
     *n_out = 0;
     if (n == 0) return SPHE_OK;
-    if (!s->slab_counters) CU(cudaMalloc(&s->slab_counters, 8 * sizeof(int)));
+    if (!s->slab_counters) CU(cudaMalloc(&s->slab_counters, 16 * sizeof(int)));
     size_t cp = (size_t)s->cap;
     int* d_cnt = s->slab_counters + 7;
     int* d_ids = (int*)s->stage;
     float *d_pos = s->stage + cp, *d_vel = s->stage + 4 * cp, *d_rho = s->stage + 7 * cp, *d_sed = s->stage + 8 * cp;
     CU(cudaMemsetAsync(d_cnt, 0, sizeof(int), s->st));
-    launch_slab_gather_owned(s->st, n, s->posA, s->velA, s->rho, s->sedA, s->idsA, d_cnt, d_ids, d_pos, d_vel, d_rho, d_sed);
+    launch_slab_gather_owned(s->st, n, slab_extent_dev(s), s->posA, s->velA, s->rho, s->sedA, s->idsA, d_cnt, d_ids, d_pos, d_vel, d_rho, d_sed);
     int m = 0;
     CU(cudaMemcpyAsync(&m, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));
@@ -1384,21 +1411,21 @@ int sphe_slab_send(sphe_sim* s) {
     TRY(setup_grid(s));            // the classification needs the global grid (a host that never asked for slab_info has none yet)
     TRY(slab_fold_ready(s));
     const int incoming = 2 * s->mbox_cap;
-    if ((long long)s->n + incoming > s->cap) TRY(slab_settle(s));   // exact count before deciding to grow
-    TRY(reserve(s, std::max(s->n + incoming, 1)));
+    if ((long long)slab_extent_bound(s) + incoming > s->cap) TRY(slab_settle(s));   // exact count before deciding to grow
+    TRY(reserve(s, std::max(slab_extent_bound(s) + incoming, 1)));
     const int q = ++s->peer_seq, par = q & 1;
     // what goes LEFT lands in the left neighbour's "from the right" buffer, and vice versa
     float4* dl = s->slab.has_left ? mbox_buffer(s->peer_mbox[0], s->mbox_buf, 1, par) : nullptr;
     float4* dr = s->slab.has_right ? mbox_buffer(s->peer_mbox[1], s->mbox_buf, 0, par) : nullptr;
     int* fl = s->slab.has_left ? mbox_flag(s->peer_mbox[0], s->mbox_buf, 1, par) : nullptr;
     int* fr = s->slab.has_right ? mbox_flag(s->peer_mbox[1], s->mbox_buf, 0, par) : nullptr;
-    CU(cudaMemsetAsync(s->slab_counters, 0, 8 * sizeof(int), s->st));
-    launch_slab_classify(s->st, s->n, s->slab_pending ? s->d_n : nullptr, s->posA, s->velA, s->idsA, s->sedA, s->G, s->slab, s->posB, s->velB,
-                         s->idsB, s->sedB, dl, dr, s->mbox_cap, s->slab_counters, true);
+    CU(cudaMemsetAsync(s->slab_counters, 0, 16 * sizeof(int), s->st));
+    launch_slab_classify(s->st, slab_extent_bound(s), slab_extent_dev(s), s->posA, s->velA, s->idsA, s->sedA, s->G, s->slab,
+                         dl, dr, s->mbox_cap, s->slab_counters, true);
     launch_slab_forward(s->st, s->transit[0], s->transit[1], s->transit_n, dl, dr, s->mbox_cap, s->slab_counters, true);
     launch_slab_headers(s->st, s->slab_counters, dl, dr, fl, fr, q);
     s->launches += 3;
-    std::swap(s->posA, s->posB); std::swap(s->velA, s->velB); std::swap(s->idsA, s->idsB); std::swap(s->sedA, s->sedB);
+    s->extent_base = slab_extent_bound(s);
     s->binned = false; s->slot_valid = false;
     s->slab_cap_sent = s->mbox_cap;
     s->slab_unpacked = false;
@@ -1436,6 +1463,8 @@ int sphe_slab_recv(sphe_sim* s, long long* ticket) {
     s->slab_seq = t + 1;
     s->slab_pending = (int)(s->slab_seq - s->slab_done);
     s->n = (int)std::min<long long>((long long)s->n + ml + mr, s->cap);
+    s->extent = (int)std::min<long long>((long long)s->extent_base + ml + mr, s->cap);
+    s->extent_pending = true;
     s->binned = false; s->slot_valid = false;
     if (ticket) *ticket = t;
     CU(cudaGetLastError());
@@ -1796,7 +1825,8 @@ int sphe_sediment_total_fx(sphe_sim* s, long long* sum) {
     long long* d = nullptr;
     CU(cudaMalloc(&d, sizeof(long long)));
     CU(cudaMemsetAsync(d, 0, sizeof(long long), s->st));
-    launch_sum_i32(s->st, s->n, (const int*)s->sedA, s->slab_on ? s->idsA : nullptr, d);
+    launch_sum_i32(s->st, s->slab_on ? slab_extent_bound(s) : s->n, (const int*)s->sedA, s->slab_on ? s->idsA : nullptr, d,
+                   s->slab_on ? slab_extent_dev(s) : nullptr);
     CU(cudaMemcpyAsync(sum, d, sizeof(long long), cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));
     CU(cudaFree(d));

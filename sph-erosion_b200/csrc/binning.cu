@@ -13,17 +13,19 @@ namespace sphe {
 // One thread per particle (storage order).  Storage order is last step's sorted order, so
 // consecutive lanes mostly share a cell: counts are aggregated per run of equal cells inside the
 // warp (shfl + ballot) and only the run head issues the atomic.
-__global__ void __launch_bounds__(256) k_hash(int n_hi, const int* __restrict__ n_dev, const float4* __restrict__ posq, GridP G,
+__global__ void __launch_bounds__(256) k_hash(int n_hi, const int* __restrict__ n_dev, const float4* __restrict__ posq, const int* __restrict__ ids, GridP G,
                                               uint32_t* __restrict__ cell, int* __restrict__ count) {
     const int n = n_dev ? __ldg(n_dev) : n_hi;  // exact count from the device in slab mode, else the launch bound
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned lane = threadIdx.x & 31;
     uint32_t c = 0xffffffffu;
     if (i < n) {
-        float4 p = posq[i];
-        int cx, cy, cz;
-        cell_coords(G, p.x, p.y, p.z, cx, cy, cz);
-        c = (uint32_t)((cx * G.ny + cy) * G.nz + cz);
+        if (!ids || ids[i] != -1) {   // slab mode: an entry the exchange dropped has no cell
+            float4 p = posq[i];
+            int cx, cy, cz;
+            cell_coords(G, p.x, p.y, p.z, cx, cy, cz);
+            c = (uint32_t)((cx * G.ny + cy) * G.nz + cz);
+        }
         cell[i] = c;
     }
     uint32_t prev = __shfl_up_sync(SPHE_FULL, c, 1);
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(int ntiles, int* __restrict
     }
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(long long ncells, int n_total, const int* __restrict__ n_dev, int* __restrict__ count,
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(long long ncells, int* __restrict__ count,
                                                              const int* __restrict__ tile_off,
                                                              int* __restrict__ cell_start, int* __restrict__ cursor) {
     long long base = (long long)blockIdx.x * SCAN_TILE;
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(long long ncells, i
             if (e0 + k < ncells) { cell_start[e0 + k] = run; cursor[e0 + k] = run; count[e0 + k] = 0; run += v[k]; }
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) cell_start[ncells] = n_dev ? __ldg(n_dev) : n_total;
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) cell_start[ncells] = tile_base + total;   // number of live particles
 }
 
 // ---------------------------------------------------------------- counting-sort scatter
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(256) k_scatter(int n_hi, const int* __restrict
         base = atomicAdd(&cursor[c], next - (int)lane);
     }
     base = __shfl_sync(SPHE_FULL, base, hl);
-    if (i < n) tmp[base + ((int)lane - hl)] = make_uint2((uint32_t)ids[i], (uint32_t)i);
+    if (i < n && c != 0xffffffffu) tmp[base + ((int)lane - hl)] = make_uint2((uint32_t)ids[i], (uint32_t)i);
 }
 
 // ---------------------------------------------------------------- rank inside the cell + reorder
@@ -217,17 +219,17 @@ __global__ void __launch_bounds__(256) k_rank_reorder(int n_hi, const int* __res
 }
 
 // ---------------------------------------------------------------- launch wrappers
-void launch_hash(cudaStream_t st, int n, const int* n_dev, const float4* posq, const GridP& G, uint32_t* cell, int* count) {
+void launch_hash(cudaStream_t st, int n, const int* n_dev, const float4* posq, const int* ids, const GridP& G, uint32_t* cell, int* count) {
     if (n <= 0) return;
-    k_hash<<<(n + 255) / 256, 256, 0, st>>>(n, n_dev, posq, G, cell, count);
+    k_hash<<<(n + 255) / 256, 256, 0, st>>>(n, n_dev, posq, ids, G, cell, count);
 }
 
 int scan_tiles_for(long long ncells) { return (int)((ncells + SCAN_TILE - 1) / SCAN_TILE); }
 
-void launch_scan(cudaStream_t st, long long ncells, int n_total, const int* n_dev, int* count, int* tile_sum, int* cell_start, int* cursor) {
+void launch_scan(cudaStream_t st, long long ncells, int* count, int* tile_sum, int* cell_start, int* cursor) {
     int ntiles = scan_tiles_for(ncells);
     k_scan_reduce<<<ntiles, SCAN_THREADS, 0, st>>>(ncells, count, tile_sum);
-    k_scan_final<<<ntiles, SCAN_THREADS, 0, st>>>(ncells, n_total, n_dev, count, tile_sum, cell_start, cursor);
+    k_scan_final<<<ntiles, SCAN_THREADS, 0, st>>>(ncells, count, tile_sum, cell_start, cursor);
 }
 
 void launch_scatter(cudaStream_t st, int n, const int* n_dev, const uint32_t* cell, const int* ids, int* cursor, uint2* tmp) {

@@ -10,9 +10,11 @@
 namespace sphe {
 
 // ---- binning.cu
-void launch_hash(cudaStream_t st, int n, const int* n_dev, const float4* posq, const GridP& G, uint32_t* cell, int* count);
+// ids != NULL (slab mode): entries with id == -1 are dead (dropped by the exchange): no cell, not counted, not scattered
+void launch_hash(cudaStream_t st, int n, const int* n_dev, const float4* posq, const int* ids, const GridP& G, uint32_t* cell, int* count);
 int scan_tiles_for(long long ncells);
-void launch_scan(cudaStream_t st, long long ncells, int n_total, const int* n_dev, int* count, int* tile_sum, int* cell_start, int* cursor);
+// cell_start[ncells] = number of LIVE particles (the sum of the counts): the count every later kernel of the step works on
+void launch_scan(cudaStream_t st, long long ncells, int* count, int* tile_sum, int* cell_start, int* cursor);
 void launch_scatter(cudaStream_t st, int n, const int* n_dev, const uint32_t* cell, const int* ids, int* cursor, uint2* tmp);
 void launch_rank_reorder(cudaStream_t st, int n, const int* n_dev, const uint2* tmp, const uint32_t* cell, const int* cell_start,
                          const float4* posq_in, const float4* velv_in, const float* sed_in,
@@ -55,7 +57,7 @@ void launch_terrain_collide(cudaStream_t st, int n, const float* pc, const float
 void launch_heights_from_u8(cudaStream_t st, int cells, const unsigned char* img, int* hfx, int* hmax);
 void launch_heights_from_f32(cudaStream_t st, int cells, const float* src, int* hfx, int* hmax);
 void launch_heights_to_f32(cudaStream_t st, int cells, const int* hfx, float* dst);
-void launch_sum_i32(cudaStream_t st, int n, const int* a, const int* ghost_ids, long long* out);
+void launch_sum_i32(cudaStream_t st, int n, const int* a, const int* ghost_ids, long long* out, const int* n_dev = nullptr);
 
 // ---- slab.cu (multi-GPU x-slabs)
 struct SlabP {
@@ -67,9 +69,8 @@ struct SlabP {
     // box quirk moved from the -x wall to the +x wall (cell column >= far_x0, the last slab's x0).
     int wrap_left = 0, wrap_right = 0, far_x0 = 0x7fffffff;
 };
-void launch_slab_classify(cudaStream_t st, int n, const int* n_dev, const float4* posq, const float4* velv, const int* ids, const float* sed,
-                          const GridP& G, const SlabP& S, float4* keep_pos, float4* keep_vel, int* keep_ids, float* keep_sed,
-                          float4* send_left, float4* send_right, int cap_records, int* counters, bool remote = false);
+void launch_slab_classify(cudaStream_t st, int n, const int* n_dev, const float4* posq, const float4* velv, int* ids, const float* sed,
+                          const GridP& G, const SlabP& S, float4* send_left, float4* send_right, int cap_records, int* counters, bool remote = false);
 // flag_* != NULL: peer-memory exchange, the buffers and flags live in the neighbour GPUs' mailboxes
 void launch_slab_headers(cudaStream_t st, int* counters, float4* send_left, float4* send_right, int* flag_left = nullptr,
                          int* flag_right = nullptr, int seq = 0);
@@ -81,7 +82,7 @@ void launch_slab_append(cudaStream_t st, int max_l, int max_r, const float4* rec
                         const SlabP& S, int cap_particles, float4* posq, float4* velv, int* ids, float* sed, int* counters, int* n_out,
                         float4* transit_l, float4* transit_r, int* transit_n,
                         const int* flag_l = nullptr, const int* flag_r = nullptr, int seq = 0, long long timeout_cycles = 0);
-void launch_slab_gather_owned(cudaStream_t st, int n, const float4* posq, const float4* velv, const float* rho, const float* sed,
+void launch_slab_gather_owned(cudaStream_t st, int n, const int* n_dev, const float4* posq, const float4* velv, const float* rho, const float* sed,
                               const int* ids, int* counter, int* out_ids, float* out_pos, float* out_vel, float* out_rho,
                               float* out_sed);
 void launch_pack_state_ids(cudaStream_t st, int n, const float* pos, const float* vel, const int* ids_in, float4* posq, float4* velv,

@@ -59,28 +59,31 @@ __device__ __forceinline__ void block_append4(const bool flag[4], int* const cou
     for (int k = 0; k < 4; k++) slot[k] = flag[k] ? bbase[k] + wsum[k][w] + __popc(m[k] & ((1u << lane) - 1u)) : -1;
 }
 
-// counters: [0] kept (owned + retained ghosts), [1] to left, [2] to right, [3] owned
+// counters: [0] kept (owned + retained ghosts), [1] to left, [2] to right, [3] owned, [8] extent of the arrays (append base)
+// IN PLACE: nothing is copied.  A particle that stays keeps its slot; last step's ghosts and particles that left the halo
+// zone are marked DEAD (id = -1: the ghost bit is set, so every owned-only pass skips them) and the next binning -- which
+// gathers every live particle into the sorted arrays anyway -- drops them (k_hash gives them no cell).  Only the ~5 % of
+// the particles in the halo zones are read in full and written, as 32-byte records.  (Round 1 rewrote all arrays here:
+// 80 B/particle, 0.04-0.09 ms per step.)
 // REMOTE: send_left / send_right point into the NEIGHBOUR GPU's mailbox (peer memory over NVLink, see the
 // peer-memory exchange below): the records are stored where they will be consumed, no staging copy and no
 // transport call, and every storing thread fences at system scope so the stores are performed at the peer
 // before this grid completes and k_slab_publish raises the flag.
+#define SPHE_DEAD_ID (-1)
 template <bool REMOTE>
 __global__ void __launch_bounds__(256) k_slab_classify(int n_hi, const int* __restrict__ n_dev, const float4* __restrict__ posq, const float4* __restrict__ velv,
-                                                       const int* __restrict__ ids, const float* __restrict__ sed, GridP G,
-                                                       SlabP S, float4* __restrict__ keep_pos, float4* __restrict__ keep_vel,
-                                                       int* __restrict__ keep_ids, float* __restrict__ keep_sed,
+                                                       int* __restrict__ ids, const float* __restrict__ sed, GridP G, SlabP S,
                                                        float4* __restrict__ send_left, float4* __restrict__ send_right,
                                                        int cap_records, int* __restrict__ counters) {
-    const int n = n_dev ? __ldg(n_dev) : n_hi;  // exact count from the device in slab mode, else the launch bound
+    const int n = n_dev ? __ldg(n_dev) : n_hi;  // exact extent from the device, else the launch bound
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool live = false, own = false, to_l = false, to_r = false;
-    float4 p = make_float4(0, 0, 0, 0), v = p;
+    float4 p = make_float4(0, 0, 0, 0);
     int id = 0;
-    float sd = 0.f;
     if (i < n) {
         id = ids[i];
         if (!(id & SPHE_GHOST_BIT)) {
-            p = posq[i]; v = velv[i]; sd = sed[i];
+            p = posq[i];
             int cx = cell_axis(p.x, G.gx, G.cell, G.gnx);
             own = (cx >= S.x0 || !S.has_left) && (cx < S.x1 || !S.has_right);
             // a particle exactly on the -x wall is clamped to the +x wall (collisionS, fluid_system.h:375-382:
@@ -91,27 +94,28 @@ __global__ void __launch_bounds__(256) k_slab_classify(int n_hi, const int* __re
             // left the slab but still within the halo zone: stays here as a ghost
             live = own || (!far && cx >= S.x0 - S.halo && cx < S.x1 + S.halo);
         }
+        const int nid = live ? (own ? id : (id | SPHE_GHOST_BIT)) : SPHE_DEAD_ID;
+        if (nid != id) ids[i] = nid;
+        if (i == 0) counters[8] = n;
     }
     const bool flag[4] = {live, to_l, to_r, own};
     int* const ctr[4] = {&counters[0], &counters[1], &counters[2], &counters[3]};
     int slot[4];
     block_append4(flag, ctr, slot);
-    const int k = slot[0], l = slot[1], r = slot[2];
-    if (live) {
-        keep_pos[k] = make_float4(p.x, p.y, p.z, 0.f);
-        keep_vel[k] = make_float4(v.x, v.y, v.z, 0.f);
-        keep_ids[k] = own ? id : (id | SPHE_GHOST_BIT);
-        keep_sed[k] = sd;
+    const int l = slot[1], r = slot[2];
+    if (to_l || to_r) {
+        const float4 v = velv[i];
+        const float sd = sed[i];
+        if (to_l && l < cap_records) {
+            send_left[2 * (l + 1)] = make_float4(p.x, p.y, p.z, sd);
+            send_left[2 * (l + 1) + 1] = make_float4(v.x, v.y, v.z, __int_as_float(id));
+        }
+        if (to_r && r < cap_records) {
+            send_right[2 * (r + 1)] = make_float4(p.x, p.y, p.z, sd);
+            send_right[2 * (r + 1) + 1] = make_float4(v.x, v.y, v.z, __int_as_float(id));
+        }
+        if (REMOTE) __threadfence_system();
     }
-    if (to_l && l < cap_records) {
-        send_left[2 * (l + 1)] = make_float4(p.x, p.y, p.z, sd);
-        send_left[2 * (l + 1) + 1] = make_float4(v.x, v.y, v.z, __int_as_float(id));
-    }
-    if (to_r && r < cap_records) {
-        send_right[2 * (r + 1)] = make_float4(p.x, p.y, p.z, sd);
-        send_right[2 * (r + 1) + 1] = make_float4(v.x, v.y, v.z, __int_as_float(id));
-    }
-    if (REMOTE && (to_l || to_r)) __threadfence_system();
 }
 
 __device__ __forceinline__ int ld_acquire_sys(const int* p) {
@@ -142,7 +146,7 @@ __global__ void k_slab_headers(int* __restrict__ counters, float4* __restrict__ 
     }
 }
 
-// Appends the payload of both received buffers behind the kept particles.  All counts are read from
+// Appends the payload of both received buffers behind the current extent of the arrays (counters[8]).  All counts are read from
 // device memory (the kept count from the pack counters, the payload counts from the headers), so the
 // host does not have to know them before this launch.  counters[4] += owned among the appended,
 // counters[5] = records taken from the left buffer, counters[6] = from the right buffer.
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(256) k_slab_append(int max_l, int max_r, const
         __syncthreads();
         if (!arrived) { rec_l = nullptr; rec_r = nullptr; }
     }
-    const int kept = counters[0];
+    const int kept = counters[8];   // append base: the extent k_slab_classify saw (dead entries included)
     const int head_l = rec_l ? __float_as_int(__ldcg(&rec_l[0]).x) : 0;
     const int head_r = rec_r ? __float_as_int(__ldcg(&rec_r[0]).x) : 0;
     int from_l = min(head_l, max_l), from_r = min(head_r, max_r);
@@ -240,14 +244,15 @@ __global__ void __launch_bounds__(256) k_slab_forward(const float4* __restrict__
 }
 
 // owned particles only, storage order, packed xyz (tests, checkpoints, rendering hand-off)
-__global__ void __launch_bounds__(256) k_slab_gather_owned(int n, const float4* __restrict__ posq, const float4* __restrict__ velv,
+__global__ void __launch_bounds__(256) k_slab_gather_owned(int n_hi, const int* __restrict__ n_dev, const float4* __restrict__ posq, const float4* __restrict__ velv,
                                                            const float* __restrict__ rho, const float* __restrict__ sed,
                                                            const int* __restrict__ ids, int* __restrict__ counter,
                                                            int* __restrict__ out_ids, float* __restrict__ out_pos,
                                                            float* __restrict__ out_vel, float* __restrict__ out_rho,
                                                            float* __restrict__ out_sed) {
+    const int n = n_dev ? __ldg(n_dev) : n_hi;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool own = (i < n) && !(ids[i] & SPHE_GHOST_BIT);
+    bool own = (i < n) && !(ids[i] & SPHE_GHOST_BIT);   // dead entries (id = -1) carry the ghost bit too
     int k = warp_append(own, counter);
     if (!own) return;
     float4 p = posq[i], v = velv[i];
@@ -268,16 +273,13 @@ __global__ void k_pack_state_ids(int n, const float* __restrict__ pos, const flo
     sed[i] = 0.f;
 }
 
-void launch_slab_classify(cudaStream_t st, int n, const int* n_dev, const float4* posq, const float4* velv, const int* ids, const float* sed,
-                          const GridP& G, const SlabP& S, float4* keep_pos, float4* keep_vel, int* keep_ids, float* keep_sed,
-                          float4* send_left, float4* send_right, int cap_records, int* counters, bool remote) {
+void launch_slab_classify(cudaStream_t st, int n, const int* n_dev, const float4* posq, const float4* velv, int* ids, const float* sed,
+                          const GridP& G, const SlabP& S, float4* send_left, float4* send_right, int cap_records, int* counters, bool remote) {
     if (n <= 0) return;
     if (remote)
-        k_slab_classify<true><<<(n + 255) / 256, 256, 0, st>>>(n, n_dev, posq, velv, ids, sed, G, S, keep_pos, keep_vel, keep_ids, keep_sed,
-                                                              send_left, send_right, cap_records, counters);
+        k_slab_classify<true><<<(n + 255) / 256, 256, 0, st>>>(n, n_dev, posq, velv, ids, sed, G, S, send_left, send_right, cap_records, counters);
     else
-        k_slab_classify<false><<<(n + 255) / 256, 256, 0, st>>>(n, n_dev, posq, velv, ids, sed, G, S, keep_pos, keep_vel, keep_ids, keep_sed,
-                                                               send_left, send_right, cap_records, counters);
+        k_slab_classify<false><<<(n + 255) / 256, 256, 0, st>>>(n, n_dev, posq, velv, ids, sed, G, S, send_left, send_right, cap_records, counters);
 }
 void launch_slab_forward(cudaStream_t st, const float4* transit_l, const float4* transit_r, int* transit_n, float4* send_left,
                          float4* send_right, int cap_records, int* counters, bool remote) {
@@ -300,11 +302,11 @@ void launch_slab_append(cudaStream_t st, int max_l, int max_r, const float4* rec
         k_slab_append<false><<<(m + 255) / 256, 256, 0, st>>>(max_l, max_r, rec_l, rec_r, nullptr, nullptr, 0, 0, G, S, cap_particles,
                                                              posq, velv, ids, sed, counters, n_out, transit_l, transit_r, transit_n);
 }
-void launch_slab_gather_owned(cudaStream_t st, int n, const float4* posq, const float4* velv, const float* rho, const float* sed,
+void launch_slab_gather_owned(cudaStream_t st, int n, const int* n_dev, const float4* posq, const float4* velv, const float* rho, const float* sed,
                               const int* ids, int* counter, int* out_ids, float* out_pos, float* out_vel, float* out_rho,
                               float* out_sed) {
     if (n > 0)
-        k_slab_gather_owned<<<(n + 255) / 256, 256, 0, st>>>(n, posq, velv, rho, sed, ids, counter, out_ids, out_pos, out_vel,
+        k_slab_gather_owned<<<(n + 255) / 256, 256, 0, st>>>(n, n_dev, posq, velv, rho, sed, ids, counter, out_ids, out_pos, out_vel,
                                                             out_rho, out_sed);
 }
 void launch_pack_state_ids(cudaStream_t st, int n, const float* pos, const float* vel, const int* ids_in, float4* posq, float4* velv,

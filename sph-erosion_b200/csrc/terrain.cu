@@ -422,7 +422,8 @@ __global__ void k_heights_to_f32(int cells, const int* __restrict__ hfx, float* 
     if (c < cells) dst[c] = (float)hfx[c] * (1.0f / 4096.0f);
 }
 // 64-bit sums for the conservation checks: out[0] += sum of a[0..n)
-__global__ void __launch_bounds__(256) k_sum_i32(int n, const int* __restrict__ a, const int* __restrict__ ghost_ids, long long* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_sum_i32(int n_hi, const int* __restrict__ n_dev, const int* __restrict__ a, const int* __restrict__ ghost_ids, long long* __restrict__ out) {
+    const int n = n_dev ? __ldg(n_dev) : n_hi;
     long long s = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         if (!ghost_ids || !(ghost_ids[i] & SPHE_GHOST_BIT)) s += a[i];
@@ -491,8 +492,8 @@ void launch_heights_from_f32(cudaStream_t st, int cells, const float* src, int* 
 void launch_heights_to_f32(cudaStream_t st, int cells, const int* hfx, float* dst) {
     k_heights_to_f32<<<nb(cells, 256), 256, 0, st>>>(cells, hfx, dst);
 }
-void launch_sum_i32(cudaStream_t st, int n, const int* a, const int* ghost_ids, long long* out) {
-    if (n > 0) k_sum_i32<<<min(nb(n, 256), 1184), 256, 0, st>>>(n, a, ghost_ids, out);
+void launch_sum_i32(cudaStream_t st, int n, const int* a, const int* ghost_ids, long long* out, const int* n_dev) {
+    if (n > 0) k_sum_i32<<<min(nb(n, 256), 1184), 256, 0, st>>>(n, n_dev, a, ghost_ids, out);
 }
 
 }  // namespace sphe
