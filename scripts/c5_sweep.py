@@ -36,7 +36,7 @@ for n_axis in axes:
             line = {"particles": n, "h": h, "mean_neighbours": nb, "variant": [dv, fv], "list_capacity": "%d/%d" % (sim.nlist_capacity(), sim.nlist_smem_entries()), "ms_per_step": ms / steps,
                     "particle_updates_per_s": n / (ms / steps * 1e-3), "per_kernel_ms": t,
                     "hbm_GBps_algorithmic": {k: bench.ALGO_BYTES[k] * n / (t[k] * 1e-3) / 1e9 for k in ("hash", "scatter", "reorder", "density", "force") if t[k] > 0},
-                    "algorithmic_bytes": "SURVEY.md 8(d): hash 24, scan 6, scatter 52, reorder 68, density 20, force 64",,
+                    "algorithmic_bytes": "SURVEY.md 8(d): hash 24, scan 6, scatter 52, reorder 68, density 20, force 64",
                     "hbm_frac_step": 234 * n / (ms / steps * 1e-3) / 1e9 / peak}
             print(json.dumps(line), flush=True)
             if out: out.write(json.dumps(line) + "\n"); out.flush()
