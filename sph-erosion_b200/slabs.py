@@ -603,6 +603,99 @@ def make_gpu_slab(pkg, device, rank, world, box_half, params, bounds_x, cap_reco
     return sim, backend, cols
 
 
+def parity_gate_multi(pkg, dist, dev, sim, drv, grid, tshare, windowed, box, params, variant, attach, world, rank):
+    """In-bench parity at FULL size for N > 1: the state the timed region left is gathered on rank 0, every rank takes
+    one more step through the ordinary exchange, and rank 0 takes the SAME step with ONE handle holding the whole scene
+    (all N slabs' particles, the whole terrain) on its own GPU.  Bar: the N-slab result equals the single-domain result
+    BIT FOR BIT (positions, velocities, densities, carried sediment per particle, every terrain row a rank owns); a
+    particle that crossed more than one slab in a step is forwarded a step late and may differ -- those are counted,
+    everything else must be exact.  The single-domain path itself is held to the oracle by the N = 1 gate
+    (bench.parity_gate).  `attach` builds a fresh terrain replica."""
+    import time
+    t0 = time.perf_counter()
+
+    def snapshot():
+        drv.drain()
+        ids, pos, vel, rho, sed = sim.slab_download()
+        rows = None
+        if grid is not None:
+            h = grid.heights_fx()
+            own = tshare.own if windowed else ((0, h.shape[0]) if rank == 0 else (0, 0))
+            rows = (own, h[own[0]:own[1]].copy())
+        out = [None] * world if rank == 0 else None
+        dist.gather_object((ids, pos, vel, rho, sed.view(np.int32), rows), out, dst=0)
+        return out
+
+    before = snapshot()
+    drv.step()
+    after = snapshot()
+    tr = sim.slab_transit()
+    moving = [None] * world if rank == 0 else None
+    dist.gather_object(tr["to_left"] + tr["to_right"], moving, dst=0)
+    if rank != 0:
+        return None
+
+    def by_id(parts, k, n):
+        ids = np.concatenate([p[0] for p in parts])
+        a = np.concatenate([p[k] for p in parts])
+        out = np.zeros((n,) + a.shape[1:], a.dtype)
+        out[ids] = a
+        return ids, out
+
+    ids0 = np.concatenate([p[0] for p in before])
+    n = int(ids0.shape[0])
+    res = {"particles": n, "reference": "one handle holding all %d slabs' particles and the whole terrain, same step, on rank 0's GPU" % world}
+    res["every_particle_owned_once"] = bool(n == int(ids0.max()) + 1 and np.array_equal(np.sort(ids0), np.arange(n)))
+    if not res["every_particle_owned_once"]:
+        return False, res
+    _, pos0 = by_id(before, 1, n); _, vel0 = by_id(before, 2, n); _, sed0 = by_id(before, 4, n)
+    one = pkg.FluidSystemSPH(device=dev.index)
+    for k, v in params.items():
+        if k == "g":
+            one.params.g[0], one.params.g[1], one.params.g[2] = v
+        else:
+            setattr(one.params, k, v)
+    one.set_box(box); one.set_variant(*variant)
+    one.upload_state(pos0, vel0)
+    g1 = None
+    if grid is not None:
+        g1 = attach()
+        rows_total = g1.shape()[0]
+        hfx = np.zeros((rows_total, g1.shape()[1]), np.int32)
+        for p in before:
+            (a, b), r = p[5]
+            hfx[a:b] = r
+        g1.set_heights(hfx.astype(np.float32) / np.float32(4096.0))      # exact: |fx| < 2^24
+        assert np.array_equal(g1.heights_fx(), hfx)
+        one.set_sediment_fx(sed0)
+    one.Run(g1)
+    exact = {}
+    for name, k in (("pos", 1), ("vel", 2), ("density", 3)):
+        _, got = by_id(after, k, n)
+        want = one.download(name)
+        same = got.view(np.uint32).reshape(n, -1) == want.view(np.uint32).reshape(n, -1)
+        exact[name] = int((~same.all(axis=1)).sum())
+        scale = max(float(np.abs(want).max()), 1e-30)
+        res[name + "_max_err_over_scale"] = float(np.abs(got.astype(np.float64) - want).max() / scale)
+    res["particles_not_bit_equal"] = exact
+    res["records_forwarded_late"] = int(sum(moving))
+    worst = max(exact.values())
+    ok = worst <= 2 * res["records_forwarded_late"]
+    if grid is not None:
+        _, seda = by_id(after, 4, n)
+        want = np.rint(one.download("sediment").astype(np.float64) * 4096.0).astype(np.int32)
+        res["sediment_particles_differing"] = int((seda != want).sum())
+        h1 = g1.heights_fx()
+        bad = 0
+        for p in after:
+            (a, b), r = p[5]
+            bad += int((h1[a:b] != r).sum())
+        res["terrain_vertices_differing"] = bad
+        ok = ok and bad == 0 and res["sediment_particles_differing"] <= 2 * res["records_forwarded_late"]
+    res["seconds"] = round(time.perf_counter() - t0, 2)
+    return bool(ok), res
+
+
 # --------------------------------------------------------------------------- bench (called by bench.py)
 def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT, terrain=False):
     import json
@@ -749,6 +842,11 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT, terrain=False):
     ms_step = float(ms.item()) / args.steps
     value = n_total / (ms_step * 1e-3)
 
+    gate = None
+    if not getattr(args, "no_parity_gate", False):
+        gate = parity_gate_multi(pkg, dist, dev, sim, drv, grid, tshare, windowed, box, params, (args.density_variant, args.force_variant),
+                                 (lambda: attach_terrain(pkg, box[1], n_axis, nx_mult=world)[0]) if terrain else None, world, rank)
+
     # end to end: every step uploads this rank's slab from pinned host memory, exchanges, steps and
     # downloads the owned particles back to pinned host memory
     e2e_steps = max(3, min(args.steps, 10))
@@ -797,6 +895,7 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT, terrain=False):
             "e2e": {"value": n_total / float(e2e_dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(io[0].item()),
                     "d2h_bytes_per_step": int(io[1].item()), "ms_per_step": float(e2e_dt.item()) * 1e3, "steps": e2e_steps,
                     "api": "sphe_slab_upload (pinned host) -> pack/exchange/append -> sphe_step -> sphe_slab_download (pinned host), per rank"},
+            "parity_sampled": gate[0] if gate else None, "parity_gate": gate[1] if gate else None,
             "gpu_launches": launches * world, "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_%s" % dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
