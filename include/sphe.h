@@ -177,6 +177,9 @@ int sphe_debug_pair_lists(sphe_sim* s, int cap, int* counts, int* entries);
  * halo travel in the same buffer, the receiver classifies each record by its own cell column.
  * Particle ids are global, < 2^30 (bit 30 marks ghost copies). */
 int sphe_slab_configure(sphe_sim* s, int x0, int x1, int has_left, int has_right);
+/* Owned particles per global cell column, hist[gnx] (load balancing: re-cut the slabs by particle-count quantiles).
+ * Computed on the device; only the gnx counts cross PCIe. */
+int sphe_slab_column_histogram(sphe_sim* s, int gnx, int* hist);
 /* Ring closure for 3 or more slabs.  The reference's box response sends a particle that sits EXACTLY on the
  * -x wall to the +x wall (collisionS, fluid_system.h:375-382: x == -len takes the `else` branch), i.e. from
  * the first slab to the last one in a single step.  wrap_left (first slab; configure it with has_left = 1):

@@ -70,6 +70,7 @@ SYMBOLS = {
     "sphe_debug_cell_start": (_i, [_vp, _vp]),
     "sphe_debug_neighbours": (_i, [_vp, _vp, _vp, _ll, C.POINTER(_ll)]),
     "sphe_debug_pair_lists": (_i, [_vp, _i, _vp, _vp]),
+    "sphe_slab_column_histogram": (_i, [_vp, _i, _vp]),
     "sphe_device_ptr": (_vp, [_vp, _i]),
     "sphe_set_stream": (_i, [_vp, _vp]),
     "sphe_set_variant": (_i, [_vp, _i, _i]),

@@ -1255,6 +1255,27 @@ int sphe_slab_unpack(sphe_sim* s, const void* dev_recv_left, int max_left, const
     return sphe_slab_result(s, t, 1, out);   // the synchronous form: one host sync per step
 }
 
+int sphe_slab_column_histogram(sphe_sim* s, int gnx, int* hist) {
+    if (!s || !hist || gnx <= 0) return fail(SPHE_ERR_ARG, "bad arguments");
+    if (!s->slab_on) return fail(SPHE_ERR_STATE, "call sphe_slab_configure first");
+    TRY(ensure_device(s));
+    TRY(setup_grid(s));
+    if (gnx != s->G.gnx) return fail(SPHE_ERR_ARG, "the global grid has %d columns, not %d", s->G.gnx, gnx);
+    TRY(slab_settle(s));
+    memset(hist, 0, (size_t)gnx * sizeof(int));
+    const int n = slab_extent_bound(s);
+    if (n == 0) return SPHE_OK;
+    int* d = nullptr;
+    CU(cudaMalloc(&d, (size_t)gnx * sizeof(int)));
+    CU(cudaMemsetAsync(d, 0, (size_t)gnx * sizeof(int), s->st));
+    if (launch_slab_column_hist(s->st, n, slab_extent_dev(s), s->posA, s->idsA, s->G, d) != 0) { cudaFree(d); return fail(SPHE_ERR_ARG, "too many cell columns (%d) for the histogram kernel", gnx); }
+    CU(cudaMemcpyAsync(hist, d, (size_t)gnx * sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    CU(cudaFree(d));
+    CU(cudaGetLastError());
+    return SPHE_OK;
+}
+
 int sphe_slab_download(sphe_sim* s, int cap, int* ids, float* pos, float* vel, float* rho, float* sed, int* n_out) {
     if (!s || !ids || !pos || !vel || !n_out) return fail(SPHE_ERR_ARG, "bad arguments");
     TRY(ensure_device(s));

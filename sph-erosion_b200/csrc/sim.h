@@ -85,6 +85,7 @@ void launch_slab_append(cudaStream_t st, int max_l, int max_r, const float4* rec
 void launch_slab_gather_owned(cudaStream_t st, int n, const int* n_dev, const float4* posq, const float4* velv, const float* rho, const float* sed,
                               const int* ids, int* counter, int* out_ids, float* out_pos, float* out_vel, float* out_rho,
                               float* out_sed);
+int launch_slab_column_hist(cudaStream_t st, int n, const int* n_dev, const float4* posq, const int* ids, const GridP& G, int* hist);
 void launch_pack_state_ids(cudaStream_t st, int n, const float* pos, const float* vel, const int* ids_in, float4* posq, float4* velv,
                            int* ids, float* sed);
 

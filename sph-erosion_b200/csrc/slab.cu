@@ -16,6 +16,7 @@
 //
 // Slot allocation uses warp-aggregated atomics (one atomicAdd per warp per destination).  The
 // resulting storage order is arbitrary; the binning pass re-establishes the canonical (cell, id) order.
+#include <algorithm>
 #include "common.cuh"
 #include "sim.h"
 
@@ -263,6 +264,20 @@ __global__ void __launch_bounds__(256) k_slab_gather_owned(int n_hi, const int* 
     out_sed[k] = sed[i];
 }
 
+// Owned particles per GLOBAL cell column (load balancing: slabs.rebalance re-cuts by particle-count quantiles): one
+// shared-memory histogram per block, flushed with one atomic per non-empty column.  hist: gnx ints, zeroed by the caller.
+__global__ void __launch_bounds__(256) k_slab_column_hist(int n_hi, const int* __restrict__ n_dev, const float4* __restrict__ posq,
+                                                          const int* __restrict__ ids, GridP G, int* __restrict__ hist) {
+    extern __shared__ int sh[];
+    const int n = n_dev ? __ldg(n_dev) : n_hi;
+    for (int c = threadIdx.x; c < G.gnx; c += blockDim.x) sh[c] = 0;
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (!(ids[i] & SPHE_GHOST_BIT)) atomicAdd(&sh[cell_axis(posq[i].x, G.gx, G.cell, G.gnx)], 1);
+    __syncthreads();
+    for (int c = threadIdx.x; c < G.gnx; c += blockDim.x) if (sh[c]) atomicAdd(&hist[c], sh[c]);
+}
+
 __global__ void k_pack_state_ids(int n, const float* __restrict__ pos, const float* __restrict__ vel, const int* __restrict__ ids_in,
                                  float4* __restrict__ posq, float4* __restrict__ velv, int* __restrict__ ids, float* __restrict__ sed) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -308,6 +323,14 @@ void launch_slab_gather_owned(cudaStream_t st, int n, const int* n_dev, const fl
     if (n > 0)
         k_slab_gather_owned<<<(n + 255) / 256, 256, 0, st>>>(n, n_dev, posq, velv, rho, sed, ids, counter, out_ids, out_pos, out_vel,
                                                             out_rho, out_sed);
+}
+int launch_slab_column_hist(cudaStream_t st, int n, const int* n_dev, const float4* posq, const int* ids, const GridP& G, int* hist) {
+    if (n <= 0) return 0;
+    const size_t smem = (size_t)G.gnx * sizeof(int);
+    if (smem > 200 * 1024) return -1;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_slab_column_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_slab_column_hist<<<std::min((n + 255) / 256, 592), 256, smem, st>>>(n, n_dev, posq, ids, G, hist);
+    return 0;
 }
 void launch_pack_state_ids(cudaStream_t st, int n, const float* pos, const float* vel, const int* ids_in, float4* posq, float4* velv,
                            int* ids, float* sed) {

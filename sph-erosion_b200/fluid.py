@@ -234,6 +234,11 @@ class FluidSystemSPH:
         """One phase (0, 1, 2) of a step whose terrain erosion is shared by several slabs (sphe_step_phase)."""
         capi.check(self._L.sphe_step_phase(self._h, grid._t if grid is not None else None, int(phase)))
 
+    def slab_column_histogram(self, gnx):
+        out = np.zeros(int(gnx), np.int32)
+        capi.check(self._L.sphe_slab_column_histogram(self._h, int(gnx), _p(out)))
+        return out
+
     def slab_download(self, cap=None):
         cap = self.count() if cap is None else int(cap)
         ids = np.zeros(cap, np.int32); pos = np.zeros((cap, 3), np.float32); vel = np.zeros((cap, 3), np.float32)

@@ -182,11 +182,9 @@ class GpuSlabBackend:
 
     # ---- load balancing (slabs.rebalance): only calls the driver already makes elsewhere
     def column_histogram(self, gnx):
-        """Owned particles per global cell column (a download: meant for every ~100 steps, not every step)."""
-        gi = self.sim.grid_info()
-        ids, pos, vel, rho, sed = self.sim.slab_download()
-        cx = np.floor((pos[:, 0].astype(np.float32) - np.float32(gi.gmin[0])) / np.float32(gi.cell))
-        return np.bincount(np.clip(cx, 0, gnx - 1).astype(np.int64), minlength=gnx)
+        """Owned particles per global cell column, counted on the device (sphe_slab_column_histogram): only gnx ints
+        cross PCIe, so a re-cut costs a small all-reduce + re-windowing the grid, not a download of the slab."""
+        return self.sim.slab_column_histogram(gnx).astype(np.int64)
 
     def reconfigure(self, x0, x1, far_x0):
         s = self.sim
@@ -716,6 +714,8 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT, terrain=False):
     n_local = pos.shape[0]
     layer = int(n_axis * n_axis * (0.0457 * 1.001 / SPACING + 1))      # particles per cell layer
     cap = max(2 * HALO * layer, 1 << 14)
+    if getattr(args, "rebalance_every", 0):
+        cap *= 2      # a re-cut moves a boundary by up to HALO columns: those particles migrate in ONE exchange, on top of the halo
     params = dict(len=box[1], dt=0.01, g=(0.0, gy, 0.0))
     sim, backend, cols = make_gpu_slab(pkg, local, rank, world, box, params, bounds, cap,
                                        (args.density_variant, args.force_variant))
