@@ -36,6 +36,7 @@ def needs_build():
 EXTRA = {"terrain.cu": ["-fmad=false"]}
 
 
+NVCC_FLAGS += os.environ.get("SPHE_NVCC_EXTRA", "").split()   # A/B builds, e.g. SPHE_NVCC_EXTRA="-DFL_THREADS=256 -DFL_MINB=3"
 if os.environ.get("SPHE_WITH_EXPERIMENTS") == "1":
     NVCC_FLAGS.append("-DSPHE_WITH_EXPERIMENTS")   # also compile csrc/experiments/ (rejected round-1 kernel variants)
 

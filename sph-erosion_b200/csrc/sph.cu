@@ -138,7 +138,6 @@ constexpr int NLIST_CAP = 64;       // entries per pair (both split passes toget
 // so the lists are a SUPERSET of the exact neighbour sets; the extra entries have clamped weights of 0 or a few ulp
 // (tests/test_gpu_parity.py::test_pair_masks_cover_the_exact_neighbour_sets reads the production lists back).
 constexpr float LIST_NEG_EPS = -9.5367431640625e-07f;
-constexpr int NLIST_THREADS = 128;
 
 // REC = true (variant 4): instead of (posC, vel.w) the pass writes ONE interleaved 32-byte record per particle,
 // rec[2i] = (x, y, z, P/rho^2), rec[2i+1] = (vx, vy, vz, m/rho), so the force pass fetches everything it needs
@@ -151,8 +150,17 @@ constexpr int NLIST_THREADS = 128;
 // 60-120 neighbours per particle (BASELINE configs[4]) overflow them and fall back to the direct walk in the force
 // pass, which costs 2-4x.  The host raises CAP to 128 / 256 when the overflow counter says so (api.cu step_device).
 // The list lives in dynamic shared memory: (CAP + 1) * THREADS ints = 33 / 66 / 66 KB.
+// Base configuration of the density pass (the "64-entry" level of the list sizing): 56 staged entries per pair, 64-thread
+// CTAs, 14 CTAs/SM = 28 warps at 71 registers and 14.6 KB of shared memory per CTA.  The pass is issue/latency bound: with
+// the 64-entry stage of round 1 (33 KB per 128-thread CTA, 80 registers) 24 warps fit -- c3 density pass 0.644 -> 0.616 ms;
+// 48 entries at 16 CTAs/SM spill too often (0.657 ms).  A/B: SPHE_NVCC_EXTRA="-DDL_CAP=.. -DDL_THREADS=.. -DDL_MINB=.."
+#ifndef DL_CAP
+#define DL_CAP 56
+#define DL_THREADS 64
+#define DL_MINB 14
+#endif
 template <bool REC, bool PF, int CAP, int THREADS, int UNROLL = 4>
-__global__ void __launch_bounds__(THREADS) k_density_list(int n_hi, const int* __restrict__ n_dev, int npairs_pad, const float4* __restrict__ posq,
+__global__ void __launch_bounds__(THREADS, CAP == DL_CAP ? DL_MINB : (CAP >= 256 ? 3 : 1)) k_density_list(int n_hi, const int* __restrict__ n_dev, int npairs_pad, const float4* __restrict__ posq,
                                                           float4* __restrict__ posq_q, float4* __restrict__ velv,
                                                           const uint32_t* __restrict__ cell_sorted,
                                                           const int* __restrict__ cell_start, GridP G, StepC C,
@@ -291,7 +299,7 @@ __global__ void __launch_bounds__(THREADS) k_density_list(int n_hi, const int* _
     if (live && !fits) atomicAdd(overflow, 1);                          // beyond the allocated rows: direct walk in the force pass
     if (live && cnt > NLIST_CAP) atomicAdd(overflow + 1, 1);            // spilled (statistics for the host's choice of CAP)
     if (live && cnt > NLIST_CAP / 2) atomicAdd(overflow + 2, 1);        // would spill at the next smaller CAP
-    if (t == 0) { overflow[3] = NLIST_CAP; overflow[4] = rows; }        // which sizing these counts belong to (the host reads them late)
+    if (t == 0) { overflow[3] = (NLIST_CAP == DL_CAP) ? 64 : NLIST_CAP; overflow[4] = rows; }   // which sizing LEVEL (64 / 128 / 256) these counts belong to (the host reads them late)
     if (fits) {
         int* dst = nlist + t;
         const int stop = min(off, NLIST_CAP * NLIST_THREADS);           // the rest is already in place
@@ -500,13 +508,18 @@ __device__ __forceinline__ void ldg_rec(const float4* __restrict__ rec, int k, f
 }
 
 #ifndef FL_MINB
-#define FL_MINB 7
+#define FL_MINB 16
+#endif
+#ifndef FL_THREADS
+#define FL_THREADS 64    // CTA size of the force pass (independent of the list layout).  The pass is latency bound (long scoreboard: gathers
+// that miss L1): 32 resident warps at 64 registers (a few spilled words) beat 28 at 72 -- c3 force pass 0.541 -> 0.517 ms;
+// 24 warps: 0.62 ms, 36 warps at 56 registers: 0.58 ms (profiles/r02/ab_force_occupancy.txt)
 #endif
 // PF = true (variant 6): the list index is fetched TWO entries ahead.  ncu source view of the plain kernel: 38 % of
 // the stall samples sit on the address computation of the next gather, i.e. on the index load it depends on
 // (index -> gather is a dependent chain; the lists stream from HBM).  One more register hides it.
 template <bool DIAG, bool REC, bool PF>
-__global__ void __launch_bounds__(NLIST_THREADS, FL_MINB) k_force_list(int n_hi, const int* __restrict__ n_dev, int npairs_pad, const float4* __restrict__ posq_q,
+__global__ void __launch_bounds__(FL_THREADS, FL_MINB) k_force_list(int n_hi, const int* __restrict__ n_dev, int npairs_pad, const float4* __restrict__ posq_q,
                                                               const float4* __restrict__ velv, const float* __restrict__ rho,
                                                               const int* __restrict__ ids, const uint32_t* __restrict__ cell_sorted,
                                                               const int* __restrict__ cell_start, GridP G, StepC C,
@@ -835,8 +848,8 @@ void launch_density(cudaStream_t st, int variant, int n, const int* n_dev, const
             if (variant == 6) k_density_list16<true><<<pp / L16_THREADS, L16_THREADS, 0, st>>>(n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount, overflow, cap);
             else k_density_list16<false><<<pp / L16_THREADS, L16_THREADS, 0, st>>>(n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount, overflow, cap);
         }
-        else if (variant == 6) SPHE_DL(false, true, 64, 128);
-        else SPHE_DL(false, false, 64, 128);
+        else if (variant == 6) SPHE_DL(false, true, DL_CAP, DL_THREADS);
+        else SPHE_DL(false, false, DL_CAP, DL_THREADS);
 #undef SPHE_DL
         return;
     }
@@ -863,7 +876,7 @@ void launch_force(cudaStream_t st, int variant, int n, const int* n_dev, const f
     if (variant == 7 || variant == 9 || variant == 10 || variant == 11) variant = 3;   // these density passes write the plain pair lists
     if (variant == 3 || variant == 6) {
         int pp = nlist_pairs_pad(n);
-        dim3 g(pp / NLIST_THREADS), b(NLIST_THREADS);
+        dim3 g((pp + FL_THREADS - 1) / FL_THREADS), b(FL_THREADS);
 #define SPHE_FL(DG, RC, PFv, dg) k_force_list<DG, RC, PFv><<<g, b, 0, st>>>(n, n_dev, pp, posq_q, velv, rho, ids, cell_sorted, cell_start, G, C, nlist, ncount, posq_out, velv_out, dg)
         if (variant == 6) { if (diag) SPHE_FL(true, false, true, *diag); else SPHE_FL(false, false, true, DiagOut{}); }
         else { if (diag) SPHE_FL(true, false, false, *diag); else SPHE_FL(false, false, false, DiagOut{}); }
