@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(256) k_rank_reorder(int n_hi, const int* __res
                                                       const float* __restrict__ sed_in,
                                                       float4* __restrict__ posq_out, float4* __restrict__ velv_out,
                                                       float* __restrict__ sed_out, int* __restrict__ ids_out,
-                                                      uint32_t* __restrict__ cell_sorted) {
+                                                      uint32_t* __restrict__ cell_sorted, int* __restrict__ src_of_slot) {
     const int n = n_dev ? __ldg(n_dev) : n_hi;  // exact count from the device in slab mode, else the launch bound
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
@@ -210,9 +210,11 @@ __global__ void __launch_bounds__(256) k_rank_reorder(int n_hi, const int* __res
     for (int k = a; k < b; k++) rank += ((tmp[k].x & SPHE_ID_MASK) < (me.x & SPHE_ID_MASK)) ? 1 : 0;
     int dst = a + rank;
     float4 p = posq_in[me.y];
-    float4 v = velv_in[me.y];
     posq_out[dst] = p;
-    velv_out[dst] = v;
+    // src_of_slot != NULL (sphe_step_host): the velocities are still on the PCIe bus; only the permutation is recorded
+    // and k_gather_vel moves them after the density pass, which does not read them
+    if (src_of_slot) src_of_slot[dst] = (int)me.y;
+    else velv_out[dst] = velv_in[me.y];
     if (sed_in) sed_out[dst] = sed_in[me.y];
     ids_out[dst] = (int)me.x;
     cell_sorted[dst] = c;
@@ -239,10 +241,23 @@ void launch_scatter(cudaStream_t st, int n, const int* n_dev, const uint32_t* ce
 
 void launch_rank_reorder(cudaStream_t st, int n, const int* n_dev, const uint2* tmp, const uint32_t* cell, const int* cell_start,
                          const float4* posq_in, const float4* velv_in, const float* sed_in,
-                         float4* posq_out, float4* velv_out, float* sed_out, int* ids_out, uint32_t* cell_sorted) {
+                         float4* posq_out, float4* velv_out, float* sed_out, int* ids_out, uint32_t* cell_sorted, int* src_of_slot) {
     if (n <= 0) return;
     k_rank_reorder<<<(n + 255) / 256, 256, 0, st>>>(n, n_dev, tmp, cell, cell_start, posq_in, velv_in, sed_in,
-                                                    posq_out, velv_out, sed_out, ids_out, cell_sorted);
+                                                    posq_out, velv_out, sed_out, ids_out, cell_sorted, src_of_slot);
+}
+
+// velocities into sorted order after the fact (see k_rank_reorder); .w = m/rho was written by the density pass and stays
+__global__ void __launch_bounds__(256) k_gather_vel(int n, const int* __restrict__ src_of_slot, const float4* __restrict__ velv_in,
+                                                    float4* __restrict__ velv_out) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const float4 v = velv_in[src_of_slot[s]];
+    float* o = reinterpret_cast<float*>(velv_out + s);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z;
+}
+void launch_gather_vel(cudaStream_t st, int n, const int* src_of_slot, const float4* velv_in, float4* velv_out) {
+    if (n > 0) k_gather_vel<<<(n + 255) / 256, 256, 0, st>>>(n, src_of_slot, velv_in, velv_out);
 }
 
 }  // namespace sphe

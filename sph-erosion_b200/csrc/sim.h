@@ -18,7 +18,8 @@ void launch_scan(cudaStream_t st, long long ncells, int* count, int* tile_sum, i
 void launch_scatter(cudaStream_t st, int n, const int* n_dev, const uint32_t* cell, const int* ids, int* cursor, uint2* tmp);
 void launch_rank_reorder(cudaStream_t st, int n, const int* n_dev, const uint2* tmp, const uint32_t* cell, const int* cell_start,
                          const float4* posq_in, const float4* velv_in, const float* sed_in,
-                         float4* posq_out, float4* velv_out, float* sed_out, int* ids_out, uint32_t* cell_sorted);
+                         float4* posq_out, float4* velv_out, float* sed_out, int* ids_out, uint32_t* cell_sorted, int* src_of_slot = nullptr);
+void launch_gather_vel(cudaStream_t st, int n, const int* src_of_slot, const float4* velv_in, float4* velv_out);
 
 // ---- terrain.cu
 // Device view of a terrain (replacement of the reference's Grid, Erosion/grid.h:26-51).
