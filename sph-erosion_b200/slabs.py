@@ -622,6 +622,9 @@ def parity_gate_multi(pkg, dist, dev, sim, drv, grid, tshare, windowed, box, par
             rows = (own, h[own[0]:own[1]].copy())
         out = [None] * world if rank == 0 else None
         dist.gather_object((ids, pos, vel, rho, sed.view(np.int32), rows), out, dst=0)
+        # rank 0 is still unpickling ~1 GB at N = 8 when the others are done sending: nobody may enter the next exchange
+        # before it has, or its neighbours' device-side flag waits run into their timeout
+        dist.barrier()
         return out
 
     before = snapshot()
