@@ -647,6 +647,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU halo/migration transport: peer = pack kernel stores into the neighbours' mailboxes over NVLink (default); nccl = NCCL P2P group")
+    ap.add_argument("--zone-sums", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU slab-local terrain: transport of the boundary-zone sums (peer = through the slab mailboxes, one launch per sum; nccl = P2P groups)")
     ap.add_argument("--terrain-share", default="window", choices=["window", "allreduce"],
                     help="multi-GPU terrain: window = slab-local rows + boundary-zone sums with the x-neighbours (default); allreduce = full replicas, 2 all-reduces per step")
     ap.add_argument("--rebalance-every", type=int, default=0, help="multi-GPU, no terrain: re-cut the slabs by particle count every K steps (0 = never; the bench scenes are balanced by construction)")

@@ -232,6 +232,12 @@ int sphe_slab_peer_setup(sphe_sim* s, int cap_records, int reserve_particles);
 int sphe_slab_peer_handle(sphe_sim* s, void* handle64);
 int sphe_slab_peer_connect(sphe_sim* s, const void* left_handle64, const void* right_handle64);
 int sphe_slab_peer_connect_local(sphe_sim* s, sphe_sim* left, sphe_sim* right);
+/* The same mailbox with room for terrain zone sums (slab-local terrain): zone_ints = ints of one boundary zone of the erosion
+ * accumulators (2W rows x cols).  sphe_slab_zone_sum adds the x-neighbours' copies of the zones into `want` (which = 0,
+ * between sphe_step_phase 0 and 1) or `delta` (which = 1, between 1 and 2) in ONE launch: remote stores + flags, no host sync.
+ * off_left / off_right: first element of the zone shared with that neighbour, -1 = none. */
+int sphe_slab_peer_setup_zones(sphe_sim* s, int cap_records, int reserve_particles, int zone_ints);
+int sphe_slab_zone_sum(sphe_sim* s, sphe_terrain* t, int which, long long off_left, long long off_right, int count);
 int sphe_slab_peer_timeout(sphe_sim* s, long long clock_cycles);
 int sphe_slab_send(sphe_sim* s);
 int sphe_slab_recv(sphe_sim* s, long long* ticket);

@@ -38,13 +38,13 @@ sim.slab_upload(pos[part], vel[part], part.astype(np.int32))
 if one_gpu:
     sim.slab_peer_timeout(400_000_000_000)   # ranks time-slice one GPU: a waiting kernel can sit out whole time slices
 total0 = grid.total_fx()
-mode = os.environ.get("TERRAIN_SHARE", "window" if not one_gpu else "allreduce")
+mode = os.environ.get("TERRAIN_SHARE", "window")   # the windowed zone sums travel through the mailboxes: no NCCL P2P needed, also on one GPU
 cell_t = 2.4 / 256
 if mode == "window" and 256 // world < 2 * slabs.terrain_margin_rows(sim.grid_info().cell, cell_t):
     mode = "allreduce"      # slabs narrower than two boundary zones: the windowed scheme does not apply
 if mode == "window":
     share = slabs.TerrainWindowShare(grid, dev, rank, world, slabs.terrain_row_cuts(sim.grid_info(), cols, -1.2, cell_t),
-                                     slabs.terrain_margin_rows(sim.grid_info().cell, cell_t), dist=dist)
+                                     slabs.terrain_margin_rows(sim.grid_info().cell, cell_t), dist=dist, peer=True)
 else:
     share = slabs.TerrainShare(grid, dev, reduce)
 drv = slabs.PeerSlabDriver(sim, rank, world, cap, n + 4 * cap, share)

@@ -21,7 +21,7 @@ if terrain:
     grid, tinfo = bench.attach_terrain(pkg, box[1], n_axis, nx_mult=world)
     gi = sim.grid_info()
     share = slabs.TerrainWindowShare(grid, dev, rank, world, slabs.terrain_row_cuts(gi, cols, tinfo["terrain_origin"][0], tinfo["terrain_cell"]),
-                                     slabs.terrain_margin_rows(gi.cell, tinfo["terrain_cell"]), dist=dist)
+                                     slabs.terrain_margin_rows(gi.cell, tinfo["terrain_cell"]), dist=dist, peer=os.environ.get("ZONES", "peer") == "peer")
 drv = slabs.PeerSlabDriver(sim, rank, world, cap, int(pos.shape[0] * 1.3) + 6 * cap, share)
 drv.connect(dist)
 for _ in range(int(os.environ.get("SETTLE", "150")) if terrain else 10): drv.step()
@@ -39,9 +39,9 @@ for k in range(K):
     drv.tickets.append(sim.slab_recv()); drv.tickets = drv.tickets[-4:]; e[2].record(); h.append(time.perf_counter())
     if terrain:
         sim.step_phase(grid, 0); e[3].record(); h.append(time.perf_counter())
-        share.swap(share.want, share.zone_l, share.zone_r); e[4].record(); h.append(time.perf_counter())
+        share.sum_zones(sim, 0); e[4].record(); h.append(time.perf_counter())
         sim.step_phase(grid, 1); e[5].record(); h.append(time.perf_counter())
-        share.swap(share.delta, share.zone_l, share.zone_r); e[6].record(); h.append(time.perf_counter())
+        share.sum_zones(sim, 1); e[6].record(); h.append(time.perf_counter())
         sim.step_phase(grid, 2); e[7].record(); h.append(time.perf_counter())
     else:
         sim.Run(); e[3].record(); h.append(time.perf_counter())

@@ -139,6 +139,11 @@ struct sphe_sim {
     char* peer_mbox[2] = {nullptr, nullptr};   // left / right neighbour's mailbox, mapped into this process
     bool peer_ipc[2] = {false, false};         // opened with cudaIpcOpenMemHandle (close on destroy)
     int peer_seq = 0;              // exchanges sent so far; sequence number of the current one
+    // terrain zone sums over the same mailbox: [side][which = want / delta][parity] buffers of zone_ints ints + 8 flags
+    int zone_ints = 0;
+    size_t zone_base = 0;          // byte offset of the zone region in the mailbox
+    int zone_seq[2] = {0, 0};      // zone sums done so far, per accumulator
+    int* zone_done = nullptr;      // device word: blocks of the running k_zone_sum that have stored
     long long peer_timeout = 4000000000LL;     // clock cycles a consumer waits for its flags (~2 s)
     float grid_h = -1.f, grid_len = -1.f;
 
@@ -1079,7 +1084,7 @@ int sphe_slab_configure(sphe_sim* s, int x0, int x1, int has_left, int has_right
     s->slab.wrap_left = s->slab.wrap_right = 0; s->slab.far_x0 = 0x7fffffff;
     s->slab_on = true;
     s->grid_h = -1.f;  // re-window the grid
-    if (!s->slab_counters) CU(cudaMalloc(&s->slab_counters, 16 * sizeof(int)));
+    if (!s->slab_counters) { CU(cudaMalloc(&s->slab_counters, 16 * sizeof(int))); CU(cudaMemset(s->slab_counters, 0, 16 * sizeof(int))); }
     if (!s->d_n) CU(cudaMalloc(&s->d_n, sizeof(int)));
     if (!s->slab_host) CU(cudaMallocHost(&s->slab_host, sphe_sim::SLAB_RING * 8 * sizeof(int)));
     for (int k = 0; k < 2; k++) if (!s->transit[k]) CU(cudaMalloc(&s->transit[k], 2 * SPHE_TRANSIT_CAP * sizeof(float4)));
@@ -1156,7 +1161,7 @@ int sphe_slab_pack(sphe_sim* s, void* dev_send_left, void* dev_send_right, int c
     TRY(setup_grid(s));
     // room for everything that can arrive, so nothing has to grow between pack and unpack
     TRY(reserve(s, std::max(slab_extent_bound(s) + reserve_incoming, 1)));
-    CU(cudaMemsetAsync(s->slab_counters, 0, 16 * sizeof(int), s->st));
+    CU(cudaMemsetAsync(s->slab_counters, 0, 15 * sizeof(int), s->st));   // [15] = sticky zone-sum error, folded into [7] by k_slab_headers
     launch_slab_classify(s->st, slab_extent_bound(s), slab_extent_dev(s), s->posA, s->velA, s->idsA, s->sedA, s->G, s->slab,
                          (float4*)dev_send_left, (float4*)dev_send_right, cap_records, s->slab_counters);
     launch_slab_forward(s->st, s->transit[0], s->transit[1], s->transit_n, s->slab.has_left ? (float4*)dev_send_left : nullptr,
@@ -1328,8 +1333,17 @@ int sphe_slab_download(sphe_sim* s, int cap, int* ids, float* pos, float* vel, f
 static inline float4* mbox_buffer(char* base, size_t buf, int side, int parity) { return (float4*)(base + (size_t)(2 * side + parity) * buf); }
 static inline int* mbox_flag(char* base, size_t buf, int side, int parity) { return (int*)(base + 4 * buf + (size_t)(2 * side + parity) * 128); }
 
-int sphe_slab_peer_setup(sphe_sim* s, int cap_records, int reserve_particles) {
-    if (!s || cap_records < 1) return fail(SPHE_ERR_ARG, "bad arguments");
+static inline int* zone_buffer(char* base, size_t zone_base, int zone_ints, int side, int which, int parity) {
+    return (int*)(base + zone_base + (size_t)((side * 2 + which) * 2 + parity) * (((size_t)zone_ints * 4 + 255) & ~(size_t)255));
+}
+static inline int* zone_flag(char* base, size_t zone_base, int zone_ints, int side, int which, int parity) {
+    return (int*)(base + zone_base + 8 * (((size_t)zone_ints * 4 + 255) & ~(size_t)255) + (size_t)((side * 2 + which) * 2 + parity) * 128);
+}
+
+int sphe_slab_peer_setup(sphe_sim* s, int cap_records, int reserve_particles) { return sphe_slab_peer_setup_zones(s, cap_records, reserve_particles, 0); }
+
+int sphe_slab_peer_setup_zones(sphe_sim* s, int cap_records, int reserve_particles, int zone_ints) {
+    if (!s || cap_records < 1 || zone_ints < 0) return fail(SPHE_ERR_ARG, "bad arguments");
     if (!s->slab_on) return fail(SPHE_ERR_STATE, "call sphe_slab_configure first");
     TRY(ensure_device(s));
     CU(cudaStreamSynchronize(s->st));
@@ -1341,6 +1355,11 @@ int sphe_slab_peer_setup(sphe_sim* s, int cap_records, int reserve_particles) {
     s->mbox_cap = cap_records;
     s->mbox_buf = (((size_t)cap_records + 1) * 32 + 255) & ~(size_t)255;
     size_t bytes = 4 * s->mbox_buf + 4 * 128;
+    s->zone_ints = zone_ints;
+    s->zone_base = (bytes + 255) & ~(size_t)255;
+    s->zone_seq[0] = s->zone_seq[1] = 0;
+    if (zone_ints > 0) bytes = s->zone_base + 8 * ((((size_t)zone_ints * 4 + 255) & ~(size_t)255) + 128);
+    if (!s->zone_done) { CU(cudaMalloc(&s->zone_done, sizeof(int))); CU(cudaMemset(s->zone_done, 0, sizeof(int))); }
     cudaError_t e = cudaMalloc(&s->mbox, bytes);
     if (e != cudaSuccess) return fail(SPHE_ERR_NOMEM, "mailbox of %zu bytes: %s", bytes, cudaGetErrorString(e));
     CU(cudaMemset(s->mbox, 0, bytes));
@@ -1447,7 +1466,7 @@ int sphe_slab_send(sphe_sim* s) {
     float4* dr = s->slab.has_right ? mbox_buffer(s->peer_mbox[1], s->mbox_buf, 0, par) : nullptr;
     int* fl = s->slab.has_left ? mbox_flag(s->peer_mbox[0], s->mbox_buf, 1, par) : nullptr;
     int* fr = s->slab.has_right ? mbox_flag(s->peer_mbox[1], s->mbox_buf, 0, par) : nullptr;
-    CU(cudaMemsetAsync(s->slab_counters, 0, 16 * sizeof(int), s->st));
+    CU(cudaMemsetAsync(s->slab_counters, 0, 15 * sizeof(int), s->st));   // [15] = sticky zone-sum error, folded into [7] by k_slab_headers
     launch_slab_classify(s->st, slab_extent_bound(s), slab_extent_dev(s), s->posA, s->velA, s->idsA, s->sedA, s->G, s->slab,
                          dl, dr, s->mbox_cap, s->slab_counters, true);
     launch_slab_forward(s->st, s->transit[0], s->transit[1], s->transit_n, dl, dr, s->mbox_cap, s->slab_counters, true);
@@ -1495,6 +1514,34 @@ int sphe_slab_recv(sphe_sim* s, long long* ticket) {
     s->extent_pending = true;
     s->binned = false; s->slot_valid = false;
     if (ticket) *ticket = t;
+    CU(cudaGetLastError());
+    return SPHE_OK;
+}
+
+// Sum of an erosion accumulator over the boundary zones with the two x-neighbours, through the peer mailboxes
+// (k_zone_sum): which = 0 `want` (between phase 0 and 1), 1 `delta` (between phase 1 and 2); off_left / off_right = first
+// element of the zone shared with that neighbour in the accumulator array, -1 = none; count = ints per zone.
+int sphe_slab_zone_sum(sphe_sim* s, sphe_terrain* t, int which, long long off_left, long long off_right, int count) {
+    if (!s || !t || which < 0 || which > 1 || count < 0) return fail(SPHE_ERR_ARG, "bad arguments");
+    if (!s->slab_on || !s->mbox || s->zone_ints <= 0) return fail(SPHE_ERR_STATE, "call sphe_slab_peer_setup_zones first");
+    if (count > s->zone_ints) return fail(SPHE_ERR_ARG, "zone of %d ints > %d reserved in the mailbox", count, s->zone_ints);
+    if ((off_left >= 0 && !s->peer_mbox[0]) || (off_right >= 0 && !s->peer_mbox[1])) return fail(SPHE_ERR_STATE, "neighbour mailbox not connected");
+    const long long cells = (long long)t->rows * t->cols;
+    if ((off_left >= 0 && off_left + count > cells) || (off_right >= 0 && off_right + count > cells)) return fail(SPHE_ERR_ARG, "zone outside the terrain");
+    TRY(ensure_device(s));
+    TRY(terrain_ready(t));
+    const int q = ++s->zone_seq[which], par = q & 1;
+    int* arr = which ? t->delta : t->want;
+    // what goes LEFT lands in the left neighbour's "from the right" buffer, and vice versa
+    int* out_l = off_left >= 0 ? zone_buffer(s->peer_mbox[0], s->zone_base, s->zone_ints, 1, which, par) : nullptr;
+    int* out_r = off_right >= 0 ? zone_buffer(s->peer_mbox[1], s->zone_base, s->zone_ints, 0, which, par) : nullptr;
+    int* fo_l = off_left >= 0 ? zone_flag(s->peer_mbox[0], s->zone_base, s->zone_ints, 1, which, par) : nullptr;
+    int* fo_r = off_right >= 0 ? zone_flag(s->peer_mbox[1], s->zone_base, s->zone_ints, 0, which, par) : nullptr;
+    launch_zone_sum(s->st, arr, (int)off_left, (int)off_right, count, out_l, out_r, fo_l, fo_r,
+                    zone_buffer(s->mbox, s->zone_base, s->zone_ints, 0, which, par), zone_buffer(s->mbox, s->zone_base, s->zone_ints, 1, which, par),
+                    zone_flag(s->mbox, s->zone_base, s->zone_ints, 0, which, par), zone_flag(s->mbox, s->zone_base, s->zone_ints, 1, which, par),
+                    q, s->peer_timeout, s->zone_done, s->slab_counters + 15);
+    s->launches += 1;
     CU(cudaGetLastError());
     return SPHE_OK;
 }

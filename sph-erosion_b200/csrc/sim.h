@@ -77,6 +77,8 @@ void launch_slab_headers(cudaStream_t st, int* counters, float4* send_left, floa
                          int* flag_right = nullptr, int seq = 0);
 // records in transit: received from one side, owned further along (k_slab_append -> k_slab_forward at the next pack)
 #define SPHE_TRANSIT_CAP 8192
+void launch_zone_sum(cudaStream_t st, int* arr, int off_l, int off_r, int n, int* out_l, int* out_r, int* flag_out_l, int* flag_out_r,
+                     const int* in_l, const int* in_r, const int* flag_in_l, const int* flag_in_r, int seq, long long timeout, int* done, int* err);
 void launch_slab_forward(cudaStream_t st, const float4* transit_l, const float4* transit_r, int* transit_n, float4* send_left,
                          float4* send_right, int cap_records, int* counters, bool remote);
 void launch_slab_append(cudaStream_t st, int max_l, int max_r, const float4* rec_l, const float4* rec_r, const GridP& G,

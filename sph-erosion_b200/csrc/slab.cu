@@ -139,6 +139,7 @@ __global__ void k_slab_headers(int* __restrict__ counters, float4* __restrict__ 
         if (send_left) send_left[0] = make_float4(__int_as_float(counters[1]), 0.f, 0.f, 0.f);
         if (send_right) send_right[0] = make_float4(__int_as_float(counters[2]), 0.f, 0.f, 0.f);
         counters[4] = 0; counters[5] = 0; counters[6] = 0;   // the unpack counters of this step
+        if (counters[15]) counters[7] = 1;                    // a terrain zone sum of the last step timed out (k_zone_sum)
         if (flag_left || flag_right) {
             __threadfence_system();
             if (flag_left) st_release_sys(flag_left, seq);
@@ -221,6 +222,48 @@ __global__ void __launch_bounds__(256) k_slab_append(int max_l, int max_r, const
     warp_append(own, &counters[4]);
 }
 
+// Terrain zone sums over peer memory (slab-local terrain): the 2W accumulator rows around a slab
+// boundary are touched by both neighbours; each rank STORES its copy of the zone into the neighbour's mailbox over NVLink,
+// raises the neighbour's flag when the whole grid has stored (last block), waits for the neighbour's own flag and adds
+// what arrived -- one launch, no transport library, no host sync.  Every element is read (step 1) and updated (step 3) by
+// the same thread, so the phases of different blocks may overlap.  arr: the accumulator array (`want` or `delta`);
+// off_* < 0: no neighbour on that side.  err: set to 1 when a flag does not arrive within `timeout` clock cycles.
+__global__ void __launch_bounds__(256) k_zone_sum(int* __restrict__ arr, int off_l, int off_r, int n, int* out_l, int* out_r,
+                                                  int* flag_out_l, int* flag_out_r, const int* in_l, const int* in_r,
+                                                  const int* flag_in_l, const int* flag_in_r, int seq, long long timeout,
+                                                  int* __restrict__ done, int* __restrict__ err) {
+    const int i0 = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (int i = i0; i < n; i += stride) {
+        if (off_l >= 0) out_l[i] = arr[off_l + i];
+        if (off_r >= 0) out_r[i] = arr[off_r + i];
+    }
+    __threadfence_system();
+    __shared__ int last, arrived;
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(done, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (last) {
+            *done = 0;
+            __threadfence_system();
+            if (off_l >= 0) st_release_sys(flag_out_l, seq);
+            if (off_r >= 0) st_release_sys(flag_out_r, seq);
+        }
+        bool ok = true;
+        const long long t0 = clock64();
+        if (off_l >= 0) while (ld_acquire_sys(flag_in_l) < seq) { if (clock64() - t0 > timeout) { ok = false; break; } __nanosleep(100); }
+        if (off_r >= 0) while (ok && ld_acquire_sys(flag_in_r) < seq) { if (clock64() - t0 > timeout) { ok = false; break; } __nanosleep(100); }
+        if (!ok) atomicExch(err, 1);
+        arrived = ok;
+    }
+    __syncthreads();
+    if (!arrived) return;
+    for (int i = i0; i < n; i += stride) {
+        if (off_l >= 0) arr[off_l + i] += __ldcg(&in_l[i]);
+        if (off_r >= 0) arr[off_r + i] += __ldcg(&in_r[i]);
+    }
+}
+
 // Records in transit (see k_slab_append) join the send buffer of their direction; runs between k_slab_classify
 // and k_slab_headers, one block.  transit_n: [0] heading left, [1] heading right, [3] total forwarded so far.
 template <bool REMOTE>
@@ -295,6 +338,12 @@ void launch_slab_classify(cudaStream_t st, int n, const int* n_dev, const float4
         k_slab_classify<true><<<(n + 255) / 256, 256, 0, st>>>(n, n_dev, posq, velv, ids, sed, G, S, send_left, send_right, cap_records, counters);
     else
         k_slab_classify<false><<<(n + 255) / 256, 256, 0, st>>>(n, n_dev, posq, velv, ids, sed, G, S, send_left, send_right, cap_records, counters);
+}
+void launch_zone_sum(cudaStream_t st, int* arr, int off_l, int off_r, int n, int* out_l, int* out_r, int* flag_out_l, int* flag_out_r,
+                     const int* in_l, const int* in_r, const int* flag_in_l, const int* flag_in_r, int seq, long long timeout, int* done, int* err) {
+    if (n <= 0 || (off_l < 0 && off_r < 0)) return;
+    const int blocks = std::min((n + 1023) / 1024, 96);
+    k_zone_sum<<<blocks, 256, 0, st>>>(arr, off_l, off_r, n, out_l, out_r, flag_out_l, flag_out_r, in_l, in_r, flag_in_l, flag_in_r, seq, timeout, done, err);
 }
 void launch_slab_forward(cudaStream_t st, const float4* transit_l, const float4* transit_r, int* transit_n, float4* send_left,
                          float4* send_right, int cap_records, int* counters, bool remote) {

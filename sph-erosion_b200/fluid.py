@@ -202,6 +202,12 @@ class FluidSystemSPH:
         return dict(zip(("n_total", "n_owned", "to_left", "to_right", "from_left", "from_right"), list(out)))
 
     # peer-memory exchange (include/sphe.h "Peer-memory exchange")
+    def slab_zone_sum(self, grid, which, off_left, off_right, count):
+        capi.check(self._L.sphe_slab_zone_sum(self._h, grid._t, int(which), int(off_left), int(off_right), int(count)))
+
+    def slab_peer_setup_zones(self, cap_records, reserve_particles, zone_ints):
+        capi.check(self._L.sphe_slab_peer_setup_zones(self._h, int(cap_records), int(reserve_particles), int(zone_ints)))
+
     def slab_peer_setup(self, cap_records, reserve_particles=0):
         capi.check(self._L.sphe_slab_peer_setup(self._h, int(cap_records), int(reserve_particles)))
 

@@ -381,7 +381,7 @@ class TerrainWindowShare:
     NCCL P2P groups per step.  Integer sums, so the result is bit-identical to the single-GPU run on every row a
     rank owns.  swap = callable(array, zone_left, zone_right) adding the neighbours' rows in place."""
 
-    def __init__(self, grid, device, rank, world, cuts, margin, swap=None, dist=None):
+    def __init__(self, grid, device, rank, world, cuts, margin, swap=None, dist=None, peer=False):
         w, d, n = grid.accumulators()
         rows, cols = grid.shape()
         self.grid, self.rank, self.world = grid, rank, world
@@ -398,7 +398,12 @@ class TerrainWindowShare:
         self.zone_r = slice((self.own[1] - W) * cols, (self.own[1] + W) * cols) if rank < world - 1 else None
         self.zone_bytes = 2 * W * cols * 4
         self.swap = swap      # False: the caller sums the zones itself (LocalPeerGroup)
-        if swap is None:
+        # peer = True: the zones travel through the slab mailboxes (sphe_slab_zone_sum: remote stores over NVLink + device
+        # flags, one launch per sum) instead of two NCCL P2P groups per step; PeerSlabDriver reserves the room
+        self.peer = bool(peer)
+        if self.peer:
+            self.swap = None
+        elif swap is None:
             import torch
             self.dist = dist
             self.buf_l = torch.empty(2 * W * cols, dtype=torch.int32, device=device) if rank > 0 else None
@@ -423,10 +428,18 @@ class TerrainWindowShare:
             sim.Run(self.grid)
             return
         sim.step_phase(self.grid, 0)
-        self.swap(self.want, self.zone_l, self.zone_r)
+        self.sum_zones(sim, 0)
         sim.step_phase(self.grid, 1)
-        self.swap(self.delta, self.zone_l, self.zone_r)
+        self.sum_zones(sim, 1)
         sim.step_phase(self.grid, 2)
+
+    def sum_zones(self, sim, which):
+        """Adds the x-neighbours' copies of the boundary zones into `want` (which = 0) or `delta` (1)."""
+        if self.peer:
+            sim.slab_zone_sum(self.grid, which, self.zone_l.start if self.zone_l is not None else -1,
+                              self.zone_r.start if self.zone_r is not None else -1, self.zone_bytes // 4)
+        else:
+            self.swap(self.delta if which else self.want, self.zone_l, self.zone_r)
 
     def own_total_fx(self):
         return self.grid.total_fx(self.own)
@@ -445,7 +458,10 @@ class PeerSlabDriver:
         self.terrain = terrain
         self.tickets = []
         self.last = None
-        sim.slab_peer_setup(self.cap, int(reserve_particles))
+        if getattr(terrain, "peer", False):
+            sim.slab_peer_setup_zones(self.cap, int(reserve_particles), terrain.zone_bytes // 4)
+        else:
+            sim.slab_peer_setup(self.cap, int(reserve_particles))
 
     def connect(self, dist):
         """Exchange the mailbox handles (all ranks call this; it also orders every setup before any send)."""
@@ -730,7 +746,8 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT, terrain=False):
         grid, tinfo = attach_terrain(pkg, box[1], n_axis, nx_mult=world)
         if args.terrain_share == "window":
             cuts = terrain_row_cuts(sim.grid_info(), cols, tinfo["terrain_origin"][0], tinfo["terrain_cell"])
-            tshare = TerrainWindowShare(grid, dev, rank, world, cuts, terrain_margin_rows(sim.grid_info().cell, tinfo["terrain_cell"]), dist=dist)
+            tshare = TerrainWindowShare(grid, dev, rank, world, cuts, terrain_margin_rows(sim.grid_info().cell, tinfo["terrain_cell"]), dist=dist,
+                                        peer=(args.exchange == "peer" and getattr(args, "zone_sums", "peer") == "peer"))
         else:
             tshare = TerrainShare(grid, dev, lambda t: dist.all_reduce(t))
     if args.exchange == "peer":
@@ -746,9 +763,10 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT, terrain=False):
     windowed = terrain and args.terrain_share == "window"
     if windowed:
         exchange_desc += ("; terrain slab-local: each rank keeps the rows under its slab + %d margin rows current and sums the erosion accumulators "
-                          "of the %d rows around each slab boundary with that x-neighbour (2 NCCL P2P groups of %d KB per step, int32, no collective)"
+                          "of the %d rows around each slab boundary with that x-neighbour (%d KB per sum, int32, no collective; transport: %s)"
                           % (tshare.window[1] - tshare.own[1] if rank < world - 1 else tshare.own[0] - tshare.window[0],
-                             2 * (tshare.own[0] - tshare.window[0] if rank else tshare.window[1] - tshare.own[1]), tshare.zone_bytes // 1024))
+                             2 * (tshare.own[0] - tshare.window[0] if rank else tshare.window[1] - tshare.own[1]), tshare.zone_bytes // 1024,
+                             "the slab mailboxes: remote stores over NVLink + device flags, one launch per sum" if tshare.peer else "2 NCCL P2P groups per step"))
     elif terrain:
         exchange_desc += "; terrain replicated, per-vertex erosion accumulators summed with 2 NCCL all-reduces (int32) per step"
 

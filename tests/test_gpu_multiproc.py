@@ -19,7 +19,7 @@ def _free_port():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,share", [(2, "allreduce"), (4, "allreduce")])
+@pytest.mark.parametrize("world,share", [(2, "window"), (2, "allreduce"), (4, "allreduce")])
 def test_peer_check_multiprocess_one_gpu(world, share):
     env = dict(os.environ, SPHE_ONE_GPU="1", TERRAIN_SHARE=share, STEPS="10", OMP_NUM_THREADS="1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
