@@ -77,45 +77,67 @@ __global__ void __launch_bounds__(256) k_slab_classify(int n_hi, const int* __re
                                                        float4* __restrict__ send_left, float4* __restrict__ send_right,
                                                        int cap_records, int* __restrict__ counters) {
     const int n = n_dev ? __ldg(n_dev) : n_hi;  // exact extent from the device, else the launch bound
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool live = false, own = false, to_l = false, to_r = false;
-    float4 p = make_float4(0, 0, 0, 0);
-    int id = 0;
-    if (i < n) {
-        id = ids[i];
-        if (!(id & SPHE_GHOST_BIT)) {
-            p = posq[i];
-            int cx = cell_axis(p.x, G.gx, G.cell, G.gnx);
-            own = (cx >= S.x0 || !S.has_left) && (cx < S.x1 || !S.has_right);
-            // a particle exactly on the -x wall is clamped to the +x wall (collisionS, fluid_system.h:375-382:
-            // x == -len takes the else branch): it leaves the first slab for the LAST one, over the wrap link
-            const bool far = S.wrap_left && cx >= S.far_x0;
-            to_l = S.has_left && (S.wrap_left ? far : cx < S.x0 + S.halo);
-            to_r = S.has_right && !S.wrap_right && !far && cx >= S.x1 - S.halo;
-            // left the slab but still within the halo zone: stays here as a ghost
-            live = own || (!far && cx >= S.x0 - S.halo && cx < S.x1 + S.halo);
+    // Persistent grid, grid-stride over whole 256-particle tiles: the kept / owned COUNTS are accumulated per thread and
+    // cost one atomic per block at the end (same-address atomics with a return value serialise in L2 at ~1 ns each: one
+    // per 256-particle block was 0.03 ms of this pass at 4M particles); record slots are only allocated by the few
+    // tiles that hold halo-zone particles.
+    int n_live = 0, n_own = 0;
+    const int tiles = (n + 255) >> 8;
+    if (blockIdx.x == 0 && threadIdx.x == 0) counters[8] = n;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int i = (tile << 8) + threadIdx.x;
+        bool live = false, own = false, to_l = false, to_r = false;
+        float4 p = make_float4(0, 0, 0, 0);
+        int id = 0;
+        if (i < n) {
+            id = ids[i];
+            if (!(id & SPHE_GHOST_BIT)) {
+                p = posq[i];
+                int cx = cell_axis(p.x, G.gx, G.cell, G.gnx);
+                own = (cx >= S.x0 || !S.has_left) && (cx < S.x1 || !S.has_right);
+                // a particle exactly on the -x wall is clamped to the +x wall (collisionS, fluid_system.h:375-382:
+                // x == -len takes the else branch): it leaves the first slab for the LAST one, over the wrap link
+                const bool far = S.wrap_left && cx >= S.far_x0;
+                to_l = S.has_left && (S.wrap_left ? far : cx < S.x0 + S.halo);
+                to_r = S.has_right && !S.wrap_right && !far && cx >= S.x1 - S.halo;
+                // left the slab but still within the halo zone: stays here as a ghost
+                live = own || (!far && cx >= S.x0 - S.halo && cx < S.x1 + S.halo);
+            }
+            const int nid = live ? (own ? id : (id | SPHE_GHOST_BIT)) : SPHE_DEAD_ID;
+            if (nid != id) ids[i] = nid;
         }
-        const int nid = live ? (own ? id : (id | SPHE_GHOST_BIT)) : SPHE_DEAD_ID;
-        if (nid != id) ids[i] = nid;
-        if (i == 0) counters[8] = n;
+        n_live += live ? 1 : 0; n_own += own ? 1 : 0;
+        if (__syncthreads_or(to_l || to_r)) {   // block-uniform: tiles without halo-zone particles skip the slot allocation
+            const bool flag[4] = {false, to_l, to_r, false};
+            int* const ctr[4] = {&counters[0], &counters[1], &counters[2], &counters[3]};
+            int slot[4];
+            block_append4(flag, ctr, slot);
+            const int l = slot[1], r = slot[2];
+            if (to_l || to_r) {
+                const float4 v = velv[i];
+                const float sd = sed[i];
+                if (to_l && l < cap_records) {
+                    send_left[2 * (l + 1)] = make_float4(p.x, p.y, p.z, sd);
+                    send_left[2 * (l + 1) + 1] = make_float4(v.x, v.y, v.z, __int_as_float(id));
+                }
+                if (to_r && r < cap_records) {
+                    send_right[2 * (r + 1)] = make_float4(p.x, p.y, p.z, sd);
+                    send_right[2 * (r + 1) + 1] = make_float4(v.x, v.y, v.z, __int_as_float(id));
+                }
+                if (REMOTE) __threadfence_system();
+            }
+        }
     }
-    const bool flag[4] = {live, to_l, to_r, own};
-    int* const ctr[4] = {&counters[0], &counters[1], &counters[2], &counters[3]};
-    int slot[4];
-    block_append4(flag, ctr, slot);
-    const int l = slot[1], r = slot[2];
-    if (to_l || to_r) {
-        const float4 v = velv[i];
-        const float sd = sed[i];
-        if (to_l && l < cap_records) {
-            send_left[2 * (l + 1)] = make_float4(p.x, p.y, p.z, sd);
-            send_left[2 * (l + 1) + 1] = make_float4(v.x, v.y, v.z, __int_as_float(id));
-        }
-        if (to_r && r < cap_records) {
-            send_right[2 * (r + 1)] = make_float4(p.x, p.y, p.z, sd);
-            send_right[2 * (r + 1) + 1] = make_float4(v.x, v.y, v.z, __int_as_float(id));
-        }
-        if (REMOTE) __threadfence_system();
+    // counts: warp reduce, one atomic per warp leader... per block
+    __shared__ int red[2][8];
+    n_live = __reduce_add_sync(SPHE_FULL, n_live); n_own = __reduce_add_sync(SPHE_FULL, n_own);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = n_live; red[1][threadIdx.x >> 5] = n_own; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) t += red[threadIdx.x][w];
+        if (t) atomicAdd(&counters[threadIdx.x ? 3 : 0], t);
     }
 }
 
@@ -334,10 +356,11 @@ __global__ void k_pack_state_ids(int n, const float* __restrict__ pos, const flo
 void launch_slab_classify(cudaStream_t st, int n, const int* n_dev, const float4* posq, const float4* velv, int* ids, const float* sed,
                           const GridP& G, const SlabP& S, float4* send_left, float4* send_right, int cap_records, int* counters, bool remote) {
     if (n <= 0) return;
+    const int blocks = std::min((n + 255) / 256, 148 * 8);
     if (remote)
-        k_slab_classify<true><<<(n + 255) / 256, 256, 0, st>>>(n, n_dev, posq, velv, ids, sed, G, S, send_left, send_right, cap_records, counters);
+        k_slab_classify<true><<<blocks, 256, 0, st>>>(n, n_dev, posq, velv, ids, sed, G, S, send_left, send_right, cap_records, counters);
     else
-        k_slab_classify<false><<<(n + 255) / 256, 256, 0, st>>>(n, n_dev, posq, velv, ids, sed, G, S, send_left, send_right, cap_records, counters);
+        k_slab_classify<false><<<blocks, 256, 0, st>>>(n, n_dev, posq, velv, ids, sed, G, S, send_left, send_right, cap_records, counters);
 }
 void launch_zone_sum(cudaStream_t st, int* arr, int off_l, int off_r, int n, int* out_l, int* out_r, int* flag_out_l, int* flag_out_r,
                      const int* in_l, const int* in_r, const int* flag_in_l, const int* flag_in_r, int seq, long long timeout, int* done, int* err) {
