@@ -154,6 +154,9 @@ int sphe_get_particle(sphe_sim* s, int id, sphe_particle* out); /* GetParticle f
 int sphe_download(sphe_sim* s, int field, void* host_out);      /* whole field, id order */
 /* Packed positions for Draw() (fluid_system.h:185-204): xyz float32, id order. */
 int sphe_download_positions(sphe_sim* s, float* host_xyz);
+/* The same into a DEVICE buffer of the caller (e.g. a mapped OpenGL vertex buffer: CUDA-GL interop, no PCIe round trip);
+ * capacity_floats >= 3 * sphe_count(s).  One instanced draw call then replaces the reference's draw call per particle. */
+int sphe_write_positions_device(sphe_sim* s, void* device_xyz, long long capacity_floats);
 
 /* ---- neighbour-grid test hooks (state of the LAST step's binning) ---- */
 int sphe_debug_cells(sphe_sim* s, int* cell_of_id);          /* [n]  cell id per particle id       */

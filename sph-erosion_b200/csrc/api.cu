@@ -5,6 +5,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <string>
+#include <new>
 #include <vector>
 
 #include "../../include/sphe.h"
@@ -938,6 +940,26 @@ int sphe_download(sphe_sim* s, int field, void* out) {
 }
 
 int sphe_download_positions(sphe_sim* s, float* host_xyz) { return sphe_download(s, SPHE_F_POS, host_xyz); }
+
+// Renderer hand-off without the PCIe round trip: packed xyz positions in id order written straight into a DEVICE buffer
+// the caller owns -- typically an OpenGL vertex buffer mapped with cudaGraphicsGLRegisterBuffer /
+// cudaGraphicsResourceGetMappedPointer, drawn as one instanced call instead of the
+// reference's one glDrawElements per particle (fluid_system.h:185-204).  Returns after the copy kernel has finished.
+int sphe_write_positions_device(sphe_sim* s, void* device_xyz, long long capacity_floats) {
+    if (!s || !device_xyz) return fail(SPHE_ERR_ARG, "NULL argument");
+    TRY(not_in_slab_mode(s, "sphe_write_positions_device"));
+    if (capacity_floats < 3LL * s->n) return fail(SPHE_ERR_ARG, "device buffer of %lld floats < 3 x %d particles", capacity_floats, s->n);
+    if (s->n == 0) return SPHE_OK;
+    TRY(ensure_device(s));
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, device_xyz) != cudaSuccess || (a.type != cudaMemoryTypeDevice && a.type != cudaMemoryTypeManaged)) {
+        cudaGetLastError();
+        return fail(SPHE_ERR_ARG, "device_xyz is not a device pointer");
+    }
+    launch_unsort_f4(s->st, s->n, s->posA, s->idsA, (float*)device_xyz);
+    CU(cudaStreamSynchronize(s->st));
+    return SPHE_OK;
+}
 
 int sphe_get_particle(sphe_sim* s, int id, sphe_particle* out) {
     if (!s || !out) return fail(SPHE_ERR_ARG, "NULL argument");
@@ -1946,10 +1968,7 @@ struct File {
 };
 }  // namespace
 
-int sphe_save_state(sphe_sim* s, sphe_terrain* t, const char* path) {
-    if (!s || !path) return fail(SPHE_ERR_ARG, "bad arguments");
-    if (s->slab_on) return fail(SPHE_ERR_STATE, "not available in slab mode (use sphe_slab_download per rank)");
-    TRY(ensure_device(s));
+static int save_state_to(sphe_sim* s, sphe_terrain* t, const char* path) {
     const int n = s->n;
     StateHeader H{};
     memcpy(H.magic, "SPHESTA1", 8);
@@ -1966,6 +1985,17 @@ int sphe_save_state(sphe_sim* s, sphe_terrain* t, const char* path) {
         CU(cudaMemcpyAsync(sed.data(), s->stage, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s->st));
         CU(cudaStreamSynchronize(s->st));
     }
+    // everything that can fail on the device happens BEFORE the file is opened
+    TerrainHeader T{};
+    std::vector<int> hfx;
+    if (t) {
+        TRY(terrain_ready(t));
+        T.rows = t->rows; T.cols = t->cols; T.dims[0] = t->dimx; T.dims[1] = t->dimy; T.dims[2] = t->dimz;
+        for (int a = 0; a < 3; a++) T.origin[a] = t->origin[a];
+        T.scale = t->scale; T.E = t->E;
+        hfx.resize((size_t)t->rows * t->cols);
+        TRY(sphe_terrain_get_heights_fx(t, hfx.data()));
+    }
     File F; F.f = fopen(path, "wb");
     if (!F.f) return fail(SPHE_ERR_ARG, "cannot write %s", path);
     bool ok = fwrite(&H, sizeof H, 1, F.f) == 1;
@@ -1973,30 +2003,45 @@ int sphe_save_state(sphe_sim* s, sphe_terrain* t, const char* path) {
     ok = ok && (n == 0 || (fwrite(pos.data(), sizeof(float), pos.size(), F.f) == pos.size() &&
                            fwrite(vel.data(), sizeof(float), vel.size(), F.f) == vel.size() &&
                            fwrite(sed.data(), sizeof(int), sed.size(), F.f) == sed.size()));
-    if (ok && t) {
-        TRY(terrain_ready(t));
-        TerrainHeader T{};
-        T.rows = t->rows; T.cols = t->cols; T.dims[0] = t->dimx; T.dims[1] = t->dimy; T.dims[2] = t->dimz;
-        for (int a = 0; a < 3; a++) T.origin[a] = t->origin[a];
-        T.scale = t->scale; T.E = t->E;
-        std::vector<int> hfx((size_t)t->rows * t->cols);
-        TRY(sphe_terrain_get_heights_fx(t, hfx.data()));
-        ok = fwrite(&T, sizeof T, 1, F.f) == 1 && fwrite(hfx.data(), sizeof(int), hfx.size(), F.f) == hfx.size();
-    }
+    if (ok && t) ok = fwrite(&T, sizeof T, 1, F.f) == 1 && fwrite(hfx.data(), sizeof(int), hfx.size(), F.f) == hfx.size();
+    ok = ok && fflush(F.f) == 0;
     if (!ok) return fail(SPHE_ERR_ARG, "short write to %s", path);
     return SPHE_OK;
 }
 
-int sphe_load_state(sphe_sim* s, sphe_terrain* t, const char* path) {
+// Writes to "<path>.tmp" and renames: a failure never leaves a partial file under `path`.
+int sphe_save_state(sphe_sim* s, sphe_terrain* t, const char* path) {
     if (!s || !path) return fail(SPHE_ERR_ARG, "bad arguments");
-    if (s->slab_on) return fail(SPHE_ERR_STATE, "not available in slab mode");
+    if (s->slab_on) return fail(SPHE_ERR_STATE, "not available in slab mode (use sphe_slab_download per rank)");
+    TRY(ensure_device(s));
+    try {
+        const std::string tmp = std::string(path) + ".tmp";
+        int rc = save_state_to(s, t, tmp.c_str());
+        if (rc != SPHE_OK) { remove(tmp.c_str()); return rc; }
+        if (rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); return fail(SPHE_ERR_ARG, "cannot rename %s to %s", tmp.c_str(), path); }
+    } catch (const std::bad_alloc&) {
+        return fail(SPHE_ERR_NOMEM, "out of host memory while saving %s", path);
+    }
+    return SPHE_OK;
+}
+
+// The whole file is read and checked against its own length BEFORE the simulation or the terrain is touched: a corrupt or
+// truncated file leaves both exactly as they were.
+static int load_state_from(sphe_sim* s, sphe_terrain* t, const char* path) {
     File F; F.f = fopen(path, "rb");
     if (!F.f) return fail(SPHE_ERR_ARG, "cannot read %s", path);
+    if (fseek(F.f, 0, SEEK_END) != 0) return fail(SPHE_ERR_ARG, "cannot seek in %s", path);
+    const long long file_bytes = ftell(F.f);
+    rewind(F.f);
     StateHeader H;
-    if (fread(&H, sizeof H, 1, F.f) != 1 || memcmp(H.magic, "SPHESTA1", 8) != 0) return fail(SPHE_ERR_ARG, "%s is not a sphe state file", path);
+    if (file_bytes < (long long)sizeof H || fread(&H, sizeof H, 1, F.f) != 1 || memcmp(H.magic, "SPHESTA1", 8) != 0)
+        return fail(SPHE_ERR_ARG, "%s is not a sphe state file", path);
     if (H.n < 0 || H.n_labels < 0 || (H.n_labels != 0 && H.n_labels != H.n)) return fail(SPHE_ERR_ARG, "%s: corrupt header", path);
     if (H.has_terrain && !t) return fail(SPHE_ERR_ARG, "%s holds a terrain: pass a terrain handle to receive it", path);
     const size_t n = (size_t)H.n;
+    // sizes from the file are only trusted as far as the file is long
+    long long need = (long long)sizeof H + (long long)H.n_labels * 4 + (long long)n * 28;
+    if (need > file_bytes) return fail(SPHE_ERR_ARG, "%s: truncated particle data (%lld bytes for %d particles, file has %lld)", path, need, H.n, file_bytes);
     std::vector<int> labels((size_t)H.n_labels), sed(n);
     std::vector<float> pos(3 * n), vel(3 * n);
     bool ok = labels.empty() || fread(labels.data(), sizeof(int), labels.size(), F.f) == labels.size();
@@ -2004,6 +2049,23 @@ int sphe_load_state(sphe_sim* s, sphe_terrain* t, const char* path) {
                            fread(vel.data(), sizeof(float), vel.size(), F.f) == vel.size() &&
                            fread(sed.data(), sizeof(int), sed.size(), F.f) == sed.size()));
     if (!ok) return fail(SPHE_ERR_ARG, "%s: truncated particle data", path);
+    TerrainHeader T{};
+    std::vector<float> h;
+    if (H.has_terrain) {
+        if (fread(&T, sizeof T, 1, F.f) != 1) return fail(SPHE_ERR_ARG, "%s: truncated terrain header", path);
+        if (T.rows < 2 || T.cols < 2 || T.rows > 65536 || T.cols > 65536 || (long long)T.rows * T.cols > (1LL << 30))
+            return fail(SPHE_ERR_ARG, "%s: terrain of %d x %d vertices", path, T.rows, T.cols);
+        need += (long long)sizeof T + (long long)T.rows * T.cols * 4;
+        if (need > file_bytes) return fail(SPHE_ERR_ARG, "%s: truncated terrain heights", path);
+        std::vector<int> hfx((size_t)T.rows * T.cols);
+        if (fread(hfx.data(), sizeof(int), hfx.size(), F.f) != hfx.size()) return fail(SPHE_ERR_ARG, "%s: truncated terrain heights", path);
+        h.resize(hfx.size());
+        for (size_t i = 0; i < hfx.size(); i++) {
+            if (hfx[i] > (1 << 24) || hfx[i] < -(1 << 24)) return fail(SPHE_ERR_ARG, "%s: height out of the exactly representable range", path);
+            h[i] = (float)hfx[i] * (1.0f / 4096.0f);     // exact: |hfx| < 2^24, and set_heights rounds h * 4096 back to hfx
+        }
+    }
+    // ---- nothing above touched s or t
     s->P = H.P;
     for (int a = 0; a < 3; a++) { s->origin[a] = H.origin[a]; s->box[a] = H.box[a]; }
     s->box_user = H.box_user != 0;
@@ -2013,21 +2075,22 @@ int sphe_load_state(sphe_sim* s, sphe_terrain* t, const char* path) {
     s->labels = labels; s->labels_identity = labels.empty();
     if (n > 0) TRY(sphe_set_sediment_fx(s, sed.data()));
     if (H.has_terrain) {
-        TerrainHeader T;
-        if (fread(&T, sizeof T, 1, F.f) != 1 || T.rows < 2 || T.cols < 2) return fail(SPHE_ERR_ARG, "%s: truncated terrain header", path);
-        std::vector<int> hfx((size_t)T.rows * T.cols);
-        if (fread(hfx.data(), sizeof(int), hfx.size(), F.f) != hfx.size()) return fail(SPHE_ERR_ARG, "%s: truncated terrain heights", path);
-        std::vector<float> h(hfx.size());
-        for (size_t i = 0; i < hfx.size(); i++) {
-            if (hfx[i] > (1 << 24) || hfx[i] < -(1 << 24)) return fail(SPHE_ERR_ARG, "%s: height out of the exactly representable range", path);
-            h[i] = (float)hfx[i] * (1.0f / 4096.0f);     // exact: |hfx| < 2^24, and set_heights rounds h * 4096 back to hfx
-        }
         t->dimx = T.dims[0]; t->dimy = T.dims[1]; t->dimz = T.dims[2];
         TRY(sphe_terrain_set_heights(t, h.data(), T.rows, T.cols));
         TRY(sphe_terrain_set_transform(t, T.origin, T.scale));
         t->E = T.E;
     }
     return SPHE_OK;
+}
+
+int sphe_load_state(sphe_sim* s, sphe_terrain* t, const char* path) {
+    if (!s || !path) return fail(SPHE_ERR_ARG, "bad arguments");
+    if (s->slab_on) return fail(SPHE_ERR_STATE, "not available in slab mode");
+    try {
+        return load_state_from(s, t, path);
+    } catch (const std::bad_alloc&) {
+        return fail(SPHE_ERR_NOMEM, "out of host memory while loading %s", path);
+    }
 }
 
 }  // extern "C"

@@ -99,6 +99,10 @@ class FluidSystemSPH:
         capi.check(self._L.sphe_step_host(self._h, getattr(grid, "_t", None), n, _p(pos), _p(vel), _p(po), _p(vo), _p(rho)))
         return po, vo, rho
 
+    def write_positions_device(self, device_ptr, capacity_floats):
+        """Packed xyz positions (id order) into a caller-owned device buffer, e.g. a mapped GL vertex buffer."""
+        capi.check(self._L.sphe_write_positions_device(self._h, C.c_void_p(int(device_ptr)), int(capacity_floats)))
+
     def set_l2_flush(self, nbytes): capi.check(self._L.sphe_set_l2_flush(self._h, int(nbytes)))
 
     def timed_steps(self, steps, grid=None, per_kernel=True):

@@ -88,6 +88,18 @@ public:
 #else
     void Draw(const Shader&, int) {}
 #endif
+    // Renderer hand-off without the PCIe round trip: packed xyz positions (id order) into a DEVICE buffer, e.g. an OpenGL
+    // vertex buffer mapped through CUDA-GL interop (DrawInstanced below); capacity in floats.
+    void PositionsToDevice(void* device_xyz, long long capacity_floats) {
+        check(sphe_write_positions_device(m_S, device_xyz, capacity_floats), "PositionsToDevice");
+    }
+#ifdef SPHE_WITH_GL_INTEROP
+    // One instanced draw instead of the reference's glDrawElements per particle (fluid_system.h:190-203).  The instance
+    // buffer is registered with CUDA once (cudaGraphicsGLRegisterBuffer) and filled on the device every frame; the vertex
+    // shader adds the per-instance offset (attribute `instance_attr`, divisor 1) to the unit sphere scaled by 0.01.
+    // Needs <cuda_gl_interop.h> and GLEW on the include path (not in this image: compiled by nobody here).
+    void DrawInstanced(GLuint sphere_vao, GLsizei sphere_index_count, GLuint instance_attr = 3);
+#endif
     const std::vector<float>& Positions() {
         int n = sphe_count(m_S);
         m_Pos.resize(3 * (size_t)n);
@@ -116,6 +128,36 @@ private:
     bool m_UseTerrain = false;
     std::vector<float> m_Pos;
 };
+
+#ifdef SPHE_WITH_GL_INTEROP
+#include <cuda_gl_interop.h>
+inline void FluidSystemSPH::DrawInstanced(GLuint sphere_vao, GLsizei sphere_index_count, GLuint instance_attr) {
+    static GLuint vbo = 0;
+    static cudaGraphicsResource* res = nullptr;
+    static size_t cap_floats = 0;
+    const size_t need = 3 * (size_t)sphe_count(m_S);
+    if (need == 0) return;
+    if (need > cap_floats) {       // (re)create and register the instance buffer when the particle count grows
+        if (res) { cudaGraphicsUnregisterResource(res); res = nullptr; }
+        if (!vbo) glGenBuffers(1, &vbo);
+        glBindBuffer(GL_ARRAY_BUFFER, vbo);
+        glBufferData(GL_ARRAY_BUFFER, need * sizeof(float), nullptr, GL_DYNAMIC_DRAW);
+        cudaGraphicsGLRegisterBuffer(&res, vbo, cudaGraphicsRegisterFlagsWriteDiscard);
+        cap_floats = need;
+        glBindVertexArray(sphere_vao);
+        glEnableVertexAttribArray(instance_attr);
+        glVertexAttribPointer(instance_attr, 3, GL_FLOAT, GL_FALSE, 3 * sizeof(float), (void*)0);
+        glVertexAttribDivisor(instance_attr, 1);
+    }
+    void* dev = nullptr; size_t bytes = 0;
+    cudaGraphicsMapResources(1, &res, 0);
+    cudaGraphicsResourceGetMappedPointer(&dev, &bytes, res);
+    PositionsToDevice(dev, (long long)(bytes / sizeof(float)));
+    cudaGraphicsUnmapResources(1, &res, 0);
+    glBindVertexArray(sphere_vao);
+    glDrawElementsInstanced(GL_TRIANGLES, sphere_index_count, GL_UNSIGNED_INT, nullptr, (GLsizei)(need / 3));
+}
+#endif
 
 #ifdef SPHE_WITH_GL
 #include "shader.h"

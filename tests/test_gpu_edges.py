@@ -113,3 +113,26 @@ def test_odd_counts_random_cloud(n):
     pos = rng.uniform(-0.21, 0.21, (n, 3)).astype(np.float32)
     vel = rng.normal(0, 0.5, (n, 3)).astype(np.float32)
     lockstep(pos, vel, port.default_params(dt=0.005), 2)
+
+
+def test_positions_into_a_device_buffer_match_the_download():
+    """Renderer hand-off: sphe_write_positions_device fills a caller-owned DEVICE buffer -- the pointer a
+    mapped OpenGL vertex buffer gives -- with the packed id-order positions the host download returns; a host pointer or
+    a buffer that is too small is refused."""
+    import torch
+    m = product()
+    s = m.FluidSystemSPH()
+    s.Initialize(3375); s.SetDeltaTime(0.01)
+    for _ in range(3):
+        s.Run()
+    n = s.count()
+    buf = torch.zeros(3 * n + 7, dtype=torch.float32, device="cuda")
+    s.write_positions_device(buf.data_ptr(), buf.numel())
+    torch.cuda.synchronize()
+    assert np.array_equal(buf[:3 * n].cpu().numpy().reshape(n, 3), s.download("pos"))
+    assert float(buf[3 * n:].abs().sum()) == 0.0
+    with pytest.raises(m.capi.SpheError):
+        s.write_positions_device(buf.data_ptr(), 3 * n - 1)
+    host = np.zeros(3 * n, np.float32)
+    with pytest.raises(m.capi.SpheError):
+        s.write_positions_device(host.ctypes.data, host.size)

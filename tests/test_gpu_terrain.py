@@ -266,3 +266,32 @@ def test_checkpoint_resume_continues_bit_for_bit(tmp_path):
     bad = tmp_path / "bad.sphe"; bad.write_bytes(b"not a state file at all" * 10)
     with pytest.raises(m.capi.SpheError, match="not a sphe state file"):
         two.load_state(str(bad))
+
+
+def test_load_state_rejects_corrupt_files_without_touching_the_simulation(tmp_path):
+    """A truncated file, a header that promises more particles than the file holds, an oversized terrain: each is an
+    error and leaves the simulation and the terrain exactly as they were (sphe_load_state reads and checks the whole
+    file before it mutates anything); saving never leaves a partial file behind."""
+    m = product()
+    s = m.FluidSystemSPH(); s.params.dt = 0.004; s.params.len = 0.3
+    pos = np.random.default_rng(2).uniform(-0.25, 0.25, (5000, 3)).astype(np.float32)
+    s.upload_state(pos, np.zeros_like(pos))
+    g = m.Grid(40, 255, 40); g.set_heights(np.full((40, 40), 3.0, np.float32)); g.set_transform((-0.3, -0.3, -0.3), 0.015)
+    s.Run(g)
+    good = tmp_path / "good.sphe"
+    s.save_state(str(good), g)
+    assert not (tmp_path / "good.sphe.tmp").exists()
+    raw = good.read_bytes()
+    p0, h0, n0 = s.download("pos"), g.heights_fx(), s.count()
+    cases = {"truncated_particles": raw[:len(raw) // 3], "truncated_terrain": raw[:-1000]}
+    huge = bytearray(raw); huge[8:12] = (2 ** 30).to_bytes(4, "little")      # n = 2^30 particles in a 200 KB file
+    cases["huge_n"] = bytes(huge)
+    for name, data in cases.items():
+        f = tmp_path / (name + ".sphe"); f.write_bytes(data)
+        with pytest.raises(m.capi.SpheError):
+            s.load_state(str(f), g)
+        assert s.count() == n0 and np.array_equal(s.download("pos"), p0) and np.array_equal(g.heights_fx(), h0), name
+    s.load_state(str(good), g)
+    assert np.array_equal(s.download("pos"), p0) and np.array_equal(g.heights_fx(), h0)
+    with pytest.raises(m.capi.SpheError):
+        s.save_state(str(tmp_path / "no_such_dir" / "x.sphe"), g)
