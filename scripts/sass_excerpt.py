@@ -5,7 +5,7 @@ that holds the most packed-math instructions (FFMA2/FADD2/FMUL2), i.e. the candi
 import collections, re, subprocess, sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OBJ = os.path.join(ROOT, "sph-erosion_b200", "build", "sph.o")
-KERNELS = [("k_density_listILb0ELb1ELi64ELi128ELi4E", "k_density_list<REC=0, PF=1, CAP=64, THREADS=128, UNROLL=4> (default density pass): the loop tests 4 candidates for 2 targets"),
+KERNELS = [("k_density_listILb0ELb1ELi56ELi64ELi4E", "k_density_list<REC=0, PF=1, CAP=56, THREADS=64, UNROLL=4> (default density pass): the loop tests 4 candidates for 2 targets"),
            ("k_force_listILb0ELb0ELb0E", "k_force_list<DIAG=0, REC=0, PF=0> (default force pass): the loop handles 1 list entry for 2 targets")]
 names = subprocess.run(["cuobjdump", "-sass", OBJ], capture_output=True, text=True).stdout
 funcs = re.findall(r"Function : (\S+)", names)

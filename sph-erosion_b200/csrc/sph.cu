@@ -221,8 +221,9 @@ __global__ void __launch_bounds__(THREADS, CAP == DL_CAP ? DL_MINB : (CAP >= 256
             // branch-free append: store at the current slot (the trash slot once saturated), advance only on a pass
             asm volatile("st.shared.u32 [%0], %1;" ::"r"(min(wp, cap_sa)), "r"(k) : "memory");
             asm("{ .reg .pred q; setp.ge.f32 q, %1, %3; @q add.u32 %0, %0, %2; }" : "+r"(wp) : "f"(fmaxf(w.x, w.y)), "n"(4 * NLIST_THREADS), "f"(LIST_NEG_EPS * C.hh));
-            w.x = fmaxf(w.x, 0.f);
-            w.y = fmaxf(w.y, 0.f);
+            // clamp without the two FMNMX: w + |w| = 2 max(w, 0) EXACTLY, in one packed add (FADD2 takes |.| on an operand);
+            // the sum then carries a factor 2^3 that the final scale removes exactly -- bit-identical to clamping
+            w = __fadd2_rn(w, make_float2(fabsf(w.x), fabsf(w.y)));
             acc = __ffma2_rn(__fmul2_rn(w, w), w, acc);
         };
         // SPILL: the shared-memory list holds CAP entries; when a run saturates it, that run is walked again (rare,
@@ -307,7 +308,8 @@ __global__ void __launch_bounds__(THREADS, CAP == DL_CAP ? DL_MINB : (CAP >= 256
         for (int o = 0, e = 0; o < stop; o += NLIST_THREADS, e++) dst[(size_t)e * npairs_pad] = lbase[o];
     }
     if (!live) return;
-    float ra = acc.x * C.densK, rb = acc.y * C.densK;
+    const float dk = C.densK * 0.125f;   // exact: the accumulators hold 8 x sum (h^2 - r^2)^3 (see `test`)
+    float ra = acc.x * dk, rb = acc.y * dk;
     float Pa = C.k * (ra - C.p0), Pb = C.k * (rb - C.p0);
     rho[a] = ra;
     if (REC) {
@@ -558,7 +560,9 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MINB) k_force_list(int n_hi, co
         d2 = __ffma2_rn(dy, dy, d2);
         d2 = __ffma2_rn(dz, dz, d2);
         float2 w = __fadd2_rn(make_float2(C.hh, C.hh), make_float2(-d2.x, -d2.y));
-        w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f);
+        // clamps as w + |w| = 2 max(w, 0) (one FADD2 instead of two FMNMX, exact): CF and F then carry a factor 2, N and A a
+        // factor 4, removed exactly in the epilogue call below -- bit-identical to clamping
+        w = __fadd2_rn(w, make_float2(fabsf(w.x), fabsf(w.y)));
         float2 vw = __fmul2_rn(w, make_float2(vj.w, vj.w));
         float2 t7 = __ffma2_rn(d2, make_float2(-7.0f, -7.0f), make_float2(C.hh3, C.hh3));
         CF = __ffma2_rn(vw, t7, CF);
@@ -567,7 +571,7 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MINB) k_force_list(int n_hi, co
         float2 rinv = make_float2(rsqrt_ftz(fmaxf(d2.x, 1e-30f)), rsqrt_ftz(fmaxf(d2.y, 1e-30f)));
         float2 r = __fmul2_rn(d2, rinv);
         float2 hm = __fadd2_rn(make_float2(C.h, C.h), make_float2(-r.x, -r.y));
-        hm.x = fmaxf(hm.x, 0.f); hm.y = fmaxf(hm.y, 0.f);
+        hm = __fadd2_rn(hm, make_float2(fabsf(hm.x), fabsf(hm.y)));   // 2 max(h - r, 0)
         float2 tv = __fmul2_rn(hm, make_float2(vj.w, vj.w));
         float2 dvx = __fadd2_rn(make_float2(vj.x, vj.x), make_float2(-VX.x, -VX.y));
         float2 dvy = __fadd2_rn(make_float2(vj.y, vj.y), make_float2(-VY.x, -VY.y));
@@ -676,7 +680,9 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MINB) k_force_list(int n_hi, co
         const float fx = p ? F_x.y : F_x.x, fy = p ? F_y.y : F_y.x, fz = p ? F_z.y : F_z.x;
         const float nx = p ? N_x.y : N_x.x, ny = p ? N_y.y : N_y.x, nz = p ? N_z.y : N_z.x;
         const float cf = p ? CF.y : CF.x;
-        force_epilogue<DIAG>(i, pi, vi, rho[i], ax, ay, az, fx, fy, fz, nx, ny, nz, cf, p ? maxb : maxa, C, ids, posq_out, velv_out, D);
+        // exact powers of two: the clamps in `body` were 2 max(., 0) (A and N carry 4x, F and CF 2x)
+        force_epilogue<DIAG>(i, pi, vi, rho[i], 0.25f * ax, 0.25f * ay, 0.25f * az, 0.5f * fx, 0.5f * fy, 0.5f * fz, 0.25f * nx, 0.25f * ny, 0.25f * nz,
+                             0.5f * cf, p ? maxb : maxa, C, ids, posq_out, velv_out, D);
     }
 }
 
