@@ -122,7 +122,7 @@ __device__ __forceinline__ void fan_entry(bool low, int sel, int k, int& dx, int
     dx = e[0]; dz = e[1]; which = e[2];
 }
 
-__device__ bool corner(const TerrainDev& T, bool low, V3 pc, V3 pn, float cx, float cz, V3& cp, V3& n) {
+__device__ __noinline__ bool corner(const TerrainDev& T, bool low, V3 pc, V3 pn, float cx, float cz, V3& cp, V3& n) {
     float ox = floorf(pc.x) + (low ? 0.0f : 1.0f), oz = floorf(pc.z) + (low ? 0.0f : 1.0f);
     float s = low ? 1.0f : -1.0f;
     float d0 = norm2(ox - pc.x, oz - pc.z);
