@@ -516,6 +516,7 @@ def run_gpu_arm(args):
     ms_instrumented, per_kernel, _ = sim.timed_steps(args.steps, grid=grid, per_kernel=True)
     if grid is not None:
         tinfo["terrain_contacts_per_step"] = contacts / args.steps
+        tinfo["contact_cull_survivors_last_step"] = dict(zip(("same_cell", "one_axis", "both_axes"), sim.terrain_survivors()))
         tinfo["sediment_in_flight_fx"] = sed_end
         tinfo["conservation_exact"] = bool(total_end == tot0)
         tinfo["replayed_window_bit_identical"] = bool(np.array_equal(state_end[0], sim.download("pos")) and np.array_equal(state_end[2], grid.heights()))

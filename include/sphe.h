@@ -302,6 +302,8 @@ int sphe_terrain_total_fx_rows(sphe_terrain* t, int row0, int row1, long long* s
  * reads or writes within 2 rows of an interior window edge is counted: window_violations must stay 0. */
 int sphe_terrain_set_window(sphe_terrain* t, int row0, int row1);
 int sphe_terrain_window_violations(sphe_terrain* t, long long* count);
+/* survivors of the exact contact cull in the last step, per Grid::collision path class (same cell / one axis / both axes) */
+int sphe_terrain_survivors(sphe_sim* s, int out[3]);
 int sphe_terrain_contacts(sphe_terrain* t, long long* total, int reset); /* particle-terrain contacts since the last reset */
 int sphe_sediment_total_fx(sphe_sim* s, long long* sum);        /* sum of carried sediment (owned particles), fixed point */
 int sphe_set_sediment_fx(sphe_sim* s, const int* sediment_by_id);

@@ -6,7 +6,7 @@ i=0
 for F in "${CFG[@]}"; do
   SPHE_NVCC_EXTRA="$F" python sph-erosion_b200/build.py > gpurun_out/abb/build_$i.log 2>&1 || tail -5 gpurun_out/abb/build_$i.log
   for W in ${WL:-c3}; do
-    timeout 600 python bench.py --workload $W --no-cpu-baseline --no-reference-gravity --no-parity-gate > gpurun_out/abb/bench_${W}_$i.json 2> gpurun_out/abb/bench_${W}_$i.err
+    timeout 600 python bench.py --workload $W --no-cpu-baseline --no-reference-gravity --no-parity-gate ${BARGS} > gpurun_out/abb/bench_${W}_$i.json 2> gpurun_out/abb/bench_${W}_$i.err
     python - <<PY
 import json
 try:

@@ -71,6 +71,7 @@ SYMBOLS = {
     "sphe_debug_neighbours": (_i, [_vp, _vp, _vp, _ll, C.POINTER(_ll)]),
     "sphe_debug_pair_lists": (_i, [_vp, _i, _vp, _vp]),
     "sphe_slab_column_histogram": (_i, [_vp, _i, _vp]),
+    "sphe_terrain_survivors": (_i, [_vp, _vp]),
     "sphe_write_positions_device": (_i, [_vp, _vp, _ll]),
     "sphe_slab_peer_setup_zones": (_i, [_vp, _i, _i, _i]),
     "sphe_slab_zone_sum": (_i, [_vp, _vp, _i, _ll, _ll, _i]),

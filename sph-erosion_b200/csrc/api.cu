@@ -1913,6 +1913,17 @@ int sphe_terrain_contacts(sphe_terrain* t, long long* total, int reset) {
     return SPHE_OK;
 }
 
+// Survivors of the contact cull in the last step, per Grid::collision path class (same cell / one axis / both axes).
+int sphe_terrain_survivors(sphe_sim* s, int out[3]) {
+    if (!s || !out) return fail(SPHE_ERR_ARG, "bad arguments");
+    out[0] = out[1] = out[2] = 0;
+    if (!s->surv_count) return SPHE_OK;
+    TRY(ensure_device(s));
+    CU(cudaMemcpyAsync(out, s->surv_count, 3 * sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    return SPHE_OK;
+}
+
 int sphe_sediment_total_fx(sphe_sim* s, long long* sum) {
     if (!s || !sum) return fail(SPHE_ERR_ARG, "bad arguments");
     TRY(ensure_device(s));

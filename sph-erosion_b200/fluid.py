@@ -113,6 +113,11 @@ class FluidSystemSPH:
                                             mk if per_kernel else None, C.byref(nl)))
         return ms.value, dict(zip(capi.K_NAMES, [float(x) for x in mk])), nl.value
 
+    def terrain_survivors(self):
+        out = (C.c_int * 3)()
+        capi.check(self._L.sphe_terrain_survivors(self._h, out))
+        return [int(x) for x in out]
+
     def sediment_total_fx(self):
         v = C.c_longlong(0)
         capi.check(self._L.sphe_sediment_total_fx(self._h, C.byref(v)))
