@@ -105,6 +105,11 @@ struct sphe_sim {
 
     long long ncells = 0, ncells_cap = 0;
     int *count = nullptr, *cell_start = nullptr, *cursor = nullptr, *tile_sum = nullptr;
+    // single-launch scan (decoupled look-back): status words of the tiles, the tile ticket, and the host's running counts
+    unsigned long long* scan_state = nullptr;
+    unsigned* scan_ticket = nullptr;
+    unsigned scan_ticket_base = 0, scan_epoch = 0;
+    bool scan_onepass = true;
     GridP G{};
     bool grid_user = false;
     float glo[3], ghi[3];
@@ -331,6 +336,9 @@ static int setup_grid(sphe_sim* s) {
         TRY(grow(&s->cell_start, 0, padded, s->st, false));
         TRY(grow(&s->cursor, 0, padded, s->st, false));
         TRY(grow(&s->tile_sum, 0, (size_t)scan_tiles_for(nc) + 1, s->st, false));
+        TRY(grow(&s->scan_state, 0, (size_t)scan_tiles_for(nc) + 1, s->st, false));
+        CU(cudaMemsetAsync(s->scan_state, 0, ((size_t)scan_tiles_for(nc) + 1) * sizeof(unsigned long long), s->st));   // epoch 0 = never valid
+        if (!s->scan_ticket) { CU(cudaMalloc(&s->scan_ticket, sizeof(unsigned))); CU(cudaMemsetAsync(s->scan_ticket, 0, sizeof(unsigned), s->st)); s->scan_ticket_base = 0; }
         s->ncells_cap = nc;
     }
     CU(cudaMemsetAsync(s->count, 0, ((size_t)nc + 1) * sizeof(int), s->st));
@@ -389,7 +397,19 @@ static int step_device(sphe_sim* s, sphe_terrain* t, int terrain_phases = 7) {
     const int* nd_in = !s->slab_on ? nullptr : (s->extent_pending ? s->d_n : (s->live_dev ? s->cell_start + s->ncells : nullptr));
     const int* nd = s->slab_on ? s->cell_start + s->ncells : nullptr;
     { Scope k(s, SPHE_K_HASH); launch_hash(s->st, n_in, nd_in, s->posA, s->slab_on ? s->idsA : nullptr, s->G, s->cell, s->count); }
-    { Scope k(s, SPHE_K_SCAN, 2); launch_scan(s->st, s->ncells, s->count, s->tile_sum, s->cell_start, s->cursor); }
+    if (s->scan_onepass) {
+        Scope k(s, SPHE_K_SCAN, 1);
+        const int ntiles = scan_tiles_for(s->ncells);
+        // epochs run 1 .. 2^30 - 1 and then start over after clearing the status words (one memset every ~10^9 steps)
+        if (++s->scan_epoch >= (1u << 30)) {
+            s->scan_epoch = 1;
+            CU(cudaMemsetAsync(s->scan_state, 0, ((size_t)scan_tiles_for(s->ncells_cap) + 1) * sizeof(unsigned long long), s->st));
+        }
+        launch_scan_onepass(s->st, s->ncells, s->count, s->cell_start, s->cursor, s->scan_state, s->scan_ticket, s->scan_ticket_base, s->scan_epoch);
+        s->scan_ticket_base += (unsigned)ntiles;    // wraps together with the device word
+    } else {
+        Scope k(s, SPHE_K_SCAN, 2); launch_scan(s->st, s->ncells, s->count, s->tile_sum, s->cell_start, s->cursor);
+    }
     { Scope k(s, SPHE_K_SCATTER); launch_scatter(s->st, n_in, nd_in, s->cell, s->idsA, s->cursor, s->tmp); }
     // sphe_step_host: the velocities are still arriving on the io stream.  Nothing before the force pass reads them, so the
     // reorder only records the permutation and they are gathered after the density pass (below), which hides their upload.
@@ -568,7 +588,7 @@ void sphe_destroy(sphe_sim* s) {
         cudaStreamSynchronize(s->st);
         void* ptrs[] = {s->posA, s->posB, s->posC, s->velA, s->velB, s->idsA, s->idsB, s->sedA, s->sedB, s->rho, s->cell,
                         s->cell_sorted, s->tmp, s->stage, s->slot_of_id, s->req_vertex, s->req_amount, s->surv, s->surv_count, s->nlist, s->ncount, s->count, s->cell_start, s->cursor, s->tile_sum,
-                        s->flush_buf, s->slab_counters, s->D.acc, s->D.fpress, s->D.fvisc, s->D.fgrav, s->D.fsurf, s->D.normal, s->D.neighb};
+                        s->flush_buf, s->slab_counters, s->scan_state, s->scan_ticket, s->nmask, s->zone_done, s->D.acc, s->D.fpress, s->D.fvisc, s->D.fgrav, s->D.fsurf, s->D.normal, s->D.neighb};
         for (void* p : ptrs) if (p) cudaFree(p);
         for (int k = 0; k < 2; k++) if (s->peer_mbox[k] && s->peer_ipc[k]) cudaIpcCloseMemHandle(s->peer_mbox[k]);
         if (s->mbox) cudaFree(s->mbox);

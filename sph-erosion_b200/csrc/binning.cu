@@ -164,6 +164,102 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(long long ncells, i
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) cell_start[ncells] = tile_base + total;   // number of live particles
 }
 
+// ---------------------------------------------------------------- the same scan in ONE launch (decoupled look-back)
+// Round 1 scanned in two launches (tile sums, then every block re-summed the tile sums before it): 17 us at 0.78M cells,
+// pure latency.  Here every tile publishes its aggregate, looks back over its predecessors' status words a warp at a time
+// until it meets one that already knows its inclusive prefix, and publishes its own (Merrill & Garland).  Status words carry
+// the launch's epoch, so nothing has to be cleared between steps; tiles are handed out by a ticket so a tile's predecessors
+// always run no later than it does.
+//   word = epoch << 34 | status << 32 | value;  status 1 = aggregate of the tile, 2 = inclusive prefix up to the tile
+__device__ __forceinline__ unsigned long long scan_pack(unsigned epoch, unsigned status, int value) {
+    return ((unsigned long long)epoch << 34) | ((unsigned long long)status << 32) | (unsigned)value;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_onepass(long long ncells, int* __restrict__ count, int* __restrict__ cell_start,
+                                                               int* __restrict__ cursor, volatile unsigned long long* state,
+                                                               unsigned* __restrict__ ticket, unsigned ticket_base, unsigned epoch) {
+    __shared__ int s_tile, s_prefix;
+    if (threadIdx.x == 0) s_tile = (int)(atomicAdd(ticket, 1u) - ticket_base);
+    __syncthreads();
+    const int tile = s_tile;
+    const long long e0 = (long long)tile * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int s = 0;
+    if (e0 + SCAN_ITEMS <= ncells) {
+        const int4* c4 = reinterpret_cast<const int4*>(count + e0);
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS / 4; k++) {
+            int4 t = c4[k];
+            v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) v[k] = (e0 + k < ncells) ? count[e0 + k] : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) s += v[k];
+    int total;
+    const int inc = block_incl_scan(s, &total);
+    if (threadIdx.x < 32) {
+        const unsigned lane = threadIdx.x;
+        if (tile == 0) {
+            if (lane == 0) { state[0] = scan_pack(epoch, 2u, total); s_prefix = 0; }
+        } else {
+            if (lane == 0) { state[tile] = scan_pack(epoch, 1u, total); __threadfence(); }
+            // warp-wide look-back: lane l inspects tile (p - l); stop at the nearest tile that has its inclusive prefix
+            int run = 0;
+            for (int p = tile - 1;;) {
+                const int q = p - (int)lane;
+                unsigned long long w = 0;
+                unsigned st = 3u;                                  // 3 = before the first tile: contributes nothing, ends the walk
+                if (q >= 0) {
+                    w = state[q];
+                    st = ((unsigned)(w >> 34) == epoch) ? (unsigned)((w >> 32) & 3u) : 0u;
+                }
+                const unsigned invalid = __ballot_sync(SPHE_FULL, st == 0u);
+                const unsigned done = __ballot_sync(SPHE_FULL, st >= 2u);
+                // usable lanes: those nearer than the first invalid one
+                const unsigned first_invalid = invalid ? (unsigned)(__ffs((int)invalid) - 1) : 32u;
+                const unsigned first_done = done ? (unsigned)(__ffs((int)done) - 1) : 32u;
+                if (first_done < first_invalid) {
+                    // sum lanes 0 .. first_done (inclusive; a "before the first tile" lane adds 0)
+                    const int c = (lane <= first_done && st != 3u) ? (int)(unsigned)w : 0;
+                    run += __reduce_add_sync(SPHE_FULL, c);
+                    break;
+                }
+                if (first_invalid == 32u) {   // 32 aggregates, none with a prefix yet: take them all and look further back
+                    run += __reduce_add_sync(SPHE_FULL, (int)(unsigned)w);
+                    p -= 32;
+                }
+                // else: a predecessor has not published yet -> look again
+            }
+            if (lane == 0) { s_prefix = run; __threadfence(); state[tile] = scan_pack(epoch, 2u, run + total); }
+        }
+    }
+    __syncthreads();
+    const int tile_base = s_prefix;
+    int run = tile_base + inc - s;
+    if (e0 + SCAN_ITEMS <= ncells) {
+        int o[SCAN_ITEMS];
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) { o[k] = run; run += v[k]; }
+        int4* s4 = reinterpret_cast<int4*>(cell_start + e0);
+        int4* u4 = reinterpret_cast<int4*>(cursor + e0);
+        int4* z4 = reinterpret_cast<int4*>(count + e0);
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS / 4; k++) {
+            int4 t = make_int4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+            s4[k] = t; u4[k] = t; z4[k] = make_int4(0, 0, 0, 0);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            if (e0 + k < ncells) { cell_start[e0 + k] = run; cursor[e0 + k] = run; count[e0 + k] = 0; run += v[k]; }
+        }
+    }
+    if (tile == (int)gridDim.x - 1 && threadIdx.x == 0) cell_start[ncells] = tile_base + total;   // number of live particles
+}
+
 // ---------------------------------------------------------------- counting-sort scatter
 // slot = cursor[cell]++ (run-aggregated).  The order INSIDE a cell is whatever the atomics give;
 // k_rank_reorder makes it canonical.
@@ -227,6 +323,13 @@ void launch_hash(cudaStream_t st, int n, const int* n_dev, const float4* posq, c
 }
 
 int scan_tiles_for(long long ncells) { return (int)((ncells + SCAN_TILE - 1) / SCAN_TILE); }
+
+// state: ntiles 64-bit status words (any contents with an older epoch); ticket: one word, monotonically increasing
+void launch_scan_onepass(cudaStream_t st, long long ncells, int* count, int* cell_start, int* cursor, unsigned long long* state,
+                         unsigned* ticket, unsigned ticket_base, unsigned epoch) {
+    int ntiles = scan_tiles_for(ncells);
+    k_scan_onepass<<<ntiles, SCAN_THREADS, 0, st>>>(ncells, count, cell_start, cursor, state, ticket, ticket_base, epoch);
+}
 
 void launch_scan(cudaStream_t st, long long ncells, int* count, int* tile_sum, int* cell_start, int* cursor) {
     int ntiles = scan_tiles_for(ncells);

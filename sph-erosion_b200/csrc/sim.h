@@ -13,6 +13,8 @@ namespace sphe {
 // ids != NULL (slab mode): entries with id == -1 are dead (dropped by the exchange): no cell, not counted, not scattered
 void launch_hash(cudaStream_t st, int n, const int* n_dev, const float4* posq, const int* ids, const GridP& G, uint32_t* cell, int* count);
 int scan_tiles_for(long long ncells);
+void launch_scan_onepass(cudaStream_t st, long long ncells, int* count, int* cell_start, int* cursor, unsigned long long* state,
+                         unsigned* ticket, unsigned ticket_base, unsigned epoch);
 // cell_start[ncells] = number of LIVE particles (the sum of the counts): the count every later kernel of the step works on
 void launch_scan(cudaStream_t st, long long ncells, int* count, int* tile_sum, int* cell_start, int* cursor);
 void launch_scatter(cudaStream_t st, int n, const int* n_dev, const uint32_t* cell, const int* ids, int* cursor, uint2* tmp);
