@@ -41,8 +41,12 @@ __global__ void __launch_bounds__(256) k_hash(int n_hi, const int* __restrict__ 
 // ---------------------------------------------------------------- exclusive scan over cells
 // Reduce-then-scan in two launches: per-tile sums, then per-tile scan (each block sums the tile sums before it).
 // The final pass also primes the scatter cursor and clears the counts for the next step.
-constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 16;
+#ifndef SCAN_THREADS_
+#define SCAN_THREADS_ 256
+#define SCAN_ITEMS_ 16
+#endif
+constexpr int SCAN_THREADS = SCAN_THREADS_;
+constexpr int SCAN_ITEMS = SCAN_ITEMS_;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 __device__ __forceinline__ int warp_incl_scan(int v) {
@@ -263,27 +267,47 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_onepass(long long ncells,
 // ---------------------------------------------------------------- counting-sort scatter
 // slot = cursor[cell]++ (run-aggregated).  The order INSIDE a cell is whatever the atomics give;
 // k_rank_reorder makes it canonical.
+#ifndef SCATTER_ROUNDS
+#define SCATTER_ROUNDS 4
+#endif
+// A block takes SCATTER_ROUNDS x 256 consecutive particles, one round per 256: the loads of all rounds are issued first
+// and the cursor atomics of all rounds are in flight together (the atomic's return is the kernel's critical path:
+// ncu long_scoreboard 45 warps per issue with one particle per thread).
 __global__ void __launch_bounds__(256) k_scatter(int n_hi, const int* __restrict__ n_dev, const uint32_t* __restrict__ cell, const int* __restrict__ ids,
                                                  int* __restrict__ cursor, uint2* __restrict__ tmp) {
     const int n = n_dev ? __ldg(n_dev) : n_hi;  // exact count from the device in slab mode, else the launch bound
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned lane = threadIdx.x & 31;
-    uint32_t c = (i < n) ? cell[i] : 0xffffffffu;
-    uint32_t prev = __shfl_up_sync(SPHE_FULL, c, 1);
-    bool head = (lane == 0) || (c != prev);
-    unsigned heads = __ballot_sync(SPHE_FULL, head);
-    // lane of my run's head = highest head bit at or below my lane
-    unsigned below = heads & ((2u << lane) - 1u);
-    if (lane == 31) below = heads;
-    int hl = 31 - __clz(below);
-    int base = 0;
-    if (head && c != 0xffffffffu) {
-        unsigned above = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
-        int next = above ? (__ffs(above) - 1) : 32;
-        base = atomicAdd(&cursor[c], next - (int)lane);
+    const unsigned lane = threadIdx.x & 31;
+    const int i0 = blockIdx.x * (256 * SCATTER_ROUNDS) + threadIdx.x;
+    uint32_t c[SCATTER_ROUNDS];
+    int id[SCATTER_ROUNDS], hl[SCATTER_ROUNDS], base[SCATTER_ROUNDS];
+#pragma unroll
+    for (int r = 0; r < SCATTER_ROUNDS; r++) {
+        const int i = i0 + r * 256;
+        c[r] = (i < n) ? cell[i] : 0xffffffffu;
+        id[r] = (i < n) ? ids[i] : 0;
     }
-    base = __shfl_sync(SPHE_FULL, base, hl);
-    if (i < n && c != 0xffffffffu) tmp[base + ((int)lane - hl)] = make_uint2((uint32_t)ids[i], (uint32_t)i);
+#pragma unroll
+    for (int r = 0; r < SCATTER_ROUNDS; r++) {
+        uint32_t prev = __shfl_up_sync(SPHE_FULL, c[r], 1);
+        bool head = (lane == 0) || (c[r] != prev);
+        unsigned heads = __ballot_sync(SPHE_FULL, head);
+        // lane of my run's head = highest head bit at or below my lane
+        unsigned below = heads & ((2u << lane) - 1u);
+        if (lane == 31) below = heads;
+        hl[r] = 31 - __clz(below);
+        base[r] = 0;
+        if (head && c[r] != 0xffffffffu) {
+            unsigned above = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
+            int next = above ? (__ffs(above) - 1) : 32;
+            base[r] = atomicAdd(&cursor[c[r]], next - (int)lane);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < SCATTER_ROUNDS; r++) {
+        const int i = i0 + r * 256;
+        const int b = __shfl_sync(SPHE_FULL, base[r], hl[r]);
+        if (i < n && c[r] != 0xffffffffu) tmp[b + ((int)lane - hl[r])] = make_uint2((uint32_t)id[r], (uint32_t)i);
+    }
 }
 
 // ---------------------------------------------------------------- rank inside the cell + reorder
@@ -339,7 +363,7 @@ void launch_scan(cudaStream_t st, long long ncells, int* count, int* tile_sum, i
 
 void launch_scatter(cudaStream_t st, int n, const int* n_dev, const uint32_t* cell, const int* ids, int* cursor, uint2* tmp) {
     if (n <= 0) return;
-    k_scatter<<<(n + 255) / 256, 256, 0, st>>>(n, n_dev, cell, ids, cursor, tmp);
+    k_scatter<<<(n + 256 * SCATTER_ROUNDS - 1) / (256 * SCATTER_ROUNDS), 256, 0, st>>>(n, n_dev, cell, ids, cursor, tmp);
 }
 
 void launch_rank_reorder(cudaStream_t st, int n, const int* n_dev, const uint2* tmp, const uint32_t* cell, const int* cell_start,
