@@ -410,13 +410,13 @@ static int step_device(sphe_sim* s, sphe_terrain* t, int terrain_phases = 7) {
     } else {
         Scope k(s, SPHE_K_SCAN, 2); launch_scan(s->st, s->ncells, s->count, s->tile_sum, s->cell_start, s->cursor);
     }
-    { Scope k(s, SPHE_K_SCATTER); launch_scatter(s->st, n_in, nd_in, s->cell, s->idsA, s->cursor, s->tmp); }
+    { Scope k(s, SPHE_K_SCATTER); launch_scatter(s->st, n_in, nd_in, s->cell, s->idsA, s->cursor, s->tmp, s->cell_sorted); }
     // sphe_step_host: the velocities are still arriving on the io stream.  Nothing before the force pass reads them, so the
     // reorder only records the permutation and they are gathered after the density pass (below), which hides their upload.
     int* const late_vel = s->io.wait_vel ? s->slot_of_id : nullptr;
     { Scope k(s, SPHE_K_REORDER);
-      launch_rank_reorder(s->st, n, nd, s->tmp, s->cell, s->cell_start, s->posA, s->velA, s->sedA, s->posB, s->velB, s->sedB,
-                          s->idsB, s->cell_sorted, late_vel); }
+      launch_rank_reorder(s->st, n, nd, s->tmp, s->cell_sorted, s->cell_start, s->posA, s->velA, s->sedA, s->posB, s->velB, s->sedB,
+                          s->idsB, late_vel); }
     const int vd = s->variant_density, vf = s->variant_force;
     if (vf == 20 && vd != 20) return fail(SPHE_ERR_ARG, "force variant 20 reads the masks of density variant 20");
     s->masks_valid = false; s->lists_valid = false;

@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_onepass(long long ncells,
 // and the cursor atomics of all rounds are in flight together (the atomic's return is the kernel's critical path:
 // ncu long_scoreboard 45 warps per issue with one particle per thread).
 __global__ void __launch_bounds__(256) k_scatter(int n_hi, const int* __restrict__ n_dev, const uint32_t* __restrict__ cell, const int* __restrict__ ids,
-                                                 int* __restrict__ cursor, uint2* __restrict__ tmp) {
+                                                 int* __restrict__ cursor, uint2* __restrict__ tmp, uint32_t* __restrict__ cell_sorted) {
     const int n = n_dev ? __ldg(n_dev) : n_hi;  // exact count from the device in slab mode, else the launch bound
     const unsigned lane = threadIdx.x & 31;
     const int i0 = blockIdx.x * (256 * SCATTER_ROUNDS) + threadIdx.x;
@@ -306,38 +306,48 @@ __global__ void __launch_bounds__(256) k_scatter(int n_hi, const int* __restrict
     for (int r = 0; r < SCATTER_ROUNDS; r++) {
         const int i = i0 + r * 256;
         const int b = __shfl_sync(SPHE_FULL, base[r], hl[r]);
-        if (i < n && c[r] != 0xffffffffu) tmp[b + ((int)lane - hl[r])] = make_uint2((uint32_t)id[r], (uint32_t)i);
+        // every slot of a cell's range holds that cell's id, whatever the final in-cell order: the sorted cell ids are final here
+        if (i < n && c[r] != 0xffffffffu) {
+            const int slot = b + ((int)lane - hl[r]);
+            tmp[slot] = make_uint2((uint32_t)id[r], (uint32_t)i);
+            cell_sorted[slot] = c[r];
+        }
     }
 }
 
 // ---------------------------------------------------------------- rank inside the cell + reorder
 // One thread per scattered slot.  rank = number of particles of the same cell with a smaller id;
 // destination = cell_start + rank.  Then gather the particle's state from its old storage slot.
-__global__ void __launch_bounds__(256) k_rank_reorder(int n_hi, const int* __restrict__ n_dev, const uint2* __restrict__ tmp, const uint32_t* __restrict__ cell,
+__global__ void __launch_bounds__(256) k_rank_reorder(int n_hi, const int* __restrict__ n_dev, const uint2* __restrict__ tmp, const uint32_t* __restrict__ cell_sorted,
                                                       const int* __restrict__ cell_start,
                                                       const float4* __restrict__ posq_in, const float4* __restrict__ velv_in,
                                                       const float* __restrict__ sed_in,
                                                       float4* __restrict__ posq_out, float4* __restrict__ velv_out,
                                                       float* __restrict__ sed_out, int* __restrict__ ids_out,
-                                                      uint32_t* __restrict__ cell_sorted, int* __restrict__ src_of_slot) {
+                                                      int* __restrict__ src_of_slot) {
     const int n = n_dev ? __ldg(n_dev) : n_hi;  // exact count from the device in slab mode, else the launch bound
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    uint2 me = tmp[s];
-    uint32_t c = cell[me.y];
-    int a = cell_start[c], b = cell_start[c + 1];
+    // The chain of dependent loads is what this kernel waits on (ncu long_scoreboard 29 warps per issue): the cell id comes
+    // from the scatter (coalesced, no gather through the old slot) and the state gathers are issued before the ranking loop.
+    const uint2 me = tmp[s];
+    const uint32_t c = cell_sorted[s];
+    const float4 p = posq_in[me.y];
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!src_of_slot) v = velv_in[me.y];
+    float sd = 0.f;
+    if (sed_in) sd = sed_in[me.y];
+    const int a = cell_start[c], b = cell_start[c + 1];
     int rank = 0;
     for (int k = a; k < b; k++) rank += ((tmp[k].x & SPHE_ID_MASK) < (me.x & SPHE_ID_MASK)) ? 1 : 0;
-    int dst = a + rank;
-    float4 p = posq_in[me.y];
+    const int dst = a + rank;
     posq_out[dst] = p;
     // src_of_slot != NULL (sphe_step_host): the velocities are still on the PCIe bus; only the permutation is recorded
     // and k_gather_vel moves them after the density pass, which does not read them
     if (src_of_slot) src_of_slot[dst] = (int)me.y;
-    else velv_out[dst] = velv_in[me.y];
-    if (sed_in) sed_out[dst] = sed_in[me.y];
+    else velv_out[dst] = v;
+    if (sed_in) sed_out[dst] = sd;
     ids_out[dst] = (int)me.x;
-    cell_sorted[dst] = c;
 }
 
 // ---------------------------------------------------------------- launch wrappers
@@ -361,17 +371,17 @@ void launch_scan(cudaStream_t st, long long ncells, int* count, int* tile_sum, i
     k_scan_final<<<ntiles, SCAN_THREADS, 0, st>>>(ncells, count, tile_sum, cell_start, cursor);
 }
 
-void launch_scatter(cudaStream_t st, int n, const int* n_dev, const uint32_t* cell, const int* ids, int* cursor, uint2* tmp) {
+void launch_scatter(cudaStream_t st, int n, const int* n_dev, const uint32_t* cell, const int* ids, int* cursor, uint2* tmp, uint32_t* cell_sorted) {
     if (n <= 0) return;
-    k_scatter<<<(n + 256 * SCATTER_ROUNDS - 1) / (256 * SCATTER_ROUNDS), 256, 0, st>>>(n, n_dev, cell, ids, cursor, tmp);
+    k_scatter<<<(n + 256 * SCATTER_ROUNDS - 1) / (256 * SCATTER_ROUNDS), 256, 0, st>>>(n, n_dev, cell, ids, cursor, tmp, cell_sorted);
 }
 
-void launch_rank_reorder(cudaStream_t st, int n, const int* n_dev, const uint2* tmp, const uint32_t* cell, const int* cell_start,
+void launch_rank_reorder(cudaStream_t st, int n, const int* n_dev, const uint2* tmp, const uint32_t* cell_sorted, const int* cell_start,
                          const float4* posq_in, const float4* velv_in, const float* sed_in,
-                         float4* posq_out, float4* velv_out, float* sed_out, int* ids_out, uint32_t* cell_sorted, int* src_of_slot) {
+                         float4* posq_out, float4* velv_out, float* sed_out, int* ids_out, int* src_of_slot) {
     if (n <= 0) return;
-    k_rank_reorder<<<(n + 255) / 256, 256, 0, st>>>(n, n_dev, tmp, cell, cell_start, posq_in, velv_in, sed_in,
-                                                    posq_out, velv_out, sed_out, ids_out, cell_sorted, src_of_slot);
+    k_rank_reorder<<<(n + 255) / 256, 256, 0, st>>>(n, n_dev, tmp, cell_sorted, cell_start, posq_in, velv_in, sed_in,
+                                                    posq_out, velv_out, sed_out, ids_out, src_of_slot);
 }
 
 // velocities into sorted order after the fact (see k_rank_reorder); .w = m/rho was written by the density pass and stays

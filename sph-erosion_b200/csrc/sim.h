@@ -17,10 +17,11 @@ void launch_scan_onepass(cudaStream_t st, long long ncells, int* count, int* cel
                          unsigned* ticket, unsigned ticket_base, unsigned epoch);
 // cell_start[ncells] = number of LIVE particles (the sum of the counts): the count every later kernel of the step works on
 void launch_scan(cudaStream_t st, long long ncells, int* count, int* tile_sum, int* cell_start, int* cursor);
-void launch_scatter(cudaStream_t st, int n, const int* n_dev, const uint32_t* cell, const int* ids, int* cursor, uint2* tmp);
-void launch_rank_reorder(cudaStream_t st, int n, const int* n_dev, const uint2* tmp, const uint32_t* cell, const int* cell_start,
+// also writes the FINAL sorted cell ids (every slot of a cell's range holds that cell's id)
+void launch_scatter(cudaStream_t st, int n, const int* n_dev, const uint32_t* cell, const int* ids, int* cursor, uint2* tmp, uint32_t* cell_sorted);
+void launch_rank_reorder(cudaStream_t st, int n, const int* n_dev, const uint2* tmp, const uint32_t* cell_sorted, const int* cell_start,
                          const float4* posq_in, const float4* velv_in, const float* sed_in,
-                         float4* posq_out, float4* velv_out, float* sed_out, int* ids_out, uint32_t* cell_sorted, int* src_of_slot = nullptr);
+                         float4* posq_out, float4* velv_out, float* sed_out, int* ids_out, int* src_of_slot = nullptr);
 void launch_gather_vel(cudaStream_t st, int n, const int* src_of_slot, const float4* velv_in, float4* velv_out);
 
 // ---- terrain.cu
