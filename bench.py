@@ -566,6 +566,9 @@ def run_gpu_arm(args):
                                      % (args.steps, 100.0 * (ms_instrumented / ms - 1.0)),
                 "per_kernel_ms_per_step": {k: v / args.steps for k, v in per_kernel.items()},
                 "per_kernel_hbm_frac": frac_of(ALGO_BYTES),
+                "per_kernel_hbm_frac_note": "SURVEY 8(d) bytes / live time / peak; a value above 1 (scatter) means this implementation moves "
+                                            "fewer bytes than the SURVEY's per-particle figure assumes, not that HBM ran above its peak",
+                "per_kernel_traffic": {k: ncu_traffic(k, args.workload) for k in per_kernel if ncu_traffic(k, args.workload)},
                 "layout": {"what": "the same with the bytes this implementation's arrays make compulsory (DESIGN.md section 3), labelled, not the official figure",
                            "bytes_per_particle": LAYOUT_BYTES, "per_kernel_hbm_frac": frac_of(LAYOUT_BYTES)}}
     # secondary figure: the bytes the neighbour passes GATHER -- candidates x 16 B per pass -- served by
