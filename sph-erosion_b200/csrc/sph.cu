@@ -154,6 +154,17 @@ constexpr float LIST_NEG_EPS = -9.5367431640625e-07f;
 // CTAs, 14 CTAs/SM = 28 warps at 71 registers and 14.6 KB of shared memory per CTA.  The pass is issue/latency bound: with
 // the 64-entry stage of round 1 (33 KB per 128-thread CTA, 80 registers) 24 warps fit -- c3 density pass 0.644 -> 0.616 ms;
 // 48 entries at 16 CTAs/SM spill too often (0.657 ms).  A/B: SPHE_NVCC_EXTRA="-DDL_CAP=.. -DDL_THREADS=.. -DDL_MINB=.."
+#ifndef DL_LD256
+#define DL_LD256 1
+#endif
+struct __align__(32) F8 { float4 a, b; };
+// ld.global.nc.v8.f32 (LDG.E.256.CONSTANT on sm_100a): p must be 32-byte aligned
+__device__ __forceinline__ F8 ldg256(const float4* p) {
+    F8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
+    return r;
+}
 #ifndef DL_CAP
 #define DL_CAP 56
 #define DL_THREADS 64
@@ -272,6 +283,29 @@ __global__ void __launch_bounds__(THREADS, CAP == DL_CAP ? DL_MINB : (CAP >= 256
                 bounds(r + 1, sn, en);   // next run's bounds in flight (r + 1 == 9 yields an empty range)
                 const int off_run = OFF();
                 int k = s;
+#if DL_LD256
+                // 256-bit candidate loads: two consecutive candidates (32 B, k even) per request.  The pass keeps the L1 data
+                // pipe 75 % busy with ~5.6 wavefronts per 128-bit request (the lanes of a warp walk runs staggered by their
+                // cells); a request costs its wavefronts whatever its width, so half the requests is half the wavefronts.
+                // Same candidates in the same order: lists and sums are bit-identical to the 128-bit path.
+                if ((k & 1) && k < e) { test(k, __ldg(&posq[k])); k++; }
+                if (k + 4 <= e) {
+                    F8 q01 = ldg256(&posq[k]), q23 = ldg256(&posq[k + 2]);
+#pragma unroll 1
+                    for (; k + 8 <= e; k += 4) {
+                        const F8 n01 = ldg256(&posq[k + 4]), n23 = ldg256(&posq[k + 6]);
+                        test(k, q01.a); test(k + 1, q01.b); test(k + 2, q23.a); test(k + 3, q23.b);
+                        q01 = n01; q23 = n23;
+                    }
+                    test(k, q01.a); test(k + 1, q01.b); test(k + 2, q23.a); test(k + 3, q23.b);
+                    k += 4;
+                }
+                if (k + 2 <= e) {
+                    const F8 q = ldg256(&posq[k]);
+                    test(k, q.a); test(k + 1, q.b);
+                    k += 2;
+                }
+#else
                 if (k + 4 <= e) {
                     // (a ping-pong version without the register rotation needs 88 registers -> 5 CTAs/SM: no faster, measured)
                     float4 q0 = __ldg(&posq[k]), q1 = __ldg(&posq[k + 1]), q2 = __ldg(&posq[k + 2]), q3 = __ldg(&posq[k + 3]);
@@ -284,6 +318,7 @@ __global__ void __launch_bounds__(THREADS, CAP == DL_CAP ? DL_MINB : (CAP >= 256
                     test(k, q0); test(k + 1, q1); test(k + 2, q2); test(k + 3, q3);
                     k += 4;
                 }
+#endif
 #pragma unroll 1
                 for (; k < e; k++) test(k, __ldg(&posq[k]));
                 if (wp > cap_sa) spill(s, e, off_run / NLIST_THREADS);
