@@ -482,6 +482,26 @@ __global__ void __launch_bounds__(L16_THREADS) k_density_list16(int n_hi, const 
                 unsigned code = (unsigned)r << 12;
                 const int off_run = off;
                 int k = s;
+#if DL_LD256
+                // 256-bit candidate loads (see k_density_list)
+                if ((k & 1) && k < e) { test(code, __ldg(&posq[k])); k++; code++; }
+                if (k + 4 <= e) {
+                    F8 q01 = ldg256(&posq[k]), q23 = ldg256(&posq[k + 2]);
+#pragma unroll 1
+                    for (; k + 8 <= e; k += 4, code += 4) {
+                        const F8 n01 = ldg256(&posq[k + 4]), n23 = ldg256(&posq[k + 6]);
+                        test(code, q01.a); test(code + 1, q01.b); test(code + 2, q23.a); test(code + 3, q23.b);
+                        q01 = n01; q23 = n23;
+                    }
+                    test(code, q01.a); test(code + 1, q01.b); test(code + 2, q23.a); test(code + 3, q23.b);
+                    k += 4; code += 4;
+                }
+                if (k + 2 <= e) {
+                    const F8 q = ldg256(&posq[k]);
+                    test(code, q.a); test(code + 1, q.b);
+                    k += 2; code += 2;
+                }
+#else
                 if (k + 4 <= e) {
                     float4 q0 = __ldg(&posq[k]), q1 = __ldg(&posq[k + 1]), q2 = __ldg(&posq[k + 2]), q3 = __ldg(&posq[k + 3]);
 #pragma unroll 1
@@ -493,6 +513,7 @@ __global__ void __launch_bounds__(L16_THREADS) k_density_list16(int n_hi, const 
                     test(code, q0); test(code + 1, q1); test(code + 2, q2); test(code + 3, q3);
                     k += 4; code += 4;
                 }
+#endif
 #pragma unroll 1
                 for (; k < e; k++, code++) test(code, __ldg(&posq[k]));
                 if (off > L16_CAP * T) spill(s, e, off_run / T);
