@@ -302,6 +302,12 @@ int sphe_terrain_total_fx_rows(sphe_terrain* t, int row0, int row1, long long* s
  * reads or writes within 2 rows of an interior window edge is counted: window_violations must stay 0. */
 int sphe_terrain_set_window(sphe_terrain* t, int row0, int row1);
 int sphe_terrain_window_violations(sphe_terrain* t, long long* count);
+/* Moving a window (the slabs were re-cut): a replica is current only inside its window, so the caller first brings every
+ * row up to date from its owner -- heights_device is the DEVICE array of fixed-point heights (rows*cols int32) the ranks
+ * sum their owned rows into (slabs.py TerrainWindowShare.recut) -- then sets the new window and calls refresh, which
+ * rebuilds the derived cull map over it.  Between two steps only. */
+int sphe_terrain_heights_device(sphe_terrain* t, void** hfx, long long* cells);
+int sphe_terrain_refresh(sphe_terrain* t);
 /* survivors of the exact contact cull in the last step, per Grid::collision path class (same cell / one axis / both axes) */
 int sphe_terrain_survivors(sphe_sim* s, int out[3]);
 int sphe_terrain_contacts(sphe_terrain* t, long long* total, int reset); /* particle-terrain contacts since the last reset */

@@ -132,6 +132,8 @@ SYMBOLS = {
     "sphe_save_state": (_i, [_vp, _vp, C.c_char_p]),
     "sphe_load_state": (_i, [_vp, _vp, C.c_char_p]),
     "sphe_terrain_accumulators": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_ll)]),
+    "sphe_terrain_heights_device": (_i, [_vp, C.POINTER(_vp), C.POINTER(_ll)]),
+    "sphe_terrain_refresh": (_i, [_vp]),
 }
 
 _lib = None

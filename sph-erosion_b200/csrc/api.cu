@@ -1891,6 +1891,23 @@ int sphe_terrain_accumulators(sphe_terrain* t, void** want, void** delta, long l
     return SPHE_OK;
 }
 
+int sphe_terrain_heights_device(sphe_terrain* t, void** hfx, long long* cells) {
+    if (!t || !hfx) return fail(SPHE_ERR_ARG, "bad arguments");
+    TRY(terrain_ready(t));
+    *hfx = t->hfx;
+    if (cells) *cells = (long long)t->rows * t->cols;
+    return SPHE_OK;
+}
+
+int sphe_terrain_refresh(sphe_terrain* t) {
+    if (!t) return fail(SPHE_ERR_ARG, "NULL terrain");
+    TRY(terrain_ready(t));
+    CU(cudaDeviceSynchronize());
+    launch_terrain_lmax(0, terrain_view(t));
+    CU(cudaDeviceSynchronize());
+    return SPHE_OK;
+}
+
 int sphe_terrain_total_fx_rows(sphe_terrain* t, int row0, int row1, long long* sum) {
     if (!t || !sum) return fail(SPHE_ERR_ARG, "bad arguments");
     TRY(terrain_ready(t));

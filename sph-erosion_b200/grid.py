@@ -108,6 +108,17 @@ class Grid:
         capi.check(self._L.sphe_terrain_accumulators(self._t, C.byref(w), C.byref(d), C.byref(n)))
         return w.value, d.value, n.value
 
+    def heights_device(self):
+        """(device address, length) of the fixed-point heights (int32): re-cuts of a slab-local terrain sum the owners'
+        rows into it (sphe_terrain_heights_device); call refresh() afterwards."""
+        h, n = C.c_void_p(0), C.c_longlong(0)
+        capi.check(self._L.sphe_terrain_heights_device(self._t, C.byref(h), C.byref(n)))
+        return h.value, n.value
+
+    def refresh(self):
+        """Rebuild the cull map over the current window after the heights were written from outside (sphe_terrain_refresh)."""
+        capi.check(self._L.sphe_terrain_refresh(self._t))
+
     def total_fx(self, rows=None):
         """Sum of the fixed-point heights (of the rows [rows[0], rows[1]) when given)."""
         v = C.c_longlong(0)

@@ -44,17 +44,19 @@ def partition_columns(gnx, world, boundaries_x=None, gmin_x=None, cell=None):
     return out
 
 
-def balanced_cuts(hist, world, old_cuts=None, max_shift=None):
+def balanced_cuts(hist, world, old_cuts=None, max_shift=None, min_width=None):
     """Column cuts that give every slab about the same number of particles ("slab boundaries by
     particle-count quantiles of cell-x, re-cut every K steps").  hist[c] = particles in global cell column c (summed
     over the ranks); returns world-1 ascending cut columns.  Every slab keeps at least 2*HALO columns; with old_cuts
     every cut stays HALO columns inside the span of its two old neighbours (one exchange moves data one slab over, halo
     included; a large imbalance converges over a few re-cuts) and, if given, moves by at
-    most max_shift columns."""
+    most max_shift columns.  min_width: columns every slab keeps (default 2*HALO; a shared terrain needs room for the two
+    boundary zones of a slab, TerrainWindowShare.min_columns)."""
     hist = np.asarray(hist, np.int64)
     gnx = hist.shape[0]
-    if gnx < world * 2 * HALO:
-        raise ValueError("%d columns cannot hold %d slabs of at least %d columns" % (gnx, world, 2 * HALO))
+    mw = max(2 * HALO, int(min_width or 0))
+    if gnx < world * mw:
+        raise ValueError("%d columns cannot hold %d slabs of at least %d columns" % (gnx, world, mw))
     cum = np.concatenate([[0], np.cumsum(hist)])
     total = int(cum[-1])
     cuts = []
@@ -72,33 +74,33 @@ def balanced_cuts(hist, world, old_cuts=None, max_shift=None):
     # minimum widths, left to right then right to left
     lo = 0
     for i in range(world - 1):
-        cuts[i] = max(cuts[i], lo + 2 * HALO); lo = cuts[i]
+        cuts[i] = max(cuts[i], lo + mw); lo = cuts[i]
     hi = gnx
     for i in range(world - 2, -1, -1):
-        cuts[i] = min(cuts[i], hi - 2 * HALO); hi = cuts[i]
+        cuts[i] = min(cuts[i], hi - mw); hi = cuts[i]
     return cuts
 
 
-def rebalance(backend, dist_reduce, rank, world, cols, max_shift=None):
+def rebalance(backend, dist_reduce, rank, world, cols, max_shift=None, min_width=None):
     """Re-cuts the slabs by particle count.  backend: column_histogram(gnx) + reconfigure(x0, x1, far_x0);
     dist_reduce(array) sums an int64 numpy array over the ranks in place.  Call it BETWEEN steps with nothing in
     flight (after drain()); the next exchange migrates the particles that changed owner.  Returns the new column
-    ranges.  Not for runs that share a terrain (the row windows would have to move with the cuts)."""
+    ranges.  A run that shares a terrain moves its row windows afterwards (TerrainWindowShare.recut)."""
     gnx = cols[-1][1]
     hist = np.asarray(backend.column_histogram(gnx), np.int64)
     dist_reduce(hist)
-    cuts = balanced_cuts(hist, world, [c[0] for c in cols[1:]], max_shift)
+    cuts = balanced_cuts(hist, world, [c[0] for c in cols[1:]], max_shift, min_width)
     edges = [0] + cuts + [gnx]
     new_cols = [(edges[r], edges[r + 1]) for r in range(world)]
     backend.reconfigure(new_cols[rank][0], new_cols[rank][1], new_cols[-1][0])
     return new_cols
 
 
-def rebalance_local(backends, cols, max_shift=None):
+def rebalance_local(backends, cols, max_shift=None, min_width=None):
     """The same for K slabs driven by one process (LocalPeerGroup / tests): the histogram sum is a plain sum."""
     gnx = cols[-1][1]
     hist = sum(np.asarray(b.column_histogram(gnx), np.int64) for b in backends)
-    cuts = balanced_cuts(hist, len(backends), [c[0] for c in cols[1:]], max_shift)
+    cuts = balanced_cuts(hist, len(backends), [c[0] for c in cols[1:]], max_shift, min_width)
     edges = [0] + cuts + [gnx]
     new_cols = [(edges[r], edges[r + 1]) for r in range(len(backends))]
     for r, b in enumerate(backends):
@@ -384,19 +386,12 @@ class TerrainWindowShare:
     def __init__(self, grid, device, rank, world, cuts, margin, swap=None, dist=None, peer=False):
         w, d, n = grid.accumulators()
         rows, cols = grid.shape()
-        self.grid, self.rank, self.world = grid, rank, world
+        self.grid, self.rank, self.world, self.device = grid, rank, world, device
         self.want = device_int32_view(w, n, device)
         self.delta = device_int32_view(d, n, device)
-        self.own = (0 if rank == 0 else cuts[rank - 1], rows if rank == world - 1 else cuts[rank])
-        W = int(margin)
-        if world > 1 and min(b - a for a, b in zip([0] + list(cuts), list(cuts) + [rows])) < 2 * W:
-            raise ValueError("a slab covers fewer than %d terrain rows: the boundary zones of its two neighbours would overlap" % (2 * W))
-        self.window = (max(self.own[0] - W, 0), min(self.own[1] + W, rows))
-        grid.set_window(*self.window)
-        # the rows both this rank and a neighbour can touch: [cut - W, cut + W) around each interior boundary
-        self.zone_l = slice((self.own[0] - W) * cols, (self.own[0] + W) * cols) if rank > 0 else None
-        self.zone_r = slice((self.own[1] - W) * cols, (self.own[1] + W) * cols) if rank < world - 1 else None
-        self.zone_bytes = 2 * W * cols * 4
+        self.W = int(margin)
+        self._place(cuts)
+        self.zone_bytes = 2 * self.W * cols * 4
         self.swap = swap      # False: the caller sums the zones itself (LocalPeerGroup)
         # peer = True: the zones travel through the slab mailboxes (sphe_slab_zone_sum: remote stores over NVLink + device
         # flags, one launch per sum) instead of two NCCL P2P groups per step; PeerSlabDriver reserves the room
@@ -406,9 +401,75 @@ class TerrainWindowShare:
         elif swap is None:
             import torch
             self.dist = dist
-            self.buf_l = torch.empty(2 * W * cols, dtype=torch.int32, device=device) if rank > 0 else None
-            self.buf_r = torch.empty(2 * W * cols, dtype=torch.int32, device=device) if rank < world - 1 else None
+            self.buf_l = torch.empty(2 * self.W * cols, dtype=torch.int32, device=device) if rank > 0 else None
+            self.buf_r = torch.empty(2 * self.W * cols, dtype=torch.int32, device=device) if rank < world - 1 else None
             self.swap = self._swap_p2p
+
+    def _place(self, cuts):
+        """Owned rows, window and boundary zones for the cut rows `cuts` (world - 1 ascending rows)."""
+        rows, cols = self.grid.shape()
+        rank, world, W = self.rank, self.world, self.W
+        if world > 1 and min(b - a for a, b in zip([0] + list(cuts), list(cuts) + [rows])) < 2 * W:
+            raise ValueError("a slab covers fewer than %d terrain rows: the boundary zones of its two neighbours would overlap" % (2 * W))
+        self.cuts = [int(c) for c in cuts]
+        self.own = (0 if rank == 0 else self.cuts[rank - 1], rows if rank == world - 1 else self.cuts[rank])
+        self.window = (max(self.own[0] - W, 0), min(self.own[1] + W, rows))
+        self.grid.set_window(*self.window)
+        # the rows both this rank and a neighbour can touch: [cut - W, cut + W) around each interior boundary
+        self.zone_l = slice((self.own[0] - W) * cols, (self.own[0] + W) * cols) if rank > 0 else None
+        self.zone_r = slice((self.own[1] - W) * cols, (self.own[1] + W) * cols) if rank < world - 1 else None
+
+    def bind_columns(self, grid_info, origin_x, scale):
+        """Remember how neighbour-grid columns map to terrain rows, so a re-cut of the slabs can move the windows."""
+        self._map = (grid_info, float(origin_x), float(scale))
+        return self
+
+    def rows_of(self, cols):
+        gi, ox, sc = self._map
+        return terrain_row_cuts(gi, cols, ox, sc)
+
+    def min_columns(self):
+        """Neighbour-grid columns a slab must keep so that it covers its two boundary zones (2 W rows) with room to spare."""
+        gi, ox, sc = self._map
+        return int(np.ceil((2 * self.W + 2) * sc / gi.cell)) + 1
+
+    # Re-cut (between two steps, nothing in flight).  A rank's replica is current only inside its window, so before the
+    # windows move every row is brought up to date from its OWNER: each rank contributes its owned rows, zero elsewhere,
+    # and the integer sum over the ranks is the whole current heightfield (rare: once per re-cut, 4 bytes per vertex).
+    def recut_owned_rows(self):
+        """This rank's contribution to the sum: its heights on the rows it owns, 0 elsewhere (a new device tensor)."""
+        rows, cols = self.grid.shape()
+        h = device_int32_view(self.grid.heights_device()[0], rows * cols, self.device)
+        out = h.clone()
+        out[:self.own[0] * cols] = 0
+        out[self.own[1] * cols:] = 0
+        return out
+
+    def recut_install(self, full, cuts):
+        """full = the sum of every rank's recut_owned_rows(); installs it, moves the window to `cuts` and rebuilds the cull map."""
+        rows, cols = self.grid.shape()
+        h = device_int32_view(self.grid.heights_device()[0], rows * cols, self.device)
+        h.copy_(full)
+        self._place(cuts)
+        self.grid.refresh()
+
+    def recut(self, cuts, reduce):
+        """reduce(tensor): in-place sum over the ranks (dist.all_reduce)."""
+        import torch
+        t = self.recut_owned_rows()
+        reduce(t)
+        torch.cuda.synchronize()
+        self.recut_install(t, cuts)
+
+    @staticmethod
+    def recut_local(shares, cuts):
+        """The same for K replicas driven by one process (LocalPeerGroup / tests)."""
+        parts = [sh.recut_owned_rows() for sh in shares]
+        full = parts[0]
+        for p in parts[1:]:
+            full = full + p
+        for sh in shares:
+            sh.recut_install(full, cuts)
 
     def _swap_p2p(self, arr, zl, zr):
         d, P = self.dist, self.dist.P2POp
@@ -495,18 +556,24 @@ class PeerSlabDriver:
 
     def rebalance(self, dist, cols, backend, max_shift=None):
         """Re-cut the slabs by particle count (slabs.rebalance) between two steps; every rank calls it.  backend: the
-        GpuSlabBackend make_gpu_slab returned for this sim.  Returns the new column ranges."""
+        GpuSlabBackend make_gpu_slab returned for this sim.  With a slab-local terrain (TerrainWindowShare bound to the
+        columns with bind_columns) the row windows move with the cuts.  Returns the new column ranges."""
         import torch
-        if self.terrain is not None:
-            raise RuntimeError("re-cutting is not available for runs that share a terrain (the row windows would have to move)")
+        t = self.terrain
+        if t is not None and not hasattr(t, "_map"):
+            raise RuntimeError("re-cutting a run that shares a terrain needs TerrainWindowShare.bind_columns(grid_info, origin_x, scale)")
         self.drain()
+        on_gpu = dist.get_backend() == "nccl"
 
         def reduce(hist):
-            t = torch.from_numpy(hist).to(torch.device("cuda", torch.cuda.current_device())) if dist.get_backend() == "nccl" else torch.from_numpy(hist)
-            dist.all_reduce(t)
-            hist[:] = t.cpu().numpy()
+            x = torch.from_numpy(hist).to(torch.device("cuda", torch.cuda.current_device())) if on_gpu else torch.from_numpy(hist)
+            dist.all_reduce(x)
+            hist[:] = x.cpu().numpy()
 
-        return rebalance(backend, reduce, self.rank, self.world, cols, max_shift)
+        new_cols = rebalance(backend, reduce, self.rank, self.world, cols, max_shift, t.min_columns() if t is not None else None)
+        if t is not None:
+            t.recut(t.rows_of(new_cols), lambda x: dist.all_reduce(x))
+        return new_cols
 
 
 class LocalPeerGroup:
@@ -748,6 +815,7 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT, terrain=False):
             cuts = terrain_row_cuts(sim.grid_info(), cols, tinfo["terrain_origin"][0], tinfo["terrain_cell"])
             tshare = TerrainWindowShare(grid, dev, rank, world, cuts, terrain_margin_rows(sim.grid_info().cell, tinfo["terrain_cell"]), dist=dist,
                                         peer=(args.exchange == "peer" and getattr(args, "zone_sums", "peer") == "peer"))
+            tshare.bind_columns(sim.grid_info(), tinfo["terrain_origin"][0], tinfo["terrain_cell"])
         else:
             tshare = TerrainShare(grid, dev, lambda t: dist.all_reduce(t))
     if args.exchange == "peer":
@@ -787,13 +855,17 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT, terrain=False):
         dist.all_reduce(t)
         return int(t.item())
 
+    # re-cuts by particle count: plain slabs, or slabs with a slab-local terrain (the row windows move with the cuts)
+    recut = getattr(args, "rebalance_every", 0) if args.exchange == "peer" and (not terrain or args.terrain_share == "window") else 0
+    recuts = 0
     if grid is not None:
         tot0 = terrain_total() + sediment_all()
-        for _ in range(args.settle):
+        for k in range(args.settle):
+            if recut and k and k % recut == 0:
+                cols = drv.rebalance(dist, cols, backend); recuts += 1
             drv.step()
         drv.drain()
         tinfo["settle_steps"] = args.settle
-    recut = getattr(args, "rebalance_every", 0) if args.exchange == "peer" and not terrain else 0
     for _ in range(args.warmup):
         drv.step()
     if grid is not None:
@@ -807,7 +879,7 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT, terrain=False):
     e0.record()
     for k in range(args.steps):
         if recut and k and k % recut == 0:
-            cols = drv.rebalance(dist, cols, backend)      # inside the timed region: its cost is part of the step budget
+            cols = drv.rebalance(dist, cols, backend); recuts += 1      # inside the timed region: its cost is part of the step budget
         drv.step()
     e1.record()
     sync_all()
@@ -909,6 +981,7 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT, terrain=False):
                        "records_forwarded_beyond_the_neighbour": int(owned[3].item()), "h": 0.0457, "spacing": SPACING, "dt": 0.01,
                        "box_half_extents": list(box), "gravity_y": gy, "slab_columns": cols,
                        "halo_records_per_step_all_ranks": int(owned[1].item()),
+                       "rebalance_every": recut, "recuts_done": recuts,
                        "exchange": exchange_desc, "exchange_mode": args.exchange,
                        "exchange_resends": getattr(drv, "resends", 0), "exchange_lag": args.slab_lag if args.exchange == "nccl" else None,
                        "l2": "working set per GPU (%.0f MB of particle arrays + neighbour lists) exceeds L2" % (n_local * 400 / 1e6),

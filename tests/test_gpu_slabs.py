@@ -186,6 +186,12 @@ def test_peer_recv_times_out_instead_of_hanging():
         sims[0].slab_result(t, True)
 
 
+def _local_top(hts, pos, cell):
+    rows, cols = hts.shape
+    ix = np.clip(((pos[:, 0] + 1.2) / cell).astype(int), 0, rows - 2); iz = np.clip(((pos[:, 2] + 0.3) / cell).astype(int), 0, cols - 2)
+    return np.maximum.reduce([hts[ix, iz], hts[ix + 1, iz], hts[ix, iz + 1], hts[ix + 1, iz + 1]])
+
+
 def _terrain_scene(m, n=30000, seed=5):
     """Particles raining on a rough 256 x 64 terrain strip that fills the floor of a (1.2, 0.3, 0.3) box."""
     rng = np.random.default_rng(seed)
@@ -364,3 +370,68 @@ def test_rebalance_on_the_gpu_keeps_results_bit_equal():
     for a, name in ((p, "pos"), (v, "vel"), (rho, "density")):
         assert np.array_equal(a, one.download(name)), name
     assert max(counts[0]) > 0.6 * n and max(counts[-1]) < 0.5 * n and min(counts[-1]) > 0.15 * n, counts
+
+
+def test_rebalance_with_slab_local_terrain_windows_keeps_results_bit_equal():
+    """Re-cuts with a shared eroding terrain (TerrainWindowShare.recut): an unbalanced rain on 3 equal-width slabs, each with
+    its own terrain replica and row window; before steps 3, 5 and 7 the slabs are re-cut by particle count, every row is
+    brought up to date from its owner, the windows move with the cuts and the cull maps are rebuilt.  Particle state,
+    carried sediment and every owned / window terrain row stay BIT-EQUAL to the single-handle run; conservation is exact."""
+    import torch
+    m = product()
+    slabs = importlib.import_module("sph-erosion_b200.slabs")
+    box = (1.2, 0.3, 0.3)
+    params = dict(len=0.3, dt=0.004, g=(0.0, -9.82, 0.0))
+    g1, pos, vel = _terrain_scene(m)
+    # squeeze the rain into the left 45 % of the strip (each particle keeps its height above the LOCAL surface)
+    hts = g1.heights()
+    cell_t = 2.4 / 256
+    above = pos[:, 1] - (-0.3 + _local_top(hts, pos, cell_t) * cell_t)
+    pos = pos.copy(); pos[:, 0] = (-1.15 + (pos[:, 0] + 1.15) * np.float32(0.45)).astype(np.float32)
+    pos[:, 1] = (-0.3 + _local_top(hts, pos, cell_t) * cell_t + above).astype(np.float32)
+    n = pos.shape[0]
+    one = _single(m, box, params, (6, 3), pos, vel)
+    total0 = g1.total_fx()
+    K, cap = 3, 1 << 15
+    sims, backs, replicas = [], [], []
+    for r in range(K):
+        sim, b, cols = slabs.make_gpu_slab(m, torch.cuda.current_device(), r, K, box, params, None, cap, (6, 3))
+        sims.append(sim); backs.append(b); replicas.append(_terrain_scene(m)[0])
+    gi = sims[0].grid_info()
+    cx = np.clip(np.floor((pos[:, 0] - np.float32(gi.gmin[0])) / np.float32(gi.cell)), 0, cols[-1][1] - 1).astype(np.int64)
+    owner = np.searchsorted([c[1] for c in cols], cx, side="right")
+    for r in range(K):
+        part = np.nonzero(owner == r)[0]
+        sims[r].slab_upload(pos[part], vel[part], part.astype(np.int32))
+    W = slabs.terrain_margin_rows(gi.cell, cell_t)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    shares = [slabs.TerrainWindowShare(replicas[r], dev, r, K, slabs.terrain_row_cuts(gi, cols, -1.2, cell_t), W, swap=False)
+              .bind_columns(gi, -1.2, cell_t) for r in range(K)]
+    group = slabs.LocalPeerGroup(sims, cap, n + 4 * cap, shares=shares)
+    counts, windows = [], [tuple(sh.window for sh in shares)]
+    for step in range(10):
+        if step in (3, 5, 7):
+            group.drain()
+            counts.append([s.slab_info()["n_owned"] for s in sims])
+            cols = slabs.rebalance_local(backs, cols, min_width=shares[0].min_columns())
+            slabs.TerrainWindowShare.recut_local(shares, shares[0].rows_of(cols))
+            windows.append(tuple(sh.window for sh in shares))
+        one.Run(g1)
+        group.step()
+    group.drain()
+    counts.append([s.slab_info()["n_owned"] for s in sims])
+    assert len(set(windows)) > 1, "the windows must have moved"
+    assert g1.contacts() > 1000 and sum(g.contacts() for g in replicas) == g1.contacts()
+    assert all(g.window_violations() == 0 for g in replicas)
+    want = g1.heights_fx()
+    assert not np.array_equal(want, _terrain_scene(m)[0].heights_fx()), "the terrain must have eroded"
+    for r, (g, sh) in enumerate(zip(replicas, shares)):
+        got = g.heights_fx()
+        assert np.array_equal(got[sh.window[0]:sh.window[1]], want[sh.window[0]:sh.window[1]]), "slab %d: window rows" % r
+    p, v, rho, sed = _gather(sims, n)
+    assert np.array_equal(p, one.download("pos")) and np.array_equal(v, one.download("vel"))
+    assert np.array_equal(rho, one.download("density"))
+    sed_k = sum(s.sediment_total_fx() for s in sims)
+    assert sed_k == one.sediment_total_fx() and sed_k > 0
+    assert sum(sh.own_total_fx() for sh in shares) + sed_k == total0, "sum(owned rows) + sum(carried sediment) is conserved exactly"
+    assert max(counts[-1]) < max(counts[0]), counts
