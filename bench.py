@@ -655,7 +655,7 @@ def main():
                     help="multi-GPU slab-local terrain: transport of the boundary-zone sums (peer = through the slab mailboxes, one launch per sum; nccl = P2P groups)")
     ap.add_argument("--terrain-share", default="window", choices=["window", "allreduce"],
                     help="multi-GPU terrain: window = slab-local rows + boundary-zone sums with the x-neighbours (default); allreduce = full replicas, 2 all-reduces per step")
-    ap.add_argument("--rebalance-every", type=int, default=0, help="multi-GPU, no terrain: re-cut the slabs by particle count every K steps (0 = never; the bench scenes are balanced by construction)")
+    ap.add_argument("--rebalance-every", type=int, default=0, help="multi-GPU: re-cut the slabs by particle count every K steps; a slab-local terrain moves its row windows with the cuts (0 = never; the bench scenes are balanced by construction)")
     ap.add_argument("--layout", default="auto", choices=["auto", "tiled", "contiguous"], help="multi-GPU scene layout (slabs.channel_block)")
     ap.add_argument("--slab-lag", type=int, default=2, help="multi-GPU: steps the host may run ahead (0 = one host sync per step)")
     ap.add_argument("--settle", type=int, default=150, help="untimed steps before warm-up when the workload has a terrain")
