@@ -239,6 +239,46 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+class near_gpu:
+    """Context manager: run the enclosed host code on the CPUs NVML names as local to GPU `index` (same NUMA node / PCIe root),
+    so pinned buffers allocated and first touched inside land in memory next to that GPU.  Restores the affinity on exit
+    (the CPU baselines use every core).  A no-op when NVML or sched_setaffinity is unavailable.  .cpus = what was set."""
+
+    def __init__(self, index):
+        self.index, self.old, self.cpus = index, None, None
+
+    def __enter__(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[self.index])
+                except (ValueError, IndexError):
+                    phys = self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+            old = os.sched_getaffinity(0)
+            cpus &= old
+            if cpus and cpus != old:
+                os.sched_setaffinity(0, cpus)
+                self.old, self.cpus = old, sorted(cpus)
+        except Exception:
+            self.old = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.old is not None:
+            try:
+                os.sched_setaffinity(0, self.old)
+            except OSError:
+                pass
+        return False
+
+
 def ncu_traffic(kernel, workload="c2"):
     """dram read+write bytes per launch of `kernel` on `workload` from the committed ncu summaries
     (profiles/ncu_traffic.json), or None when that kernel/workload pair has not been captured."""
@@ -525,9 +565,10 @@ def run_gpu_arm(args):
 
     # end to end: host (pinned) buffers in, host buffers out, every step, through sphe_step_host
     e2e_steps = max(3, min(args.steps, 20))
-    hp = torch.from_numpy(pos).pin_memory(); hv = torch.zeros_like(hp).pin_memory()
-    op = torch.empty_like(hp).pin_memory(); ov = torch.empty_like(hp).pin_memory()
-    orho = torch.empty(n, dtype=torch.float32).pin_memory()
+    with near_gpu(local) as numa:      # pinned buffers on the NUMA node next to the GPU
+        hp = torch.from_numpy(pos).pin_memory(); hv = torch.zeros_like(hp).pin_memory()
+        op = torch.zeros_like(hp).pin_memory(); ov = torch.zeros_like(hp).pin_memory()
+        orho = torch.zeros(n, dtype=torch.float32).pin_memory()
     sim2 = pkg.FluidSystemSPH(device=local)
     sim2.params.len = L; sim2.params.g[1] = gy; sim2.SetDeltaTime(0.01)
     sim2.set_variant(args.density_variant, args.force_variant)
@@ -544,7 +585,8 @@ def run_gpu_arm(args):
     e2e_dt = (time.perf_counter() - t) / e2e_steps
     e2e = {"value": n / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 28 * n,
            "ms_per_step": e2e_dt * 1e3, "steps": e2e_steps,
-           "api": "sphe_step_host (pinned host pos/vel in, pos/vel/density out, id order)"}
+           "api": "sphe_step_host (pinned host pos/vel in, pos/vel/density out, id order)",
+           "pinned_buffers": ("allocated from the %d CPUs NVML lists as local to the GPU" % len(numa.cpus)) if numa.cpus else "default placement"}
 
     peak, peak_src = measured_peak()
     dom = max(("density", "force", "terrain"), key=lambda k: per_kernel[k])

@@ -786,7 +786,7 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT, terrain=False):
     import time
     import torch
     import torch.distributed as dist
-    from bench import ClockSampler, measured_peak, scene_gravity, attach_terrain, emit, ALGO_BYTES, SPACING
+    from bench import ClockSampler, measured_peak, scene_gravity, attach_terrain, emit, near_gpu, ALGO_BYTES, SPACING
 
     rank, world = dist.get_rank(), dist.get_world_size()
     local = torch.cuda.current_device()
@@ -946,8 +946,9 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT, terrain=False):
     o_ids, o_pos, o_vel, o_rho, _ = sim.slab_download()
     m = o_ids.shape[0]
     capn = int(m * 1.25) + 1024
-    hp = torch.zeros((capn, 3), dtype=torch.float32).pin_memory(); hv = torch.zeros_like(hp).pin_memory()
-    hi = torch.zeros(capn, dtype=torch.int32).pin_memory(); hr = torch.zeros(capn, dtype=torch.float32).pin_memory()
+    with near_gpu(local) as numa:      # pinned buffers on the NUMA node next to this rank's GPU
+        hp = torch.zeros((capn, 3), dtype=torch.float32).pin_memory(); hv = torch.zeros_like(hp).pin_memory()
+        hi = torch.zeros(capn, dtype=torch.int32).pin_memory(); hr = torch.zeros(capn, dtype=torch.float32).pin_memory()
     hp[:m] = torch.from_numpy(o_pos); hv[:m] = torch.from_numpy(o_vel); hi[:m] = torch.from_numpy(o_ids)
     h2d = d2h = 0
     sync_all()
@@ -988,7 +989,8 @@ def bench_multi(args, pkg, n_axis, jitter, desc, METRIC, UNIT, terrain=False):
                        "density_variant": args.density_variant, "force_variant": args.force_variant, **tinfo},
             "e2e": {"value": n_total / float(e2e_dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(io[0].item()),
                     "d2h_bytes_per_step": int(io[1].item()), "ms_per_step": float(e2e_dt.item()) * 1e3, "steps": e2e_steps,
-                    "api": "sphe_slab_upload (pinned host) -> pack/exchange/append -> sphe_step -> sphe_slab_download (pinned host), per rank"},
+                    "api": "sphe_slab_upload (pinned host) -> pack/exchange/append -> sphe_step -> sphe_slab_download (pinned host), per rank",
+                    "pinned_buffers": ("allocated from the %d CPUs NVML lists as local to the rank's GPU" % len(numa.cpus)) if numa.cpus else "default placement"},
             "parity_sampled": gate[0] if gate else None, "parity_gate": gate[1] if gate else None,
             "gpu_launches": launches * world, "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_%s" % dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
