@@ -376,9 +376,10 @@ __global__ void __launch_bounds__(THREADS, CAP == DL_CAP ? DL_MINB : (CAP >= 256
 // occupancy of this pass (+30 %).  Here an entry is 16 bits -- run index (4 bits) | offset inside the run (12 bits) --
 // so 128 entries per pair fit the SAME 33 KB per CTA; the flush expands them to particle indices with the run starts
 // kept in shared memory (9 ints per thread).  A run longer than 4095 particles marks the pair as overflowed.
-constexpr int L16_CAP = 128, L16_THREADS = 128;
+constexpr int L16_CAP = 128, L16_THREADS = 128;   // the 128-entry level; the 256-entry level runs <256, 64>: 35 KB per CTA, 6 CTAs/SM
+// (32-bit entries need 66 KB for 256 x 64: 3 CTAs/SM = 6 warps, the density pass at 115 neighbours was occupancy starved)
 
-template <bool PF>
+template <bool PF, int L16_CAP = sphe::L16_CAP, int L16_THREADS = sphe::L16_THREADS>
 __global__ void __launch_bounds__(L16_THREADS) k_density_list16(int n_hi, const int* __restrict__ n_dev, int npairs_pad, const float4* __restrict__ posq,
                                                                 float4* __restrict__ posq_q, float4* __restrict__ velv,
                                                                 const uint32_t* __restrict__ cell_sorted,
@@ -905,7 +906,11 @@ void launch_density(cudaStream_t st, int variant, int n, const int* n_dev, const
         // cap = rows allocated per pair.  The shared-memory part stays at 64 entries (occupancy), longer lists spill; only
         // when MOST pairs spill (smem_cap, chosen by the host from the spill statistics) the wide-shared-memory
         // instantiations take over (explicit prefetch: ptxas serialises the gathers of those otherwise, 48 registers)
+#ifdef SPHE_DL256_32BIT
         if (smem_cap > 128) SPHE_DL(false, true, 256, 64);
+#else
+        if (smem_cap > 128) k_density_list16<true, 256, 64><<<pp / 64, 64, 0, st>>>(n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount, overflow, cap);
+#endif
         else if (smem_cap > 64) {   // 128 staged entries: the 16-bit kernel holds them in the same 33 KB (6 CTAs/SM)
             if (variant == 6) k_density_list16<true><<<pp / L16_THREADS, L16_THREADS, 0, st>>>(n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount, overflow, cap);
             else k_density_list16<false><<<pp / L16_THREADS, L16_THREADS, 0, st>>>(n, n_dev, pp, posq, posq_q, velv, cell_sorted, cell_start, G, C, rho, nlist, ncount, overflow, cap);
