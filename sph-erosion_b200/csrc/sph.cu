@@ -407,7 +407,11 @@ __global__ void __launch_bounds__(L16_THREADS) k_density_list16(int n_hi, const 
     float2 acc = make_float2(0.f, 0.f);
     unsigned short* const lbase = list16 + tid;
     int* const sb = sbase + tid;
-    int off = 0, off0 = 0;  // slot * T
+    const unsigned lbase_sa = (unsigned)__cvta_generic_to_shared(lbase);
+    const unsigned cap_sa = lbase_sa + 2u * L16_CAP * T;
+    unsigned wp = lbase_sa;                                    // append cursor: shared-memory byte address
+    auto OFF = [&]() { return (int)((wp - lbase_sa) >> 1); };  // slot * T
+    int off0 = 0;
     bool too_long = false;
 #pragma unroll 1
     for (int p = 0; p < npass; p++) {
@@ -419,7 +423,7 @@ __global__ void __launch_bounds__(L16_THREADS) k_density_list16(int n_hi, const 
         const int czlo = p ? czb : cza, czhi = merged ? czb : czlo;
         const int cy = (int)(col % (uint32_t)G.ny), cx = (int)(col / (uint32_t)G.ny);
         const int z0 = czlo > 0 ? czlo - 1 : 0, z1 = czhi < G.nz - 1 ? czhi + 1 : czhi;
-        if (p == 1) off0 = off;
+        if (p == 1) off0 = OFF();
         auto test = [&](const unsigned code, const float4 pj) {
             float2 dx = __fadd2_rn(X, make_float2(-pj.x, -pj.x));
             float2 dy = __fadd2_rn(Y, make_float2(-pj.y, -pj.y));
@@ -428,10 +432,10 @@ __global__ void __launch_bounds__(L16_THREADS) k_density_list16(int n_hi, const 
             d2 = __ffma2_rn(dy, dy, d2);
             d2 = __ffma2_rn(dz, dz, d2);
             float2 w = __fadd2_rn(make_float2(C.hh, C.hh), make_float2(-d2.x, -d2.y));
-            lbase[min(off, L16_CAP * T)] = (unsigned short)code;   // branch-free append
-            off += (fmaxf(w.x, w.y) >= LIST_NEG_EPS * C.hh) ? T : 0;
-            w.x = fmaxf(w.x, 0.f);
-            w.y = fmaxf(w.y, 0.f);
+            // branch-free append through a shared-memory BYTE-address cursor and the w + |w| clamp, as in k_density_list
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(min(wp, cap_sa)), "h"((unsigned short)code) : "memory");
+            asm("{ .reg .pred q; setp.ge.f32 q, %1, %3; @q add.u32 %0, %0, %2; }" : "+r"(wp) : "f"(fmaxf(w.x, w.y)), "n"(2 * L16_THREADS), "f"(LIST_NEG_EPS * C.hh));
+            w = __fadd2_rn(w, make_float2(fabsf(w.x), fabsf(w.y)));
             acc = __ffma2_rn(__fmul2_rn(w, w), w, acc);
         };
         // entries beyond the shared-memory capacity go straight to their rows in HBM (see k_density_list)
@@ -467,10 +471,10 @@ __global__ void __launch_bounds__(L16_THREADS) k_density_list16(int n_hi, const 
                 if (p == 0) sb[r * T] = s;
                 too_long |= (e - s) > 4095;
                 const unsigned rb = (unsigned)r << 12;
-                const int off_run = off;
+                const int off_run = OFF();
 #pragma unroll 4
                 for (int k = s; k < e; k++) test(rb + (unsigned)(k - s), __ldg(&posq[k]));
-                if (off > L16_CAP * T) spill(s, e, off_run / T);
+                if (wp > cap_sa) spill(s, e, off_run / T);
             }
         } else {
             int s, e, sn, en;
@@ -481,7 +485,7 @@ __global__ void __launch_bounds__(L16_THREADS) k_density_list16(int n_hi, const 
                 if (p == 0) sb[r * T] = s;
                 too_long |= (e - s) > 4095;
                 unsigned code = (unsigned)r << 12;
-                const int off_run = off;
+                const int off_run = OFF();
                 int k = s;
 #if DL_LD256
                 // 256-bit candidate loads (see k_density_list)
@@ -517,11 +521,12 @@ __global__ void __launch_bounds__(L16_THREADS) k_density_list16(int n_hi, const 
 #endif
 #pragma unroll 1
                 for (; k < e; k++, code++) test(code, __ldg(&posq[k]));
-                if (off > L16_CAP * T) spill(s, e, off_run / T);
+                if (wp > cap_sa) spill(s, e, off_run / T);
                 s = sn; e = en;
             }
         }
     }
+    const int off = OFF();
     if (npass == 1) off0 = off;
     const int cnt = off / T;
     const bool fits = cnt <= max(rows, L16_CAP) && !too_long;
@@ -547,7 +552,8 @@ __global__ void __launch_bounds__(L16_THREADS) k_density_list16(int n_hi, const 
         }
     }
     if (!live) return;
-    float ra = acc.x * C.densK, rb = acc.y * C.densK;
+    const float dk = C.densK * 0.125f;   // exact: the accumulators hold 8 x sum (h^2 - r^2)^3 (see `test`)
+    float ra = acc.x * dk, rb = acc.y * dk;
     float Pa = C.k * (ra - C.p0), Pb = C.k * (rb - C.p0);
     rho[a] = ra;
     posq_q[a] = make_float4(pa.x, pa.y, pa.z, Pa / (ra * ra));
