@@ -85,3 +85,62 @@ def test_terrain_window_zones(monkeypatch):
     # slabs narrower than two zones are refused
     with pytest.raises(ValueError):
         slabs.TerrainWindowShare(StubGrid(64, cols), None, 1, 4, [16, 32, 48], W, swap=False)
+
+
+def test_balanced_cuts_respect_the_minimum_width():
+    hist = np.zeros(200, np.int64); hist[:20] = 1000           # everything in the first 20 columns
+    free = slabs.balanced_cuts(hist, 4)
+    assert free[0] < 12, "without a minimum width the first slab shrinks towards 2*HALO columns"
+    cuts = slabs.balanced_cuts(hist, 4, min_width=30)
+    edges = [0] + cuts + [200]
+    assert all(b - a >= 30 for a, b in zip(edges, edges[1:])), cuts
+    with pytest.raises(ValueError):
+        slabs.balanced_cuts(hist, 4, min_width=51)
+
+
+class StubGridH(StubGrid):
+    """StubGrid with a heights array behind heights_device() / refresh() (numpy stands in for the device tensor)."""
+    store = {}
+
+    def __init__(self, rows, cols, fill):
+        super().__init__(rows, cols)
+        self.h = np.full(rows * cols, fill, np.int32)
+        self.key = len(StubGridH.store) + 1
+        StubGridH.store[self.key] = self.h
+        self.refreshed = 0
+
+    def heights_device(self):
+        return self.key, self.h.size
+
+    def refresh(self):
+        self.refreshed += 1
+
+
+def test_terrain_recut_brings_every_row_up_to_date_from_its_owner(monkeypatch):
+    """TerrainWindowShare.recut_local: each replica is current only inside its window; after the re-cut every replica holds
+    the OWNERS' rows everywhere, the windows sit at the new cuts and the cull maps were rebuilt."""
+    class Arr(np.ndarray):
+        def clone(self): return self.copy().view(Arr)
+        def copy_(self, o): self[...] = o
+    monkeypatch.setattr(slabs, "device_int32_view",
+                        lambda ptr, n, device: StubGridH.store[ptr].view(Arr) if ptr in StubGridH.store else np.zeros(n, np.int32))
+    rows, cols, world, W = 400, 8, 3, 10
+    grids = [StubGridH(rows, cols, fill=-7) for _ in range(world)]          # -7 = stale everywhere
+    shares = [slabs.TerrainWindowShare(grids[r], None, r, world, [100, 250], W, swap=False) for r in range(world)]
+    gi = SimpleNamespace(gmin=[0.0, 0, 0], cell=0.05)
+    for sh in shares:
+        sh.bind_columns(gi, 0.0, 0.01)                                       # 5 terrain rows per neighbour-grid column
+    for r, sh in enumerate(shares):                                          # every replica current on its window: row index * 10 + owner tag on owned rows
+        h = grids[r].h.reshape(rows, cols)
+        for x in range(sh.window[0], sh.window[1]):
+            h[x] = 10 * x
+    assert shares[0].min_columns() * 5 >= 2 * W
+    new_cols = [(0, 30), (30, 60), (60, 80)]                                 # rows 150, 300
+    assert shares[0].rows_of(new_cols) == [150, 300]
+    slabs.TerrainWindowShare.recut_local(shares, shares[0].rows_of(new_cols))
+    want = (10 * np.arange(rows, dtype=np.int32))[:, None].repeat(cols, 1)
+    for r, (g, sh) in enumerate(zip(grids, shares)):
+        assert np.array_equal(g.h.reshape(rows, cols), want), "replica %d" % r
+        assert g.refreshed == 1 and g.window == sh.window
+    assert [sh.own for sh in shares] == [(0, 150), (150, 300), (300, 400)]
+    assert shares[1].window == (140, 310) and shares[1].zone_l == shares[0].zone_r
