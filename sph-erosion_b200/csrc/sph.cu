@@ -123,37 +123,36 @@ __global__ void __launch_bounds__(128) k_force_tpp(int n_hi, const int* __restri
     force_epilogue<DIAG>(i, pi, vi, rho_i, ax, ay, az, fx, fy, fz, nx, ny, nz, cf, maxid, C, ids, posq_out, velv_out, D);
 }
 
-// ------------------------------------------------------------------ variant 2: test ONCE, neighbour lists in HBM
-// ncu on k_force_pair (profiles/r01_ncu_force_pair.txt): 82 registers -> 5 CTAs/SM, long-scoreboard bound
-// (issue active 44 %), and the candidate test duplicates what the density pass already did.  Variant 2
-// splits the work differently:
-//   k_density_list : pass 1 + the candidate test for BOTH passes.  Two targets per thread, packed math,
-//                    branch-free append of passing candidates into a per-thread shared-memory list, which is
-//                    then written to HBM entry-major ([entry][pair], fully coalesced).  ~40 registers.
-//   k_force_list   : passes 2+3 + integrate, walking the stored list only (no candidate test at all).
-// Cost: one extra 4-byte write + read per stored neighbour (about 40 per pair).
-constexpr int NLIST_CAP = 64;       // entries per pair (both split passes together)
+// ------------------------------------------------------------------ the default passes: test ONCE, pair lists in HBM
+//   k_density_list : pass 1 + the candidate test for BOTH passes.  Two targets per thread (consecutive particles of the sorted
+//                    order, i.e. the same or adjacent cells), packed math (FADD2 / FMUL2 / FFMA2: one instruction serves both
+//                    targets), branch-free append of every candidate within h of either target to a per-thread list staged in
+//                    shared memory, flushed to HBM entry-major ([entry][pair]: a row is contiguous, fully coalesced).
+//   k_force_list   : passes 2+3 + integrate + box (+ the terrain cull), walking the stored list only -- no candidate test.
+// Cost: one 4-byte write + read per stored entry (about 50 per pair at 25 neighbours per particle).
+// (History -- thread per particle, pair kernels without lists, 4 targets per thread, lane-strided lists: csrc/experiments,
+// DESIGN.md section 3.)
+constexpr int NLIST_CAP = 64;       // nominal entries per pair at the base level (sizing levels: 64 / 128 / 256)
 // A candidate enters a pair list when hh - d2 >= -2^-20 hh with the FMA-contracted d2.  The reference predicate is
 // sqrt(d2_exact) <= h  <=>  d2_exact <= T with T within 1 ulp of hh, and the contracted d2 is within 3 ulp of the exact one,
 // so the lists are a SUPERSET of the exact neighbour sets; the extra entries have clamped weights of 0 or a few ulp
 // (tests/test_gpu_parity.py::test_pair_masks_cover_the_exact_neighbour_sets reads the production lists back).
 constexpr float LIST_NEG_EPS = -9.5367431640625e-07f;
 
-// REC = true (variant 4): instead of (posC, vel.w) the pass writes ONE interleaved 32-byte record per particle,
-// rec[2i] = (x, y, z, P/rho^2), rec[2i+1] = (vx, vy, vz, m/rho), so the force pass fetches everything it needs
-// about a neighbour with a single 256-bit gather (LDG.E.256, new on sm_100) instead of two 128-bit ones.
-// PF = true (variant 6): software-pipelined candidate stream.  ncu source view of the plain kernel: 45 % of the
-// stall samples sit on the first use of the gathered positions and 9 % on the run bounds (cell_start) -- the
-// kernel waits on its own loads.  Here the next group of four candidates and the next run's bounds are
-// already in flight while the current group is processed.
-// CAP / THREADS: list capacity per pair and CTA size.  64 entries are plenty at the reference's ~25 neighbours; scenes with
-// 60-120 neighbours per particle (BASELINE configs[4]) overflow them and fall back to the direct walk in the force
-// pass, which costs 2-4x.  The host raises CAP to 128 / 256 when the overflow counter says so (api.cu step_device).
-// The list lives in dynamic shared memory: (CAP + 1) * THREADS ints = 33 / 66 / 66 KB.
-// Base configuration of the density pass (the "64-entry" level of the list sizing): 56 staged entries per pair, 64-thread
-// CTAs, 14 CTAs/SM = 28 warps at 71 registers and 14.6 KB of shared memory per CTA.  The pass is issue/latency bound: with
-// the 64-entry stage of round 1 (33 KB per 128-thread CTA, 80 registers) 24 warps fit -- c3 density pass 0.644 -> 0.616 ms;
-// 48 entries at 16 CTAs/SM spill too often (0.657 ms).  A/B: SPHE_NVCC_EXTRA="-DDL_CAP=.. -DDL_THREADS=.. -DDL_MINB=.."
+// Template parameters of k_density_list:
+// REC  = true: instead of (posC, vel.w) the pass writes ONE interleaved 32-byte record per particle for the force pass
+//        (one 256-bit gather instead of two 128-bit ones).  Measured neutral (the gathers are latency bound); not instantiated
+//        by the default dispatch.
+// PF   = true (density variant 6, the default): software-pipelined candidate stream -- the next four candidates and the next
+//        run's bounds are in flight while the current four are processed (ncu source view of the plain kernel: 45 % of the
+//        stall samples on the first use of the gathered positions, 9 % on the run bounds).
+// CAP / THREADS: entries per pair staged in shared memory and CTA size; the list is (CAP + 1) * THREADS ints.  Longer lists
+//        spill to their HBM rows directly (see `spill`), lists beyond the allocated rows fall back to a direct walk in the
+//        force pass; the host raises the level (128 / 256 staged entries: k_density_list16) when the spill counters say so
+//        (api.cu step_device).
+// Base level: 56 staged entries per pair, 64-thread CTAs, 14 CTAs/SM = 28 warps at 72 registers and 14.6 KB of shared memory
+// per CTA.  With the 64-entry stage of round 1 (33 KB per 128-thread CTA, 80 registers) 24 warps fit -- c3 density pass
+// 0.644 -> 0.616 ms; 48 entries at 16 CTAs/SM spill too often (0.657 ms).  A/B: SPHE_NVCC_EXTRA="-DDL_CAP=.. -DDL_THREADS=.. -DDL_MINB=.."
 #ifndef DL_LD256
 #define DL_LD256 1
 #endif
